@@ -1,0 +1,29 @@
+/* oracle/port.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C restatement ("port") of the xiph/daala per-block hot path, used by
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg as the
+ * CHECKER.  Nothing in daala_b200/ may include, link or call this.
+ * Pinned against the real reference (oracle/_ref/libdaala_ref.so, built from
+ * /root/reference by oracle/Makefile) in tests/test_oracle_port.py.
+ */
+#ifndef DAALA_ORACLE_PORT_H
+#define DAALA_ORACLE_PORT_H
+#include <stdint.h>
+
+typedef int32_t od_coeff;
+
+/* port_dct.c -- src/dct.c */
+void port_bin_fdct(int ln, od_coeff *y, const od_coeff *x, int xstride);
+void port_bin_idct(int ln, od_coeff *x, int xstride, const od_coeff *y);
+void port_bin_fdct2d(int ln, od_coeff *y, int ystride, const od_coeff *x, int xstride);
+void port_bin_idct2d(int ln, od_coeff *x, int xstride, const od_coeff *y, int ystride);
+
+/* port_filter.c -- src/filter.c */
+void port_pre_filter4(od_coeff y[4], const od_coeff x[4]);
+void port_post_filter4(od_coeff x[4], const od_coeff y[4]);
+void port_prefilter_split(od_coeff *c0, int stride, int bs, int hfilter, int vfilter);
+void port_postfilter_split(od_coeff *c0, int stride, int bs, int hfilter, int vfilter);
+void port_apply_prefilter_frame_sbs(od_coeff *c0, int stride, int nhsb, int nvsb, int xdec, int ydec);
+void port_apply_postfilter_frame_sbs(od_coeff *c0, int stride, int nhsb, int nvsb, int xdec, int ydec);
+
+#endif
