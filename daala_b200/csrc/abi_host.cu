@@ -1,0 +1,235 @@
+// C-ABI layer of libdaala_b200.so.
+//
+//  * Section A of include/daala_b200.h: the reference's od_* symbols with HOST
+//    pointers.  Each call packs its operand into pinned staging memory, runs
+//    the matching kernel on a private stream and unpacks the result --
+//    synchronous and bit-exact, like the C functions they replace
+//    (reference: src/dct.c, src/filter.c).
+//  * Section B: thin wrappers that forward device pointers to the launchers
+//    in frame_transform.cu.
+//
+// No CPU fallback: a missing/unusable GPU is fatal for section A (the
+// reference prototypes return void) and an error code for section B.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "daala_b200.h"
+#include "frame_transform.h"
+
+extern "C" {
+int daala_b200_launch_forward(const FrameXformParams* prm, int nplanes, cudaStream_t stream);
+int daala_b200_launch_inverse(const FrameXformParams* prm, int nplanes, cudaStream_t stream);
+int daala_b200_launch_inverse_lapped_only(const FrameXformParams* prm, int nplanes, cudaStream_t stream);
+int daala_b200_launch_plane_sb_filter(int32_t* c, int stride, int nhsb, int nvsb, int xdec, int ydec,
+                                      int post, cudaStream_t stream);
+int daala_b200_launch_block_transform(int32_t* blocks, int count, int ln, int mode, cudaStream_t stream);
+int daala_b200_launch_filter4(int32_t* v, long count, int post, cudaStream_t stream);
+int daala_b200_launch_split_filter(int32_t* blocks, int count, int n, int post, int hfilter, int vfilter,
+                                   cudaStream_t stream);
+}
+
+namespace {
+
+[[noreturn]] void fatal(const char* what, cudaError_t err) {
+  fprintf(stderr, "libdaala_b200: fatal: %s: %s (no CPU fallback exists)\n", what,
+          cudaGetErrorString(err));
+  abort();
+}
+
+#define CK(call)                                    \
+  do {                                              \
+    cudaError_t e_ = (call);                        \
+    if (e_ != cudaSuccess) fatal(#call, e_);        \
+  } while (0)
+
+// Per-process staging context for the host-pointer entry points.
+struct HostCtx {
+  cudaStream_t stream = nullptr;
+  void* pinned = nullptr;
+  void* dev = nullptr;
+  size_t cap = 0;
+  std::mutex mu;
+
+  void ensure(size_t bytes) {
+    if (!stream) {
+      int n = 0;
+      cudaError_t e = cudaGetDeviceCount(&n);
+      if (e != cudaSuccess || n == 0) fatal("cudaGetDeviceCount", e == cudaSuccess ? cudaErrorNoDevice : e);
+      CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    }
+    if (bytes > cap) {
+      size_t ncap = cap ? cap : (size_t)1 << 20;
+      while (ncap < bytes) ncap <<= 1;
+      if (pinned) CK(cudaFreeHost(pinned));
+      if (dev) CK(cudaFree(dev));
+      CK(cudaMallocHost(&pinned, ncap));
+      CK(cudaMalloc(&dev, ncap));
+      cap = ncap;
+    }
+  }
+  void h2d(size_t bytes) { CK(cudaMemcpyAsync(dev, pinned, bytes, cudaMemcpyHostToDevice, stream)); }
+  void d2h(size_t bytes) {
+    CK(cudaMemcpyAsync(pinned, dev, bytes, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+};
+
+HostCtx& ctx() {
+  static HostCtx c;
+  return c;
+}
+
+void check_launch(int rc, const char* what) {
+  if (rc != 0) fatal(what, (cudaError_t)rc);
+}
+
+void dct1d(int ln, bool inverse, od_coeff* out, int out_stride, const od_coeff* in, int in_stride) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g(c.mu);
+  const int n = 1 << ln;
+  c.ensure(sizeof(od_coeff) * n * n);
+  od_coeff* p = (od_coeff*)c.pinned;
+  // The 1-D kernel transforms rows of a packed n x n block; only row 0 is used.
+  memset(p, 0, sizeof(od_coeff) * n * n);
+  for (int i = 0; i < n; i++) p[i] = in[i * in_stride];
+  c.h2d(sizeof(od_coeff) * n * n);
+  check_launch(daala_b200_launch_block_transform((int32_t*)c.dev, 1, ln, inverse ? 3 : 2, c.stream),
+               "block_transform(1d)");
+  c.d2h(sizeof(od_coeff) * n);
+  for (int i = 0; i < n; i++) out[i * out_stride] = p[i];
+}
+
+void dct2d(int ln, bool inverse, od_coeff* out, int out_stride, const od_coeff* in, int in_stride) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g(c.mu);
+  const int n = 1 << ln;
+  c.ensure(sizeof(od_coeff) * n * n);
+  od_coeff* p = (od_coeff*)c.pinned;
+  for (int i = 0; i < n; i++) memcpy(p + i * n, in + (size_t)i * in_stride, sizeof(od_coeff) * n);
+  c.h2d(sizeof(od_coeff) * n * n);
+  check_launch(daala_b200_launch_block_transform((int32_t*)c.dev, 1, ln, inverse ? 1 : 0, c.stream),
+               "block_transform(2d)");
+  c.d2h(sizeof(od_coeff) * n * n);
+  for (int i = 0; i < n; i++) memcpy(out + (size_t)i * out_stride, p + i * n, sizeof(od_coeff) * n);
+}
+
+void filter4(bool post, od_coeff* out, const od_coeff* in) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g(c.mu);
+  c.ensure(sizeof(od_coeff) * 4);
+  memcpy(c.pinned, in, sizeof(od_coeff) * 4);
+  c.h2d(sizeof(od_coeff) * 4);
+  check_launch(daala_b200_launch_filter4((int32_t*)c.dev, 1, post, c.stream), "filter4");
+  c.d2h(sizeof(od_coeff) * 4);
+  memcpy(out, c.pinned, sizeof(od_coeff) * 4);
+}
+
+void split_filter(bool post, od_coeff* c0, int stride, int bs, int hfilter, int vfilter) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g(c.mu);
+  const int n = 4 << bs;
+  c.ensure(sizeof(od_coeff) * n * n);
+  od_coeff* p = (od_coeff*)c.pinned;
+  for (int i = 0; i < n; i++) memcpy(p + i * n, c0 + (size_t)i * stride, sizeof(od_coeff) * n);
+  c.h2d(sizeof(od_coeff) * n * n);
+  check_launch(daala_b200_launch_split_filter((int32_t*)c.dev, 1, n, post, hfilter, vfilter, c.stream),
+               "split_filter");
+  c.d2h(sizeof(od_coeff) * n * n);
+  for (int i = 0; i < n; i++) memcpy(c0 + (size_t)i * stride, p + i * n, sizeof(od_coeff) * n);
+}
+
+void plane_sb_filter(bool post, od_coeff* c0, int stride, int nhsb, int nvsb, int xdec, int ydec) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g(c.mu);
+  const int w = (nhsb * 64) >> xdec, h = (nvsb * 64) >> ydec;
+  const size_t bytes = sizeof(od_coeff) * (size_t)w * h;
+  c.ensure(bytes);
+  od_coeff* p = (od_coeff*)c.pinned;
+  for (int i = 0; i < h; i++) memcpy(p + (size_t)i * w, c0 + (size_t)i * stride, sizeof(od_coeff) * w);
+  c.h2d(bytes);
+  check_launch(daala_b200_launch_plane_sb_filter((int32_t*)c.dev, w, nhsb, nvsb, xdec, ydec, post, c.stream),
+               "plane_sb_filter");
+  c.d2h(bytes);
+  for (int i = 0; i < h; i++) memcpy(c0 + (size_t)i * stride, p + (size_t)i * w, sizeof(od_coeff) * w);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- Section A ------------------------------------------------------------
+#define DAALA_B200_DCT(N, LN)                                                                     \
+  void od_bin_fdct##N(od_coeff* y, const od_coeff* x, int xstride) { dct1d(LN, false, y, 1, x, xstride); } \
+  void od_bin_idct##N(od_coeff* x, int xstride, const od_coeff* y) { dct1d(LN, true, x, xstride, y, 1); }  \
+  void od_bin_fdct##N##x##N(od_coeff* y, int ystride, const od_coeff* x, int xstride) {          \
+    dct2d(LN, false, y, ystride, x, xstride);                                                    \
+  }                                                                                              \
+  void od_bin_idct##N##x##N(od_coeff* x, int xstride, const od_coeff* y, int ystride) {          \
+    dct2d(LN, true, x, xstride, y, ystride);                                                     \
+  }
+DAALA_B200_DCT(4, 2)
+DAALA_B200_DCT(8, 3)
+DAALA_B200_DCT(16, 4)
+DAALA_B200_DCT(32, 5)
+DAALA_B200_DCT(64, 6)
+
+const od_dct_func_2d OD_FDCT_2D_CUDA[6] = {od_bin_fdct4x4,   od_bin_fdct8x8,   od_bin_fdct16x16,
+                                           od_bin_fdct32x32, od_bin_fdct64x64, nullptr};
+const od_dct_func_2d OD_IDCT_2D_CUDA[6] = {od_bin_idct4x4,   od_bin_idct8x8,   od_bin_idct16x16,
+                                           od_bin_idct32x32, od_bin_idct64x64, nullptr};
+
+void od_pre_filter4(od_coeff _y[4], const od_coeff _x[4]) { filter4(false, _y, _x); }
+void od_post_filter4(od_coeff _x[4], const od_coeff _y[4]) { filter4(true, _x, _y); }
+
+void od_prefilter_split(od_coeff* c0, int stride, int bs, int f, int hfilter, int vfilter) {
+  (void)f;  // OD_FILT_SIZE() == 0: always the 4-point filter (src/filter.h:77)
+  split_filter(false, c0, stride, bs, hfilter, vfilter);
+}
+
+void od_postfilter_split(od_coeff* c0, int stride, int bs, int f, int q, unsigned char* skip,
+                         int skip_stride, int hfilter, int vfilter) {
+  (void)f; (void)q; (void)skip; (void)skip_stride;  // deblocking branch is compiled out upstream
+  split_filter(true, c0, stride, bs, hfilter, vfilter);
+}
+
+void od_apply_prefilter_frame_sbs(od_coeff* c, int stride, int nhsb, int nvsb, int xdec, int ydec) {
+  plane_sb_filter(false, c, stride, nhsb, nvsb, xdec, ydec);
+}
+
+void od_apply_postfilter_frame_sbs(od_coeff* c, int stride, int nhsb, int nvsb, int xdec, int ydec,
+                                   int q, unsigned char* skip, int skip_stride) {
+  (void)q; (void)skip; (void)skip_stride;
+  plane_sb_filter(true, c, stride, nhsb, nvsb, xdec, ydec);
+}
+
+// ---- Section B ------------------------------------------------------------
+int daala_b200_forward_frame(const daala_b200_frame* f, int nplanes, void* stream) {
+  return daala_b200_launch_forward(f, nplanes, (cudaStream_t)stream);
+}
+int daala_b200_inverse_frame(const daala_b200_frame* f, int nplanes, void* stream) {
+  return daala_b200_launch_inverse(f, nplanes, (cudaStream_t)stream);
+}
+int daala_b200_inverse_frame_lapped(const daala_b200_frame* f, int nplanes, void* stream) {
+  return daala_b200_launch_inverse_lapped_only(f, nplanes, (cudaStream_t)stream);
+}
+int daala_b200_plane_sb_filter(int32_t* c, int stride, int nhsb, int nvsb, int xdec, int ydec, int post,
+                               void* stream) {
+  return daala_b200_launch_plane_sb_filter(c, stride, nhsb, nvsb, xdec, ydec, post, (cudaStream_t)stream);
+}
+int daala_b200_block_transform(int32_t* blocks, int count, int ln, int mode, void* stream) {
+  return daala_b200_launch_block_transform(blocks, count, ln, mode, (cudaStream_t)stream);
+}
+
+int daala_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* daala_b200_version(void) { return "daala_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,513 @@
+// Fused lapped-transform frame kernels for sm_100a.
+//
+// Forward  (encoder analysis), one CTA per superblock of one plane:
+//   u8 pixels -> (p-128)<<4 -> superblock-edge prefilter -> per split node
+//   interior-cross prefilter (top-down) -> leaf fDCT (4..64 points, 2-D)
+//   -> keyframe DC Haar pyramid (bottom-up) -> int32 coefficient plane `d`.
+//   Restates, for a whole frame in one launch, what the reference does with
+//   od_ref_plane_to_coeff (src/state.c:1259) + od_apply_prefilter_frame_sbs
+//   (src/filter.c:1529) + od_compute_dcts (src/encode.c:1455).
+//
+// Inverse (reconstruction), two launches:
+//   k_inverse_sb:   d -> inverse DC Haar (top-down) -> leaf iDCT -> split
+//                   postfilters (bottom-up) -> int32 plane `c`
+//                   (od_block_encode's idct_2d, src/encode.c:1397, and
+//                   od_postfilter_split, src/filter.c:1485, for a whole frame)
+//   k_sb_postfilter_store: superblock-edge postfilter + clamp to u8
+//                   (od_apply_postfilter_frame_sbs src/filter.c:1561 +
+//                   od_coeff_to_ref_plane src/state.c:1323).
+//
+// Work mapping: a 1-D N-point transform is straight-line integer lifting code
+// (gen/dct_lifting.cuh) run by ONE thread on N registers; the 2-D transform is
+// a column pass and a row pass over a shared-memory tile whose pitch is odd
+// (5 mod 32), so both passes are bank-conflict free without a transpose.
+// Tensor cores are not used: these are rounding lifting networks, not GEMMs.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gen/dct_lifting.cuh"
+#include "lapped_filter.cuh"
+#include "frame_transform.h"
+
+namespace daala_b200 {
+
+constexpr int kThreads = 256;
+constexpr int kMaxB = 64;            // superblock edge in luma pixels
+constexpr int kHalo = 2;             // lapping reaches 2 samples across an edge
+constexpr int kMaxT = kMaxB + 2 * kHalo;
+constexpr int kMaxPitch = kMaxT + 1; // 69 = 5 mod 32; chroma 37 = 5 mod 32
+
+// ---------------------------------------------------------------------------
+// Leaf-size lookup for one superblock.  `leaf[v*8+u]` = log2 of the transform
+// size, in PLANE pixels, covering the 8x8-luma unit (u, v) of this superblock:
+// max(obs, xdec) - xdec + 2 with obs the entry of the reference's
+// state->bsize map (OD_BLOCK_SIZE4x4, src/block_size.h; recursion rule
+// src/encode.c:1467-1470).
+// ---------------------------------------------------------------------------
+struct SbCtx {
+  int B;        // superblock edge in plane pixels (64 >> xdec)
+  int P;        // tile pitch in ints
+  int ushift;   // plane pixels -> 8x8-luma unit: 3 - xdec
+  int x0, y0;   // plane coordinates of the superblock origin
+};
+
+__device__ __forceinline__ int leaf_log(const unsigned char* leaf, const SbCtx& s, int px, int py) {
+  return leaf[(py >> s.ushift) * 8 + (px >> s.ushift)];
+}
+
+__device__ __forceinline__ void load_leaf_map(unsigned char* leaf, const unsigned char* bsize,
+                                               int bstride, int sbx, int sby, int xdec) {
+  if (threadIdx.x < 64) {
+    int u = threadIdx.x & 7, v = threadIdx.x >> 3;
+    int obs = bsize[(sby * 8 + v) * bstride + sbx * 8 + u];
+    int bs = obs > xdec ? obs : xdec;
+    leaf[threadIdx.x] = (unsigned char)(bs - xdec + 2);
+  }
+}
+
+// Is the node of edge S (plane px) whose origin is (nx, ny) (superblock-local)
+// split further?  The reference looks at the block size stored at the node's
+// top-left corner (src/encode.c:1466).
+__device__ __forceinline__ bool node_is_split(const unsigned char* leaf, const SbCtx& s, int nx,
+                                              int ny, int logS) {
+  return leaf_log(leaf, s, nx, ny) < logS;
+}
+
+// ---------------------------------------------------------------------------
+// One pass of 1-D transforms over every leaf of size 2^L in the tile.
+// kFwd:  pass 0 = columns, pass 1 = rows   (od_bin_fdctNxN, src/dct.c:151-156)
+// !kFwd: pass 0 = rows,    pass 1 = columns (od_bin_idctNxN, src/dct.c:158-163)
+// `tile` points at the superblock's (0,0) sample inside the shared tile.
+// ---------------------------------------------------------------------------
+template <int L, bool kFwd>
+__device__ __forceinline__ void transform_pass(int* tile, const unsigned char* leaf,
+                                               const SbCtx& s, bool along_columns) {
+  constexpr int N = 1 << L;
+  const int B = s.B;
+  const int items = B * (B >> L);
+  for (int item = threadIdx.x; item < items; item += kThreads) {
+    int a = item % B;        // position across the transform direction
+    int m = item / B;        // which N-segment along the transform direction
+    int px = along_columns ? a : m * N;
+    int py = along_columns ? m * N : a;
+    if (leaf_log(leaf, s, px, py) != L) continue;
+    int* p = tile + py * s.P + px;
+    const int stride = along_columns ? s.P : 1;
+    int v[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) v[k] = p[k * stride];
+    if (kFwd) Lifting<N>::fwd(v); else Lifting<N>::inv(v);
+#pragma unroll
+    for (int k = 0; k < N; k++) p[k * stride] = v[k];
+  }
+}
+
+template <bool kFwd>
+__device__ __forceinline__ void transform_all_leaves(int* tile, const unsigned char* leaf,
+                                                     const SbCtx& s, unsigned size_mask) {
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    const bool cols = kFwd ? (pass == 0) : (pass == 1);
+    if (size_mask & (1u << 6)) transform_pass<6, kFwd>(tile, leaf, s, cols);
+    if (size_mask & (1u << 5)) transform_pass<5, kFwd>(tile, leaf, s, cols);
+    if (size_mask & (1u << 4)) transform_pass<4, kFwd>(tile, leaf, s, cols);
+    if (size_mask & (1u << 3)) transform_pass<3, kFwd>(tile, leaf, s, cols);
+    if (size_mask & (1u << 2)) transform_pass<2, kFwd>(tile, leaf, s, cols);
+    __syncthreads();
+  }
+}
+
+// Interior-cross lapping of every split node of edge 2^logS.
+// Prefilter: horizontal edge (vertical taps) first, then the vertical edge
+// (od_prefilter_split, src/filter.c:1467-1481); postfilter: the reverse
+// (od_postfilter_split, src/filter.c:1510-1525).  A direction is disabled when
+// the node sticks out of the picture; the reference compares PLANE coordinates
+// with the LUMA picture size (src/encode.c:1487-1488) -- reproduced literally.
+template <bool kPost>
+__device__ __forceinline__ void split_filter_level(int* tile, const unsigned char* leaf,
+                                                   const SbCtx& s, int logS, int pic_w, int pic_h,
+                                                   bool vertical_taps) {
+  const int S = 1 << logS;
+  const int B = s.B;
+  const int items = B * (B >> logS);
+  for (int item = threadIdx.x; item < items; item += kThreads) {
+    int a = item % B;   // coordinate along the edge
+    int m = item / B;   // node index across the edge
+    int nx, ny;
+    if (vertical_taps) { nx = a & ~(S - 1); ny = m * S; }
+    else { nx = m * S; ny = a & ~(S - 1); }
+    if (!node_is_split(leaf, s, nx, ny, logS)) continue;
+    if (vertical_taps) {
+      if (s.x0 + nx + S > pic_w) continue;  // hfilter gate
+      lap4_inplace<kPost>(tile + (ny + S / 2 - 2) * s.P + a, s.P);
+    } else {
+      if (s.y0 + ny + S > pic_h) continue;  // vfilter gate
+      lap4_inplace<kPost>(tile + a * s.P + nx + S / 2 - 2, 1);
+    }
+  }
+}
+
+// DC Haar pyramid over the children of every split node of edge 2^logS
+// (src/encode.c:1497-1510 forward; the inverse applies the same kernel with
+// the two middle terms swapped, cf. od_quantize_haar_dc_level :1651).
+template <bool kInverse>
+__device__ __forceinline__ void haar_dc_level(int* tile, const unsigned char* leaf, const SbCtx& s,
+                                              int logS) {
+  const int S = 1 << logS;
+  const int per_row = s.B >> logS;
+  const int items = per_row * per_row;
+  for (int item = threadIdx.x; item < items; item += kThreads) {
+    int nx = (item % per_row) * S, ny = (item / per_row) * S;
+    if (!node_is_split(leaf, s, nx, ny, logS)) continue;
+    int* p00 = tile + ny * s.P + nx;
+    int* p01 = p00 + S / 2;
+    int* p10 = p00 + (S / 2) * s.P;
+    int* p11 = p10 + S / 2;
+    int ll = *p00, hl, lh, hh = *p11;
+    // OD_HAAR_KERNEL(ll, lh, hl, hh), src/tf.h:35-46
+    if (kInverse) { lh = *p01; hl = *p10; } else { lh = *p10; hl = *p01; }
+    ll += hl;
+    hh -= lh;
+    int t = (ll - hh) >> 1;
+    lh = t - lh;
+    hl = t - hl;
+    ll -= lh;
+    hh += hl;
+    *p00 = ll;
+    *p11 = hh;
+    if (kInverse) { *p01 = lh; *p10 = hl; } else { *p10 = lh; *p01 = hl; }
+  }
+}
+
+__device__ __forceinline__ unsigned leaf_size_mask(const unsigned char* leaf) {
+  unsigned m = 0;
+  // 64 entries; every thread computes the same mask (broadcast reads).
+#pragma unroll 8
+  for (int i = 0; i < 64; i++) m |= 1u << leaf[i];
+  return m;
+}
+
+// ---------------------------------------------------------------------------
+// Forward kernel.  grid = (nhsb*nvsb, nplanes).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_forward_sb(const __grid_constant__ FrameXformParams prm) {
+  __shared__ int tile_s[kMaxT * kMaxPitch];
+  __shared__ unsigned char leaf[64];
+  const PlaneXform& pl = prm.plane[blockIdx.y];
+  const int xdec = pl.xdec;
+  const int sbx = blockIdx.x % prm.nhsb, sby = blockIdx.x / prm.nhsb;
+  SbCtx s;
+  s.B = kMaxB >> xdec;
+  const int T = s.B + 2 * kHalo;
+  s.P = T + 1;
+  s.ushift = 3 - xdec;
+  s.x0 = sbx * s.B;
+  s.y0 = sby * s.B;
+  const int pw = prm.nhsb * s.B, ph = prm.nvsb * s.B;
+  load_leaf_map(leaf, prm.bsize, prm.bstride, sbx, sby, xdec);
+  // Stage the (B+4)^2 pixel window as (p-128) << OD_COEFF_SHIFT (src/state.c:1233).
+  const uint8_t* src = pl.pixels;
+  for (int i = threadIdx.x; i < T * T; i += kThreads) {
+    int r = i / T, c = i % T;
+    int gx = s.x0 + c - kHalo, gy = s.y0 + r - kHalo;
+    int v = 0;
+    if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = ((int)src[(size_t)gy * pl.pixel_stride + gx] - 128) * 16;
+    tile_s[r * s.P + c] = v;
+  }
+  __syncthreads();
+  // Superblock-edge prefilter: all horizontal edges first (vertical taps),
+  // then all vertical edges (src/filter.c:1541-1557).
+  {
+    const bool top = sby > 0, bottom = sby + 1 < prm.nvsb;
+    for (int i = threadIdx.x; i < 2 * T; i += kThreads) {
+      int c = i % T, e = i / T;
+      if (e == 0 ? top : bottom) lap4_inplace<false>(tile_s + (e ? s.B : 0) * s.P + c, s.P);
+    }
+    __syncthreads();
+    const bool left = sbx > 0, right = sbx + 1 < prm.nhsb;
+    for (int i = threadIdx.x; i < 2 * s.B; i += kThreads) {
+      int r = i % s.B + kHalo, e = i / s.B;
+      if (e == 0 ? left : right) lap4_inplace<false>(tile_s + r * s.P + (e ? s.B : 0), 1);
+    }
+    __syncthreads();
+  }
+  int* tile = tile_s + kHalo * s.P + kHalo;
+  const int logB = 6 - xdec;
+  // Top-down split prefilters.
+#pragma unroll 1
+  for (int logS = logB; logS >= 3; logS--) {
+    split_filter_level<false>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, true);
+    __syncthreads();
+    split_filter_level<false>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, false);
+    __syncthreads();
+  }
+  const unsigned mask = leaf_size_mask(leaf);
+  transform_all_leaves<true>(tile, leaf, s, mask);
+  if (prm.haar_dc) {
+#pragma unroll 1
+    for (int logS = 3; logS <= logB; logS++) {
+      haar_dc_level<false>(tile, leaf, s, logS);
+      __syncthreads();
+    }
+  }
+  int32_t* dst = pl.coeffs + (size_t)s.y0 * pl.coeff_stride + s.x0;
+  for (int i = threadIdx.x; i < s.B * s.B; i += kThreads) {
+    int r = i / s.B, c = i % s.B;
+    dst[(size_t)r * pl.coeff_stride + c] = tile[r * s.P + c];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Inverse kernel 1: coefficients -> lapped-domain samples (int32 plane).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_inverse_sb(const __grid_constant__ FrameXformParams prm) {
+  __shared__ int tile_s[kMaxB * (kMaxB + 5)];
+  __shared__ unsigned char leaf[64];
+  const PlaneXform& pl = prm.plane[blockIdx.y];
+  const int xdec = pl.xdec;
+  const int sbx = blockIdx.x % prm.nhsb, sby = blockIdx.x / prm.nhsb;
+  SbCtx s;
+  s.B = kMaxB >> xdec;
+  s.P = s.B + 5;
+  s.ushift = 3 - xdec;
+  s.x0 = sbx * s.B;
+  s.y0 = sby * s.B;
+  load_leaf_map(leaf, prm.bsize, prm.bstride, sbx, sby, xdec);
+  int* tile = tile_s;
+  const int32_t* srcp = pl.coeffs + (size_t)s.y0 * pl.coeff_stride + s.x0;
+  for (int i = threadIdx.x; i < s.B * s.B; i += kThreads) {
+    int r = i / s.B, c = i % s.B;
+    tile[r * s.P + c] = srcp[(size_t)r * pl.coeff_stride + c];
+  }
+  __syncthreads();
+  const int logB = 6 - xdec;
+  if (prm.haar_dc) {
+#pragma unroll 1
+    for (int logS = logB; logS >= 3; logS--) {
+      haar_dc_level<true>(tile, leaf, s, logS);
+      __syncthreads();
+    }
+  }
+  const unsigned mask = leaf_size_mask(leaf);
+  transform_all_leaves<false>(tile, leaf, s, mask);
+  // Bottom-up split postfilters: vertical edge first, then horizontal.
+#pragma unroll 1
+  for (int logS = 3; logS <= logB; logS++) {
+    split_filter_level<true>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, false);
+    __syncthreads();
+    split_filter_level<true>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, true);
+    __syncthreads();
+  }
+  int32_t* dst = pl.lapped + (size_t)s.y0 * pl.lapped_stride + s.x0;
+  for (int i = threadIdx.x; i < s.B * s.B; i += kThreads) {
+    int r = i / s.B, c = i % s.B;
+    dst[(size_t)r * pl.lapped_stride + c] = tile[r * s.P + c];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Inverse kernel 2: superblock-edge postfilter + clamp to 8 bits.
+// One CTA per superblock; reads a (B+4)^2 window of the lapped plane.
+// Vertical edges first (horizontal taps), then horizontal edges
+// (src/filter.c:1599-1617); store OD_CLAMP255(((v + 8) >> 4) + 128)
+// (src/state.c:1300-1303).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_sb_postfilter_store(const __grid_constant__ FrameXformParams prm) {
+  __shared__ int tile_s[kMaxT * kMaxPitch];
+  const PlaneXform& pl = prm.plane[blockIdx.y];
+  const int xdec = pl.xdec;
+  const int sbx = blockIdx.x % prm.nhsb, sby = blockIdx.x / prm.nhsb;
+  const int B = kMaxB >> xdec;
+  const int T = B + 2 * kHalo;
+  const int P = T + 1;
+  const int x0 = sbx * B, y0 = sby * B;
+  const int pw = prm.nhsb * B, ph = prm.nvsb * B;
+  for (int i = threadIdx.x; i < T * T; i += kThreads) {
+    int r = i / T, c = i % T;
+    int gx = x0 + c - kHalo, gy = y0 + r - kHalo;
+    int v = 0;
+    if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = pl.lapped[(size_t)gy * pl.lapped_stride + gx];
+    tile_s[r * P + c] = v;
+  }
+  __syncthreads();
+  const bool left = sbx > 0, right = sbx + 1 < prm.nhsb;
+  for (int i = threadIdx.x; i < 2 * T; i += kThreads) {
+    int r = i % T, e = i / T;
+    if (e == 0 ? left : right) lap4_inplace<true>(tile_s + r * P + (e ? B : 0), 1);
+  }
+  __syncthreads();
+  const bool top = sby > 0, bottom = sby + 1 < prm.nvsb;
+  for (int i = threadIdx.x; i < 2 * B; i += kThreads) {
+    int c = i % B + kHalo, e = i / B;
+    if (e == 0 ? top : bottom) lap4_inplace<true>(tile_s + (e ? B : 0) * P + c, P);
+  }
+  __syncthreads();
+  uint8_t* dst = pl.pixels_out + (size_t)y0 * pl.pixel_out_stride + x0;
+  // Four pixels per thread, packed into one 32-bit store.
+  for (int i = threadIdx.x; i < B * B / 4; i += kThreads) {
+    int r = i / (B / 4), c4 = (i % (B / 4)) * 4;
+    const int* p = tile_s + (r + kHalo) * P + c4 + kHalo;
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int v = ((p[k] + 8) >> 4) + 128;
+      v = v < 0 ? 0 : (v > 255 ? 255 : v);
+      w |= (unsigned)v << (8 * k);
+    }
+    *reinterpret_cast<unsigned*>(dst + (size_t)r * pl.pixel_out_stride + c4) = w;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Plane-wide superblock-edge filters on an int32 plane, in place (the
+// stand-alone forms of od_apply_prefilter_frame_sbs / _postfilter_).
+// One launch per direction; `vertical_taps` selects horizontal edges.
+// ---------------------------------------------------------------------------
+template <bool kPost>
+__global__ void k_plane_sb_edges(int32_t* c, int stride, int nhsb, int nvsb, int sbw, int sbh,
+                                 bool vertical_taps) {
+  const int w = nhsb * sbw, h = nvsb * sbh;
+  const int along = vertical_taps ? w : h;
+  const int edges = (vertical_taps ? nvsb : nhsb) - 1;
+  const long total = (long)along * edges;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    int a = (int)(i % along), e = (int)(i / along) + 1;
+    if (vertical_taps) lap4_inplace<kPost>(c + (size_t)(e * sbh - 2) * stride + a, stride);
+    else lap4_inplace<kPost>(c + (size_t)a * stride + e * sbw - 2, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Batched stand-alone block transforms: `count` packed n x n blocks
+// (row-major, contiguous).  One CTA per block; used by the per-call od_bin_*
+// entry points and by the dcttest-style parity tests.
+// mode: 0 = 2-D forward, 1 = 2-D inverse, 2 = 1-D forward (rows), 3 = 1-D inverse (rows)
+// ---------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(64)
+k_block_transform(int32_t* blocks, int mode) {
+  constexpr int N = 1 << L;
+  constexpr int P = N + 5;
+  __shared__ int t[N * P];
+  int32_t* blk = blocks + (size_t)blockIdx.x * N * N;
+  for (int i = threadIdx.x; i < N * N; i += blockDim.x) t[(i / N) * P + (i % N)] = blk[i];
+  __syncthreads();
+  const bool fwd = (mode & 1) == 0;
+  const int passes = mode < 2 ? 2 : 1;
+  for (int pass = 0; pass < passes; pass++) {
+    bool cols = mode < 2 ? (fwd ? pass == 0 : pass == 1) : false;
+    if (threadIdx.x < N) {
+      int* p = cols ? t + threadIdx.x : t + threadIdx.x * P;
+      int stride = cols ? P : 1;
+      int v[N];
+#pragma unroll
+      for (int k = 0; k < N; k++) v[k] = p[k * stride];
+      if (fwd) Lifting<N>::fwd(v); else Lifting<N>::inv(v);
+#pragma unroll
+      for (int k = 0; k < N; k++) p[k * stride] = v[k];
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < N * N; i += blockDim.x) blk[i] = t[(i / N) * P + (i % N)];
+}
+
+// Batched 4-point filters: `count` groups of four ints.
+__global__ void k_filter4_batch(int32_t* v, long count, int post) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < count;
+       i += (long)gridDim.x * blockDim.x) {
+    if (post) lap4_inplace<true>(v + 4 * i, 1); else lap4_inplace<false>(v + 4 * i, 1);
+  }
+}
+
+// Interior-cross filter of `count` packed n x n nodes (od_prefilter_split /
+// od_postfilter_split on stand-alone blocks).
+__global__ void k_split_filter_batch(int32_t* blocks, int n, int post, int hfilter, int vfilter) {
+  int32_t* b = blocks + (size_t)blockIdx.x * n * n;
+  for (int phase = 0; phase < 2; phase++) {
+    bool vertical_taps = post ? phase == 1 : phase == 0;
+    if (vertical_taps ? hfilter : vfilter) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (vertical_taps) {
+          if (post) lap4_inplace<true>(b + (n / 2 - 2) * n + i, n); else lap4_inplace<false>(b + (n / 2 - 2) * n + i, n);
+        } else {
+          if (post) lap4_inplace<true>(b + i * n + n / 2 - 2, 1); else lap4_inplace<false>(b + i * n + n / 2 - 2, 1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace daala_b200
+
+using namespace daala_b200;
+
+extern "C" {
+
+int daala_b200_launch_forward(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
+  dim3 grid(prm->nhsb * prm->nvsb, nplanes);
+  k_forward_sb<<<grid, kThreads, 0, stream>>>(*prm);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_launch_inverse(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
+  dim3 grid(prm->nhsb * prm->nvsb, nplanes);
+  k_inverse_sb<<<grid, kThreads, 0, stream>>>(*prm);
+  k_sb_postfilter_store<<<grid, kThreads, 0, stream>>>(*prm);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_launch_inverse_lapped_only(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
+  dim3 grid(prm->nhsb * prm->nvsb, nplanes);
+  k_inverse_sb<<<grid, kThreads, 0, stream>>>(*prm);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_launch_plane_sb_filter(int32_t* c, int stride, int nhsb, int nvsb, int xdec, int ydec,
+                                      int post, cudaStream_t stream) {
+  const int sbw = 64 >> xdec, sbh = 64 >> ydec;
+  for (int phase = 0; phase < 2; phase++) {
+    bool vertical_taps = post ? phase == 1 : phase == 0;
+    long total = vertical_taps ? (long)nhsb * sbw * (nvsb - 1) : (long)nvsb * sbh * (nhsb - 1);
+    if (total <= 0) continue;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (post) k_plane_sb_edges<true><<<blocks, 256, 0, stream>>>(c, stride, nhsb, nvsb, sbw, sbh, vertical_taps);
+    else k_plane_sb_edges<false><<<blocks, 256, 0, stream>>>(c, stride, nhsb, nvsb, sbw, sbh, vertical_taps);
+  }
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_launch_block_transform(int32_t* blocks, int count, int ln, int mode, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  switch (ln) {
+    case 2: k_block_transform<2><<<count, 64, 0, stream>>>(blocks, mode); break;
+    case 3: k_block_transform<3><<<count, 64, 0, stream>>>(blocks, mode); break;
+    case 4: k_block_transform<4><<<count, 64, 0, stream>>>(blocks, mode); break;
+    case 5: k_block_transform<5><<<count, 64, 0, stream>>>(blocks, mode); break;
+    case 6: k_block_transform<6><<<count, 64, 0, stream>>>(blocks, mode); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_launch_filter4(int32_t* v, long count, int post, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  int blocks = (int)((count + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_filter4_batch<<<blocks, 256, 0, stream>>>(v, count, post);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_launch_split_filter(int32_t* blocks, int count, int n, int post, int hfilter, int vfilter,
+                                   cudaStream_t stream) {
+  if (count <= 0) return 0;
+  k_split_filter_batch<<<count, 64, 0, stream>>>(blocks, n, post, hfilter, vfilter);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+/* daala_b200.h -- C ABI of libdaala_b200.so: a B200 (sm_100a) implementation of
+ * the per-block encode hot path of xiph/daala.
+ *
+ * Two families of entry points:
+ *
+ * (1) DROP-IN SYMBOLS (section A): the reference's own od_* names and
+ *     prototypes, taking HOST pointers, synchronous, individually bit-exact.
+ *     They are what daalaenc/daaladec (or the od_state_opt_vtbl /
+ *     od_enc_opt_vtbl slots, reference src/state.h:112-131, src/encint.h:77-98)
+ *     bind to; INTEGRATION.md shows the vtable initialiser a maintainer adds.
+ *     Each call stages its operands through pinned memory and launches a
+ *     kernel, so they are functional, not fast.
+ *
+ * (2) BATCH ENTRY POINTS (section B, daala_b200_*): DEVICE pointers + a CUDA
+ *     stream; whole frames per launch.  This is the throughput path that the
+ *     host driver (daala_b200/ Python mirror, or a batching shim inside
+ *     libdaalaenc) uses.  All return 0 on success or a cudaError_t value.
+ *
+ * There is no CPU fallback: if no CUDA device is usable the drop-in symbols
+ * abort() with a message (the reference's hot-path functions return void and
+ * cannot report errors; cf. od_fatal_impl, src/internal.c:394) and the batch
+ * entry points return the CUDA error.
+ */
+#ifndef DAALA_B200_H
+#define DAALA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t od_coeff; /* reference: src/filter.h:29 */
+
+/* ======================================================================== */
+/* A. Drop-in symbols (host pointers)                                        */
+/* ======================================================================== */
+
+/* 1-D reversible integer DCT-II / inverse.  reference: src/dct.h:70-183,
+   definitions src/dct.c:87,127,166,286,366,659,4219,4321,4422,4622. */
+void od_bin_fdct4(od_coeff y[4], const od_coeff *x, int xstride);
+void od_bin_idct4(od_coeff *x, int xstride, const od_coeff y[4]);
+void od_bin_fdct8(od_coeff y[8], const od_coeff *x, int xstride);
+void od_bin_idct8(od_coeff *x, int xstride, const od_coeff y[8]);
+void od_bin_fdct16(od_coeff y[16], const od_coeff *x, int xstride);
+void od_bin_idct16(od_coeff *x, int xstride, const od_coeff y[16]);
+void od_bin_fdct32(od_coeff y[32], const od_coeff *x, int xstride);
+void od_bin_idct32(od_coeff *x, int xstride, const od_coeff y[32]);
+void od_bin_fdct64(od_coeff y[64], const od_coeff *x, int xstride);
+void od_bin_idct64(od_coeff *x, int xstride, const od_coeff y[64]);
+
+/* 2-D separable transforms = the od_dct_func_2d slots fdct_2d[]/idct_2d[] of
+   od_state_opt_vtbl.  reference: src/dct.c:151,158,351,358,792,800,4890-4920;
+   typedef src/dct.h:62-63. */
+void od_bin_fdct4x4(od_coeff *y, int ystride, const od_coeff *x, int xstride);
+void od_bin_idct4x4(od_coeff *x, int xstride, const od_coeff *y, int ystride);
+void od_bin_fdct8x8(od_coeff *y, int ystride, const od_coeff *x, int xstride);
+void od_bin_idct8x8(od_coeff *x, int xstride, const od_coeff *y, int ystride);
+void od_bin_fdct16x16(od_coeff *y, int ystride, const od_coeff *x, int xstride);
+void od_bin_idct16x16(od_coeff *x, int xstride, const od_coeff *y, int ystride);
+void od_bin_fdct32x32(od_coeff *y, int ystride, const od_coeff *x, int xstride);
+void od_bin_idct32x32(od_coeff *x, int xstride, const od_coeff *y, int ystride);
+void od_bin_fdct64x64(od_coeff *y, int ystride, const od_coeff *x, int xstride);
+void od_bin_idct64x64(od_coeff *x, int xstride, const od_coeff *y, int ystride);
+
+typedef void (*od_dct_func_2d)(od_coeff *out, int out_stride, const od_coeff *in, int in_stride);
+/* reference: OD_FDCT_2D_C / OD_IDCT_2D_C, src/dct.c:54-68 (last entry NULL). */
+extern const od_dct_func_2d OD_FDCT_2D_CUDA[6];
+extern const od_dct_func_2d OD_IDCT_2D_CUDA[6];
+
+/* 4-point lapped pre/post filter and its appliers.
+   reference: src/filter.h:44-87, definitions src/filter.c:147,195,1459,1485,
+   1529,1561. */
+void od_pre_filter4(od_coeff _y[4], const od_coeff _x[4]);
+void od_post_filter4(od_coeff _x[4], const od_coeff _y[4]);
+void od_prefilter_split(od_coeff *c0, int stride, int bs, int f, int hfilter, int vfilter);
+void od_postfilter_split(od_coeff *c0, int stride, int bs, int f, int q, unsigned char *skip,
+                         int skip_stride, int hfilter, int vfilter);
+void od_apply_prefilter_frame_sbs(od_coeff *c, int stride, int nhsb, int nvsb, int xdec, int ydec);
+void od_apply_postfilter_frame_sbs(od_coeff *c, int stride, int nhsb, int nvsb, int xdec, int ydec,
+                                   int q, unsigned char *skip, int skip_stride);
+
+/* ======================================================================== */
+/* B. Batch entry points (device pointers, asynchronous on `stream`)         */
+/* ======================================================================== */
+
+/* One plane of a frame resident in HBM; plane size is implied by the frame
+   geometry ((nhsb*64) >> xdec) x ((nvsb*64) >> xdec). */
+typedef struct daala_b200_plane {
+  const uint8_t *pixels;   /* forward input (u8) */
+  int32_t *coeffs;         /* forward output / inverse input: the `d` plane, blocks in place */
+  int32_t *lapped;         /* inverse intermediate: `c` plane before the superblock postfilter */
+  uint8_t *pixels_out;     /* inverse output (u8) */
+  int pixel_stride;
+  int coeff_stride;
+  int lapped_stride;
+  int pixel_out_stride;
+  int xdec;                /* xdec == ydec: 0 or 1 */
+  int pad_;
+} daala_b200_plane;
+
+typedef struct daala_b200_frame {
+  daala_b200_plane plane[3];
+  const uint8_t *bsize;    /* device copy of state->bsize: one byte (0..4) per 8x8 luma unit */
+  int bstride;
+  int nhsb, nvsb;
+  int pic_w, pic_h;        /* luma picture size (info.pic_width/pic_height) */
+  int haar_dc;             /* 1 on keyframes: DC Haar pyramid of od_compute_dcts */
+} daala_b200_frame;
+
+/* u8 planes -> coefficient planes: od_ref_plane_to_coeff (src/state.c:1259) +
+   od_apply_prefilter_frame_sbs (src/filter.c:1529) + od_compute_dcts
+   (src/encode.c:1455) for every superblock of every plane, one launch. */
+int daala_b200_forward_frame(const daala_b200_frame *f, int nplanes, void *stream);
+
+/* coefficient planes -> u8 planes: per-leaf idct_2d (src/encode.c:1397) +
+   od_postfilter_split (src/filter.c:1485) bottom-up, then
+   od_apply_postfilter_frame_sbs (src/filter.c:1561) + od_coeff_to_ref_plane
+   (src/state.c:1323).  Two launches. */
+int daala_b200_inverse_frame(const daala_b200_frame *f, int nplanes, void *stream);
+/* First half only (writes plane[].lapped). */
+int daala_b200_inverse_frame_lapped(const daala_b200_frame *f, int nplanes, void *stream);
+
+/* In-place superblock-edge filters of one int32 plane on the device. */
+int daala_b200_plane_sb_filter(int32_t *c, int stride, int nhsb, int nvsb, int xdec, int ydec,
+                               int post, void *stream);
+
+/* `count` packed (1<<ln)^2 blocks, contiguous, transformed in place.
+   mode 0/1: 2-D forward/inverse; mode 2/3: every row as a 1-D forward/inverse. */
+int daala_b200_block_transform(int32_t *blocks, int count, int ln, int mode, void *stream);
+
+/* Library/device information.  Returns the number of usable CUDA devices. */
+int daala_b200_device_count(void);
+const char *daala_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAALA_B200_H */

@@ -1,0 +1,11 @@
+/* oracle/port_pipeline.c -- TEST INFRASTRUCTURE ONLY.
+ * pipeline_driver.inc bound to the plain-C port (port_dct.c, port_filter.c). */
+#include "port.h"
+#define PIPE(name) oracle_port_##name
+#define X_FDCT2D(ln, y, ys, x, xs) port_bin_fdct2d(ln, y, ys, x, xs)
+#define X_IDCT2D(ln, x, xs, y, ys) port_bin_idct2d(ln, x, xs, y, ys)
+#define X_PRE_SPLIT(c, stride, bs, h, v) port_prefilter_split(c, stride, bs, h, v)
+#define X_POST_SPLIT(c, stride, bs, h, v) port_postfilter_split(c, stride, bs, h, v)
+#define X_PRE_SBS(c, stride, nhsb, nvsb, xdec) port_apply_prefilter_frame_sbs(c, stride, nhsb, nvsb, xdec, xdec)
+#define X_POST_SBS(c, stride, nhsb, nvsb, xdec) port_apply_postfilter_frame_sbs(c, stride, nhsb, nvsb, xdec, xdec)
+#include "pipeline_driver.inc"

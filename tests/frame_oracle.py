@@ -1,0 +1,33 @@
+"""Frame-level CPU oracle calls (test infrastructure): drives
+oracle/pipeline_driver.inc through either the real reference build
+(oracle/_ref) or the plain-C port."""
+import ctypes
+
+import numpy as np
+
+from tests.oracle_lib import addr
+
+
+def forward_plane(lib, prefix, src, geom, pli, bsize, haar_dc):
+    ph, pw = geom.plane_shape(pli)
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    assert src.shape == (ph, pw)
+    c = np.zeros((ph, pw), np.int32)
+    d = np.zeros((ph, pw), np.int32)
+    bs = np.ascontiguousarray(bsize, dtype=np.uint8)
+    fn = getattr(lib, "oracle_%s_forward_plane" % prefix)
+    fn(addr(src), pw, addr(c), addr(d), geom.nhsb, geom.nvsb, geom.xdec[pli], addr(bs),
+       bs.shape[1], geom.pic_w, geom.pic_h, int(haar_dc))
+    return d
+
+
+def inverse_plane(lib, prefix, d, geom, pli, bsize, haar_dc, lapped_only=False):
+    ph, pw = geom.plane_shape(pli)
+    d = np.ascontiguousarray(d, dtype=np.int32).copy()
+    c = np.zeros((ph, pw), np.int32)
+    out = np.zeros((ph, pw), np.uint8)
+    bs = np.ascontiguousarray(bsize, dtype=np.uint8)
+    fn = getattr(lib, "oracle_%s_inverse_plane" % prefix)
+    fn(addr(d), addr(c), addr(out), pw, geom.nhsb, geom.nvsb, geom.xdec[pli], addr(bs), bs.shape[1],
+       geom.pic_w, geom.pic_h, int(haar_dc), int(lapped_only))
+    return c if lapped_only else out

@@ -1,0 +1,154 @@
+"""GPU parity of the fused lapped-transform kernels (through the C ABI of
+libdaala_b200.so) against the CPU oracle: bit-exact, integer work."""
+import ctypes
+import zlib
+
+import numpy as np
+import pytest
+
+from tests import frame_oracle, oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def checkers():
+    """(name, lib, prefix) for every available oracle: the real reference when
+    oracle/_ref is present, and always the plain-C port."""
+    out = [("port", oracle_lib.load_port(), "port")]
+    ref = oracle_lib.load_ref()
+    if ref is not None:
+        out.append(("ref", ref, "ref"))
+    return out
+
+
+@pytest.mark.parametrize("mode", ["mixed", "4", "8", "16", "32", "64"])
+@pytest.mark.parametrize("size", [(200, 130), (64, 64), (320, 192)])
+@pytest.mark.parametrize("haar", [1, 0])
+def test_forward_inverse_frame_matches_oracle(torch_cuda, mode, size, haar):
+    torch = torch_cuda
+    from daala_b200 import synth
+    from daala_b200.frame import FrameBuffers, Geometry
+    geom = Geometry(*size)
+    planes, _ = synth.frame(size[0], size[1], f=1)
+    planes = synth.pad_planes(planes, geom)
+    bsize = synth.block_size_map(geom, mode, seed=zlib.crc32(repr((mode, size)).encode()) & 0xffff)
+    fb = FrameBuffers(geom)
+    fb.haar_dc = haar
+    fb.upload(planes, bsize)
+    fb.forward()
+    fb.inverse()
+    torch.cuda.synchronize()
+    for name, lib, prefix in checkers():
+        for pli in range(3):
+            d_gpu = fb.coeffs[pli].cpu().numpy()
+            d_cpu = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, haar)
+            assert np.array_equal(d_gpu, d_cpu), "forward %s plane %d" % (name, pli)
+            lap_cpu = frame_oracle.inverse_plane(lib, prefix, d_cpu, geom, pli, bsize, haar, lapped_only=True)
+            assert np.array_equal(fb.lapped[pli].cpu().numpy(), lap_cpu), "lapped %s plane %d" % (name, pli)
+            rec_cpu = frame_oracle.inverse_plane(lib, prefix, d_cpu, geom, pli, bsize, haar)
+            rec_gpu = fb.pixels_out[pli].cpu().numpy()
+            assert np.array_equal(rec_gpu, rec_cpu), "recon %s plane %d" % (name, pli)
+            # lossless transform chain: reconstruction == source
+            assert np.array_equal(rec_gpu, planes[pli])
+
+
+@pytest.mark.parametrize("size", [(1920, 1080), (3840, 2160)])
+def test_full_size_round_trip_is_lossless(torch_cuda, size):
+    """BASELINE.json sizes: no quantisation => inverse(forward(x)) == x exactly
+    (the reversibility property dcttest checks per block, src/dct.c:8825)."""
+    torch = torch_cuda
+    from daala_b200 import synth
+    from daala_b200.frame import FrameBuffers, Geometry
+    geom = Geometry(*size)
+    planes, _ = synth.frame(size[0], size[1], f=0)
+    planes = synth.pad_planes(planes, geom)
+    bsize = synth.block_size_map(geom, "mixed", seed=3)
+    fb = FrameBuffers(geom)
+    fb.upload(planes, bsize)
+    fb.forward()
+    fb.inverse()
+    torch.cuda.synchronize()
+    for pli in range(3):
+        assert np.array_equal(fb.pixels_out[pli].cpu().numpy(), planes[pli])
+    # and the coefficient plane is not trivially the input
+    assert fb.coeffs[0].abs().max().item() > 255
+
+
+@pytest.mark.parametrize("ln", [2, 3, 4, 5, 6])
+def test_dropin_dct_symbols_match_oracle(torch_cuda, ln):
+    """Section A of include/daala_b200.h: od_bin_fdctNxN / od_bin_idctNxN /
+    od_bin_fdctN with host pointers, like dcttest's function tables
+    (src/dct.c:8259-8260)."""
+    from daala_b200 import _native
+    L = _native.lib()
+    port = oracle_lib.load_port()
+    n = 1 << ln
+    rng = np.random.default_rng(ln)
+    fwd = getattr(L, "od_bin_fdct%dx%d" % (n, n))
+    inv = getattr(L, "od_bin_idct%dx%d" % (n, n))
+    f1 = getattr(L, "od_bin_fdct%d" % n)
+    i1 = getattr(L, "od_bin_idct%d" % n)
+    a = oracle_lib.addr
+    for t in range(5):
+        # ieee1180-style ranges (src/dct.c:8379-8409): (-256,255), (-5,5), (-300,300), scaled by 16
+        lo, hi = [(-256, 255), (-5, 5), (-300, 300), (-256, 255), (-300, 300)][t]
+        x = (rng.integers(lo, hi + 1, size=(n, n + 3)) * 16).astype(np.int32)
+        y_gpu = np.zeros((n, n + 1), np.int32)
+        y_cpu = np.zeros((n, n + 1), np.int32)
+        fwd(a(y_gpu), n + 1, a(x), n + 3)
+        port.port_bin_fdct2d(ln, a(y_cpu), n + 1, a(x), n + 3)
+        assert np.array_equal(y_gpu, y_cpu)
+        x_gpu = np.zeros((n, n + 3), np.int32)
+        inv(a(x_gpu), n + 3, a(y_gpu), n + 1)
+        assert np.array_equal(x_gpu[:, :n], x[:, :n])
+        v = np.ascontiguousarray(x[0, :n])
+        y1g = np.zeros(n, np.int32)
+        y1c = np.zeros(n, np.int32)
+        f1(a(y1g), a(v), 1)
+        port.port_bin_fdct(ln, a(y1c), a(v), 1)
+        assert np.array_equal(y1g, y1c)
+        v2 = np.zeros(n, np.int32)
+        i1(a(v2), 1, a(y1g))
+        assert np.array_equal(v2, v)
+
+
+def test_dropin_filter_symbols_match_oracle(torch_cuda):
+    from daala_b200 import _native
+    L = _native.lib()
+    port = oracle_lib.load_port()
+    a = oracle_lib.addr
+    rng = np.random.default_rng(5)
+    x = rng.integers(-4096, 4096, size=4, dtype=np.int32)
+    yg, yc = np.zeros(4, np.int32), np.zeros(4, np.int32)
+    L.od_pre_filter4(a(yg), a(x))
+    port.port_pre_filter4(a(yc), a(x))
+    assert np.array_equal(yg, yc)
+    xg = np.zeros(4, np.int32)
+    L.od_post_filter4(a(xg), a(yg))
+    assert np.array_equal(xg, x)
+    for xdec in (0, 1):
+        nhsb, nvsb = 3, 2
+        w, h = (nhsb * 64) >> xdec, (nvsb * 64) >> xdec
+        c = rng.integers(-2048, 2048, size=(h, w + 8), dtype=np.int32)
+        g, p = c.copy(), c.copy()
+        L.od_apply_prefilter_frame_sbs(a(g), w + 8, nhsb, nvsb, xdec, xdec)
+        port.port_apply_prefilter_frame_sbs(a(p), w + 8, nhsb, nvsb, xdec, xdec)
+        assert np.array_equal(g, p)
+        L.od_apply_postfilter_frame_sbs(a(g), w + 8, nhsb, nvsb, xdec, xdec, 0, None, 0)
+        assert np.array_equal(g, c)
+    for bs in (1, 2, 3, 4):
+        n = 4 << bs
+        c = rng.integers(-2048, 2048, size=(n, n + 4), dtype=np.int32)
+        g, p = c.copy(), c.copy()
+        L.od_prefilter_split(a(g), n + 4, bs, 0, 1, 1)
+        port.port_prefilter_split(a(p), n + 4, bs, 1, 1)
+        assert np.array_equal(g, p)
+        L.od_postfilter_split(a(g), n + 4, bs, 0, 0, None, 0, 1, 1)
+        assert np.array_equal(g, c)
