@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- Daala per-block encode hot path on B200: Mpixels/s on 4K 4:2:0 intra.
+
+A "step" = one pass of the hot path over a batch of `--frames` synthetic
+3840x2160 4:2:0 frames (SURVEY.md 8(d) content, seeded):
+    u8 planes -> lapped prefilter + fDCT (block sizes 4..64 by a quadtree map)
+              -> [PVQ band quantisation when built] -> iDCT + lapped postfilter -> u8
+Frames shard by superblock row over the ranks (one process per GPU); the only
+exchange is one NCCL all-gather per step of the 2-row lapped borders.
+
+  value : luma picture pixels x frames / device time, inputs resident in HBM
+  e2e   : same, with pinned-host inputs copied H2D and the reconstruction
+          copied D2H inside the timed region
+  --impl reference : the reference's own CPU code (oracle/_ref, all host
+          threads) on a bounded sample of the same workload
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "encoder Mpixels/s on 4K YUV420 intra"
+UNIT = "Mpixels/s"
+PIC_W, PIC_H = 3840, 2160
+FWD_BYTES_PER_PX = 7.5   # SURVEY.md 8(d) K_fwd: 1.5 B in + 6 B out per padded luma pixel (4:2:0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=16, help="4K frames per step (whole job)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------
+# synthetic workload (host side)
+# --------------------------------------------------------------------------
+def make_host_frames(geom, nframes, distinct=4):
+    """`distinct` different synthetic frames, cycled to `nframes`; padded planes + bsize maps."""
+    import numpy as np
+    from daala_b200 import synth
+    frames = []
+    seed = 12345
+    for f in range(min(distinct, nframes)):
+        planes, seed = synth.frame(geom.pic_w, geom.pic_h, f=f, seed=seed)
+        frames.append((synth.pad_planes(planes, geom), synth.block_size_map(geom, "mixed", seed=100 + f)))
+    return [frames[i % len(frames)] for i in range(nframes)]
+
+
+# --------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx = float(parts[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# CPU reference pipeline (the reference's own functions via oracle/_ref)
+# --------------------------------------------------------------------------
+def cpu_pipeline_lib():
+    from tests import oracle_lib
+    ref = None
+    path = os.path.join(ROOT, "oracle", "_ref", "libdaala_ref.so")
+    if os.path.exists(path):
+        import ctypes
+        ref = ctypes.CDLL(path)
+    if ref is not None:
+        return ref, "ref", "reference"
+    return oracle_lib.load_port(), "port", "port"
+
+
+def cpu_frame(lib, prefix, geom, planes, bsize):
+    from tests import frame_oracle
+    for pli in range(3):
+        d = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
+        frame_oracle.inverse_plane(lib, prefix, d, geom, pli, bsize, 1)
+
+
+def cpu_throughput(geom, host_frames, nframes, threads):
+    """Mpx/s of the CPU pipeline over `nframes` frames on `threads` threads
+    (ctypes releases the GIL inside the C calls)."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib, prefix, kind = cpu_pipeline_lib()
+    jobs = [host_frames[i % len(host_frames)] for i in range(nframes)]
+    t0 = time.perf_counter()
+    if threads == 1:
+        for planes, bsize in jobs:
+            cpu_frame(lib, prefix, geom, planes, bsize)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(lambda j: cpu_frame(lib, prefix, geom, j[0], j[1]), jobs))
+    dt = time.perf_counter() - t0
+    return geom.luma_pixels * nframes / dt / 1e6, dt, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from daala_b200.frame import Geometry
+    geom = Geometry(PIC_W, PIC_H)
+    cores = len(os.sched_getaffinity(0))
+    host_frames = make_host_frames(geom, 2, distinct=2)
+    per_step = max(1, cores)
+    for _ in range(min(args.warmup, 1)):
+        cpu_throughput(geom, host_frames, per_step, cores)
+    times = []
+    kind = "port"
+    for _ in range(args.steps):
+        _, dt, kind = cpu_throughput(geom, host_frames, per_step, cores)
+        times.append(dt)
+    total = sum(times)
+    value = geom.luma_pixels * per_step * args.steps / total / 1e6
+    sample = "%d x 3840x2160 4:2:0 frames per step on %d host threads (transform path: prefilter+fDCT+iDCT+postfilter)" % (per_step, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "3840x2160 4:2:0 all-intra, lapped transform hot path (CPU reference functions)",
+                   "frames_per_step": per_step},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from daala_b200.frame import FrameBuffers, Geometry
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    geom = Geometry(PIC_W, PIC_H)
+    F = args.frames
+    r0, nrows = geom.shard_rows(rank, world)
+    host_frames = make_host_frames(geom, F)
+    fb = FrameBuffers(geom, dev, nframes=F)
+    fb.sb_row0, fb.sb_rows = r0, nrows
+
+    # pinned host staging: this rank's rows (+2-sample halo) of every plane, and its output rows
+    def rows(pli, halo):
+        sb = 64 >> geom.xdec[pli]
+        ph = geom.plane_shape(pli)[0]
+        return max(0, r0 * sb - halo), min(ph, (r0 + nrows) * sb + halo)
+
+    pin_in = []
+    pin_out = []
+    for pli in range(3):
+        a, b = rows(pli, 2)
+        t = torch.empty((F, b - a, geom.plane_shape(pli)[1]), dtype=torch.uint8).pin_memory()
+        for f in range(F):
+            t[f].copy_(torch.from_numpy(host_frames[f][0][pli][a:b]))
+        pin_in.append(t)
+        a, b = rows(pli, 0)
+        pin_out.append(torch.empty((F, b - a, geom.plane_shape(pli)[1]), dtype=torch.uint8).pin_memory())
+    pin_bsize = torch.empty((F,) + geom.bsize_shape, dtype=torch.uint8).pin_memory()
+    for f in range(F):
+        pin_bsize[f].copy_(torch.from_numpy(host_frames[f][1]))
+    h2d_bytes = sum(t.numel() for t in pin_in) + pin_bsize.numel()
+    d2h_bytes = sum(t.numel() for t in pin_out)
+
+    def h2d():
+        for pli in range(3):
+            a, b = rows(pli, 2)
+            fb.pixels[pli][:, a:b].copy_(pin_in[pli], non_blocking=True)
+        fb.bsize.copy_(pin_bsize, non_blocking=True)
+
+    def d2h():
+        for pli in range(3):
+            a, b = rows(pli, 0)
+            pin_out[pli].copy_(fb.pixels_out[pli][:, a:b], non_blocking=True)
+
+    # border exchange buffers (multi-GPU): top 2 + bottom 2 lapped rows of my shard, all planes
+    if world > 1:
+        widths = [geom.plane_shape(p)[1] for p in range(3)]
+        send = torch.zeros((F * 4 * sum(widths),), dtype=torch.int32, device=dev)
+        gathered = torch.zeros((world, send.numel()), dtype=torch.int32, device=dev)
+
+    def exchange():
+        off = 0
+        views = []
+        for pli in range(3):
+            a, b = rows(pli, 0)
+            w = geom.plane_shape(pli)[1]
+            n = F * 4 * w
+            v = send[off:off + n].view(F, 4, w)
+            v[:, 0:2].copy_(fb.lapped[pli][:, a:a + 2])
+            v[:, 2:4].copy_(fb.lapped[pli][:, b - 2:b])
+            views.append((off, n, w, a, b))
+            off += n
+        dist.all_gather_into_tensor(gathered, send)
+        for pli, (off, n, w, a, b) in enumerate(views):
+            if rank > 0:
+                fb.lapped[pli][:, a - 2:a].copy_(gathered[rank - 1, off:off + n].view(F, 4, w)[:, 2:4])
+            if rank < world - 1:
+                fb.lapped[pli][:, b:b + 2].copy_(gathered[rank + 1, off:off + n].view(F, 4, w)[:, 0:2])
+
+    launches = {"n": 0}
+
+    def step():
+        fb.forward()
+        fb.inverse(lapped_only=True)
+        if world > 1:
+            exchange()
+        fb.sb_postfilter_store()
+        launches["n"] += 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # upload once, warm up
+    h2d()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # correctness guard: lossless chain => reconstruction == source on my rows
+    torch.cuda.synchronize()
+    for pli in range(3):
+        a, b = rows(pli, 0)
+        assert torch.equal(fb.pixels_out[pli][:, a:b], fb.pixels[pli][:, a:b]), "round trip mismatch"
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    ms = timed(step, args.steps)
+    n_launch = launches["n"]
+
+    def e2e_step():
+        h2d()
+        step()
+        d2h()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # dominant kernel alone (forward), CUDA events on the launching stream
+    reps = max(5, args.steps)
+    ms_fwd = timed(fb.forward, reps) / reps
+    ms_inv = timed(lambda: fb.inverse(lapped_only=True), reps) / reps
+    ms_post = timed(fb.sb_postfilter_store, reps) / reps
+
+    px_job = geom.luma_pixels * F
+    value = px_job / (ms / args.steps * 1e-3) / 1e6
+    e2e = px_job / (ms_e2e / args.steps * 1e-3) / 1e6
+    padded_luma_shard = geom.frame_w * (nrows * 64) * F
+    algo_bytes = FWD_BYTES_PER_PX * padded_luma_shard
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured"
+    else:
+        peak, peak_src = 6650.0, "fallback"
+    achieved = algo_bytes / (ms_fwd * 1e-3) / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "3840x2160 4:2:0 all-intra: lapped prefilter + fDCT(4..64, quadtree map) + iDCT + postfilter",
+                   "frames_per_step": F, "parallelism": "sbrow%d" % world,
+                   "l2": "inputs larger than L2 (%.0f MB of planes per step)" % ((geom.padded_samples * F * 9) / 1e6),
+                   "block_sizes": "synthetic quadtree map, sizes 4..64"},
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": n_launch,
+        "clocks": clocks,
+        "roofline": {"kernel": "k_forward_sb", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+                     "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                     "algorithmic_bytes_per_launch": int(algo_bytes), "ms_per_launch": round(ms_fwd, 4)},
+        "kernels_ms": {"k_forward_sb": round(ms_fwd, 4), "k_inverse_sb": round(ms_inv, 4),
+                       "k_sb_postfilter_store": round(ms_post, 4)},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_frames = make_host_frames(geom, 2, distinct=2)
+        v, dt, kind = cpu_throughput(geom, cpu_frames, 2, 1)
+        out["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": 1, "kind": kind,
+                               "sample": "2 x 3840x2160 4:2:0 frames, same transform path, 1 thread, %.1f s" % dt}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdaala_b200.so")
 
 c_int = ctypes.c_int
+c_ll = ctypes.c_longlong
 c_void_p = ctypes.c_void_p
 
 
@@ -19,6 +20,8 @@ class Plane(ctypes.Structure):
         ("pixels", c_void_p), ("coeffs", c_void_p), ("lapped", c_void_p), ("pixels_out", c_void_p),
         ("pixel_stride", c_int), ("coeff_stride", c_int), ("lapped_stride", c_int),
         ("pixel_out_stride", c_int), ("xdec", c_int), ("pad_", c_int),
+        ("pixel_frame_pitch", c_ll), ("coeff_frame_pitch", c_ll), ("lapped_frame_pitch", c_ll),
+        ("pixel_out_frame_pitch", c_ll),
     ]
 
 
@@ -27,6 +30,8 @@ class Frame(ctypes.Structure):
     _fields_ = [
         ("plane", Plane * 3), ("bsize", c_void_p), ("bstride", c_int), ("nhsb", c_int),
         ("nvsb", c_int), ("pic_w", c_int), ("pic_h", c_int), ("haar_dc", c_int),
+        ("nframes", c_int), ("sb_row0", c_int), ("sb_rows", c_int), ("pad_", c_int),
+        ("bsize_frame_pitch", c_ll),
     ]
 
 
@@ -44,7 +49,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         fp = ctypes.POINTER(Frame)
         for name in ("daala_b200_forward_frame", "daala_b200_inverse_frame",
-                     "daala_b200_inverse_frame_lapped"):
+                     "daala_b200_inverse_frame_lapped", "daala_b200_sb_postfilter_store_frame"):
             fn = getattr(L, name)
             fn.argtypes = [fp, c_int, c_void_p]
             fn.restype = c_int

@@ -196,7 +196,8 @@ k_forward_sb(const __grid_constant__ FrameXformParams prm) {
   __shared__ unsigned char leaf[64];
   const PlaneXform& pl = prm.plane[blockIdx.y];
   const int xdec = pl.xdec;
-  const int sbx = blockIdx.x % prm.nhsb, sby = blockIdx.x / prm.nhsb;
+  const int sbx = blockIdx.x % prm.nhsb, sby = prm.sb_row0 + blockIdx.x / prm.nhsb;
+  const int fr = blockIdx.z;
   SbCtx s;
   s.B = kMaxB >> xdec;
   const int T = s.B + 2 * kHalo;
@@ -205,9 +206,9 @@ k_forward_sb(const __grid_constant__ FrameXformParams prm) {
   s.x0 = sbx * s.B;
   s.y0 = sby * s.B;
   const int pw = prm.nhsb * s.B, ph = prm.nvsb * s.B;
-  load_leaf_map(leaf, prm.bsize, prm.bstride, sbx, sby, xdec);
+  load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, xdec);
   // Stage the (B+4)^2 pixel window as (p-128) << OD_COEFF_SHIFT (src/state.c:1233).
-  const uint8_t* src = pl.pixels;
+  const uint8_t* src = pl.pixels + fr * pl.pixel_frame_pitch;
   for (int i = threadIdx.x; i < T * T; i += kThreads) {
     int r = i / T, c = i % T;
     int gx = s.x0 + c - kHalo, gy = s.y0 + r - kHalo;
@@ -251,7 +252,7 @@ k_forward_sb(const __grid_constant__ FrameXformParams prm) {
       __syncthreads();
     }
   }
-  int32_t* dst = pl.coeffs + (size_t)s.y0 * pl.coeff_stride + s.x0;
+  int32_t* dst = pl.coeffs + fr * pl.coeff_frame_pitch + (size_t)s.y0 * pl.coeff_stride + s.x0;
   for (int i = threadIdx.x; i < s.B * s.B; i += kThreads) {
     int r = i / s.B, c = i % s.B;
     dst[(size_t)r * pl.coeff_stride + c] = tile[r * s.P + c];
@@ -267,16 +268,17 @@ k_inverse_sb(const __grid_constant__ FrameXformParams prm) {
   __shared__ unsigned char leaf[64];
   const PlaneXform& pl = prm.plane[blockIdx.y];
   const int xdec = pl.xdec;
-  const int sbx = blockIdx.x % prm.nhsb, sby = blockIdx.x / prm.nhsb;
+  const int sbx = blockIdx.x % prm.nhsb, sby = prm.sb_row0 + blockIdx.x / prm.nhsb;
+  const int fr = blockIdx.z;
   SbCtx s;
   s.B = kMaxB >> xdec;
   s.P = s.B + 5;
   s.ushift = 3 - xdec;
   s.x0 = sbx * s.B;
   s.y0 = sby * s.B;
-  load_leaf_map(leaf, prm.bsize, prm.bstride, sbx, sby, xdec);
+  load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, xdec);
   int* tile = tile_s;
-  const int32_t* srcp = pl.coeffs + (size_t)s.y0 * pl.coeff_stride + s.x0;
+  const int32_t* srcp = pl.coeffs + fr * pl.coeff_frame_pitch + (size_t)s.y0 * pl.coeff_stride + s.x0;
   for (int i = threadIdx.x; i < s.B * s.B; i += kThreads) {
     int r = i / s.B, c = i % s.B;
     tile[r * s.P + c] = srcp[(size_t)r * pl.coeff_stride + c];
@@ -300,7 +302,7 @@ k_inverse_sb(const __grid_constant__ FrameXformParams prm) {
     split_filter_level<true>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, true);
     __syncthreads();
   }
-  int32_t* dst = pl.lapped + (size_t)s.y0 * pl.lapped_stride + s.x0;
+  int32_t* dst = pl.lapped + fr * pl.lapped_frame_pitch + (size_t)s.y0 * pl.lapped_stride + s.x0;
   for (int i = threadIdx.x; i < s.B * s.B; i += kThreads) {
     int r = i / s.B, c = i % s.B;
     dst[(size_t)r * pl.lapped_stride + c] = tile[r * s.P + c];
@@ -319,7 +321,9 @@ k_sb_postfilter_store(const __grid_constant__ FrameXformParams prm) {
   __shared__ int tile_s[kMaxT * kMaxPitch];
   const PlaneXform& pl = prm.plane[blockIdx.y];
   const int xdec = pl.xdec;
-  const int sbx = blockIdx.x % prm.nhsb, sby = blockIdx.x / prm.nhsb;
+  const int sbx = blockIdx.x % prm.nhsb, sby = prm.sb_row0 + blockIdx.x / prm.nhsb;
+  const int fr = blockIdx.z;
+  const int32_t* lap = pl.lapped + fr * pl.lapped_frame_pitch;
   const int B = kMaxB >> xdec;
   const int T = B + 2 * kHalo;
   const int P = T + 1;
@@ -329,7 +333,7 @@ k_sb_postfilter_store(const __grid_constant__ FrameXformParams prm) {
     int r = i / T, c = i % T;
     int gx = x0 + c - kHalo, gy = y0 + r - kHalo;
     int v = 0;
-    if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = pl.lapped[(size_t)gy * pl.lapped_stride + gx];
+    if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = lap[(size_t)gy * pl.lapped_stride + gx];
     tile_s[r * P + c] = v;
   }
   __syncthreads();
@@ -345,7 +349,7 @@ k_sb_postfilter_store(const __grid_constant__ FrameXformParams prm) {
     if (e == 0 ? top : bottom) lap4_inplace<true>(tile_s + (e ? B : 0) * P + c, P);
   }
   __syncthreads();
-  uint8_t* dst = pl.pixels_out + (size_t)y0 * pl.pixel_out_stride + x0;
+  uint8_t* dst = pl.pixels_out + fr * pl.pixel_out_frame_pitch + (size_t)y0 * pl.pixel_out_stride + x0;
   // Four pixels per thread, packed into one 32-bit store.
   for (int i = threadIdx.x; i < B * B / 4; i += kThreads) {
     int r = i / (B / 4), c4 = (i % (B / 4)) * 4;
@@ -449,21 +453,27 @@ using namespace daala_b200;
 extern "C" {
 
 int daala_b200_launch_forward(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
-  dim3 grid(prm->nhsb * prm->nvsb, nplanes);
+  dim3 grid(prm->nhsb * prm->sb_rows, nplanes, prm->nframes);
   k_forward_sb<<<grid, kThreads, 0, stream>>>(*prm);
   return (int)cudaGetLastError();
 }
 
 int daala_b200_launch_inverse(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
-  dim3 grid(prm->nhsb * prm->nvsb, nplanes);
+  dim3 grid(prm->nhsb * prm->sb_rows, nplanes, prm->nframes);
   k_inverse_sb<<<grid, kThreads, 0, stream>>>(*prm);
   k_sb_postfilter_store<<<grid, kThreads, 0, stream>>>(*prm);
   return (int)cudaGetLastError();
 }
 
 int daala_b200_launch_inverse_lapped_only(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
-  dim3 grid(prm->nhsb * prm->nvsb, nplanes);
+  dim3 grid(prm->nhsb * prm->sb_rows, nplanes, prm->nframes);
   k_inverse_sb<<<grid, kThreads, 0, stream>>>(*prm);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_launch_sb_postfilter_store(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
+  dim3 grid(prm->nhsb * prm->sb_rows, nplanes, prm->nframes);
+  k_sb_postfilter_store<<<grid, kThreads, 0, stream>>>(*prm);
   return (int)cudaGetLastError();
 }
 

@@ -38,25 +38,40 @@ class Geometry:
     def luma_pixels(self):
         return self.pic_w * self.pic_h
 
+    @property
+    def padded_samples(self):
+        return sum(h * w for h, w in (self.plane_shape(p) for p in range(self.nplanes)))
+
+    def shard_rows(self, rank, world):
+        """Contiguous superblock rows of `rank` (34 rows over 8
+        ranks -> 5,5,4,4,4,4,4,4)."""
+        base, extra = divmod(self.nvsb, world)
+        n = base + (1 if rank < extra else 0)
+        r0 = rank * base + min(rank, extra)
+        return r0, n
+
 
 class FrameBuffers:
-    """Device buffers of one frame: u8 planes in, int32 d planes, int32 lapped
-    planes, u8 planes out and the block-size map.  `batch` frames are stacked
-    along the superblock-row axis (independent frames simply extend nvsb for
-    the all-intra transform path... NOT used: each frame keeps its own edges),
-    so a batch is a list of FrameBuffers instead."""
+    """Device buffers of a batch of `nframes` frames of one geometry: u8 planes
+    in, int32 coefficient (`d`) planes, int32 lapped (`c`) planes, u8 planes
+    out, and one block-size map per frame.  Tensors are [nframes, h, w]."""
 
-    def __init__(self, geom, device="cuda:0"):
+    def __init__(self, geom, device="cuda:0", nframes=1):
         self.geom = geom
+        self.nframes = nframes
         self.device = torch.device(device)
         g = geom
-        self.pixels = [torch.zeros(g.plane_shape(p), dtype=torch.uint8, device=self.device) for p in range(g.nplanes)]
-        self.coeffs = [torch.zeros(g.plane_shape(p), dtype=torch.int32, device=self.device) for p in range(g.nplanes)]
-        self.lapped = [torch.zeros(g.plane_shape(p), dtype=torch.int32, device=self.device) for p in range(g.nplanes)]
-        self.pixels_out = [torch.zeros(g.plane_shape(p), dtype=torch.uint8, device=self.device) for p in range(g.nplanes)]
-        self.bsize = torch.zeros(g.bsize_shape, dtype=torch.uint8, device=self.device)
+
+        def alloc(dtype, p):
+            return torch.zeros((nframes,) + g.plane_shape(p), dtype=dtype, device=self.device)
+
+        self.pixels = [alloc(torch.uint8, p) for p in range(g.nplanes)]
+        self.coeffs = [alloc(torch.int32, p) for p in range(g.nplanes)]
+        self.lapped = [alloc(torch.int32, p) for p in range(g.nplanes)]
+        self.pixels_out = [alloc(torch.uint8, p) for p in range(g.nplanes)]
+        self.bsize = torch.zeros((nframes,) + g.bsize_shape, dtype=torch.uint8, device=self.device)
         self.haar_dc = 1
-        self._desc = None
+        self.sb_row0, self.sb_rows = 0, g.nvsb
 
     def descriptor(self):
         g = self.geom
@@ -67,34 +82,44 @@ class FrameBuffers:
             pl.coeffs = self.coeffs[p].data_ptr()
             pl.lapped = self.lapped[p].data_ptr()
             pl.pixels_out = self.pixels_out[p].data_ptr()
-            pl.pixel_stride = self.pixels[p].stride(0)
-            pl.coeff_stride = self.coeffs[p].stride(0)
-            pl.lapped_stride = self.lapped[p].stride(0)
-            pl.pixel_out_stride = self.pixels_out[p].stride(0)
+            pl.pixel_stride = self.pixels[p].stride(1)
+            pl.coeff_stride = self.coeffs[p].stride(1)
+            pl.lapped_stride = self.lapped[p].stride(1)
+            pl.pixel_out_stride = self.pixels_out[p].stride(1)
+            pl.pixel_frame_pitch = self.pixels[p].stride(0)
+            pl.coeff_frame_pitch = self.coeffs[p].stride(0)
+            pl.lapped_frame_pitch = self.lapped[p].stride(0)
+            pl.pixel_out_frame_pitch = self.pixels_out[p].stride(0)
             pl.xdec = g.xdec[p]
         f.bsize = self.bsize.data_ptr()
-        f.bstride = self.bsize.stride(0)
+        f.bstride = self.bsize.stride(1)
+        f.bsize_frame_pitch = self.bsize.stride(0)
         f.nhsb, f.nvsb = g.nhsb, g.nvsb
         f.pic_w, f.pic_h = g.pic_w, g.pic_h
         f.haar_dc = int(self.haar_dc)
+        f.nframes = self.nframes
+        f.sb_row0, f.sb_rows = self.sb_row0, self.sb_rows
         return f
 
     # --- host <-> device -------------------------------------------------
-    def upload(self, planes, bsize=None):
+    def upload(self, planes, bsize=None, frame=0):
         for p, a in enumerate(planes):
-            self.pixels[p].copy_(torch.from_numpy(np.ascontiguousarray(a)), non_blocking=True)
+            self.pixels[p][frame].copy_(torch.from_numpy(np.ascontiguousarray(a)), non_blocking=True)
         if bsize is not None:
-            self.bsize.copy_(torch.from_numpy(np.ascontiguousarray(bsize)), non_blocking=True)
+            self.bsize[frame].copy_(torch.from_numpy(np.ascontiguousarray(bsize)), non_blocking=True)
 
     # --- kernels ---------------------------------------------------------
-    def forward(self, stream=None):
+    def _call(self, name, stream):
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         f = self.descriptor()
-        _native.check(_native.lib().daala_b200_forward_frame(ctypes.byref(f), self.geom.nplanes,
-                                                             ctypes.c_void_p(s.cuda_stream)), "forward_frame")
+        fn = getattr(_native.lib(), name)
+        _native.check(fn(ctypes.byref(f), self.geom.nplanes, ctypes.c_void_p(s.cuda_stream)), name)
+
+    def forward(self, stream=None):
+        self._call("daala_b200_forward_frame", stream)
 
     def inverse(self, stream=None, lapped_only=False):
-        s = stream if stream is not None else torch.cuda.current_stream(self.device)
-        f = self.descriptor()
-        fn = _native.lib().daala_b200_inverse_frame_lapped if lapped_only else _native.lib().daala_b200_inverse_frame
-        _native.check(fn(ctypes.byref(f), self.geom.nplanes, ctypes.c_void_p(s.cuda_stream)), "inverse_frame")
+        self._call("daala_b200_inverse_frame_lapped" if lapped_only else "daala_b200_inverse_frame", stream)
+
+    def sb_postfilter_store(self, stream=None):
+        self._call("daala_b200_sb_postfilter_store_frame", stream)

@@ -97,6 +97,11 @@ typedef struct daala_b200_plane {
   int pixel_out_stride;
   int xdec;                /* xdec == ydec: 0 or 1 */
   int pad_;
+  /* Elements between consecutive frames of a batch in each buffer (0 when nframes == 1). */
+  long long pixel_frame_pitch;
+  long long coeff_frame_pitch;
+  long long lapped_frame_pitch;
+  long long pixel_out_frame_pitch;
 } daala_b200_plane;
 
 typedef struct daala_b200_frame {
@@ -106,6 +111,11 @@ typedef struct daala_b200_frame {
   int nhsb, nvsb;
   int pic_w, pic_h;        /* luma picture size (info.pic_width/pic_height) */
   int haar_dc;             /* 1 on keyframes: DC Haar pyramid of od_compute_dcts */
+  int nframes;             /* frames in the batch (>= 1); same geometry, independent content */
+  int sb_row0, sb_rows;    /* superblock rows [sb_row0, sb_row0 + sb_rows) are processed: the
+                              multi-GPU shard of this rank; whole frame = 0, nvsb */
+  int pad_;
+  long long bsize_frame_pitch;
 } daala_b200_frame;
 
 /* u8 planes -> coefficient planes: od_ref_plane_to_coeff (src/state.c:1259) +
@@ -120,6 +130,11 @@ int daala_b200_forward_frame(const daala_b200_frame *f, int nplanes, void *strea
 int daala_b200_inverse_frame(const daala_b200_frame *f, int nplanes, void *stream);
 /* First half only (writes plane[].lapped). */
 int daala_b200_inverse_frame_lapped(const daala_b200_frame *f, int nplanes, void *stream);
+
+/* Second half only (reads plane[].lapped incl. 2 rows of halo around the
+   processed superblock rows, writes plane[].pixels_out).  A multi-GPU rank calls
+   _lapped, exchanges the border rows with its neighbours, then this. */
+int daala_b200_sb_postfilter_store_frame(const daala_b200_frame *f, int nplanes, void *stream);
 
 /* In-place superblock-edge filters of one int32 plane on the device. */
 int daala_b200_plane_sb_filter(int32_t *c, int stride, int nhsb, int nvsb, int xdec, int ydec,

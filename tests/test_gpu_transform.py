@@ -47,13 +47,13 @@ def test_forward_inverse_frame_matches_oracle(torch_cuda, mode, size, haar):
     torch.cuda.synchronize()
     for name, lib, prefix in checkers():
         for pli in range(3):
-            d_gpu = fb.coeffs[pli].cpu().numpy()
+            d_gpu = fb.coeffs[pli][0].cpu().numpy()
             d_cpu = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, haar)
             assert np.array_equal(d_gpu, d_cpu), "forward %s plane %d" % (name, pli)
             lap_cpu = frame_oracle.inverse_plane(lib, prefix, d_cpu, geom, pli, bsize, haar, lapped_only=True)
-            assert np.array_equal(fb.lapped[pli].cpu().numpy(), lap_cpu), "lapped %s plane %d" % (name, pli)
+            assert np.array_equal(fb.lapped[pli][0].cpu().numpy(), lap_cpu), "lapped %s plane %d" % (name, pli)
             rec_cpu = frame_oracle.inverse_plane(lib, prefix, d_cpu, geom, pli, bsize, haar)
-            rec_gpu = fb.pixels_out[pli].cpu().numpy()
+            rec_gpu = fb.pixels_out[pli][0].cpu().numpy()
             assert np.array_equal(rec_gpu, rec_cpu), "recon %s plane %d" % (name, pli)
             # lossless transform chain: reconstruction == source
             assert np.array_equal(rec_gpu, planes[pli])
@@ -76,7 +76,7 @@ def test_full_size_round_trip_is_lossless(torch_cuda, size):
     fb.inverse()
     torch.cuda.synchronize()
     for pli in range(3):
-        assert np.array_equal(fb.pixels_out[pli].cpu().numpy(), planes[pli])
+        assert np.array_equal(fb.pixels_out[pli][0].cpu().numpy(), planes[pli])
     # and the coefficient plane is not trivially the input
     assert fb.coeffs[0].abs().max().item() > 255
 
@@ -152,3 +152,46 @@ def test_dropin_filter_symbols_match_oracle(torch_cuda):
         assert np.array_equal(g, p)
         L.od_postfilter_split(a(g), n + 4, bs, 0, 0, None, 0, 1, 1)
         assert np.array_equal(g, c)
+
+
+def test_batched_and_row_sharded_launches_equal_whole_frame(torch_cuda):
+    """nframes > 1 batches and sb_row0/sb_rows shards (the multi-GPU split of
+    SURVEY.md 8(e)) must reproduce the single whole-frame launch bit for bit."""
+    torch = torch_cuda
+    from daala_b200 import synth
+    from daala_b200.frame import FrameBuffers, Geometry
+    geom = Geometry(320, 250)
+    nf = 3
+    whole = FrameBuffers(geom, nframes=nf)
+    parts = FrameBuffers(geom, nframes=nf)
+    singles = []
+    for f in range(nf):
+        planes, _ = synth.frame(320, 250, f=f)
+        planes = synth.pad_planes(planes, geom)
+        bsize = synth.block_size_map(geom, "mixed", seed=f)
+        whole.upload(planes, bsize, frame=f)
+        parts.upload(planes, bsize, frame=f)
+        one = FrameBuffers(geom)
+        one.upload(planes, bsize)
+        one.forward()
+        one.inverse()
+        singles.append(one)
+    whole.forward()
+    whole.inverse()
+    # shards: superblock rows split 3 ways; lapped halo rows come from the
+    # neighbouring shard's output, which lives in the same buffer here.
+    for rank in range(3):
+        parts.sb_row0, parts.sb_rows = geom.shard_rows(rank, 3)
+        parts.forward()
+        parts.inverse(lapped_only=True)
+    for rank in range(3):
+        parts.sb_row0, parts.sb_rows = geom.shard_rows(rank, 3)
+        parts.sb_postfilter_store()
+    torch.cuda.synchronize()
+    for pli in range(3):
+        assert torch.equal(whole.coeffs[pli], parts.coeffs[pli])
+        assert torch.equal(whole.pixels_out[pli], parts.pixels_out[pli])
+        for f in range(nf):
+            assert torch.equal(whole.coeffs[pli][f], singles[f].coeffs[pli][0])
+            assert torch.equal(whole.pixels_out[pli][f], singles[f].pixels_out[pli][0])
+            assert torch.equal(whole.pixels_out[pli][f], whole.pixels[pli][f])

@@ -1,0 +1,93 @@
+"""Pins the plain-C PVQ port (oracle/port_pvq.c) against the real reference
+(static pvq_theta / pvq_search_rdo_double of src/pvq_encoder.c reached through
+oracle/ref_hooks_pvq.c, and the exported src/pvq.c functions)."""
+import ctypes
+
+import numpy as np
+
+from tests import pvq_cases
+from tests.oracle_lib import addr
+
+
+def test_fixed_point_helpers_match_reference(port, ref):
+    rng = np.random.default_rng(3)
+    for fn in (ref.od_pvq_cos, ref.od_pvq_sin):
+        fn.restype = ctypes.c_int16  # od_val16
+    for x in list(range(-70000, 70000, 997)) + [0, 32768, 65536, 98304, 131072]:
+        assert np.int16(ref.od_pvq_cos(x)) == np.int16(port.port_pvq_cos(x))
+        assert np.int16(ref.od_pvq_sin(x)) == np.int16(port.port_pvq_sin(x))
+    for beta in (4096, 6144, 5000):
+        for cg0 in [0, 1, 100, 256, 300, 1000, 5000, 20000]:
+            for q0 in (8, 64, 400, 1100):
+                assert ref.od_gain_expand(cg0, q0, beta) == port.port_gain_expand(cg0, q0, beta), (cg0, q0, beta)
+        for qcg in range(0, 5000, 37):
+            assert ref.od_pvq_compute_max_theta(qcg, beta) == port.port_pvq_compute_max_theta(qcg, beta)
+        for n in (15, 8, 32, 128):
+            for qcg in range(0, 6000, 101):
+                assert ref.od_pvq_compute_k(qcg, -1, -1, 1, n, beta, 1) == port.port_pvq_compute_k(qcg, -1, 1, n, beta)
+            for it in range(0, 40):
+                assert ref.od_pvq_compute_k(512, it, 0, 0, n, beta, 1) == port.port_pvq_compute_k(512, it, 0, n, beta)
+    for ts in range(0, 30):
+        for t in range(0, 30):
+            assert ref.od_pvq_compute_theta(t, ts) == port.port_pvq_compute_theta(t, ts)
+    for n in (15, 8, 32, 128):
+        for _ in range(50):
+            x = rng.integers(-3000, 3000, size=n).astype(np.int16)
+            for beta in (4096, 6144):
+                for q0 in (8, 100, 900):
+                    g1, g2 = ctypes.c_int32(0), ctypes.c_int32(0)
+                    a = ref.od_pvq_compute_gain(addr(x), n, q0, ctypes.byref(g1), beta, 2)
+                    b = port.port_pvq_compute_gain(addr(x), n, q0, ctypes.byref(g2), beta, 2)
+                    assert (a, g1.value) == (b, g2.value)
+            x32 = (x.astype(np.int32) * 37)
+            assert ref.od_vector_log_mag(addr(x32), n) == port.port_vector_log_mag(addr(x32), n)
+            r = rng.integers(-3000, 3000, size=n).astype(np.int16)
+            ra, rb = r.copy(), r.copy()
+            sa, sb = ctypes.c_int(0), ctypes.c_int(0)
+            gr = int(np.sqrt(float((r.astype(np.int64) ** 2).sum())))
+            ma = ref.od_compute_householder(addr(ra), n, gr, ctypes.byref(sa), 0)
+            mb = port.port_compute_householder(addr(rb), n, gr, ctypes.byref(sb), 0)
+            assert ma == mb and sa.value == sb.value and np.array_equal(ra, rb)
+            oa, ob = np.zeros(n, np.int16), np.zeros(n, np.int16)
+            ref.od_apply_householder(addr(oa), addr(x), addr(ra), n)
+            port.port_apply_householder(addr(ob), addr(x), addr(rb), n)
+            assert np.array_equal(oa, ob)
+
+
+def test_pulse_search_matches_reference(port, ref):
+    rng = np.random.default_rng(4)
+    ref.oracle_ref_pvq_search_rdo_double.restype = ctypes.c_double
+    port.port_pvq_search_rdo_double.restype = ctypes.c_double
+    for n in (15, 8, 32, 128, 14, 7, 31, 127):
+        for t in range(40):
+            x = np.round(rng.laplace(0, 400, size=n) * np.exp(-np.arange(n) / (n / 3))).astype(np.int16)
+            ya, yb = np.zeros(n, np.int32), np.zeros(n, np.int32)
+            prev = 0
+            for k in sorted(set(int(v) for v in rng.integers(1, 40, size=3))):
+                g2 = float(rng.uniform(0.5, 50))
+                ca = ref.oracle_ref_pvq_search_rdo_double(addr(x), n, k, addr(ya), ctypes.c_double(g2),
+                                                         ctypes.c_double(0.147), prev)
+                cb = port.port_pvq_search_rdo_double(addr(x), n, k, addr(yb), ctypes.c_double(g2),
+                                                     ctypes.c_double(0.147), prev)
+                assert np.array_equal(ya, yb) and ca == cb
+                assert np.abs(ya).sum() == k
+                prev = k
+
+
+def test_pvq_theta_port_matches_reference(port, ref):
+    qm, qm_inv = pvq_cases.reference_qm(ref)
+    count = 0
+    nonskip = 0
+    withref = 0
+    for c in pvq_cases.cases(seed=1, per_combo=8):
+        a = pvq_cases.run_theta(ref, "ref", c, qm, qm_inv)
+        b = pvq_cases.run_theta(port, "port", c, qm, qm_inv)
+        key = (c["n"], c["kind"], c["is_keyframe"], c["pli"], c["beta"], c["q0"])
+        assert (a["gain"], a["itheta"], a["max_theta"], a["k"]) == (b["gain"], b["itheta"], b["max_theta"], b["k"]), key
+        assert np.array_equal(a["y"], b["y"]), key
+        assert np.array_equal(a["out"], b["out"]), key
+        assert a["skip_diff"] == b["skip_diff"], key
+        count += 1
+        nonskip += a["k"] > 0
+        withref += a["itheta"] > 0
+    assert count > 1000 and nonskip > 300 and withref > 100, (count, nonskip, withref)
