@@ -44,13 +44,19 @@ constexpr int kMaxPitch = kMaxT + 1; // 69 = 5 mod 32; chroma 37 = 5 mod 32
 // state->bsize map (OD_BLOCK_SIZE4x4, src/block_size.h; recursion rule
 // src/encode.c:1467-1470).
 // ---------------------------------------------------------------------------
-struct SbCtx {
-  int B;        // superblock edge in plane pixels (64 >> xdec)
-  int P;        // tile pitch in ints
-  int ushift;   // plane pixels -> 8x8-luma unit: 3 - xdec
+// B, P and the unit shift are compile-time (kernels are specialised per
+// plane decimation) so that all index arithmetic is shifts and constant
+// multiplies -- runtime integer division would saturate the XU pipe.
+template <int B_, int P_>
+struct SbCtxT {
+  static constexpr int B = B_;                      // superblock edge in plane pixels (64 >> xdec)
+  static constexpr int P = P_;                      // tile pitch in ints
+  static constexpr int ushift = (B_ == 64) ? 3 : 2; // plane pixels -> 8x8-luma unit: 3 - xdec
+  static constexpr int logB = (B_ == 64) ? 6 : 5;
   int x0, y0;   // plane coordinates of the superblock origin
 };
 
+template <class SbCtx>
 __device__ __forceinline__ int leaf_log(const unsigned char* leaf, const SbCtx& s, int px, int py) {
   return leaf[(py >> s.ushift) * 8 + (px >> s.ushift)];
 }
@@ -68,6 +74,7 @@ __device__ __forceinline__ void load_leaf_map(unsigned char* leaf, const unsigne
 // Is the node of edge S (plane px) whose origin is (nx, ny) (superblock-local)
 // split further?  The reference looks at the block size stored at the node's
 // top-left corner (src/encode.c:1466).
+template <class SbCtx>
 __device__ __forceinline__ bool node_is_split(const unsigned char* leaf, const SbCtx& s, int nx,
                                               int ny, int logS) {
   return leaf_log(leaf, s, nx, ny) < logS;
@@ -79,12 +86,12 @@ __device__ __forceinline__ bool node_is_split(const unsigned char* leaf, const S
 // !kFwd: pass 0 = rows,    pass 1 = columns (od_bin_idctNxN, src/dct.c:158-163)
 // `tile` points at the superblock's (0,0) sample inside the shared tile.
 // ---------------------------------------------------------------------------
-template <int L, bool kFwd>
+template <int L, bool kFwd, class SbCtx>
 __device__ __forceinline__ void transform_pass(int* tile, const unsigned char* leaf,
                                                const SbCtx& s, bool along_columns) {
   constexpr int N = 1 << L;
-  const int B = s.B;
-  const int items = B * (B >> L);
+  constexpr int B = SbCtx::B;
+  constexpr int items = B * (B >> L);
   for (int item = threadIdx.x; item < items; item += kThreads) {
     int a = item % B;        // position across the transform direction
     int m = item / B;        // which N-segment along the transform direction
@@ -102,17 +109,17 @@ __device__ __forceinline__ void transform_pass(int* tile, const unsigned char* l
   }
 }
 
-template <bool kFwd>
+template <bool kFwd, class SbCtx>
 __device__ __forceinline__ void transform_all_leaves(int* tile, const unsigned char* leaf,
                                                      const SbCtx& s, unsigned size_mask) {
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
     const bool cols = kFwd ? (pass == 0) : (pass == 1);
-    if (size_mask & (1u << 6)) transform_pass<6, kFwd>(tile, leaf, s, cols);
-    if (size_mask & (1u << 5)) transform_pass<5, kFwd>(tile, leaf, s, cols);
-    if (size_mask & (1u << 4)) transform_pass<4, kFwd>(tile, leaf, s, cols);
-    if (size_mask & (1u << 3)) transform_pass<3, kFwd>(tile, leaf, s, cols);
-    if (size_mask & (1u << 2)) transform_pass<2, kFwd>(tile, leaf, s, cols);
+    if (SbCtx::logB >= 6 && (size_mask & (1u << 6))) transform_pass<6, kFwd, SbCtx>(tile, leaf, s, cols);
+    if (size_mask & (1u << 5)) transform_pass<5, kFwd, SbCtx>(tile, leaf, s, cols);
+    if (size_mask & (1u << 4)) transform_pass<4, kFwd, SbCtx>(tile, leaf, s, cols);
+    if (size_mask & (1u << 3)) transform_pass<3, kFwd, SbCtx>(tile, leaf, s, cols);
+    if (size_mask & (1u << 2)) transform_pass<2, kFwd, SbCtx>(tile, leaf, s, cols);
     __syncthreads();
   }
 }
@@ -123,12 +130,12 @@ __device__ __forceinline__ void transform_all_leaves(int* tile, const unsigned c
 // (od_postfilter_split, src/filter.c:1510-1525).  A direction is disabled when
 // the node sticks out of the picture; the reference compares PLANE coordinates
 // with the LUMA picture size (src/encode.c:1487-1488) -- reproduced literally.
-template <bool kPost>
+template <bool kPost, class SbCtx>
 __device__ __forceinline__ void split_filter_level(int* tile, const unsigned char* leaf,
                                                    const SbCtx& s, int logS, int pic_w, int pic_h,
                                                    bool vertical_taps) {
   const int S = 1 << logS;
-  const int B = s.B;
+  constexpr int B = SbCtx::B;
   const int items = B * (B >> logS);
   for (int item = threadIdx.x; item < items; item += kThreads) {
     int a = item % B;   // coordinate along the edge
@@ -150,14 +157,14 @@ __device__ __forceinline__ void split_filter_level(int* tile, const unsigned cha
 // DC Haar pyramid over the children of every split node of edge 2^logS
 // (src/encode.c:1497-1510 forward; the inverse applies the same kernel with
 // the two middle terms swapped, cf. od_quantize_haar_dc_level :1651).
-template <bool kInverse>
+template <bool kInverse, class SbCtx>
 __device__ __forceinline__ void haar_dc_level(int* tile, const unsigned char* leaf, const SbCtx& s,
                                               int logS) {
   const int S = 1 << logS;
-  const int per_row = s.B >> logS;
+  const int per_row = SbCtx::B >> logS;
   const int items = per_row * per_row;
   for (int item = threadIdx.x; item < items; item += kThreads) {
-    int nx = (item % per_row) * S, ny = (item / per_row) * S;
+    int nx = (item & (per_row - 1)) * S, ny = (item >> (SbCtx::logB - logS)) * S;
     if (!node_is_split(leaf, s, nx, ny, logS)) continue;
     int* p00 = tile + ny * s.P + nx;
     int* p01 = p00 + S / 2;
@@ -188,33 +195,30 @@ __device__ __forceinline__ unsigned leaf_size_mask(const unsigned char* leaf) {
 }
 
 // ---------------------------------------------------------------------------
-// Forward kernel.  grid = (nhsb*nvsb, nplanes).
+// Forward kernel.  grid = (nhsb*sb_rows, nplanes, nframes).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_forward_sb(const __grid_constant__ FrameXformParams prm) {
-  __shared__ int tile_s[kMaxT * kMaxPitch];
-  __shared__ unsigned char leaf[64];
-  const PlaneXform& pl = prm.plane[blockIdx.y];
-  const int xdec = pl.xdec;
+template <int XDEC>
+__device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, const PlaneXform& pl,
+                                                int* tile_s, unsigned char* leaf) {
+  constexpr int B = kMaxB >> XDEC;
+  constexpr int T = B + 2 * kHalo;
+  constexpr int P = T + 1;
+  using Sb = SbCtxT<B, P>;
   const int sbx = blockIdx.x % prm.nhsb, sby = prm.sb_row0 + blockIdx.x / prm.nhsb;
   const int fr = blockIdx.z;
-  SbCtx s;
-  s.B = kMaxB >> xdec;
-  const int T = s.B + 2 * kHalo;
-  s.P = T + 1;
-  s.ushift = 3 - xdec;
-  s.x0 = sbx * s.B;
-  s.y0 = sby * s.B;
-  const int pw = prm.nhsb * s.B, ph = prm.nvsb * s.B;
-  load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, xdec);
+  Sb s;
+  s.x0 = sbx * B;
+  s.y0 = sby * B;
+  const int pw = prm.nhsb * B, ph = prm.nvsb * B;
+  load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, XDEC);
   // Stage the (B+4)^2 pixel window as (p-128) << OD_COEFF_SHIFT (src/state.c:1233).
   const uint8_t* src = pl.pixels + fr * pl.pixel_frame_pitch;
   for (int i = threadIdx.x; i < T * T; i += kThreads) {
-    int r = i / T, c = i % T;
+    int r = i / T, c = i - r * T;
     int gx = s.x0 + c - kHalo, gy = s.y0 + r - kHalo;
     int v = 0;
     if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = ((int)src[(size_t)gy * pl.pixel_stride + gx] - 128) * 16;
-    tile_s[r * s.P + c] = v;
+    tile_s[r * P + c] = v;
   }
   __syncthreads();
   // Superblock-edge prefilter: all horizontal edges first (vertical taps),
@@ -222,22 +226,21 @@ k_forward_sb(const __grid_constant__ FrameXformParams prm) {
   {
     const bool top = sby > 0, bottom = sby + 1 < prm.nvsb;
     for (int i = threadIdx.x; i < 2 * T; i += kThreads) {
-      int c = i % T, e = i / T;
-      if (e == 0 ? top : bottom) lap4_inplace<false>(tile_s + (e ? s.B : 0) * s.P + c, s.P);
+      int e = i >= T, c = i - e * T;
+      if (e == 0 ? top : bottom) lap4_inplace<false>(tile_s + (e ? B : 0) * P + c, P);
     }
     __syncthreads();
     const bool left = sbx > 0, right = sbx + 1 < prm.nhsb;
-    for (int i = threadIdx.x; i < 2 * s.B; i += kThreads) {
-      int r = i % s.B + kHalo, e = i / s.B;
-      if (e == 0 ? left : right) lap4_inplace<false>(tile_s + r * s.P + (e ? s.B : 0), 1);
+    for (int i = threadIdx.x; i < 2 * B; i += kThreads) {
+      int r = i % B + kHalo, e = i / B;
+      if (e == 0 ? left : right) lap4_inplace<false>(tile_s + r * P + (e ? B : 0), 1);
     }
     __syncthreads();
   }
-  int* tile = tile_s + kHalo * s.P + kHalo;
-  const int logB = 6 - xdec;
+  int* tile = tile_s + kHalo * P + kHalo;
   // Top-down split prefilters.
 #pragma unroll 1
-  for (int logS = logB; logS >= 3; logS--) {
+  for (int logS = Sb::logB; logS >= 3; logS--) {
     split_filter_level<false>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, true);
     __syncthreads();
     split_filter_level<false>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, false);
@@ -247,47 +250,51 @@ k_forward_sb(const __grid_constant__ FrameXformParams prm) {
   transform_all_leaves<true>(tile, leaf, s, mask);
   if (prm.haar_dc) {
 #pragma unroll 1
-    for (int logS = 3; logS <= logB; logS++) {
+    for (int logS = 3; logS <= Sb::logB; logS++) {
       haar_dc_level<false>(tile, leaf, s, logS);
       __syncthreads();
     }
   }
   int32_t* dst = pl.coeffs + fr * pl.coeff_frame_pitch + (size_t)s.y0 * pl.coeff_stride + s.x0;
-  for (int i = threadIdx.x; i < s.B * s.B; i += kThreads) {
-    int r = i / s.B, c = i % s.B;
-    dst[(size_t)r * pl.coeff_stride + c] = tile[r * s.P + c];
+  for (int i = threadIdx.x; i < B * B; i += kThreads) {
+    int r = i / B, c = i % B;
+    dst[(size_t)r * pl.coeff_stride + c] = tile[r * P + c];
   }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_forward_sb(const __grid_constant__ FrameXformParams prm) {
+  __shared__ int tile_s[kMaxT * kMaxPitch];
+  __shared__ unsigned char leaf[64];
+  const PlaneXform& pl = prm.plane[blockIdx.y];
+  if (pl.xdec == 0) forward_sb_body<0>(prm, pl, tile_s, leaf);
+  else forward_sb_body<1>(prm, pl, tile_s, leaf);
 }
 
 // ---------------------------------------------------------------------------
 // Inverse kernel 1: coefficients -> lapped-domain samples (int32 plane).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_inverse_sb(const __grid_constant__ FrameXformParams prm) {
-  __shared__ int tile_s[kMaxB * (kMaxB + 5)];
-  __shared__ unsigned char leaf[64];
-  const PlaneXform& pl = prm.plane[blockIdx.y];
-  const int xdec = pl.xdec;
+template <int XDEC>
+__device__ __forceinline__ void inverse_sb_body(const FrameXformParams& prm, const PlaneXform& pl,
+                                                int* tile, unsigned char* leaf) {
+  constexpr int B = kMaxB >> XDEC;
+  constexpr int P = B + 5;
+  using Sb = SbCtxT<B, P>;
   const int sbx = blockIdx.x % prm.nhsb, sby = prm.sb_row0 + blockIdx.x / prm.nhsb;
   const int fr = blockIdx.z;
-  SbCtx s;
-  s.B = kMaxB >> xdec;
-  s.P = s.B + 5;
-  s.ushift = 3 - xdec;
-  s.x0 = sbx * s.B;
-  s.y0 = sby * s.B;
-  load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, xdec);
-  int* tile = tile_s;
+  Sb s;
+  s.x0 = sbx * B;
+  s.y0 = sby * B;
+  load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, XDEC);
   const int32_t* srcp = pl.coeffs + fr * pl.coeff_frame_pitch + (size_t)s.y0 * pl.coeff_stride + s.x0;
-  for (int i = threadIdx.x; i < s.B * s.B; i += kThreads) {
-    int r = i / s.B, c = i % s.B;
-    tile[r * s.P + c] = srcp[(size_t)r * pl.coeff_stride + c];
+  for (int i = threadIdx.x; i < B * B; i += kThreads) {
+    int r = i / B, c = i % B;
+    tile[r * P + c] = srcp[(size_t)r * pl.coeff_stride + c];
   }
   __syncthreads();
-  const int logB = 6 - xdec;
   if (prm.haar_dc) {
 #pragma unroll 1
-    for (int logS = logB; logS >= 3; logS--) {
+    for (int logS = Sb::logB; logS >= 3; logS--) {
       haar_dc_level<true>(tile, leaf, s, logS);
       __syncthreads();
     }
@@ -296,17 +303,26 @@ k_inverse_sb(const __grid_constant__ FrameXformParams prm) {
   transform_all_leaves<false>(tile, leaf, s, mask);
   // Bottom-up split postfilters: vertical edge first, then horizontal.
 #pragma unroll 1
-  for (int logS = 3; logS <= logB; logS++) {
+  for (int logS = 3; logS <= Sb::logB; logS++) {
     split_filter_level<true>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, false);
     __syncthreads();
     split_filter_level<true>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, true);
     __syncthreads();
   }
   int32_t* dst = pl.lapped + fr * pl.lapped_frame_pitch + (size_t)s.y0 * pl.lapped_stride + s.x0;
-  for (int i = threadIdx.x; i < s.B * s.B; i += kThreads) {
-    int r = i / s.B, c = i % s.B;
-    dst[(size_t)r * pl.lapped_stride + c] = tile[r * s.P + c];
+  for (int i = threadIdx.x; i < B * B; i += kThreads) {
+    int r = i / B, c = i % B;
+    dst[(size_t)r * pl.lapped_stride + c] = tile[r * P + c];
   }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_inverse_sb(const __grid_constant__ FrameXformParams prm) {
+  __shared__ int tile_s[kMaxB * (kMaxB + 5)];
+  __shared__ unsigned char leaf[64];
+  const PlaneXform& pl = prm.plane[blockIdx.y];
+  if (pl.xdec == 0) inverse_sb_body<0>(prm, pl, tile_s, leaf);
+  else inverse_sb_body<1>(prm, pl, tile_s, leaf);
 }
 
 // ---------------------------------------------------------------------------
@@ -316,21 +332,19 @@ k_inverse_sb(const __grid_constant__ FrameXformParams prm) {
 // (src/filter.c:1599-1617); store OD_CLAMP255(((v + 8) >> 4) + 128)
 // (src/state.c:1300-1303).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_sb_postfilter_store(const __grid_constant__ FrameXformParams prm) {
-  __shared__ int tile_s[kMaxT * kMaxPitch];
-  const PlaneXform& pl = prm.plane[blockIdx.y];
-  const int xdec = pl.xdec;
+template <int XDEC>
+__device__ __forceinline__ void sb_postfilter_store_body(const FrameXformParams& prm,
+                                                         const PlaneXform& pl, int* tile_s) {
+  constexpr int B = kMaxB >> XDEC;
+  constexpr int T = B + 2 * kHalo;
+  constexpr int P = T + 1;
   const int sbx = blockIdx.x % prm.nhsb, sby = prm.sb_row0 + blockIdx.x / prm.nhsb;
   const int fr = blockIdx.z;
   const int32_t* lap = pl.lapped + fr * pl.lapped_frame_pitch;
-  const int B = kMaxB >> xdec;
-  const int T = B + 2 * kHalo;
-  const int P = T + 1;
   const int x0 = sbx * B, y0 = sby * B;
   const int pw = prm.nhsb * B, ph = prm.nvsb * B;
   for (int i = threadIdx.x; i < T * T; i += kThreads) {
-    int r = i / T, c = i % T;
+    int r = i / T, c = i - r * T;
     int gx = x0 + c - kHalo, gy = y0 + r - kHalo;
     int v = 0;
     if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = lap[(size_t)gy * pl.lapped_stride + gx];
@@ -339,7 +353,7 @@ k_sb_postfilter_store(const __grid_constant__ FrameXformParams prm) {
   __syncthreads();
   const bool left = sbx > 0, right = sbx + 1 < prm.nhsb;
   for (int i = threadIdx.x; i < 2 * T; i += kThreads) {
-    int r = i % T, e = i / T;
+    int e = i >= T, r = i - e * T;
     if (e == 0 ? left : right) lap4_inplace<true>(tile_s + r * P + (e ? B : 0), 1);
   }
   __syncthreads();
@@ -363,6 +377,14 @@ k_sb_postfilter_store(const __grid_constant__ FrameXformParams prm) {
     }
     *reinterpret_cast<unsigned*>(dst + (size_t)r * pl.pixel_out_stride + c4) = w;
   }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_sb_postfilter_store(const __grid_constant__ FrameXformParams prm) {
+  __shared__ int tile_s[kMaxT * kMaxPitch];
+  const PlaneXform& pl = prm.plane[blockIdx.y];
+  if (pl.xdec == 0) sb_postfilter_store_body<0>(prm, pl, tile_s);
+  else sb_postfilter_store_body<1>(prm, pl, tile_s);
 }
 
 // ---------------------------------------------------------------------------

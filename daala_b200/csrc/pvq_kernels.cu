@@ -1,0 +1,647 @@
+// PVQ band quantisation kernels for sm_100a.
+//
+// k_pvq_bands<NMAX>: one THREAD quantises one band (partition) of one
+//   transform block -- the full gain / theta / K candidate search of the
+//   reference's pvq_theta (src/pvq_encoder.c:333) including the double
+//   precision pulse search pvq_search_rdo_double (:93), the closed-form rate of
+//   od_pvq_rate (:247, speed > 0 branch) and the decoder-identical synthesis
+//   od_pvq_synthesis_partial (src/pvq.c:1037).  The host sorts bands into size
+//   classes (n = 15/8, 32, 128) so the threads of a warp run the same loop
+//   bounds; per-thread scratch lives in (interleaved, hence coalesced) local
+//   memory.  Every double-precision expression keeps the reference's
+//   operation order (library is built with -fmad=false) so that the chosen
+//   indices (qg, theta, K, pulses) are bit-exact.
+// k_coding_order_gather / _scatter: raster <-> coding order of whole block
+//   lists (od_raster_to_coding_order, od_coding_order_to_raster,
+//   src/partition.c:123/157, od_init_skipped_coeffs src/state.c:1347).
+// k_cfl_flip: keyframe-chroma CfL sign decision (src/pvq_encoder.c:847-871).
+// k_block_skip_diff: ordered per-block sum of the bands' skip_diff terms.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "daala_b200.h"
+#include "gen/coding_order.inc"
+#include "pvq_math.cuh"
+
+namespace daala_b200 {
+namespace pvq {
+
+constexpr int kSkipZero = 1;
+constexpr int kSkipCopy = 2;
+
+// Band boundaries in coding order (OD_BAND_OFFSETS, src/partition.c:85-91).
+__device__ __forceinline__ int band_start(int band) {
+  // 1,16,24,32,64,96,128,256,384,512
+  const int t[10] = {1, 16, 24, 32, 64, 96, 128, 256, 384, 512};
+  return t[band];
+}
+
+__device__ __forceinline__ int num_bands(int bs) { return bs == 0 ? 1 : bs == 1 ? 4 : bs == 2 ? 7 : 9; }
+
+__device__ __forceinline__ double rsqrt_small(int i) {
+  // od_rsqrt_table, src/pvq_encoder.c:53 (6-digit constants are normative).
+  const double tbl[16] = {1.000000, 0.707107, 0.577350, 0.500000, 0.447214, 0.408248, 0.377964, 0.353553,
+                          0.333333, 0.316228, 0.301511, 0.288675, 0.277350, 0.267261, 0.258199, 0.250000};
+  if (i <= 16) return tbl[i - 1];
+  return 1. / sqrt((double)i);
+}
+
+// src/pvq_encoder.c:93.  x[] (|xcoeff| as double) is caller scratch of n entries.
+__device__ double search_rdo(const int16_t* xcoeff, int n, int k, int32_t* ypulse, double g2,
+                             double pvq_norm_lambda, int prev_k, double* x) {
+  double xx = 0, xy = 0, yy = 0;
+  for (int j = 0; j < n; j++) {
+    x[j] = fabs((double)(float)xcoeff[j]);
+    xx += x[j] * x[j];
+  }
+  double norm_1 = 1. / sqrt(1e-30 + xx);
+  double lambda = pvq_norm_lambda / (1e-30 + g2);
+  int i = 0;
+  if (prev_k > 0 && prev_k <= k) {
+    for (int j = 0; j < n; j++) {
+      ypulse[j] = abs(ypulse[j]);
+      xy += x[j] * ypulse[j];
+      yy += ypulse[j] * ypulse[j];
+      i += ypulse[j];
+    }
+  } else if (k > 2) {
+    double l1_norm = 0;
+    for (int j = 0; j < n; j++) l1_norm += x[j];
+    double l1_inv = 1. / (l1_norm > 1e-100 ? l1_norm : 1e-100);
+    for (int j = 0; j < n; j++) {
+      double tmp = k * x[j] * l1_inv;
+      int f = (int)floor(tmp);
+      ypulse[j] = f > 0 ? f : 0;
+      xy += x[j] * ypulse[j];
+      yy += ypulse[j] * ypulse[j];
+      i += ypulse[j];
+    }
+  } else {
+    for (int j = 0; j < n; j++) ypulse[j] = 0;
+  }
+  int rdo_pulses = 1 + k / 4;
+  double delta_rate = 3. / n;
+  double accel_rate = 0.;
+  if (k == 1) {
+    if (n == 15) {
+      accel_rate = -8. / n;
+      delta_rate = 4.5 / n - accel_rate;
+    } else if (n == 8) {
+      accel_rate = 5.7 / n;
+      delta_rate = 9.3 / n - accel_rate;
+    }
+  }
+  for (; i < k - rdo_pulses; i++) {
+    int pos = 0;
+    double best_xy = -10, best_yy = 1;
+    for (int j = 0; j < n; j++) {
+      double tmp_xy = xy + x[j];
+      double tmp_yy = yy + 2 * ypulse[j] + 1;
+      tmp_xy *= tmp_xy;
+      if (j == 0 || tmp_xy * best_yy > best_xy * tmp_yy) {
+        best_xy = tmp_xy;
+        best_yy = tmp_yy;
+        pos = j;
+      }
+    }
+    xy = xy + x[pos];
+    yy = yy + 2 * ypulse[pos] + 1;
+    ypulse[pos]++;
+  }
+  for (; i < k; i++) {
+    double tbl[4];
+    int pos = 0;
+    double best_cost = -1e5;
+    for (int j = 0; j < 4; j++) tbl[j] = rsqrt_small((int)(yy + 2 * j + 1));
+    for (int j = 0; j < n; j++) {
+      double tmp_xy = xy + x[j];
+      int yj = ypulse[j];
+      double tmp_yy = yj < 4 ? (yj == 0 ? tbl[0] : yj == 1 ? tbl[1] : yj == 2 ? tbl[2] : tbl[3])
+                             : rsqrt_small((int)(yy + 2 * yj + 1));
+      tmp_xy = 2 * tmp_xy * norm_1 * tmp_yy - lambda * j * (delta_rate + j * accel_rate);
+      if (j == 0 || tmp_xy > best_cost) {
+        best_cost = tmp_xy;
+        pos = j;
+      }
+    }
+    xy = xy + x[pos];
+    yy = yy + 2 * ypulse[pos] + 1;
+    ypulse[pos]++;
+  }
+  for (int j = 0; j < n; j++)
+    if (xcoeff[j] < 0) ypulse[j] = -ypulse[j];
+  return xy / (1e-100 + sqrt(xx * yy));
+}
+
+// src/pvq_encoder.c:247, closed-form branch.
+__device__ double band_rate(int qg, int icgr, int theta, int ts, const int32_t* y0, int k, int n,
+                            int is_keyframe, int pli) {
+  double rate;
+  if (k == 0) {
+    rate = 0;
+  } else {
+    int sum = 0;
+    for (int i = 0; i < n - (theta != -1); i++) sum += i * abs(y0[i]);
+    double f = sum / (double)(k * n);
+    double t = log(n * 2 * (1 * f + .025)) * k / n;
+    rate = (1 + .4 * f) * n * (M_LOG2E * log(1 + (0 > t ? 0 : t))) + 3;
+  }
+  if (qg > 0 && theta >= 0) {
+    rate += .9 * (M_LOG2E * log((double)ts));
+    if (is_keyframe && pli == 0) rate += 6;
+    if (qg == icgr) rate -= .5;
+  }
+  return rate;
+}
+
+__device__ __forceinline__ int neg_interleave(int x, int ref) {
+  if (x < ref) return -2 * (x - ref) - 1;
+  if (x < 2 * ref) return 2 * (x - ref);
+  return x - 1;
+}
+
+__device__ int householder_setup(int16_t* r, int n, int32_t gr, int* sign, int shift) {
+  int m = 0;
+  int16_t maxr = 0;
+  for (int i = 0; i < n; i++) {
+    int a = abs((int)r[i]);
+    if (a > maxr) {
+      maxr = (int16_t)a;
+      m = i;
+    }
+  }
+  int s = r[m] > 0 ? 1 : -1;
+  r[m] = (int16_t)(r[m] + shr_round(gr * s, shift));
+  *sign = s;
+  return m;
+}
+
+__device__ void householder_apply(int16_t* out, const int16_t* x, const int16_t* r, int n) {
+  int32_t l2r = 0, proj = 0;
+  for (int i = 0; i < n; i++) l2r += mul16(r[i], r[i]);
+  for (int i = 0; i < n; i++) proj += mul16(r[i], x[i]);
+  int l2r_shift = (ilog((uint32_t)l2r) - 1) - 14;
+  int16_t l2r_norm = (int16_t)vshr_round(l2r, l2r_shift);
+  int16_t rcp = rcp16(l2r_norm);
+  int proj_shift = (ilog((uint32_t)abs(proj)) - 1) - 14;
+  int16_t proj_norm = (int16_t)vshr_round(proj, proj_shift);
+  int16_t proj_1 = (int16_t)mul16_q15(proj_norm, rcp);
+  int outshift = 14 - proj_shift - 1 + l2r_shift;
+  if (outshift > 30) outshift = 30;
+  if (outshift >= 0) {
+    for (int i = 0; i < n; i++) out[i] = (int16_t)(x[i] - shr_round(mul16(r[i], proj_1), outshift));
+  } else {
+    for (int i = 0; i < n; i++) out[i] = (int16_t)(x[i] - shl(mul16(r[i], proj_1), -outshift));
+  }
+}
+
+__device__ void synthesis(int32_t* xcoeff, const int32_t* ypulse, const int16_t* r16, int n, int noref,
+                          int32_t g, int32_t theta, int m, int s, const int16_t* qm_inv, int16_t* xs) {
+  int nn = n - !noref;
+  int yy = 0;
+  for (int i = 0; i < nn; i++) yy += ypulse[i] * (int32_t)ypulse[i];
+  int gshift = ilog((uint32_t)g) - 14;
+  if (gshift < 0) gshift = 0;
+  int32_t scale;
+  if (yy == 0) {
+    scale = 0;
+  } else {
+    int rshift;
+    int16_t rs = rsqrt32(yy, &rshift);
+    scale = vshr_round64(rs * (int64_t)g, rshift + gshift - 16);
+  }
+  int qshift = kQmInvShift - gshift;
+  if (noref) {
+    for (int i = 0; i < n; i++) {
+      int32_t x = mul16_32_q16(ypulse[i], scale);
+      xcoeff[i] = shr_round(x * qm_inv[i], qshift);
+    }
+  } else {
+    scale = round32(scale * (1. / 32768) * pvq_sin(theta));
+    for (int i = 0; i < m; i++) xs[i] = (int16_t)mul16_32_q16(ypulse[i], scale);
+    xs[m] = (int16_t)floor(.5 + -s * (shr_round(g, gshift)) * (1. / 32768) * pvq_cos(theta));
+    for (int i = m; i < nn; i++) xs[i + 1] = (int16_t)mul16_32_q16(ypulse[i], scale);
+    householder_apply(xs, xs, r16, n);
+    for (int i = 0; i < n; i++) xcoeff[i] = shr_round(xs[i] * qm_inv[i], qshift);
+  }
+}
+
+struct Cand {
+  int gain, k, theta, ts;
+  int32_t qtheta, qcg;
+};
+
+// One band.  Returns the coded gain index; results through pointers.
+template <int NMAX>
+__device__ int quantise_band(int32_t* out, const int32_t* x0, const int32_t* r0, int n, int q0, int32_t* y,
+                             int* itheta, int* max_theta, int* vk, int beta, double* skip_term,
+                             int is_keyframe, int pli, const int16_t* qm, const int16_t* qm_inv,
+                             double pvq_norm_lambda) {
+  const double gain_weight = 1.4;
+  const double cgain_1 = 1. / kCgainOne;
+  const double cgain_2 = cgain_1 * cgain_1;
+  const double theta_scale = (1 << kThetaShift) * 2. / M_PI;
+  const double theta_scale_1 = 1. / theta_scale;
+  const double trig_1 = 1. / 32768;
+  int32_t y_tmp[NMAX];
+  int16_t x16[NMAX];
+  int16_t r16[NMAX];
+  int16_t xr[NMAX];
+  double xd[NMAX];
+  int32_t g, gr;
+  int32_t theta = 0, best_qtheta = 0;
+  int qg = 0, best_k = 0, noref = 1, m = 0, s = 1, skip = 0;
+  int r_is_null = 1;
+  double corr = 0;
+  // od_vector_log_mag, src/pvq.c:472
+  int xshift, rshift;
+  {
+    int32_t sx = 0, sr = 0;
+    for (int i = 0; i < n; i++) {
+      int16_t tx = (int16_t)(x0[i] >> 8), tr = (int16_t)(r0[i] >> 8);
+      sx += tx * (int32_t)tx;
+      sr += tr * (int32_t)tr;
+    }
+    xshift = 9 + ilog((uint32_t)(n + sx)) / 2 - 15;
+    rshift = 9 + ilog((uint32_t)(n + sr)) / 2 - 14;
+    if (xshift < 0) xshift = 0;
+    if (rshift < 0) rshift = 0;
+  }
+  int32_t accx = 0, accr = 0;
+  for (int i = 0; i < n; i++) {
+    x16[i] = (int16_t)shr_round(x0[i] * qm[i], kQmShift + xshift);
+    r16[i] = (int16_t)shr_round(r0[i] * qm[i], kQmShift + rshift);
+    corr += mul16(x16[i], r16[i]);
+    accx += x16[i] * (int32_t)x16[i];
+    accr += r16[i] * (int32_t)r16[i];
+    if (r0[i]) r_is_null = 0;
+  }
+  const int cfl_enabled = is_keyframe && pli != 0;
+  int32_t cg = compute_gain_from_energy(accx, q0, &g, beta, xshift);
+  int32_t cgr = compute_gain_from_energy(accr, q0, &gr, beta, rshift);
+  if (cfl_enabled) cgr = kCgainOne;
+  int icgr = shr_round(cgr, kCgainShift);
+  int32_t gain_offset = cgr - shl(icgr, kCgainShift);
+  double dist = gain_weight * cg * cg * cgain_2;
+  double best_dist = dist;
+  double best_cost = dist + pvq_norm_lambda * band_rate(0, 0, -1, 0, nullptr, 0, n, is_keyframe, pli);
+  *itheta = -1;
+  *max_theta = 0;
+  for (int i = 0; i < n; i++) y[i] = 0;
+  corr = corr / (1e-100 + g * (double)gr / shl(1, xshift + rshift));
+  corr = corr < 1. ? corr : 1.;
+  corr = corr > -1. ? corr : -1.;
+  double skip_dist;
+  if (is_keyframe) {
+    skip_dist = gain_weight * cg * cg * cgain_2;
+  } else {
+    skip_dist = gain_weight * (cg - cgr) * (cg - cgr) + cgr * (double)cg * (2 - 2 * corr);
+    skip_dist *= cgain_2;
+  }
+  if (!is_keyframe) {
+    int32_t scgr = gain_offset > 0 ? gain_offset : 0;
+    if (icgr == 0) {
+      best_dist = gain_weight * (cg - scgr) * (cg - scgr) + scgr * (double)cg * (2 - 2 * corr);
+      best_dist *= cgain_2;
+    }
+    best_cost = best_dist + pvq_norm_lambda * band_rate(0, icgr, 0, 0, nullptr, 0, n, is_keyframe, pli);
+    best_qtheta = 0;
+    *itheta = 0;
+    *max_theta = 0;
+    noref = 0;
+  }
+  const double dist0 = best_dist;
+  if (!r_is_null && corr > 0) {
+    Cand items[20];
+    int nitems = 0;
+    int gain_bound = (cg - gain_offset) >> kCgainShift;
+    int prev_k = 0;
+    double cos_dist = 0;
+    theta = round32(theta_scale * acos(corr));
+    m = householder_setup(r16, n, gr, &s, rshift);
+    householder_apply(xr, x16, r16, n);
+    for (int i = m; i < n - 1; i++) xr[i] = xr[i + 1];
+    for (int i = gain_bound - 1 > 1 ? gain_bound - 1 : 1; i <= gain_bound + 1; i++) {
+      int32_t qcg = shl(i, kCgainShift) + gain_offset;
+      int ts = compute_max_theta(qcg, beta);
+      int lo = (int)floor(.5 + theta * theta_scale_1 * 2 / M_PI * ts) - 2;
+      int hi = (int)ceil(theta * theta_scale_1 * 2 / M_PI * ts);
+      if (lo < 0) lo = 0;
+      if (hi > ts - 1) hi = ts - 1;
+      for (int j = lo; j <= hi; j++) {
+        Cand c;
+        c.gain = i;
+        c.theta = j;
+        c.qtheta = compute_theta(j, ts);
+        c.k = compute_k(qcg, j, 0, n, beta);
+        c.qcg = qcg;
+        c.ts = ts;
+        // stable insertion by (k, gain): the order glibc's merge-sort qsort
+        // produces at src/pvq_encoder.c:504
+        int p = nitems++;
+        while (p > 0 && (items[p - 1].k > c.k || (items[p - 1].k == c.k && items[p - 1].gain > c.gain))) {
+          items[p] = items[p - 1];
+          p--;
+        }
+        items[p] = c;
+      }
+    }
+    for (int idx = 0; idx < nitems; idx++) {
+      const Cand c = items[idx];
+      const int32_t qcg = c.qcg, qtheta = c.qtheta;
+      const int k = c.k;
+      double dist_theta = 2 - 2. * pvq_cos(theta - qtheta) * trig_1;
+      dist = gain_weight * (qcg - cg) * (qcg - cg) + qcg * (double)cg * dist_theta;
+      dist *= cgain_2;
+      if (dist > dist0 + 1.0 * pvq_norm_lambda && k != 0) continue;
+      double sin_prod = pvq_sin(theta) * trig_1 * pvq_sin(qtheta) * trig_1;
+      if (k == 0) {
+        cos_dist = 0;
+        for (int i = 0; i < n - 1; i++) y_tmp[i] = 0;
+      } else if (k != prev_k) {
+        cos_dist = search_rdo(xr, n - 1, k, y_tmp, qcg * (double)cg * sin_prod * cgain_2, pvq_norm_lambda,
+                              prev_k, xd);
+      }
+      prev_k = k;
+      dist_theta = 2 - 2. * pvq_cos(theta - qtheta) * trig_1 + sin_prod * (2 - 2 * cos_dist);
+      dist = gain_weight * (qcg - cg) * (qcg - cg) + qcg * (double)cg * dist_theta;
+      dist *= cgain_2;
+      double cost = dist + pvq_norm_lambda * band_rate(c.gain, icgr, c.theta, c.ts, y_tmp, k, n, is_keyframe, pli);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_dist = dist;
+        qg = c.gain;
+        best_k = k;
+        best_qtheta = qtheta;
+        *itheta = c.theta;
+        *max_theta = c.ts;
+        noref = 0;
+        for (int i = 0; i < n - 1; i++) y[i] = y_tmp[i];
+      }
+    }
+  }
+  if ((is_keyframe && pli == 0) || corr < .5 || cg < (int32_t)shl(2, kCgainShift)) {
+    int gain_bound = cg >> kCgainShift;
+    int prev_k = 0;
+    for (int i = gain_bound > 1 ? gain_bound : 1; i <= gain_bound + 1; i++) {
+      int32_t qcg = shl(i, kCgainShift);
+      int k = compute_k(qcg, -1, 1, n, beta);
+      dist = gain_weight * (qcg - cg) * (qcg - cg);
+      dist *= cgain_2;
+      if (dist > dist0 && k != 0) continue;
+      double cos_dist = search_rdo(x16, n, k, y_tmp, qcg * (double)cg * cgain_2, pvq_norm_lambda, prev_k, xd);
+      prev_k = k;
+      dist = gain_weight * (qcg - cg) * (qcg - cg) + qcg * (double)cg * (2 - 2 * cos_dist);
+      dist *= cgain_2;
+      double cost = dist + pvq_norm_lambda * band_rate(i, 0, -1, 0, y_tmp, k, n, is_keyframe, pli);
+      if (cost <= best_cost) {
+        best_cost = cost;
+        best_dist = dist;
+        qg = i;
+        noref = 1;
+        best_k = k;
+        *itheta = -1;
+        *max_theta = 0;
+        for (int j = 0; j < n; j++) y[j] = y_tmp[j];
+      }
+    }
+  }
+  theta = best_qtheta;
+  if (noref) {
+    if (qg == 0) skip = kSkipZero;
+  } else {
+    if (!is_keyframe && qg == 0) skip = icgr ? kSkipZero : kSkipCopy;
+    if (qg == icgr && *itheta == 0 && !cfl_enabled) skip = kSkipCopy;
+  }
+  if (skip) {
+    if (skip == kSkipCopy) {
+      for (int i = 0; i < n; i++) out[i] = r0[i];
+    } else {
+      for (int i = 0; i < n; i++) out[i] = 0;
+    }
+  } else {
+    if (noref) gain_offset = 0;
+    g = gain_expand(shl(qg, kCgainShift) + gain_offset, q0, beta);
+    synthesis(out, y, r16, n, noref, g, theta, m, s, qm_inv, xr);
+  }
+  *vk = best_k;
+  *skip_term = skip_dist - best_dist;
+  if (is_keyframe) return noref ? qg : neg_interleave(qg, icgr);
+  return noref ? qg - 1 : neg_interleave(qg + 1, icgr + 1);
+}
+
+// ---------------------------------------------------------------------------
+// Kernels
+// ---------------------------------------------------------------------------
+
+// band_list entries: (block index << 4) | band index.
+template <int NMAX>
+__global__ void __launch_bounds__(128)
+k_pvq_bands(const __grid_constant__ daala_b200_pvq_params prm, const uint32_t* __restrict__ band_list,
+            int count) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const uint32_t e = band_list[t];
+  const int blk = (int)(e >> 4), band = (int)(e & 15);
+  const daala_b200_pvq_block b = prm.blocks[blk];
+  const int bs = b.bs, pli = b.pli;
+  const int start = band_start(band);
+  const int n = band_start(band + 1) - start;
+  const size_t off = (size_t)b.coef_off + start;
+  // quantiser of this band: od_pvq_encode, src/pvq_encoder.c:873-874
+  int qidx = bs * (bs + 1) + (band + 1) - (band + 1) / 3;
+  int q = (prm.q0 * prm.pvq_qm_q4[pli][qidx]) >> 4;
+  if (q < 1) q = 1;
+  // OD_PVQ_BETA, src/pvq.c:205-268: 1.5 only on luma with masking, sizes > 4x4
+  const int beta = (prm.use_masking && pli == 0 && bs > 0) ? kBeta15 : kBeta1;
+  // od_qm_offset(bs, xdec), src/pvq.c:306
+  const int qoff = (b.xdec ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
+  int itheta, max_theta, k;
+  double skip_term;
+  int32_t* y = prm.y + off;
+  int gain = quantise_band<NMAX>(prm.out + off, prm.in + off, prm.ref + off, n, q, y, &itheta, &max_theta, &k,
+                                 beta, &skip_term, prm.is_keyframe, pli, prm.qm + qoff, prm.qm_inv + qoff,
+                                 prm.pvq_norm_lambda);
+  const size_t r = (size_t)blk * 9 + band;
+  prm.res_gain[r] = gain;
+  prm.res_theta[r] = itheta;
+  prm.res_max_theta[r] = max_theta;
+  prm.res_k[r] = k;
+  prm.res_skip_term[r] = skip_term;
+}
+
+// Per block: ordered sum of the bands' skip_diff terms (`*skip_diff += ...`
+// runs over the bands in order at src/pvq_encoder.c:875-880; double addition
+// is not associative, so the order is kept) and the DC coefficient:
+// keyframes keep the Haar-coded DC (scalar_out[0] = dblock[0],
+// src/encode.c:1381); inter frames use the plain scalar quantiser of
+// src/encode.c:1337-1344 and reconstruct it as in :1377-1378.
+__global__ void k_block_finish(const __grid_constant__ daala_b200_pvq_params prm, int nblocks) {
+  int blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= nblocks) return;
+  const daala_b200_pvq_block b = prm.blocks[blk];
+  int nb = num_bands(b.bs);
+  double sd = 0;
+  for (int i = 0; i < nb; i++) sd += prm.res_skip_term[(size_t)blk * 9 + i];
+  prm.res_skip_diff[blk] = sd;
+  const int32_t in0 = prm.in[b.coef_off], ref0 = prm.ref[b.coef_off];
+  if (prm.is_keyframe) {
+    prm.out[b.coef_off] = in0;
+    prm.res_dc[blk] = 0;
+  } else {
+    int dc_quant = (prm.q0 * prm.pvq_qm_q4[b.pli][b.bs * (b.bs + 1)]) >> 4;
+    if (dc_quant < 1) dc_quant = 1;
+    int diff = in0 - ref0;
+    int qdc;
+    if (abs(diff) < dc_quant * 141 / 256) {
+      qdc = 0;
+    } else {
+      // OD_DIV_R0(diff, dc_quant), src/odintrin.h:123
+      int half = ((dc_quant + 1) >> 1) - 1;
+      qdc = (diff + (diff < 0 ? -half : half)) / dc_quant;
+    }
+    prm.res_dc[blk] = qdc;
+    prm.out[b.coef_off] = qdc * dc_quant + ref0;
+  }
+}
+
+// Keyframe chroma: decide the CfL flip from the first band and negate the
+// reference of the whole block when cos(theta) < 0 (src/pvq_encoder.c:847-871).
+__global__ void k_cfl_flip(const __grid_constant__ daala_b200_pvq_params prm, int nblocks) {
+  int blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= nblocks) return;
+  const daala_b200_pvq_block b = prm.blocks[blk];
+  int flip = 0;
+  if (b.pli != 0 && prm.is_keyframe) {
+    const int bs = b.bs;
+    const int qoff = (b.xdec ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3);
+    const int32_t* in = prm.in + b.coef_off;
+    int32_t* ref = prm.ref + b.coef_off;
+    int32_t xy = 0;
+    for (int i = 1; i < 16; i++) {
+      int32_t rq = ref[i] * prm.qm[qoff + i];
+      int32_t inq = in[i] * prm.qm[qoff + i];
+      // OD_SHR(rq*(int64_t)inq, OD_SHL(OD_QM_SHIFT + OD_CFL_FLIP_SHIFT, 1)), OD_CFL_FLIP_SHIFT = 4
+      xy += (int32_t)((rq * (int64_t)inq) >> ((kQmShift + 4) << 1));
+    }
+    if (xy < 0) {
+      flip = 1;
+      const int end = band_start(num_bands(bs));
+      for (int i = 1; i < end; i++) ref[i] = -ref[i];
+    }
+  }
+  prm.res_flip[blk] = flip;
+}
+
+// Raster (block inside a coefficient plane) -> coding order, one warp per block.
+// Only the coded prefix is produced: n^2 for n <= 16, 512 for 32 and 64
+// (OD_LAYOUT32/64 in src/partition.c:40-55 cover nothing beyond it).
+__device__ __forceinline__ int scan_to_raster(int i, int ln, int stride) {
+  // i in [1, coded length)
+  int v, n;
+  if (i < 16) { v = kScan4[i - 1]; n = 2; }
+  else if (i < 64) { v = kScan8[i - 16]; n = 3; }
+  else if (i < 256) { v = kScan16[i - 64]; n = 4; }
+  else { v = kScan32[i - 256]; n = 5; }
+  (void)ln;
+  return (v >> n) * stride + (v & ((1 << n) - 1));
+}
+
+__global__ void k_coding_order_gather(const __grid_constant__ daala_b200_pvq_params prm, int nblocks,
+                                      int which /*0: in <- coeffs, 1: ref <- pred*/) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nblocks) return;
+  const daala_b200_pvq_block b = prm.blocks[warp];
+  const int ln = b.bs + 2;
+  const int len = ln >= 5 ? 512 : 1 << (2 * ln);
+  const int32_t* plane = which ? prm.pred_plane[b.pli] : prm.coef_plane[b.pli];
+  if (plane) plane += b.frame * prm.plane_frame_pitch[b.pli];
+  const int stride = prm.plane_stride[b.pli];
+  int32_t* dst = (which ? prm.ref : prm.in) + b.coef_off;
+  if (plane == nullptr) {
+    for (int i = lane; i < len; i += 32) dst[i] = 0;
+    return;
+  }
+  const int32_t* src = plane + (size_t)b.y0 * stride + b.x0;
+  for (int i = lane; i < len; i += 32) dst[i] = i == 0 ? src[0] : src[scan_to_raster(i, ln, stride)];
+}
+
+// Coding order -> raster, with od_init_skipped_coeffs first (keyframe: zero
+// everything but DC; otherwise copy the prediction), then the coded prefix.
+// DC: the keyframe path keeps the block's (Haar-coded) DC, src/encode.c:1384.
+__global__ void k_coding_order_scatter(const __grid_constant__ daala_b200_pvq_params prm, int nblocks) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nblocks) return;
+  const daala_b200_pvq_block b = prm.blocks[warp];
+  const int ln = b.bs + 2, n = 1 << ln;
+  const int len = ln >= 5 ? 512 : 1 << (2 * ln);
+  const int stride = prm.plane_stride[b.pli];
+  const long long fp = b.frame * prm.plane_frame_pitch[b.pli];
+  int32_t* dst = prm.coef_plane[b.pli] + fp + (size_t)b.y0 * stride + b.x0;
+  const int32_t* pred = prm.pred_plane[b.pli] ? prm.pred_plane[b.pli] + fp + (size_t)b.y0 * stride + b.x0 : nullptr;
+  const int32_t* src = prm.out + b.coef_off;
+  if (ln >= 5) {
+    for (int i = lane; i < n * n; i += 32) {
+      int r = i >> ln, c = i & (n - 1);
+      if (prm.is_keyframe) {
+        if (i) dst[r * stride + c] = 0;
+      } else {
+        dst[r * stride + c] = pred ? pred[r * stride + c] : 0;
+      }
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < len; i += 32) {
+    if (i == 0) {
+      if (!prm.is_keyframe) dst[0] = src[0];
+    } else {
+      dst[scan_to_raster(i, ln, stride)] = src[i];
+    }
+  }
+}
+
+}  // namespace pvq
+}  // namespace daala_b200
+
+using namespace daala_b200::pvq;
+
+extern "C" {
+
+int daala_b200_pvq_encode_bands(const daala_b200_pvq_params* prm, const uint32_t* band_list, int count,
+                                int nmax, void* stream) {
+  if (count <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = 128;
+  const int blocks = (count + threads - 1) / threads;
+  if (nmax <= 16) k_pvq_bands<16><<<blocks, threads, 0, s>>>(*prm, band_list, count);
+  else if (nmax <= 32) k_pvq_bands<32><<<blocks, threads, 0, s>>>(*prm, band_list, count);
+  else k_pvq_bands<128><<<blocks, threads, 0, s>>>(*prm, band_list, count);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_pvq_block_finish(const daala_b200_pvq_params* prm, int nblocks, void* stream) {
+  if (nblocks <= 0) return 0;
+  k_block_finish<<<(nblocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*prm, nblocks);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_pvq_cfl_flip(const daala_b200_pvq_params* prm, int nblocks, void* stream) {
+  if (nblocks <= 0) return 0;
+  k_cfl_flip<<<(nblocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*prm, nblocks);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_coding_order_gather(const daala_b200_pvq_params* prm, int nblocks, int which, void* stream) {
+  if (nblocks <= 0) return 0;
+  k_coding_order_gather<<<(nblocks * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*prm, nblocks, which);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_coding_order_scatter(const daala_b200_pvq_params* prm, int nblocks, void* stream) {
+  if (nblocks <= 0) return 0;
+  k_coding_order_scatter<<<(nblocks * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*prm, nblocks);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+"""Host side of the PVQ stage: block / band list construction from the
+block-size map and the device buffers + launches of the batch entry points
+(include/daala_b200.h, "PVQ" section).
+
+Band geometry follows OD_BAND_OFFSETS (reference src/partition.c:85-91):
+4x4 -> {15}; 8x8 -> {15, 8, 8, 32}; 16x16 -> {15, 8, 8, 32, 32, 32, 128};
+32x32 and 64x64 -> {15, 8, 8, 32, 32, 32, 128, 128, 128} (only the first 512
+coefficients in coding order are coded).
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _native
+
+BAND_EDGES = [1, 16, 24, 32, 64, 96, 128, 256, 384, 512]
+NBANDS = {0: 1, 1: 4, 2: 7, 3: 9, 4: 9}
+OD_QM_STRIDE = 5456
+PVQ_LAMBDA = 0.147  # OD_PVQ_LAMBDA, src/pvq.h:51
+
+BLOCK_DTYPE = np.dtype([("coef_off", "<i4"), ("x0", "<u2"), ("y0", "<u2"), ("bs", "u1"), ("pli", "u1"),
+                        ("xdec", "u1"), ("frame", "u1")])
+
+
+class PvqParams(ctypes.Structure):
+    """struct daala_b200_pvq_params"""
+    _fields_ = [
+        ("blocks", ctypes.c_void_p), ("in_", ctypes.c_void_p), ("ref", ctypes.c_void_p),
+        ("out", ctypes.c_void_p), ("y", ctypes.c_void_p), ("res_gain", ctypes.c_void_p),
+        ("res_theta", ctypes.c_void_p), ("res_max_theta", ctypes.c_void_p), ("res_k", ctypes.c_void_p),
+        ("res_skip_term", ctypes.c_void_p), ("res_skip_diff", ctypes.c_void_p), ("res_flip", ctypes.c_void_p),
+        ("res_dc", ctypes.c_void_p), ("qm", ctypes.c_void_p), ("qm_inv", ctypes.c_void_p),
+        ("coef_plane", ctypes.c_void_p * 3), ("pred_plane", ctypes.c_void_p * 3),
+        ("plane_frame_pitch", ctypes.c_longlong * 3), ("plane_stride", ctypes.c_int * 3),
+        ("qm_stride", ctypes.c_int), ("q0", ctypes.c_int), ("is_keyframe", ctypes.c_int),
+        ("use_masking", ctypes.c_int), ("pad_", ctypes.c_int), ("pvq_norm_lambda", ctypes.c_double),
+        ("pvq_qm_q4", (ctypes.c_ubyte * 32) * 3),
+    ]
+
+
+def _bind():
+    L = _native.lib()
+    if getattr(L, "_pvq_bound", False):
+        return L
+    pp = ctypes.POINTER(PvqParams)
+    L.daala_b200_pvq_encode_bands.argtypes = [pp, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    for name in ("daala_b200_pvq_block_finish", "daala_b200_pvq_cfl_flip", "daala_b200_coding_order_scatter"):
+        getattr(L, name).argtypes = [pp, ctypes.c_int, ctypes.c_void_p]
+    L.daala_b200_coding_order_gather.argtypes = [pp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L._pvq_bound = True
+    return L
+
+
+def default_qm(hvs=True):
+    """state->qm / qm_inv for the default (HVS or flat) 8x8 base matrix."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "qm_%s.npy" % ("hvs" if hvs else "flat"))
+    a = np.load(path)
+    return a[0].copy(), a[1].copy()
+
+
+def block_list(bsize, geom, frame=0, sb_row0=0, sb_rows=None):
+    """Leaf transform blocks of one frame for every plane, from the block-size
+    map (one byte per 8x8 luma unit).  Returns a BLOCK_DTYPE array (coef_off
+    not yet assigned), ordered by transform size so warps see uniform work."""
+    sb_rows = geom.nvsb - sb_row0 if sb_rows is None else sb_rows
+    u0, u1 = sb_row0 * 8, (sb_row0 + sb_rows) * 8
+    out = []
+    bh, bw = bsize.shape
+    uy, ux = np.mgrid[0:bh, 0:bw]
+    inrows = (uy >= u0) & (uy < u1)
+    for pli in range(geom.nplanes):
+        xdec = geom.xdec[pli]
+        eff = np.maximum(bsize, xdec).astype(np.int32)  # bs = max(obs, xdec), src/encode.c:1467
+        for L in range(xdec, 5):
+            if L == 0:
+                sel = (eff == 0) & inrows
+                ys, xs = uy[sel], ux[sel]
+                # four 4x4 luma blocks per 8x8 unit
+                for dy in (0, 4):
+                    for dx in (0, 4):
+                        a = np.zeros(len(ys), BLOCK_DTYPE)
+                        a["x0"], a["y0"] = xs * 8 + dx, ys * 8 + dy
+                        a["bs"], a["pli"], a["xdec"], a["frame"] = 0, pli, xdec, frame
+                        out.append(a)
+                continue
+            span = 1 << (L - 1)  # units per block side
+            sel = (eff == L) & (uy % span == 0) & (ux % span == 0) & inrows
+            ys, xs = uy[sel], ux[sel]
+            a = np.zeros(len(ys), BLOCK_DTYPE)
+            a["x0"], a["y0"] = (xs * 8) >> xdec, (ys * 8) >> xdec
+            a["bs"], a["pli"], a["xdec"], a["frame"] = L - xdec, pli, xdec, frame
+            out.append(a)
+    blocks = np.concatenate(out)
+    order = np.argsort(blocks["bs"], kind="stable")
+    return blocks[order]
+
+
+def assign_offsets(blocks):
+    n2 = (16 << (2 * blocks["bs"].astype(np.int64)))
+    length = np.minimum(n2, 512)
+    off = np.concatenate([[0], np.cumsum(length)])
+    blocks["coef_off"] = off[:-1]
+    return int(off[-1])
+
+
+def band_lists(blocks):
+    """(block << 4 | band) lists per size class {16: n in (15, 8), 32, 128}."""
+    idx = np.arange(len(blocks), dtype=np.uint32)
+    bs = blocks["bs"]
+    cls = {16: [], 32: [], 128: []}
+    for band in range(9):
+        n = BAND_EDGES[band + 1] - BAND_EDGES[band]
+        has = np.array([NBANDS[b] > band for b in range(5)])[bs]
+        key = 16 if n <= 16 else (32 if n == 32 else 128)
+        cls[key].append((idx[has] << 4) | band)
+    # keep equal band sizes together inside the class-16 list (15s then 8s)
+    return {k: (np.concatenate(v) if v else np.zeros(0, np.uint32)) for k, v in cls.items()}
+
+
+class PvqBatch:
+    """Device state of one PVQ batch: coding-order buffers, result arrays and
+    the launch sequence gather -> [CfL flip] -> bands -> finish -> scatter."""
+
+    def __init__(self, blocks, coef_planes, pred_planes=None, q0=38, is_keyframe=1, use_masking=1,
+                 lam=PVQ_LAMBDA, qm=None, qm_inv=None, pvq_qm_q4=None, device="cuda:0"):
+        self.device = torch.device(device)
+        dev = self.device
+        self.blocks_np = blocks.copy()
+        self.total = assign_offsets(self.blocks_np)
+        self.nblocks = len(blocks)
+        self.blocks = torch.from_numpy(self.blocks_np.view(np.uint8).reshape(-1)).to(dev)
+        lists = band_lists(self.blocks_np)
+        self.lists = {k: torch.from_numpy(v.view(np.int32)).to(dev) for k, v in lists.items()}
+        z = lambda n, dt=torch.int32: torch.zeros(max(n, 1), dtype=dt, device=dev)  # noqa: E731
+        self.in_, self.ref, self.out, self.y = z(self.total), z(self.total), z(self.total), z(self.total)
+        nb9 = self.nblocks * 9
+        self.res_gain, self.res_theta, self.res_max_theta, self.res_k = z(nb9), z(nb9), z(nb9), z(nb9)
+        self.res_skip_term = z(nb9, torch.float64)
+        self.res_skip_diff = z(self.nblocks, torch.float64)
+        self.res_flip, self.res_dc = z(self.nblocks), z(self.nblocks)
+        if qm is None:
+            qm, qm_inv = default_qm(True)
+        self.qm = torch.from_numpy(qm).to(dev)
+        self.qm_inv = torch.from_numpy(qm_inv).to(dev)
+        self.coef_planes = coef_planes      # list of [F, h, w] int32 tensors
+        self.pred_planes = pred_planes      # same or None
+        p = PvqParams()
+        p.blocks = self.blocks.data_ptr()
+        p.in_, p.ref, p.out, p.y = (t.data_ptr() for t in (self.in_, self.ref, self.out, self.y))
+        p.res_gain, p.res_theta = self.res_gain.data_ptr(), self.res_theta.data_ptr()
+        p.res_max_theta, p.res_k = self.res_max_theta.data_ptr(), self.res_k.data_ptr()
+        p.res_skip_term, p.res_skip_diff = self.res_skip_term.data_ptr(), self.res_skip_diff.data_ptr()
+        p.res_flip, p.res_dc = self.res_flip.data_ptr(), self.res_dc.data_ptr()
+        p.qm, p.qm_inv, p.qm_stride = self.qm.data_ptr(), self.qm_inv.data_ptr(), OD_QM_STRIDE
+        for i, t in enumerate(coef_planes):
+            p.coef_plane[i] = t.data_ptr()
+            p.plane_stride[i] = t.stride(1)
+            p.plane_frame_pitch[i] = t.stride(0)
+            p.pred_plane[i] = pred_planes[i].data_ptr() if pred_planes is not None else None
+        p.q0, p.is_keyframe, p.use_masking = int(q0), int(is_keyframe), int(use_masking)
+        p.pvq_norm_lambda = float(lam)
+        if pvq_qm_q4 is None:
+            pvq_qm_q4 = np.full((3, 30), 16, np.uint8)
+        for pli in range(3):
+            for i in range(30):
+                p.pvq_qm_q4[pli][i] = int(pvq_qm_q4[pli][i])
+        self.params = p
+        self.is_keyframe = int(is_keyframe)
+        self.launches_per_run = 0
+
+    def _s(self, stream):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return ctypes.c_void_p(s.cuda_stream)
+
+    def gather(self, stream=None):
+        L = _bind()
+        p = ctypes.byref(self.params)
+        _native.check(L.daala_b200_coding_order_gather(p, self.nblocks, 0, self._s(stream)), "gather(in)")
+        _native.check(L.daala_b200_coding_order_gather(p, self.nblocks, 1, self._s(stream)), "gather(ref)")
+
+    def quantise(self, stream=None):
+        L = _bind()
+        p = ctypes.byref(self.params)
+        s = self._s(stream)
+        n = 0
+        if self.is_keyframe:
+            _native.check(L.daala_b200_pvq_cfl_flip(p, self.nblocks, s), "cfl_flip")
+            n += 1
+        for nmax in (128, 32, 16):
+            lst = self.lists[nmax]
+            if lst.numel():
+                _native.check(L.daala_b200_pvq_encode_bands(p, lst.data_ptr(), lst.numel(), nmax, s), "pvq_bands")
+                n += 1
+        _native.check(L.daala_b200_pvq_block_finish(p, self.nblocks, s), "block_finish")
+        return n + 1
+
+    def scatter(self, stream=None):
+        L = _bind()
+        _native.check(L.daala_b200_coding_order_scatter(ctypes.byref(self.params), self.nblocks, self._s(stream)),
+                      "scatter")
+
+    def run(self, stream=None):
+        """gather -> quantise -> scatter; returns the number of kernel launches."""
+        self.gather(stream)
+        n = self.quantise(stream)
+        self.scatter(stream)
+        return n + 3

@@ -144,6 +144,67 @@ int daala_b200_plane_sb_filter(int32_t *c, int stride, int nhsb, int nvsb, int x
    mode 0/1: 2-D forward/inverse; mode 2/3: every row as a 1-D forward/inverse. */
 int daala_b200_block_transform(int32_t *blocks, int count, int ln, int mode, void *stream);
 
+/* ---- PVQ (perceptual vector quantisation) --------------------------------- */
+
+/* One transform block of the PVQ batch. */
+typedef struct daala_b200_pvq_block {
+  int32_t coef_off;        /* offset of this block's coding-order vector in in/ref/out/y;
+                              the vector holds n^2 (n <= 16) or 512 (n >= 32) coefficients */
+  uint16_t x0, y0;         /* top-left sample of the block inside its plane */
+  uint8_t bs;              /* log2(n) - 2: 0..4 */
+  uint8_t pli;             /* plane index */
+  uint8_t xdec;            /* plane decimation (selects the 4:2:0 half of the QM tables) */
+  uint8_t frame;           /* frame of the batch this block belongs to */
+} daala_b200_pvq_block;
+
+/* All pointers are device pointers.  Result arrays are indexed [block*9 + band]
+   (PVQ_MAX_PARTITIONS = 9, reference src/pvq.h:38) or [block]. */
+typedef struct daala_b200_pvq_params {
+  const daala_b200_pvq_block *blocks;
+  int32_t *in;             /* dblock: coefficients in coding order (od_raster_to_coding_order) */
+  int32_t *ref;            /* predt: prediction in coding order; negated in place by the CfL flip */
+  int32_t *out;            /* scalar_out: de-quantised coefficients in coding order */
+  int32_t *y;              /* PVQ pulse vectors (what the entropy coder codes) */
+  int32_t *res_gain;       /* coded gain index per band: pvq_theta's return value */
+  int32_t *res_theta;      /* itheta per band (-1: no reference) */
+  int32_t *res_max_theta;
+  int32_t *res_k;          /* pulses per band */
+  double *res_skip_term;   /* per band: skip_dist - best_dist */
+  double *res_skip_diff;   /* per block: ordered sum of the terms above */
+  int32_t *res_flip;       /* per block: CfL flip flag */
+  int32_t *res_dc;         /* per block: scalar-quantised DC index (inter frames) */
+  const int16_t *qm;       /* state->qm: od_init_qm, src/pvq.c:322 (2*qm_stride entries) */
+  const int16_t *qm_inv;
+  int32_t *coef_plane[3];  /* `d` planes (raster): gather source / scatter destination */
+  const int32_t *pred_plane[3]; /* `md` planes or NULL (prediction = 0) */
+  long long plane_frame_pitch[3];
+  int plane_stride[3];
+  int qm_stride;           /* OD_QM_STRIDE = 5456 */
+  int q0;                  /* max(1, state->quantizer) */
+  int is_keyframe;
+  int use_masking;         /* activity masking: beta = 1.5 on luma blocks > 4x4 */
+  int pad_;
+  double pvq_norm_lambda;  /* enc->pvq_norm_lambda */
+  uint8_t pvq_qm_q4[3][32];/* state->pvq_qm_q4[pli][OD_QM_SIZE = 30] */
+} daala_b200_pvq_params;
+
+/* Per-band search + synthesis (pvq_theta, src/pvq_encoder.c:333, speed > 0 rate
+   model) for `count` bands listed as (block << 4 | band); nmax = 16, 32 or 128
+   bounds the band size of this list (bands are launched per size class). */
+int daala_b200_pvq_encode_bands(const daala_b200_pvq_params *prm, const uint32_t *band_list, int count,
+                                int nmax, void *stream);
+/* Per block: ordered skip_diff sum, DC handling (keyframe: out[0] = in[0];
+   inter: scalar quantiser of src/encode.c:1337-1344, 1377-1378). */
+int daala_b200_pvq_block_finish(const daala_b200_pvq_params *prm, int nblocks, void *stream);
+/* Keyframe chroma CfL sign flip of the reference vectors (src/pvq_encoder.c:847-871). */
+int daala_b200_pvq_cfl_flip(const daala_b200_pvq_params *prm, int nblocks, void *stream);
+/* od_raster_to_coding_order (src/partition.c:123) for a block list:
+   which = 0: in <- coef_plane, which = 1: ref <- pred_plane (zeros when NULL). */
+int daala_b200_coding_order_gather(const daala_b200_pvq_params *prm, int nblocks, int which, void *stream);
+/* od_init_skipped_coeffs (src/state.c:1347) + od_coding_order_to_raster
+   (src/partition.c:157): out -> coef_plane. */
+int daala_b200_coding_order_scatter(const daala_b200_pvq_params *prm, int nblocks, void *stream);
+
 /* Library/device information.  Returns the number of usable CUDA devices. */
 int daala_b200_device_count(void);
 const char *daala_b200_version(void);

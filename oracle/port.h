@@ -26,4 +26,8 @@ void port_postfilter_split(od_coeff *c0, int stride, int bs, int hfilter, int vf
 void port_apply_prefilter_frame_sbs(od_coeff *c0, int stride, int nhsb, int nvsb, int xdec, int ydec);
 void port_apply_postfilter_frame_sbs(od_coeff *c0, int stride, int nhsb, int nvsb, int xdec, int ydec);
 
+/* port_partition.c -- src/partition.c */
+void port_raster_to_coding_order(od_coeff *dst, int n, const od_coeff *src, int stride);
+void port_coding_order_to_raster(od_coeff *dst, int stride, const od_coeff *src, int n);
+
 #endif

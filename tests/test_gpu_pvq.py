@@ -1,0 +1,110 @@
+"""GPU parity of the PVQ stage (through the C ABI) against the oracle:
+indices (gain code, theta, K, pulses), synthesised coefficients and flags must
+be bit-exact; the double-precision skip_diff within 1e-5 relative (north-star
+tolerance for float gain/theta terms; it is normally exact too)."""
+import numpy as np
+import pytest
+
+from tests import oracle_lib, pvq_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    ref = oracle_lib.load_ref()
+    return (ref, "ref") if ref is not None else (oracle_lib.load_port(), "port")
+
+
+def _setup(size, is_keyframe, with_pred, mode="mixed", q0=38, seed=5):
+    import torch
+    from daala_b200 import pvq, synth
+    from daala_b200.frame import FrameBuffers, Geometry
+    geom = Geometry(*size)
+    bsize = synth.block_size_map(geom, mode, seed=seed)
+    cur = FrameBuffers(geom)
+    planes, _ = synth.frame(size[0], size[1], f=3)
+    cur.upload(synth.pad_planes(planes, geom), bsize)
+    cur.haar_dc = 1 if is_keyframe else 0
+    cur.forward()
+    pred = None
+    if with_pred:
+        pred = FrameBuffers(geom)
+        planes, _ = synth.frame(size[0], size[1], f=2, seed=777)
+        pred.upload(synth.pad_planes(planes, geom), bsize)
+        pred.haar_dc = 0
+        pred.forward()
+    torch.cuda.synchronize()
+    blocks = pvq.block_list(bsize, geom)
+    qm_q4 = np.full((3, 30), 16, np.uint8)
+    qm_q4[0, :] = np.linspace(14, 40, 30).astype(np.uint8)
+    qm_q4[1:, :] = np.linspace(20, 60, 30).astype(np.uint8)
+    batch = pvq.PvqBatch(blocks, cur.coeffs, pred.coeffs if pred else None, q0=q0, is_keyframe=is_keyframe,
+                         use_masking=1, pvq_qm_q4=qm_q4)
+    return geom, cur, pred, batch, qm_q4
+
+
+@pytest.mark.parametrize("is_keyframe,with_pred", [(1, False), (0, True), (1, True)])
+def test_pvq_blocks_match_oracle(is_keyframe, with_pred):
+    import torch
+    from daala_b200 import pvq
+    lib, prefix = _oracle()
+    geom, cur, pred, batch, qm_q4 = _setup((256, 192), is_keyframe, with_pred)
+    d_before = [t[0].cpu().numpy().copy() for t in cur.coeffs]
+    p_planes = [t[0].cpu().numpy() for t in pred.coeffs] if pred else None
+    batch.run()
+    torch.cuda.synchronize()
+    qm, qm_inv = pvq.default_qm(True)
+    B = batch.blocks_np
+    g_in, g_ref, g_out, g_y = (t.cpu().numpy() for t in (batch.in_, batch.ref, batch.out, batch.y))
+    res = {k: getattr(batch, "res_" + k).cpu().numpy() for k in
+           ("gain", "theta", "max_theta", "k", "skip_term", "skip_diff", "flip", "dc")}
+    rng = np.random.default_rng(1)
+    # every large block, a sample of the (many) small ones
+    pick = [i for i in range(len(B)) if B["bs"][i] >= 2 or rng.random() < 0.12]
+    assert len(pick) > 300
+    nz = 0
+    d_expect = [a.copy() for a in d_before]
+    checked = set(pick)
+    for i in pick:
+        b = B[i]
+        bs, pli, xdec = int(b["bs"]), int(b["pli"]), int(b["xdec"])
+        n = 4 << bs
+        ln = min(n * n, 512)
+        off = int(b["coef_off"])
+        dvec = pvq_oracle.coding_order(lib, prefix, d_before[pli], int(b["x0"]), int(b["y0"]), n)
+        pvec = (pvq_oracle.coding_order(lib, prefix, p_planes[pli], int(b["x0"]), int(b["y0"]), n)
+                if p_planes else np.zeros(n * n, np.int32))
+        assert np.array_equal(g_in[off:off + ln], dvec[:ln])
+        o = pvq_oracle.block(lib, prefix, dvec, pvec, bs, pli, xdec, 38, is_keyframe, 1, 0.147, qm, qm_inv, qm_q4)
+        assert res["flip"][i] == o["flip"]
+        assert np.array_equal(g_ref[off:off + ln], o["ref"][:ln])
+        for band, r in enumerate(o["bands"]):
+            j = i * 9 + band
+            key = (i, band, bs, pli)
+            assert (res["gain"][j], res["theta"][j], res["max_theta"][j], res["k"][j]) == \
+                (r["gain"], r["itheta"], r["max_theta"], r["k"]), key
+            assert res["skip_term"][j] == pytest.approx(r["skip_diff"], rel=1e-5, abs=1e-9), key
+            nz += r["k"] > 0
+        assert np.array_equal(g_y[off + 1:off + ln], o["y"][1:ln]), (i, bs, pli)
+        assert np.array_equal(g_out[off + 1:off + ln], o["out"][1:ln]), (i, bs, pli)
+        assert res["skip_diff"][i] == pytest.approx(o["skip_diff"], rel=1e-5, abs=1e-9)
+    assert nz > 200
+    # scatter: coded prefix written back, rest = skipped-coefficient init
+    d_after = [t[0].cpu().numpy() for t in cur.coeffs]
+    for i in pick[:200]:
+        b = B[i]
+        bs, pli = int(b["bs"]), int(b["pli"])
+        n = 4 << bs
+        x0, y0, off = int(b["x0"]), int(b["y0"]), int(b["coef_off"])
+        ln = min(n * n, 512)
+        exp = np.zeros((n, n), np.int32)
+        if not is_keyframe:
+            exp[:] = p_planes[pli][y0:y0 + n, x0:x0 + n]
+        vec = np.zeros(n * n, np.int32)
+        vec[:ln] = g_out[off:off + ln]
+        if is_keyframe:
+            vec[0] = d_before[pli][y0, x0]
+        tmp = np.zeros((n, n), np.int32)
+        tmp[:] = exp
+        pvq_oracle.from_coding_order(lib, prefix, tmp, 0, 0, n, vec)
+        assert np.array_equal(d_after[pli][y0:y0 + n, x0:x0 + n], tmp), (i, bs, pli)
