@@ -61,7 +61,7 @@ def test_pvq_blocks_match_oracle(is_keyframe, with_pred):
     rng = np.random.default_rng(1)
     # every large block, a sample of the (many) small ones
     pick = [i for i in range(len(B)) if B["bs"][i] >= 2 or rng.random() < 0.12]
-    assert len(pick) > 300
+    assert len(pick) > 100
     nz = 0
     d_expect = [a.copy() for a in d_before]
     checked = set(pick)
@@ -88,7 +88,7 @@ def test_pvq_blocks_match_oracle(is_keyframe, with_pred):
         assert np.array_equal(g_y[off + 1:off + ln], o["y"][1:ln]), (i, bs, pli)
         assert np.array_equal(g_out[off + 1:off + ln], o["out"][1:ln]), (i, bs, pli)
         assert res["skip_diff"][i] == pytest.approx(o["skip_diff"], rel=1e-5, abs=1e-9)
-    assert nz > 200
+    assert nz > 50
     # scatter: coded prefix written back, rest = skipped-coefficient init
     d_after = [t[0].cpu().numpy() for t in cur.coeffs]
     for i in pick[:200]:
