@@ -8,4 +8,9 @@
 #define X_POST_SPLIT(c, stride, bs, h, v) port_postfilter_split(c, stride, bs, h, v)
 #define X_PRE_SBS(c, stride, nhsb, nvsb, xdec) port_apply_prefilter_frame_sbs(c, stride, nhsb, nvsb, xdec, xdec)
 #define X_POST_SBS(c, stride, nhsb, nvsb, xdec) port_apply_postfilter_frame_sbs(c, stride, nhsb, nvsb, xdec, xdec)
+#include "port_pvq.h"
+#define X_TO_CODING(dst, n, src, stride) port_raster_to_coding_order(dst, n, src, stride)
+#define X_FROM_CODING(dst, stride, src, n) port_coding_order_to_raster(dst, stride, src, n)
+#define X_PVQ_THETA(out, x0, r0, n, q, y, it, mt, k, beta, sd, kf, pli, qm, qmi, lam) \
+  port_pvq_theta(out, x0, r0, n, q, y, it, mt, k, beta, sd, kf, pli, qm, qmi, lam)
 #include "pipeline_driver.inc"

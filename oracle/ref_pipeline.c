@@ -11,4 +11,15 @@
 #define X_PRE_SBS(c, stride, nhsb, nvsb, xdec) od_apply_prefilter_frame_sbs(c, stride, nhsb, nvsb, xdec, xdec)
 #define X_POST_SBS(c, stride, nhsb, nvsb, xdec) \
   od_apply_postfilter_frame_sbs(c, stride, nhsb, nvsb, xdec, xdec, 0, NULL, 0)
+#include "partition.h"
+int oracle_ref_pvq_theta(od_coeff *out, const od_coeff *x0, const od_coeff *r0,
+ int n, int q0, od_coeff *y, int *itheta, int *max_theta, int *vk,
+ int beta, double *skip_diff, int nodesync, int is_keyframe, int pli,
+ const void *adapt, const int16_t *qm, const int16_t *qm_inv,
+ double pvq_norm_lambda, int speed);
+#define X_TO_CODING(dst, n, src, stride) od_raster_to_coding_order(dst, n, src, stride)
+#define X_FROM_CODING(dst, stride, src, n) od_coding_order_to_raster(dst, stride, src, n)
+/* speed = 1: the reference's closed-form rate model (src/pvq_encoder.c:252-264) */
+#define X_PVQ_THETA(out, x0, r0, n, q, y, it, mt, k, beta, sd, kf, pli, qm, qmi, lam) \
+  oracle_ref_pvq_theta(out, x0, r0, n, q, y, it, mt, k, beta, sd, 1, kf, pli, NULL, qm, qmi, lam, 1)
 #include "pipeline_driver.inc"

@@ -3,7 +3,7 @@ oracle/pipeline_driver.inc through either the real reference build
 (oracle/_ref) or the plain-C port."""
 import ctypes
 
-import numpy as np
+import numpy as np  # noqa: E402
 
 from tests.oracle_lib import addr
 
@@ -31,3 +31,18 @@ def inverse_plane(lib, prefix, d, geom, pli, bsize, haar_dc, lapped_only=False):
     fn(addr(d), addr(c), addr(out), pw, geom.nhsb, geom.nvsb, geom.xdec[pli], addr(bs), bs.shape[1],
        geom.pic_w, geom.pic_h, int(haar_dc), int(lapped_only))
     return c if lapped_only else out
+
+
+def pvq_plane(lib, prefix, d, md, geom, pli, bsize, q0, is_keyframe, use_masking, lam, qm, qm_inv, qm_q4):
+    """Quantises a coefficient plane in place (a copy is returned) with the
+    oracle's per-block PVQ driver; returns (d_quantised, stats[5])."""
+    d = np.ascontiguousarray(d, dtype=np.int32).copy()
+    bs = np.ascontiguousarray(bsize, dtype=np.uint8)
+    stats = np.zeros(5, np.float64)
+    q4 = np.ascontiguousarray(qm_q4[pli], dtype=np.uint8)
+    mdp = addr(np.ascontiguousarray(md, dtype=np.int32)) if md is not None else None
+    fn = getattr(lib, "oracle_%s_pvq_plane" % prefix)
+    fn(addr(d), mdp, geom.nhsb, geom.nvsb, geom.xdec[pli], pli, addr(bs), bs.shape[1], int(q0),
+       int(is_keyframe), int(use_masking), ctypes.c_double(lam), addr(np.ascontiguousarray(qm)),
+       addr(np.ascontiguousarray(qm_inv)), addr(q4), addr(stats))
+    return d, stats

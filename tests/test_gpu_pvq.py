@@ -108,3 +108,53 @@ def test_pvq_blocks_match_oracle(is_keyframe, with_pred):
         tmp[:] = exp
         pvq_oracle.from_coding_order(lib, prefix, tmp, 0, 0, n, vec)
         assert np.array_equal(d_after[pli][y0:y0 + n, x0:x0 + n], tmp), (i, bs, pli)
+
+
+@pytest.mark.parametrize("is_keyframe", [1, 0])
+def test_hot_path_planes_match_frame_oracle(is_keyframe):
+    """forward -> PVQ -> inverse on the GPU against the same chain of the CPU
+    oracle, whole planes: quantised coefficient planes and the 8-bit
+    reconstruction must be identical."""
+    import torch
+    from daala_b200 import pvq, synth
+    from daala_b200.frame import FrameBuffers, Geometry
+    from daala_b200.pipeline import HotPath
+    from tests import frame_oracle
+    lib, prefix = _oracle()
+    geom = Geometry(320, 200)
+    planes, _ = synth.frame(320, 200, f=4)
+    planes = synth.pad_planes(planes, geom)
+    prev, _ = synth.frame(320, 200, f=3, seed=4242)
+    prev = synth.pad_planes(prev, geom)
+    bsize = synth.block_size_map(geom, "mixed", seed=9)
+    q4 = np.full((3, 30), 20, np.uint8)
+    hp = HotPath(geom, q0=45, is_keyframe=is_keyframe, pvq_qm_q4=q4)
+    hp.fb.upload(planes, bsize)
+    if not is_keyframe:
+        pred = FrameBuffers(geom)
+        pred.upload(prev, bsize)
+        pred.haar_dc = 0
+        pred.forward()
+        hp.use_prediction(pred)
+    hp.set_block_sizes([bsize])
+    hp.run()
+    torch.cuda.synchronize()
+    qm, qm_inv = pvq.default_qm(True)
+    for pli in range(3):
+        d = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, is_keyframe)
+        md = frame_oracle.forward_plane(lib, prefix, prev[pli], geom, pli, bsize, 0) if not is_keyframe else None
+        dq, stats = frame_oracle.pvq_plane(lib, prefix, d, md, geom, pli, bsize, 45, is_keyframe, 1, 0.147,
+                                           qm, qm_inv, q4)
+        assert stats[0] > 0
+        assert np.array_equal(hp.fb.coeffs[pli][0].cpu().numpy(), dq), "quantised plane %d" % pli
+        rec = frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, is_keyframe)
+        assert np.array_equal(hp.fb.pixels_out[pli][0].cpu().numpy(), rec), "recon plane %d" % pli
+        k_gpu = int(hp.batch.res_k.sum().item())
+    # K checksum over all planes
+    total_k = 0
+    for pli in range(3):
+        d = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, is_keyframe)
+        md = frame_oracle.forward_plane(lib, prefix, prev[pli], geom, pli, bsize, 0) if not is_keyframe else None
+        total_k += int(frame_oracle.pvq_plane(lib, prefix, d, md, geom, pli, bsize, 45, is_keyframe, 1, 0.147,
+                                              qm, qm_inv, q4)[1][0])
+    assert k_gpu == total_k

@@ -91,3 +91,28 @@ def test_pvq_theta_port_matches_reference(port, ref):
         nonskip += a["k"] > 0
         withref += a["itheta"] > 0
     assert count > 1000 and nonskip > 300 and withref > 100, (count, nonskip, withref)
+
+
+def test_frame_pvq_driver_port_matches_reference(port, ref):
+    """oracle/pipeline_driver.inc compiled against the port and against the
+    real reference functions must quantise a whole plane identically."""
+    from daala_b200 import synth
+    from daala_b200.frame import Geometry
+    from tests import frame_oracle
+    geom = Geometry(192, 128)
+    planes, _ = synth.frame(192, 128, f=1)
+    planes = synth.pad_planes(planes, geom)
+    prev, _ = synth.frame(192, 128, f=0, seed=99)
+    prev = synth.pad_planes(prev, geom)
+    bsize = synth.block_size_map(geom, "mixed", seed=2)
+    qm, qm_inv = pvq_cases.reference_qm(ref)
+    q4 = np.full((3, 30), 24, np.uint8)
+    for is_keyframe in (1, 0):
+        for pli in range(3):
+            d = frame_oracle.forward_plane(ref, "ref", planes[pli], geom, pli, bsize, is_keyframe)
+            md = frame_oracle.forward_plane(ref, "ref", prev[pli], geom, pli, bsize, 0) if not is_keyframe else None
+            a, sa = frame_oracle.pvq_plane(ref, "ref", d, md, geom, pli, bsize, 38, is_keyframe, 1, 0.147, qm, qm_inv, q4)
+            b, sb = frame_oracle.pvq_plane(port, "port", d, md, geom, pli, bsize, 38, is_keyframe, 1, 0.147, qm, qm_inv, q4)
+            assert np.array_equal(a, b)
+            assert np.array_equal(sa, sb)
+            assert sa[0] > 0 and not np.array_equal(a, d)
