@@ -15,6 +15,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <stddef.h>
+
 #include <mutex>
 
 #include "daala_b200.h"
@@ -206,6 +208,99 @@ void od_apply_postfilter_frame_sbs(od_coeff* c, int stride, int nhsb, int nvsb, 
   (void)q; (void)skip; (void)skip_stride;
   plane_sb_filter(true, c, stride, nhsb, nvsb, xdec, ydec);
 }
+
+// Motion compensation / block matching with host pointers.
+void od_mc_predict1fmv8_cuda(void* state, unsigned char* dst, const unsigned char* src, int systride,
+                             int32_t mvx, int32_t mvy, int log_xblk_sz, int log_yblk_sz) {
+  (void)state;
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g(c.mu);
+  const int nx = 1 << log_xblk_sz, ny = 1 << log_yblk_sz;
+  const int W = nx + 5, H = ny + 5;  // 2 px left/top, 3 px right/bottom (OD_SUBPEL_*_APRON_SZ)
+  const size_t win = (size_t)W * H, job_off = (win + 15) & ~(size_t)15, out_off = job_off + 16;
+  c.ensure(out_off + (size_t)nx * ny);
+  unsigned char* p = (unsigned char*)c.pinned;
+  const unsigned char* s0 = src + ((mvx >> 3) - 2) + (ptrdiff_t)((mvy >> 3) - 2) * systride;
+  for (int r = 0; r < H; r++) memcpy(p + (size_t)r * W, s0 + (ptrdiff_t)r * systride, W);
+  daala_b200_match_job job;
+  memset(&job, 0, sizeof(job));
+  job.mvx = mvx & 7; job.mvy = mvy & 7; job.x0 = 2; job.y0 = 2; job.log_blk = (uint8_t)log_xblk_sz;
+  memcpy(p + job_off, &job, sizeof(job));
+  c.h2d(out_off);
+  unsigned char* d = (unsigned char*)c.dev;
+  check_launch(daala_b200_mc_predict1fmv_batch(d, W, d + out_off, nx * ny, (const daala_b200_match_job*)(d + job_off),
+                                               1, log_yblk_sz, c.stream), "mc_predict1fmv");
+  CK(cudaMemcpyAsync(p + out_off, d + out_off, (size_t)nx * ny, cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  memcpy(dst, p + out_off, (size_t)nx * ny);
+}
+
+static void blend_host(unsigned char* dst, int dystride, const unsigned char* src[4], int oc, int s, int lx, int ly) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g(c.mu);
+  const int nx = 1 << lx, ny = 1 << ly, n2 = nx * ny;
+  c.ensure((size_t)5 * n2);
+  unsigned char* p = (unsigned char*)c.pinned;
+  for (int k = 0; k < 4; k++) memcpy(p + (size_t)k * n2, src[k], n2);
+  c.h2d((size_t)4 * n2);
+  unsigned char* d = (unsigned char*)c.dev;
+  check_launch(daala_b200_mc_blend_packed(d, n2, d + (size_t)4 * n2, nx, oc, s, lx, ly, c.stream), "mc_blend");
+  CK(cudaMemcpyAsync(p + (size_t)4 * n2, d + (size_t)4 * n2, n2, cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  for (int j = 0; j < ny; j++) memcpy(dst + (size_t)j * dystride, p + (size_t)4 * n2 + (size_t)j * nx, nx);
+}
+
+void od_mc_blend_full8_cuda(unsigned char* dst, int dystride, const unsigned char* src[4], int log_xblk_sz,
+                            int log_yblk_sz) {
+  blend_host(dst, dystride, src, 0, 3, log_xblk_sz, log_yblk_sz);
+}
+
+void od_mc_blend_full_split8_cuda(unsigned char* dst, int dystride, const unsigned char* src[4], int c, int s,
+                                  int log_xblk_sz, int log_yblk_sz) {
+  blend_host(dst, dystride, src, c, s, log_xblk_sz, log_yblk_sz);
+}
+
+static int32_t match_host(int ln, int use_satd, const unsigned char* src, int systride, const unsigned char* ref,
+                          int dystride) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g(c.mu);
+  const int n = 1 << ln, n2 = n * n;
+  const size_t job_off = (size_t)2 * n2, res_off = job_off + 16;
+  c.ensure(res_off + 16);
+  unsigned char* p = (unsigned char*)c.pinned;
+  for (int j = 0; j < n; j++) {
+    memcpy(p + (size_t)j * n, src + (ptrdiff_t)j * systride, n);
+    memcpy(p + n2 + (size_t)j * n, ref + (ptrdiff_t)j * dystride, n);
+  }
+  daala_b200_match_job job;
+  memset(&job, 0, sizeof(job));
+  job.log_blk = (uint8_t)ln;
+  memcpy(p + job_off, &job, sizeof(job));
+  c.h2d(res_off);
+  unsigned char* d = (unsigned char*)c.dev;
+  check_launch(daala_b200_mc_match_candidates(d, n, d + n2, n, (const daala_b200_match_job*)(d + job_off), 1,
+                                              use_satd, (int32_t*)(d + res_off), c.stream), "mc_match");
+  CK(cudaMemcpyAsync(p + res_off, d + res_off, 4, cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  int32_t r;
+  memcpy(&r, p + res_off, 4);
+  return r;
+}
+
+#define DAALA_B200_MATCH(N, LN)                                                                            \
+  int32_t od_mc_compute_sad8_##N##x##N##_cuda(const unsigned char* src, int systride, const unsigned char* ref, \
+                                              int dystride) {                                             \
+    return match_host(LN, 0, src, systride, ref, dystride);                                               \
+  }                                                                                                       \
+  int32_t od_mc_compute_satd8_##N##x##N##_cuda(const unsigned char* src, int systride, const unsigned char* ref, \
+                                               int dystride) {                                            \
+    return match_host(LN, 1, src, systride, ref, dystride);                                               \
+  }
+DAALA_B200_MATCH(4, 2)
+DAALA_B200_MATCH(8, 3)
+DAALA_B200_MATCH(16, 4)
+DAALA_B200_MATCH(32, 5)
+DAALA_B200_MATCH(64, 6)
 
 // ---- Section B ------------------------------------------------------------
 int daala_b200_forward_frame(const daala_b200_frame* f, int nplanes, void* stream) {

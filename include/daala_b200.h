@@ -80,6 +80,28 @@ void od_apply_prefilter_frame_sbs(od_coeff *c, int stride, int nhsb, int nvsb, i
 void od_apply_postfilter_frame_sbs(od_coeff *c, int stride, int nhsb, int nvsb, int xdec, int ydec,
                                    int q, unsigned char *skip, int skip_stride);
 
+/* Motion-compensation and block-matching slots of od_state_opt_vtbl
+   (src/state.h:113-121) and od_enc_opt_vtbl (src/encint.h:77-98).  The names
+   carry a _cuda suffix because the reference's C kernels keep their _c names in
+   the same link; the vtable initialiser of INTEGRATION.md installs them.
+   `state` is unused (the reference only reads its od_copy_nxn table). */
+void od_mc_predict1fmv8_cuda(void *state, unsigned char *dst, const unsigned char *src, int systride,
+                             int32_t mvx, int32_t mvy, int log_xblk_sz, int log_yblk_sz);
+void od_mc_blend_full8_cuda(unsigned char *dst, int dystride, const unsigned char *src[4],
+                            int log_xblk_sz, int log_yblk_sz);
+void od_mc_blend_full_split8_cuda(unsigned char *dst, int dystride, const unsigned char *src[4], int c,
+                                  int s, int log_xblk_sz, int log_yblk_sz);
+int32_t od_mc_compute_sad8_4x4_cuda(const unsigned char *src, int systride, const unsigned char *ref, int dystride);
+int32_t od_mc_compute_sad8_8x8_cuda(const unsigned char *src, int systride, const unsigned char *ref, int dystride);
+int32_t od_mc_compute_sad8_16x16_cuda(const unsigned char *src, int systride, const unsigned char *ref, int dystride);
+int32_t od_mc_compute_sad8_32x32_cuda(const unsigned char *src, int systride, const unsigned char *ref, int dystride);
+int32_t od_mc_compute_sad8_64x64_cuda(const unsigned char *src, int systride, const unsigned char *ref, int dystride);
+int32_t od_mc_compute_satd8_4x4_cuda(const unsigned char *src, int systride, const unsigned char *ref, int dystride);
+int32_t od_mc_compute_satd8_8x8_cuda(const unsigned char *src, int systride, const unsigned char *ref, int dystride);
+int32_t od_mc_compute_satd8_16x16_cuda(const unsigned char *src, int systride, const unsigned char *ref, int dystride);
+int32_t od_mc_compute_satd8_32x32_cuda(const unsigned char *src, int systride, const unsigned char *ref, int dystride);
+int32_t od_mc_compute_satd8_64x64_cuda(const unsigned char *src, int systride, const unsigned char *ref, int dystride);
+
 /* ======================================================================== */
 /* B. Batch entry points (device pointers, asynchronous on `stream`)         */
 /* ======================================================================== */
@@ -204,6 +226,51 @@ int daala_b200_coding_order_gather(const daala_b200_pvq_params *prm, int nblocks
 /* od_init_skipped_coeffs (src/state.c:1347) + od_coding_order_to_raster
    (src/partition.c:157): out -> coef_plane. */
 int daala_b200_coding_order_scatter(const daala_b200_pvq_params *prm, int nblocks, void *stream);
+
+/* ---- Motion compensation / block matching (8-bit references) ------------- */
+
+/* One OBMC block: four corner motion vectors in 1/8 pel (rotational order:
+   top-left, top-right, bottom-right, bottom-left; already scaled for the
+   plane), outside corner `oc` and split state `s` as in od_mc_predict
+   (reference src/mc.c:2006, src/state.c:627-671). */
+typedef struct daala_b200_mc_block {
+  int32_t mvx[4];
+  int32_t mvy[4];
+  uint16_t x0, y0;         /* block origin in the plane */
+  uint8_t log_xblk, log_yblk;
+  uint8_t oc, s;
+} daala_b200_mc_block;
+
+/* One block-matching candidate: square block of edge 1 << log_blk at (x0, y0),
+   displaced by (mvx, mvy) 1/8 pel in the reference plane. */
+typedef struct daala_b200_match_job {
+  int32_t mvx, mvy;
+  uint16_t x0, y0;
+  uint8_t log_blk;
+  uint8_t pad_[3];
+} daala_b200_match_job;
+
+/* OBMC prediction of `count` blocks into dst (od_state_pred_block's inner
+   operation, src/state.c:627; od_mc_predict1fmv8_c + od_mc_blend_full(_split)8_c).
+   `ref` points at pixel (0,0) of a reference plane with enough padding for the
+   displaced (n+5)^2 windows (the reference keeps OD_BUFFER_PADDING = 96 px). */
+int daala_b200_mc_predict_blocks(const uint8_t *ref, int ref_stride, uint8_t *dst, int dst_stride,
+                                 const daala_b200_mc_block *blocks, int count, void *stream);
+/* SAD (use_satd = 0) or SATD (1) of every job's interpolated reference block
+   against the current frame: od_mv_est_bma_sad's inner operation
+   (src/mcenc.c:2224) = mc_predict1fmv + od_mc_compute_sad8_c (:1333) or
+   od_mc_compute_satd8_NxN_c (:1560-1612). */
+int daala_b200_mc_match_candidates(const uint8_t *cur, int cur_stride, const uint8_t *ref, int ref_stride,
+                                   const daala_b200_match_job *jobs, int count, int use_satd, int32_t *result,
+                                   void *stream);
+/* Batched mc_predict1fmv: job q's block goes to dst + q*dst_pitch (row stride
+   = block width).  log_yblk < 0: square blocks. */
+int daala_b200_mc_predict1fmv_batch(const uint8_t *ref, int ref_stride, uint8_t *dst, int dst_pitch,
+                                    const daala_b200_match_job *jobs, int count, int log_yblk, void *stream);
+/* Blend of four packed predictions (mc_blend_full when s == 3, else
+   mc_blend_full_split). */
+int daala_b200_mc_blend_packed(const uint8_t *preds, int pitch, uint8_t *dst, int dst_stride, int oc, int s,
+                               int log_xblk, int log_yblk, void *stream);
 
 /* Library/device information.  Returns the number of usable CUDA devices. */
 int daala_b200_device_count(void);

@@ -30,4 +30,18 @@ void port_apply_postfilter_frame_sbs(od_coeff *c0, int stride, int nhsb, int nvs
 void port_raster_to_coding_order(od_coeff *dst, int n, const od_coeff *src, int stride);
 void port_coding_order_to_raster(od_coeff *dst, int stride, const od_coeff *src, int n);
 
+/* port_mc.c -- src/mc.c, src/mcenc.c */
+void port_mc_predict1fmv8(unsigned char *dst, const unsigned char *src, int systride, int32_t mvx,
+ int32_t mvy, int log_xblk_sz, int log_yblk_sz);
+void port_mc_blend_full8(unsigned char *dst, int dystride, const unsigned char *src[4],
+ int log_xblk_sz, int log_yblk_sz);
+void port_mc_blend_full_split8(unsigned char *dst, int dystride, const unsigned char *src[4], int oc,
+ int s, int log_xblk_sz, int log_yblk_sz);
+void port_mc_predict(unsigned char *dst, int dystride, const unsigned char *src, int systride,
+ const int32_t mvx[4], const int32_t mvy[4], int oc, int s, int log_xblk_sz, int log_yblk_sz);
+int32_t port_mc_compute_sad8(const unsigned char *src, int systride, const unsigned char *ref,
+ int dystride, int w, int h);
+int32_t port_mc_compute_satd8(int ln, const unsigned char *src, int systride, const unsigned char *ref,
+ int rystride);
+
 #endif

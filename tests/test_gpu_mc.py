@@ -1,0 +1,167 @@
+"""GPU parity of the motion-compensation and block-matching kernels (through
+the C ABI) against the CPU oracle: bit-exact pixels and integer SAD/SATD."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib
+from tests.oracle_lib import addr
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    ref = oracle_lib.load_ref()
+    return (ref, "ref") if ref is not None else (oracle_lib.load_port(), "port")
+
+
+def _frames(seed=0, h=256, w=320):
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    base = 128 + 60 * np.sin(x / 7.0) + 40 * np.cos(y / 5.0)
+    ref = np.clip(base + rng.integers(-20, 21, size=(h, w)), 0, 255).astype(np.uint8)
+    cur = np.clip(np.roll(base, (2, 3), (0, 1)) + rng.integers(-20, 21, size=(h, w)), 0, 255).astype(np.uint8)
+    return cur, ref
+
+
+def test_obmc_blocks_match_oracle():
+    import torch
+    from daala_b200 import mc
+    lib, prefix = _oracle()
+    cur, ref = _frames()
+    h, w = ref.shape
+    pad = mc.OD_BUFFER_PADDING
+    refp = np.pad(ref, pad, mode="edge")
+    rng = np.random.default_rng(2)
+    blocks = []
+    for ln in (2, 3, 4, 5, 6):
+        n = 1 << ln
+        for t in range(40):
+            b = np.zeros(1, mc.MC_BLOCK_DTYPE)[0]
+            b["x0"] = int(rng.integers(0, (w - n) // n + 1)) * n
+            b["y0"] = int(rng.integers(0, (h - n) // n + 1)) * n
+            mvx = rng.integers(-200, 201, size=4)
+            mvy = rng.integers(-200, 201, size=4)
+            if t % 4 == 0:
+                mvx[1:3], mvy[1:3] = mvx[0], mvy[0]
+            if t % 9 == 0:
+                mvx[:] = (mvx // 8) * 8
+                mvy[:] = (mvy // 8) * 8
+            b["mvx"], b["mvy"] = mvx, mvy
+            b["log_xblk"] = b["log_yblk"] = ln
+            b["oc"], b["s"] = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+            blocks.append(b)
+    blocks = np.array(blocks, mc.MC_BLOCK_DTYPE)
+    # non-overlapping destinations are not required for the check: compare block by block
+    rp = mc.PaddedPlane(ref)
+    dev_blocks = mc.to_device(blocks)
+    I4 = ctypes.c_int32 * 4
+    fn = lib.oracle_ref_mc_predict if prefix == "ref" else lib.port_mc_predict
+    stride = refp.shape[1]
+    for i, b in enumerate(blocks):
+        dst = torch.zeros((h, w), dtype=torch.uint8, device="cuda:0")
+        mc.predict_blocks(rp, dst, dev_blocks[i * 40:(i + 1) * 40], 1)
+        n = 1 << int(b["log_xblk"])
+        x0, y0 = int(b["x0"]), int(b["y0"])
+        exp = np.zeros((n, n), np.uint8)
+        fn(addr(exp), n, addr(refp, (y0 + pad) * stride + x0 + pad), stride, I4(*[int(v) for v in b["mvx"]]),
+           I4(*[int(v) for v in b["mvy"]]), int(b["oc"]), int(b["s"]), int(b["log_xblk"]), int(b["log_yblk"]))
+        got = dst[y0:y0 + n, x0:x0 + n].cpu().numpy()
+        assert np.array_equal(got, exp), (i, b)
+
+
+@pytest.mark.parametrize("use_satd", [0, 1])
+def test_match_candidates_match_oracle(use_satd):
+    import torch
+    from daala_b200 import mc
+    lib, prefix = _oracle()
+    cur, ref = _frames(seed=1)
+    h, w = ref.shape
+    pad = mc.OD_BUFFER_PADDING
+    refp = np.pad(ref, pad, mode="edge")
+    stride = refp.shape[1]
+    rng = np.random.default_rng(3 + use_satd)
+    jobs = []
+    for ln in (2, 3, 4, 5, 6):
+        n = 1 << ln
+        for t in range(60):
+            j = np.zeros(1, mc.MATCH_JOB_DTYPE)[0]
+            j["x0"] = int(rng.integers(0, (w - n) // 4 + 1)) * 4
+            j["y0"] = int(rng.integers(0, (h - n) // 4 + 1)) * 4
+            j["mvx"], j["mvy"] = int(rng.integers(-300, 301)), int(rng.integers(-300, 301))
+            if t % 3 == 0:
+                j["mvx"], j["mvy"] = (int(j["mvx"]) // 8) * 8, (int(j["mvy"]) // 8) * 8
+            j["log_blk"] = ln
+            jobs.append(j)
+    jobs = np.array(jobs, mc.MATCH_JOB_DTYPE)
+    rp = mc.PaddedPlane(ref)
+    cur_d = torch.from_numpy(cur).to("cuda:0")
+    out = mc.match_candidates(cur_d, rp, mc.to_device(jobs), len(jobs), use_satd=bool(use_satd)).cpu().numpy()
+    pfn = lib.oracle_ref_mc_predict1fmv8 if prefix == "ref" else lib.port_mc_predict1fmv8
+    for i, j in enumerate(jobs):
+        ln = int(j["log_blk"])
+        n = 1 << ln
+        x0, y0 = int(j["x0"]), int(j["y0"])
+        pred = np.zeros((n, n), np.uint8)
+        pfn(addr(pred), addr(refp, (y0 + pad) * stride + x0 + pad), stride, int(j["mvx"]), int(j["mvy"]), ln, ln)
+        cblk = np.ascontiguousarray(cur[y0:y0 + n, x0:x0 + n])
+        if use_satd:
+            if prefix == "ref":
+                exp = getattr(lib, "od_mc_compute_satd8_%dx%d_c" % (n, n))(addr(cblk), n, addr(pred), n)
+            else:
+                exp = lib.port_mc_compute_satd8(ln, addr(cblk), n, addr(pred), n)
+        else:
+            if prefix == "ref":
+                exp = lib.od_mc_compute_sad8_c(addr(cblk), n, addr(pred), n, n, n)
+            else:
+                exp = lib.port_mc_compute_sad8(addr(cblk), n, addr(pred), n, n, n)
+        assert out[i] == exp, (i, j, out[i], exp)
+
+
+def test_dropin_mc_symbols_match_oracle():
+    """Host-pointer vtable entries (od_mc_*_cuda) against the oracle."""
+    from daala_b200 import _native
+    L = _native.lib()
+    lib, prefix = _oracle()
+    cur, ref = _frames(seed=4, h=128, w=160)
+    h, w = ref.shape
+    rng = np.random.default_rng(8)
+    pfn = lib.oracle_ref_mc_predict1fmv8 if prefix == "ref" else lib.port_mc_predict1fmv8
+    for ln in (2, 3, 4, 5):
+        n = 1 << ln
+        for t in range(6):
+            mvx, mvy = int(rng.integers(-80, 81)), int(rng.integers(-80, 81))
+            if t == 0:
+                mvx, mvy = 16, -8
+            x0, y0 = 48, 40
+            a = np.zeros(n * n, np.uint8)
+            b = np.zeros(n * n, np.uint8)
+            L.od_mc_predict1fmv8_cuda(None, addr(a), addr(ref, y0 * w + x0), w, mvx, mvy, ln, ln)
+            pfn(addr(b), addr(ref, y0 * w + x0), w, mvx, mvy, ln, ln)
+            assert np.array_equal(a, b), (ln, mvx, mvy)
+        blk_c = np.ascontiguousarray(cur[8:8 + n, 16:16 + n + 3])
+        blk_r = np.ascontiguousarray(ref[8:8 + n, 16:16 + n + 5])
+        sad = getattr(L, "od_mc_compute_sad8_%dx%d_cuda" % (n, n))(addr(blk_c), n + 3, addr(blk_r), n + 5)
+        satd = getattr(L, "od_mc_compute_satd8_%dx%d_cuda" % (n, n))(addr(blk_c), n + 3, addr(blk_r), n + 5)
+        if prefix == "ref":
+            assert sad == lib.od_mc_compute_sad8_c(addr(blk_c), n + 3, addr(blk_r), n + 5, n, n)
+            assert satd == getattr(lib, "od_mc_compute_satd8_%dx%d_c" % (n, n))(addr(blk_c), n + 3, addr(blk_r), n + 5)
+        else:
+            assert sad == lib.port_mc_compute_sad8(addr(blk_c), n + 3, addr(blk_r), n + 5, n, n)
+            assert satd == lib.port_mc_compute_satd8(ln, addr(blk_c), n + 3, addr(blk_r), n + 5)
+        # blends
+        P4 = ctypes.c_void_p * 4
+        preds = [np.ascontiguousarray(rng.integers(0, 256, size=n * n, dtype=np.uint8)) for _ in range(4)]
+        for oc, s in ((0, 3), (1, 0), (2, 1), (3, 2)):
+            g = np.zeros((n, n + 2), np.uint8)
+            e = np.zeros((n, n + 2), np.uint8)
+            ptrs = P4(*[p.ctypes.data for p in preds])
+            if s == 3:
+                L.od_mc_blend_full8_cuda(addr(g), n + 2, ptrs, ln, ln)
+                (lib.od_mc_blend_full8_c if prefix == "ref" else lib.port_mc_blend_full8)(addr(e), n + 2, ptrs, ln, ln)
+            else:
+                L.od_mc_blend_full_split8_cuda(addr(g), n + 2, ptrs, oc, s, ln, ln)
+                (lib.od_mc_blend_full_split8_c if prefix == "ref" else lib.port_mc_blend_full_split8)(
+                    addr(e), n + 2, ptrs, oc, s, ln, ln)
+            assert np.array_equal(g, e), (ln, oc, s)
