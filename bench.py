@@ -132,7 +132,7 @@ def cpu_pipeline_lib():
     return oracle_lib.load_port(), "port", "port"
 
 
-Q0 = 38            # state->quantizer of the synthetic run
+Q0 = 72            # state->quantizer for OD_SET_QUANT = 20 (coded quantizer 20 -> 0x48, src/quantizer.c:47)
 PVQ_QM_Q4 = 16     # flat state->pvq_qm_q4 entries
 
 
