@@ -23,6 +23,7 @@
 #include "daala_b200.h"
 #include "gen/coding_order.inc"
 #include "pvq_math.cuh"
+#include "pvq_coop.cuh"
 
 namespace daala_b200 {
 namespace pvq {
@@ -471,6 +472,44 @@ k_pvq_bands(const __grid_constant__ daala_b200_pvq_params prm, const uint32_t* _
   prm.res_skip_term[r] = skip_term;
 }
 
+// Group-cooperative variant (pvq_coop.cuh): G lanes per band, registers only.
+template <int G, int E, bool kForceScan>
+__global__ void __launch_bounds__(128)
+k_pvq_bands_coop(const __grid_constant__ daala_b200_pvq_params prm, const uint32_t* __restrict__ band_list,
+                 int count) {
+  const Group<G, E> grp;
+  constexpr int kBandsPerCta = 128 / G;
+  const int t = blockIdx.x * kBandsPerCta + (threadIdx.x / G);
+  // whole groups leave together; partial warps keep the shuffle masks valid
+  if (t >= count) return;
+  const uint32_t e = band_list[t];
+  const int blk = (int)(e >> 4), band = (int)(e & 15);
+  const daala_b200_pvq_block b = prm.blocks[blk];
+  const int bs = b.bs, pli = b.pli;
+  const int start = band_start(band);
+  const int n = band_start(band + 1) - start;
+  const size_t off = (size_t)b.coef_off + start;
+  int qidx = bs * (bs + 1) + (band + 1) - (band + 1) / 3;
+  int q = (prm.q0 * prm.pvq_qm_q4[pli][qidx]) >> 4;
+  if (q < 1) q = 1;
+  const int beta = (prm.use_masking && pli == 0 && bs > 0) ? kBeta15 : kBeta1;
+  const int qoff = (b.xdec ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
+  int itheta, max_theta, k;
+  double skip_term;
+  int gain = quantise_band_coop<G, E, kForceScan>(grp, prm.out + off, prm.in + off, prm.ref + off, n, q,
+                                                  prm.y + off, &itheta, &max_theta, &k, beta, &skip_term,
+                                                  prm.is_keyframe, pli, prm.qm + qoff, prm.qm_inv + qoff,
+                                                  prm.pvq_norm_lambda);
+  if (grp.lane == 0) {
+    const size_t r = (size_t)blk * 9 + band;
+    prm.res_gain[r] = gain;
+    prm.res_theta[r] = itheta;
+    prm.res_max_theta[r] = max_theta;
+    prm.res_k[r] = k;
+    prm.res_skip_term[r] = skip_term;
+  }
+}
+
 // Per block: ordered sum of the bands' skip_diff terms (`*skip_diff += ...`
 // runs over the bands in order at src/pvq_encoder.c:875-880; double addition
 // is not associative, so the order is kept) and the DC coefficient:
@@ -617,6 +656,26 @@ int daala_b200_pvq_encode_bands(const daala_b200_pvq_params* prm, const uint32_t
   if (nmax <= 16) k_pvq_bands<16><<<blocks, threads, 0, s>>>(*prm, band_list, count);
   else if (nmax <= 32) k_pvq_bands<32><<<blocks, threads, 0, s>>>(*prm, band_list, count);
   else k_pvq_bands<128><<<blocks, threads, 0, s>>>(*prm, band_list, count);
+  return (int)cudaGetLastError();
+}
+
+// mode 0: group-cooperative kernels (default), 1: same with the literal
+// sequential arg-max scan forced (test hook), 2: scalar thread-per-band kernels.
+int daala_b200_pvq_encode_bands_mode(const daala_b200_pvq_params* prm, const uint32_t* band_list, int count,
+                                     int nmax, int mode, void* stream) {
+  if (count <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 2) return daala_b200_pvq_encode_bands(prm, band_list, count, nmax, stream);
+#define LAUNCH_COOP(G, E)                                                                          \
+  do {                                                                                              \
+    const int per = 128 / G, blocks = (count + per - 1) / per;                                      \
+    if (mode == 1) k_pvq_bands_coop<G, E, true><<<blocks, 128, 0, s>>>(*prm, band_list, count);     \
+    else k_pvq_bands_coop<G, E, false><<<blocks, 128, 0, s>>>(*prm, band_list, count);              \
+  } while (0)
+  if (nmax <= 16) LAUNCH_COOP(4, 4);
+  else if (nmax <= 32) LAUNCH_COOP(8, 4);
+  else LAUNCH_COOP(32, 4);
+#undef LAUNCH_COOP
   return (int)cudaGetLastError();
 }
 

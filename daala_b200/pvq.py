@@ -46,6 +46,8 @@ def _bind():
         return L
     pp = ctypes.POINTER(PvqParams)
     L.daala_b200_pvq_encode_bands.argtypes = [pp, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.daala_b200_pvq_encode_bands_mode.argtypes = [pp, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.c_void_p]
     for name in ("daala_b200_pvq_block_finish", "daala_b200_pvq_cfl_flip", "daala_b200_coding_order_scatter"):
         getattr(L, name).argtypes = [pp, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_coding_order_gather.argtypes = [pp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
@@ -168,7 +170,9 @@ class PvqBatch:
                 p.pvq_qm_q4[pli][i] = int(pvq_qm_q4[pli][i])
         self.params = p
         self.is_keyframe = int(is_keyframe)
-        self.launches_per_run = 0
+        # 0: group-cooperative register kernels, 1: same with the sequential
+        # arg-max scan forced (test hook), 2: scalar thread-per-band kernels
+        self.mode = 0
 
     def _s(self, stream):
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
@@ -191,7 +195,8 @@ class PvqBatch:
         for nmax in (128, 32, 16):
             lst = self.lists[nmax]
             if lst.numel():
-                _native.check(L.daala_b200_pvq_encode_bands(p, lst.data_ptr(), lst.numel(), nmax, s), "pvq_bands")
+                _native.check(L.daala_b200_pvq_encode_bands_mode(p, lst.data_ptr(), lst.numel(), nmax, self.mode, s),
+                              "pvq_bands")
                 n += 1
         _native.check(L.daala_b200_pvq_block_finish(p, self.nblocks, s), "block_finish")
         return n + 1

@@ -158,3 +158,26 @@ def test_hot_path_planes_match_frame_oracle(is_keyframe):
         total_k += int(frame_oracle.pvq_plane(lib, prefix, d, md, geom, pli, bsize, 45, is_keyframe, 1, 0.147,
                                               qm, qm_inv, q4)[1][0])
     assert k_gpu == total_k
+
+
+@pytest.mark.parametrize("is_keyframe,with_pred", [(1, False), (0, True), (1, True)])
+def test_pvq_kernel_variants_agree(is_keyframe, with_pred):
+    """The group-cooperative kernels (default), the same with the literal
+    sequential arg-max scan forced, and the scalar thread-per-band kernels must
+    produce identical indices, pulses and coefficients on a large batch."""
+    import torch
+    geom, cur, pred, batch, qm_q4 = _setup((640, 384), is_keyframe, with_pred, q0=30, seed=12)
+    outs = []
+    for mode in (0, 1, 2):
+        batch.mode = mode
+        for t in (batch.out, batch.y, batch.res_gain, batch.res_theta, batch.res_k, batch.res_skip_term):
+            t.zero_()
+        batch.gather()
+        batch.quantise()
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in (batch.out, batch.y, batch.res_gain, batch.res_theta, batch.res_max_theta,
+                                         batch.res_k, batch.res_skip_term, batch.res_skip_diff)])
+    assert int(outs[0][5].sum().item()) > 1000
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
