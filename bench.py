@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=16, help="4K frames per step (whole job)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pvq-mode", type=int, default=0, help="0 cooperative kernels, 2 scalar thread-per-band")
     return ap.parse_args()
 
 
@@ -233,6 +234,7 @@ def run_b200(args):
                  sb_row0=r0, sb_rows=nrows)
     fb = hp.fb
     hp.set_block_sizes([hf[1] for hf in host_frames])
+    hp.batch.mode = args.pvq_mode
 
     # pinned host staging: this rank's rows (+2-sample halo) of every plane, and its output rows
     def rows(pli, halo):

@@ -645,6 +645,13 @@ __global__ void k_coding_order_scatter(const __grid_constant__ daala_b200_pvq_pa
 
 using namespace daala_b200::pvq;
 
+template <int G, int E, bool kForceScan>
+static void launch_coop(const daala_b200_pvq_params* prm, const uint32_t* band_list, int count, cudaStream_t s) {
+  const int per = 128 / G, blocks = (count + per - 1) / per;
+  k_pvq_bands_coop<G, E, kForceScan><<<blocks, 128, 0, s>>>(*prm, band_list, count);
+}
+
+
 extern "C" {
 
 int daala_b200_pvq_encode_bands(const daala_b200_pvq_params* prm, const uint32_t* band_list, int count,
@@ -659,23 +666,43 @@ int daala_b200_pvq_encode_bands(const daala_b200_pvq_params* prm, const uint32_t
   return (int)cudaGetLastError();
 }
 
-// mode 0: group-cooperative kernels (default), 1: same with the literal
-// sequential arg-max scan forced (test hook), 2: scalar thread-per-band kernels.
+// mode 0: best measured mix (see below), 3: all group-cooperative, default geometry, 1: same with the literal
+// sequential arg-max scan forced (test hook), 2: scalar thread-per-band kernels,
+// 10 + c: cooperative kernels with alternative lanes-per-band geometry c (tuning).
 int daala_b200_pvq_encode_bands_mode(const daala_b200_pvq_params* prm, const uint32_t* band_list, int count,
                                      int nmax, int mode, void* stream) {
   if (count <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (mode == 2) return daala_b200_pvq_encode_bands(prm, band_list, count, nmax, stream);
-#define LAUNCH_COOP(G, E)                                                                          \
-  do {                                                                                              \
-    const int per = 128 / G, blocks = (count + per - 1) / per;                                      \
-    if (mode == 1) k_pvq_bands_coop<G, E, true><<<blocks, 128, 0, s>>>(*prm, band_list, count);     \
-    else k_pvq_bands_coop<G, E, false><<<blocks, 128, 0, s>>>(*prm, band_list, count);              \
-  } while (0)
-  if (nmax <= 16) LAUNCH_COOP(4, 4);
-  else if (nmax <= 32) LAUNCH_COOP(8, 4);
-  else LAUNCH_COOP(32, 4);
-#undef LAUNCH_COOP
+  const int cls = nmax <= 16 ? 0 : nmax <= 32 ? 1 : 2;
+  if (mode == 0) {
+    // measured best on B200 (tools/tune_pvq.py): scalar threads for the short
+    // bands, 16 lanes x 8 registers for the 128-coefficient bands
+    if (cls < 2) return daala_b200_pvq_encode_bands(prm, band_list, count, nmax, stream);
+    launch_coop<16, 8, false>(prm, band_list, count, s);
+    return (int)cudaGetLastError();
+  }
+  if (mode == 1) {
+    if (cls == 0) launch_coop<4, 4, true>(prm, band_list, count, s);
+    else if (cls == 1) launch_coop<8, 4, true>(prm, band_list, count, s);
+    else launch_coop<32, 4, true>(prm, band_list, count, s);
+  } else {
+    const int cfg = mode >= 10 ? mode - 10 : 0;  // mode 3 -> geometry 0
+    if (cls == 0) {
+      if (cfg == 0) launch_coop<4, 4, false>(prm, band_list, count, s);
+      else if (cfg == 1) launch_coop<2, 8, false>(prm, band_list, count, s);
+      else launch_coop<1, 16, false>(prm, band_list, count, s);
+    } else if (cls == 1) {
+      if (cfg == 0) launch_coop<8, 4, false>(prm, band_list, count, s);
+      else if (cfg == 1) launch_coop<4, 8, false>(prm, band_list, count, s);
+      else launch_coop<2, 16, false>(prm, band_list, count, s);
+    } else {
+      if (cfg == 0) launch_coop<32, 4, false>(prm, band_list, count, s);
+      else if (cfg == 1) launch_coop<16, 8, false>(prm, band_list, count, s);
+      else if (cfg == 2) launch_coop<8, 16, false>(prm, band_list, count, s);
+      else launch_coop<4, 32, false>(prm, band_list, count, s);
+    }
+  }
   return (int)cudaGetLastError();
 }
 

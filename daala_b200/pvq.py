@@ -170,8 +170,7 @@ class PvqBatch:
                 p.pvq_qm_q4[pli][i] = int(pvq_qm_q4[pli][i])
         self.params = p
         self.is_keyframe = int(is_keyframe)
-        # 0: group-cooperative register kernels, 1: same with the sequential
-        # arg-max scan forced (test hook), 2: scalar thread-per-band kernels
+        # kernel choice of daala_b200_pvq_encode_bands_mode (0 = measured-best mix)
         self.mode = 0
 
     def _s(self, stream):

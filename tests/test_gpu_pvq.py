@@ -168,7 +168,7 @@ def test_pvq_kernel_variants_agree(is_keyframe, with_pred):
     import torch
     geom, cur, pred, batch, qm_q4 = _setup((640, 384), is_keyframe, with_pred, q0=30, seed=12)
     outs = []
-    for mode in (0, 1, 2):
+    for mode in (2, 0, 1, 3, 11, 12, 13):
         batch.mode = mode
         for t in (batch.out, batch.y, batch.res_gain, batch.res_theta, batch.res_k, batch.res_skip_term):
             t.zero_()
