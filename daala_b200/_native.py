@@ -48,7 +48,7 @@ def lib():
                 "__graft_entry__.build()); daala_b200 has no CPU fallback")
         L = ctypes.CDLL(LIB_PATH)
         fp = ctypes.POINTER(Frame)
-        for name in ("daala_b200_forward_frame", "daala_b200_inverse_frame",
+        for name in ("daala_b200_forward_frame", "daala_b200_forward_frame_no_tma", "daala_b200_inverse_frame",
                      "daala_b200_inverse_frame_lapped", "daala_b200_sb_postfilter_store_frame"):
             fn = getattr(L, name)
             fn.argtypes = [fp, c_int, c_void_p]

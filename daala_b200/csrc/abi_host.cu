@@ -24,6 +24,7 @@
 
 extern "C" {
 int daala_b200_launch_forward(const FrameXformParams* prm, int nplanes, cudaStream_t stream);
+int daala_b200_launch_forward_no_tma(const FrameXformParams* prm, int nplanes, cudaStream_t stream);
 int daala_b200_launch_inverse(const FrameXformParams* prm, int nplanes, cudaStream_t stream);
 int daala_b200_launch_inverse_lapped_only(const FrameXformParams* prm, int nplanes, cudaStream_t stream);
 int daala_b200_launch_sb_postfilter_store(const FrameXformParams* prm, int nplanes, cudaStream_t stream);
@@ -305,6 +306,9 @@ DAALA_B200_MATCH(64, 6)
 // ---- Section B ------------------------------------------------------------
 int daala_b200_forward_frame(const daala_b200_frame* f, int nplanes, void* stream) {
   return daala_b200_launch_forward(f, nplanes, (cudaStream_t)stream);
+}
+int daala_b200_forward_frame_no_tma(const daala_b200_frame* f, int nplanes, void* stream) {
+  return daala_b200_launch_forward_no_tma(f, nplanes, (cudaStream_t)stream);
 }
 int daala_b200_inverse_frame(const daala_b200_frame* f, int nplanes, void* stream) {
   return daala_b200_launch_inverse(f, nplanes, (cudaStream_t)stream);

@@ -22,8 +22,11 @@
 // a column pass and a row pass over a shared-memory tile whose pitch is odd
 // (5 mod 32), so both passes are bank-conflict free without a transpose.
 // Tensor cores are not used: these are rounding lifting networks, not GEMMs.
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "gen/dct_lifting.cuh"
 #include "lapped_filter.cuh"
@@ -36,6 +39,50 @@ constexpr int kMaxB = 64;            // superblock edge in luma pixels
 constexpr int kHalo = 2;             // lapping reaches 2 samples across an edge
 constexpr int kMaxT = kMaxB + 2 * kHalo;
 constexpr int kMaxPitch = kMaxT + 1; // 69 = 5 mod 32; chroma 37 = 5 mod 32
+
+// ---------------------------------------------------------------------------
+// TMA staging of the 8-bit input window.  One 3-D tensor map per plane
+// (x, y, frame); the (B+4)^2 window of a superblock is fetched by ONE
+// cp.async.bulk.tensor issued by thread 0 (box width rounded up to a multiple
+// of 16 bytes: 80 for luma, 48 for chroma); out-of-frame samples are zero
+// filled by the hardware, so frame borders need no branches.
+// ---------------------------------------------------------------------------
+struct TmaMaps {
+  CUtensorMap plane[3];
+};
+
+template <int XDEC> struct RawTile {
+  static constexpr int B = kMaxB >> XDEC;
+  static constexpr int rows = B + 2 * kHalo;
+  static constexpr int width = ((B + 2 * kHalo + 15) / 16) * 16;  // 80 / 48
+  static constexpr int bytes = rows * width;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
 
 // ---------------------------------------------------------------------------
 // Leaf-size lookup for one superblock.  `leaf[v*8+u]` = log2 of the transform
@@ -197,9 +244,10 @@ __device__ __forceinline__ unsigned leaf_size_mask(const unsigned char* leaf) {
 // ---------------------------------------------------------------------------
 // Forward kernel.  grid = (nhsb*sb_rows, nplanes, nframes).
 // ---------------------------------------------------------------------------
-template <int XDEC>
+template <int XDEC, bool kTma>
 __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, const PlaneXform& pl,
-                                                int* tile_s, unsigned char* leaf) {
+                                                int* tile_s, unsigned char* leaf, const CUtensorMap* map,
+                                                unsigned char* raw, uint64_t* bar) {
   constexpr int B = kMaxB >> XDEC;
   constexpr int T = B + 2 * kHalo;
   constexpr int P = T + 1;
@@ -210,15 +258,36 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
   s.x0 = sbx * B;
   s.y0 = sby * B;
   const int pw = prm.nhsb * B, ph = prm.nvsb * B;
-  load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, XDEC);
   // Stage the (B+4)^2 pixel window as (p-128) << OD_COEFF_SHIFT (src/state.c:1233).
-  const uint8_t* src = pl.pixels + fr * pl.pixel_frame_pitch;
-  for (int i = threadIdx.x; i < T * T; i += kThreads) {
-    int r = i / T, c = i - r * T;
-    int gx = s.x0 + c - kHalo, gy = s.y0 + r - kHalo;
-    int v = 0;
-    if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = ((int)src[(size_t)gy * pl.pixel_stride + gx] - 128) * 16;
-    tile_s[r * P + c] = v;
+  if (kTma) {
+    constexpr int RW = RawTile<XDEC>::width;
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      mbar_expect_tx(bar, RawTile<XDEC>::bytes);
+      tma_load_3d(raw, map, s.x0 - kHalo, s.y0 - kHalo, fr, bar);
+    }
+    load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, XDEC);
+    __syncthreads();  // barrier initialised before anybody polls it
+    mbar_wait(bar, 0);
+    for (int i = threadIdx.x; i < T * (T / 4); i += kThreads) {
+      int r = i / (T / 4), c4 = (i - r * (T / 4)) * 4;
+      unsigned w = *reinterpret_cast<const unsigned*>(raw + r * RW + c4);
+      int* t = tile_s + r * P + c4;
+      t[0] = ((int)(w & 255u) - 128) * 16;
+      t[1] = ((int)((w >> 8) & 255u) - 128) * 16;
+      t[2] = ((int)((w >> 16) & 255u) - 128) * 16;
+      t[3] = ((int)(w >> 24) - 128) * 16;
+    }
+  } else {
+    load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, XDEC);
+    const uint8_t* src = pl.pixels + fr * pl.pixel_frame_pitch;
+    for (int i = threadIdx.x; i < T * T; i += kThreads) {
+      int r = i / T, c = i - r * T;
+      int gx = s.x0 + c - kHalo, gy = s.y0 + r - kHalo;
+      int v = 0;
+      if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = ((int)src[(size_t)gy * pl.pixel_stride + gx] - 128) * 16;
+      tile_s[r * P + c] = v;
+    }
   }
   __syncthreads();
   // Superblock-edge prefilter: all horizontal edges first (vertical taps),
@@ -267,8 +336,21 @@ k_forward_sb(const __grid_constant__ FrameXformParams prm) {
   __shared__ int tile_s[kMaxT * kMaxPitch];
   __shared__ unsigned char leaf[64];
   const PlaneXform& pl = prm.plane[blockIdx.y];
-  if (pl.xdec == 0) forward_sb_body<0>(prm, pl, tile_s, leaf);
-  else forward_sb_body<1>(prm, pl, tile_s, leaf);
+  if (pl.xdec == 0) forward_sb_body<0, false>(prm, pl, tile_s, leaf, nullptr, nullptr, nullptr);
+  else forward_sb_body<1, false>(prm, pl, tile_s, leaf, nullptr, nullptr, nullptr);
+}
+
+// Same with the input window staged by TMA (the default when the planes meet
+// the 16-byte alignment rules of tensor maps).
+__global__ void __launch_bounds__(kThreads, 2)
+k_forward_sb_tma(const __grid_constant__ FrameXformParams prm, const __grid_constant__ TmaMaps maps) {
+  __shared__ int tile_s[kMaxT * kMaxPitch];
+  __shared__ __align__(128) unsigned char raw[RawTile<0>::bytes];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ unsigned char leaf[64];
+  const PlaneXform& pl = prm.plane[blockIdx.y];
+  if (pl.xdec == 0) forward_sb_body<0, true>(prm, pl, tile_s, leaf, &maps.plane[blockIdx.y], raw, &bar);
+  else forward_sb_body<1, true>(prm, pl, tile_s, leaf, &maps.plane[blockIdx.y], raw, &bar);
 }
 
 // ---------------------------------------------------------------------------
@@ -474,7 +556,51 @@ using namespace daala_b200;
 
 extern "C" {
 
+// Tensor maps are encoded with the driver entry point fetched through the
+// runtime (no link-time dependency on libcuda).  Returns false when a plane
+// cannot be described (alignment), in which case the plain-load kernel runs.
+static bool encode_input_maps(const FrameXformParams* prm, int nplanes, TmaMaps* maps) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }
+  if (!encode) return false;
+  memset(maps, 0, sizeof(*maps));
+  for (int p = 0; p < nplanes; p++) {
+    const PlaneXform& pl = prm->plane[p];
+    const int B = kMaxB >> pl.xdec;
+    const cuuint64_t w = (cuuint64_t)prm->nhsb * B, h = (cuuint64_t)prm->nvsb * B;
+    const cuuint64_t fpitch = prm->nframes > 1 ? (cuuint64_t)pl.pixel_frame_pitch : w * h;
+    if (((uintptr_t)pl.pixels & 15) || (pl.pixel_stride & 15) || (fpitch & 15) || pl.pixel_stride <= 0) return false;
+    cuuint64_t dims[3] = {w, h, (cuuint64_t)prm->nframes};
+    cuuint64_t strides[2] = {(cuuint64_t)pl.pixel_stride, fpitch};
+    cuuint32_t box[3] = {(cuuint32_t)(pl.xdec ? RawTile<1>::width : RawTile<0>::width),
+                         (cuuint32_t)(B + 2 * kHalo), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&maps->plane[p], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)pl.pixels, dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+  }
+  return true;
+}
+
 int daala_b200_launch_forward(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
+  dim3 grid(prm->nhsb * prm->sb_rows, nplanes, prm->nframes);
+  TmaMaps maps;
+  if (encode_input_maps(prm, nplanes, &maps)) k_forward_sb_tma<<<grid, kThreads, 0, stream>>>(*prm, maps);
+  else k_forward_sb<<<grid, kThreads, 0, stream>>>(*prm);
+  return (int)cudaGetLastError();
+}
+
+// Test hook: force the plain-load variant.
+int daala_b200_launch_forward_no_tma(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
   dim3 grid(prm->nhsb * prm->sb_rows, nplanes, prm->nframes);
   k_forward_sb<<<grid, kThreads, 0, stream>>>(*prm);
   return (int)cudaGetLastError();

@@ -115,8 +115,8 @@ class FrameBuffers:
         fn = getattr(_native.lib(), name)
         _native.check(fn(ctypes.byref(f), self.geom.nplanes, ctypes.c_void_p(s.cuda_stream)), name)
 
-    def forward(self, stream=None):
-        self._call("daala_b200_forward_frame", stream)
+    def forward(self, stream=None, tma=True):
+        self._call("daala_b200_forward_frame" if tma else "daala_b200_forward_frame_no_tma", stream)
 
     def inverse(self, stream=None, lapped_only=False):
         self._call("daala_b200_inverse_frame_lapped" if lapped_only else "daala_b200_inverse_frame", stream)

@@ -144,6 +144,9 @@ typedef struct daala_b200_frame {
    od_apply_prefilter_frame_sbs (src/filter.c:1529) + od_compute_dcts
    (src/encode.c:1455) for every superblock of every plane, one launch. */
 int daala_b200_forward_frame(const daala_b200_frame *f, int nplanes, void *stream);
+/* Same result with the input window fetched by plain loads instead of TMA
+   (automatically used when a plane is not 16-byte aligned; exported as a test hook). */
+int daala_b200_forward_frame_no_tma(const daala_b200_frame *f, int nplanes, void *stream);
 
 /* coefficient planes -> u8 planes: per-leaf idct_2d (src/encode.c:1397) +
    od_postfilter_split (src/filter.c:1485) bottom-up, then

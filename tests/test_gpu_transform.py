@@ -195,3 +195,25 @@ def test_batched_and_row_sharded_launches_equal_whole_frame(torch_cuda):
             assert torch.equal(whole.coeffs[pli][f], singles[f].coeffs[pli][0])
             assert torch.equal(whole.pixels_out[pli][f], singles[f].pixels_out[pli][0])
             assert torch.equal(whole.pixels_out[pli][f], whole.pixels[pli][f])
+
+
+def test_tma_and_plain_load_forward_agree(torch_cuda):
+    """The TMA-staged forward kernel and its plain-load twin (used for
+    unaligned planes) must write identical coefficient planes."""
+    torch = torch_cuda
+    from daala_b200 import synth
+    from daala_b200.frame import FrameBuffers, Geometry
+    geom = Geometry(704, 300)
+    a = FrameBuffers(geom, nframes=2)
+    b = FrameBuffers(geom, nframes=2)
+    for f in range(2):
+        planes, _ = synth.frame(704, 300, f=f)
+        planes = synth.pad_planes(planes, geom)
+        bsize = synth.block_size_map(geom, "mixed", seed=20 + f)
+        a.upload(planes, bsize, frame=f)
+        b.upload(planes, bsize, frame=f)
+    a.forward(tma=True)
+    b.forward(tma=False)
+    torch.cuda.synchronize()
+    for pli in range(3):
+        assert torch.equal(a.coeffs[pli], b.coeffs[pli])
