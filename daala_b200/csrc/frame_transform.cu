@@ -43,9 +43,12 @@ constexpr int kMaxPitch = kMaxT + 1; // 69 = 5 mod 32; chroma 37 = 5 mod 32
 // ---------------------------------------------------------------------------
 // TMA staging of the 8-bit input window.  One 3-D tensor map per plane
 // (x, y, frame); the (B+4)^2 window of a superblock is fetched by ONE
-// cp.async.bulk.tensor issued by thread 0 (box width rounded up to a multiple
-// of 16 bytes: 80 for luma, 48 for chroma); out-of-frame samples are zero
-// filled by the hardware, so frame borders need no branches.
+// cp.async.bulk.tensor issued by thread 0.  The innermost start coordinate of
+// a tiled TMA copy must be 16-byte aligned (an unaligned x raises "illegal
+// instruction" on sm_100; measured with tools/probe/tma_probe.cu), so the box
+// starts 16 samples left of the superblock and is 96 (luma) / 64 (chroma)
+// bytes wide; the window proper begins at byte 14 of each row.  Out-of-frame
+// samples are zero filled by the hardware, so frame borders need no branches.
 // ---------------------------------------------------------------------------
 struct TmaMaps {
   CUtensorMap plane[3];
@@ -54,7 +57,9 @@ struct TmaMaps {
 template <int XDEC> struct RawTile {
   static constexpr int B = kMaxB >> XDEC;
   static constexpr int rows = B + 2 * kHalo;
-  static constexpr int width = ((B + 2 * kHalo + 15) / 16) * 16;  // 80 / 48
+  static constexpr int lead = 16;                                     // aligned start: x0 - 16
+  static constexpr int width = ((lead + B + kHalo + 15) / 16) * 16;     // 96 / 64
+  static constexpr int skip = lead - kHalo;                            // 14: first window byte
   static constexpr int bytes = rows * width;
 };
 
@@ -264,14 +269,16 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
     if (threadIdx.x == 0) {
       mbar_init(bar, 1);
       mbar_expect_tx(bar, RawTile<XDEC>::bytes);
-      tma_load_3d(raw, map, s.x0 - kHalo, s.y0 - kHalo, fr, bar);
+      tma_load_3d(raw, map, s.x0 - RawTile<XDEC>::lead, s.y0 - kHalo, fr, bar);
     }
     load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, XDEC);
     __syncthreads();  // barrier initialised before anybody polls it
     mbar_wait(bar, 0);
     for (int i = threadIdx.x; i < T * (T / 4); i += kThreads) {
       int r = i / (T / 4), c4 = (i - r * (T / 4)) * 4;
-      unsigned w = *reinterpret_cast<const unsigned*>(raw + r * RW + c4);
+      // window byte c4 sits at raw byte 14 + c4: half-word aligned, so merge two words
+      const unsigned* rw = reinterpret_cast<const unsigned*>(raw + r * RW + (RawTile<XDEC>::skip & ~3) + c4);
+      unsigned w = __funnelshift_r(rw[0], rw[1], 8 * (RawTile<XDEC>::skip & 3));
       int* t = tile_s + r * P + c4;
       t[0] = ((int)(w & 255u) - 128) * 16;
       t[1] = ((int)((w >> 8) & 255u) - 128) * 16;
@@ -343,14 +350,18 @@ k_forward_sb(const __grid_constant__ FrameXformParams prm) {
 // Same with the input window staged by TMA (the default when the planes meet
 // the 16-byte alignment rules of tensor maps).
 __global__ void __launch_bounds__(kThreads, 2)
-k_forward_sb_tma(const __grid_constant__ FrameXformParams prm, const __grid_constant__ TmaMaps maps) {
+k_forward_sb_tma(const __grid_constant__ FrameXformParams prm, const __grid_constant__ CUtensorMap map0,
+                 const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2) {
   __shared__ int tile_s[kMaxT * kMaxPitch];
   __shared__ __align__(128) unsigned char raw[RawTile<0>::bytes];
   __shared__ __align__(8) uint64_t bar;
   __shared__ unsigned char leaf[64];
   const PlaneXform& pl = prm.plane[blockIdx.y];
-  if (pl.xdec == 0) forward_sb_body<0, true>(prm, pl, tile_s, leaf, &maps.plane[blockIdx.y], raw, &bar);
-  else forward_sb_body<1, true>(prm, pl, tile_s, leaf, &maps.plane[blockIdx.y], raw, &bar);
+  // the descriptor must stay in parameter space: select between the three
+  // kernel parameters, never index an array of them (that would copy to local)
+  const CUtensorMap* map = blockIdx.y == 0 ? &map0 : (blockIdx.y == 1 ? &map1 : &map2);
+  if (pl.xdec == 0) forward_sb_body<0, true>(prm, pl, tile_s, leaf, map, raw, &bar);
+  else forward_sb_body<1, true>(prm, pl, tile_s, leaf, map, raw, &bar);
 }
 
 // ---------------------------------------------------------------------------
@@ -594,7 +605,8 @@ static bool encode_input_maps(const FrameXformParams* prm, int nplanes, TmaMaps*
 int daala_b200_launch_forward(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
   dim3 grid(prm->nhsb * prm->sb_rows, nplanes, prm->nframes);
   TmaMaps maps;
-  if (encode_input_maps(prm, nplanes, &maps)) k_forward_sb_tma<<<grid, kThreads, 0, stream>>>(*prm, maps);
+  if (encode_input_maps(prm, nplanes, &maps))
+    k_forward_sb_tma<<<grid, kThreads, 0, stream>>>(*prm, maps.plane[0], maps.plane[1], maps.plane[2]);
   else k_forward_sb<<<grid, kThreads, 0, stream>>>(*prm);
   return (int)cudaGetLastError();
 }
