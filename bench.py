@@ -269,30 +269,9 @@ def run_b200(args):
             a, b = rows(pli, 0)
             pin_out[pli].copy_(fb.pixels_out[pli][:, a:b], non_blocking=True)
 
-    # border exchange buffers (multi-GPU): top 2 + bottom 2 lapped rows of my shard, all planes
-    if world > 1:
-        widths = [geom.plane_shape(p)[1] for p in range(3)]
-        send = torch.zeros((F * 4 * sum(widths),), dtype=torch.int32, device=dev)
-        gathered = torch.zeros((world, send.numel()), dtype=torch.int32, device=dev)
-
-    def exchange():
-        off = 0
-        views = []
-        for pli in range(3):
-            a, b = rows(pli, 0)
-            w = geom.plane_shape(pli)[1]
-            n = F * 4 * w
-            v = send[off:off + n].view(F, 4, w)
-            v[:, 0:2].copy_(fb.lapped[pli][:, a:a + 2])
-            v[:, 2:4].copy_(fb.lapped[pli][:, b - 2:b])
-            views.append((off, n, w, a, b))
-            off += n
-        dist.all_gather_into_tensor(gathered, send)
-        for pli, (off, n, w, a, b) in enumerate(views):
-            if rank > 0:
-                fb.lapped[pli][:, a - 2:a].copy_(gathered[rank - 1, off:off + n].view(F, 4, w)[:, 2:4])
-            if rank < world - 1:
-                fb.lapped[pli][:, b:b + 2].copy_(gathered[rank + 1, off:off + n].view(F, 4, w)[:, 0:2])
+    # multi-GPU: one all-gather per step of the 2-row lapped borders (daala_b200/sharding.py)
+    from daala_b200.sharding import BorderExchange
+    exchange = BorderExchange(geom, fb.lapped, rank, world)
 
     launches = {"n": 0}
 

@@ -1,0 +1,121 @@
+"""CPU tests of the host logic: geometry, sharding, block/band lists, the
+exported C ABI, and the N>1 border exchange over gloo (world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_geometry_and_row_shards():
+    from daala_b200.frame import Geometry
+    g = Geometry(3840, 2160)
+    assert (g.nhsb, g.nvsb, g.frame_w, g.frame_h) == (60, 34, 3840, 2176)
+    assert g.plane_shape(1) == (1088, 1920)
+    rows = [g.shard_rows(r, 8) for r in range(8)]
+    assert [n for _, n in rows] == [5, 5, 4, 4, 4, 4, 4, 4]
+    assert rows[0][0] == 0 and all(rows[i][0] + rows[i][1] == rows[i + 1][0] for i in range(7))
+    g8 = Geometry(7680, 4320)
+    assert [g8.shard_rows(r, 8)[1] for r in range(8)] == [9, 9, 9, 9, 8, 8, 8, 8]
+
+
+@pytest.mark.parametrize("mode", ["mixed", "4", "8", "16", "32", "64"])
+def test_block_and_band_lists_cover_every_plane_once(mode):
+    from daala_b200 import pvq, synth
+    from daala_b200.frame import Geometry
+    g = Geometry(320, 200)
+    bsize = synth.block_size_map(g, mode, seed=4)
+    blocks = pvq.block_list(bsize, g)
+    for pli in range(3):
+        ph, pw = g.plane_shape(pli)
+        cover = np.zeros((ph, pw), np.int32)
+        for b in blocks[blocks["pli"] == pli]:
+            n = 4 << int(b["bs"])
+            assert b["x0"] % n == 0 and b["y0"] % n == 0
+            cover[b["y0"]:b["y0"] + n, b["x0"]:b["x0"] + n] += 1
+        assert (cover == 1).all()
+    total = pvq.assign_offsets(blocks)
+    assert total == int(np.minimum(16 << (2 * blocks["bs"].astype(np.int64)), 512).sum())
+    lists = pvq.band_lists(blocks)
+    nb = sum(pvq.NBANDS[int(b)] for b in blocks["bs"])
+    assert sum(len(v) for v in lists.values()) == nb
+    # every (block, band) pair exactly once
+    allb = np.concatenate(list(lists.values()))
+    assert len(np.unique(allb)) == len(allb)
+    # shards partition the block list
+    parts = [pvq.block_list(bsize, g, sb_row0=r0, sb_rows=n) for r0, n in (g.shard_rows(r, 2) for r in range(2))]
+    assert sum(len(p) for p in parts) == len(blocks)
+
+
+def test_library_exports_every_declared_symbol():
+    """The built library must export everything include/daala_b200.h declares
+    (no compute calls here: the build container has no GPU)."""
+    import ctypes
+    from daala_b200 import _native
+    L = _native.lib()
+    hdr = open(os.path.join(ROOT, "include", "daala_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b((?:od|daala_b200)_[a-z0-9_]+)\s*\(", hdr))
+    names |= {"OD_FDCT_2D_CUDA", "OD_IDCT_2D_CUDA"}
+    assert len(names) >= 60
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.daala_b200_version().startswith(b"daala_b200")
+    assert L.daala_b200_device_count() >= 0
+
+
+def test_native_struct_layouts_match_the_header():
+    import ctypes
+    from daala_b200 import _native, mc, pvq
+    assert ctypes.sizeof(_native.Plane) == 4 * 8 + 6 * 4 + 4 * 8
+    assert ctypes.sizeof(_native.Frame) == 3 * ctypes.sizeof(_native.Plane) + 8 + 10 * 4 + 8
+    assert pvq.BLOCK_DTYPE.itemsize == 12
+    assert mc.MC_BLOCK_DTYPE.itemsize == 40 and mc.MATCH_JOB_DTYPE.itemsize == 16
+    assert ctypes.sizeof(pvq.PvqParams) % 8 == 0
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from daala_b200.frame import Geometry
+from daala_b200.sharding import BorderExchange, plane_rows
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+geom = Geometry(256, 320)            # 4 x 5 superblocks
+F = 2
+g = torch.Generator().manual_seed(7)
+full = [torch.randint(-5000, 5000, (F,) + geom.plane_shape(p), generator=g, dtype=torch.int32) for p in range(3)]
+mine = [torch.zeros_like(t) for t in full]
+r0, n = geom.shard_rows(rank, world)
+for p in range(3):
+    a, b = plane_rows(geom, p, r0, n)
+    mine[p][:, a:b] = full[p][:, a:b]      # what this rank computed
+ex = BorderExchange(geom, mine, rank, world)
+ex()
+for p in range(3):
+    a, b = plane_rows(geom, p, r0, n, halo=2)
+    assert torch.equal(mine[p][:, a:b], full[p][:, a:b]), (rank, p)
+    # nothing else was touched
+    rest = mine[p].clone(); rest[:, a:b] = 0
+    assert int(rest.abs().sum()) == 0
+dist.barrier()
+dist.destroy_process_group()
+print("rank %%d ok" %% rank)
+'''
+
+
+def test_border_exchange_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29577", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert "rank %d ok" % r in o
