@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 
 #include "gen/dct_lifting.cuh"
@@ -108,119 +109,168 @@ struct SbCtxT {
   int x0, y0;   // plane coordinates of the superblock origin
 };
 
-template <class SbCtx>
-__device__ __forceinline__ int leaf_log(const unsigned char* leaf, const SbCtx& s, int px, int py) {
-  return leaf[(py >> s.ushift) * 8 + (px >> s.ushift)];
-}
+// Per-superblock work lists, built once in shared memory from the block-size
+// map so that every later phase iterates over exactly its active items (no
+// per-item quadtree lookups, no idle iterations):
+//   blk[c][..]  leaf blocks of transform size 4 << c (c = 0..4), position packed (y << 8 | x)
+//   node[l][..] split nodes of edge 8 << l (l = 0..3), with their filter gates
+// Leaf sizes follow od_compute_dcts (src/encode.c:1466-1470): bs = max(obs, xdec)
+// read at the block's top-left corner of the reference's state->bsize map.
+struct SbLists {
+  unsigned short blk[256 + 64 + 16 + 4 + 1];
+  unsigned short node[64 + 16 + 4 + 1];
+  int nblk[5];
+  int nnode[4];
+  unsigned char wcnt[kThreads / 32][9];  // per-warp counts while the lists are being built
+};
+__device__ __forceinline__ constexpr int blk_base(int c) { return c == 0 ? 0 : c == 1 ? 256 : c == 2 ? 320 : c == 3 ? 336 : 340; }
+__device__ __forceinline__ constexpr int node_base(int l) { return l == 0 ? 0 : l == 1 ? 64 : l == 2 ? 80 : 84; }
+constexpr unsigned short kGateH = 0x4000;  // hfilter allowed (node inside the picture horizontally)
+constexpr unsigned short kGateV = 0x8000;  // vfilter allowed
 
-__device__ __forceinline__ void load_leaf_map(unsigned char* leaf, const unsigned char* bsize,
-                                               int bstride, int sbx, int sby, int xdec) {
-  if (threadIdx.x < 64) {
-    int u = threadIdx.x & 7, v = threadIdx.x >> 3;
-    int obs = bsize[(sby * 8 + v) * bstride + sbx * 8 + u];
-    int bs = obs > xdec ? obs : xdec;
-    leaf[threadIdx.x] = (unsigned char)(bs - xdec + 2);
+// Must be called by all threads; ends with the lists visible to the CTA.
+// Deterministic compaction: per category a warp ballot gives the rank inside
+// the warp, per-warp counts in shared memory give the offsets across warps.
+template <int XDEC>
+__device__ __forceinline__ void build_lists(SbLists& L, const unsigned char* bsize, int bstride, int sbx,
+                                            int sby, int x0, int y0, int pic_w, int pic_h) {
+  constexpr int B = kMaxB >> XDEC;
+  constexpr int U = B / 4;  // 4x4 units per side
+  constexpr int kWarps = kThreads / 32;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool active = t < U * U;
+  const int ux = t % U, uy = t / U;
+  int c = -1;
+  if (active) {
+    // the 8x8-luma unit covering this 4x4 unit: luma (ux>>1, uy>>1), 4:2:0 chroma (ux, uy)
+    const int bx = XDEC ? ux : ux >> 1, by = XDEC ? uy : uy >> 1;
+    const int obs = bsize[(sby * 8 + by) * bstride + sbx * 8 + bx];
+    c = (obs > XDEC ? obs : XDEC) - XDEC;   // log2(n) - 2
   }
-}
-
-// Is the node of edge S (plane px) whose origin is (nx, ny) (superblock-local)
-// split further?  The reference looks at the block size stored at the node's
-// top-left corner (src/encode.c:1466).
-template <class SbCtx>
-__device__ __forceinline__ bool node_is_split(const unsigned char* leaf, const SbCtx& s, int nx,
-                                              int ny, int logS) {
-  return leaf_log(leaf, s, nx, ny) < logS;
+  const unsigned short pos = (unsigned short)(((uy * 4) << 8) | (ux * 4));
+  // category 0..4: leaf origin of class c; 5..8: split node of edge 8 << (cat - 5)
+  int rank[9];
+  bool flag[9];
+#pragma unroll
+  for (int cat = 0; cat < 9; cat++) {
+    bool f = false;
+    if (active) {
+      if (cat < 5) {
+        const int n4 = 1 << cat;
+        f = c == cat && !(ux & (n4 - 1)) && !(uy & (n4 - 1));
+      } else {
+        const int l = cat - 5, S = 8 << l, s4 = 2 << l;
+        // a node exists at unit positions aligned to its size and is split iff the leaf at its
+        // corner is smaller (src/encode.c:1466: the block size is read at the corner)
+        f = S <= B && !(ux & (s4 - 1)) && !(uy & (s4 - 1)) && c + 2 < 3 + l;
+      }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    flag[cat] = f;
+    rank[cat] = __popc(b & lt);
+    if (lane == 0) L.wcnt[warp][cat] = (unsigned char)__popc(b);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int cat = 0; cat < 9; cat++) {
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) {
+      const int n = L.wcnt[w][cat];
+      if (w < warp) off += n;
+      total += n;
+    }
+    if (t == 0) {
+      if (cat < 5) L.nblk[cat] = total; else L.nnode[cat - 5] = total;
+    }
+    if (flag[cat]) {
+      if (cat < 5) {
+        L.blk[blk_base(cat) + off + rank[cat]] = pos;
+      } else {
+        const int S = 8 << (cat - 5);
+        unsigned short v = pos;
+        // gates compare PLANE coordinates with the LUMA picture size (src/encode.c:1487-1488)
+        if (x0 + ux * 4 + S <= pic_w) v |= kGateH;
+        if (y0 + uy * 4 + S <= pic_h) v |= kGateV;
+        L.node[node_base(cat - 5) + off + rank[cat]] = v;
+      }
+    }
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
-// One pass of 1-D transforms over every leaf of size 2^L in the tile.
+// One pass of 1-D transforms over every leaf of size 2^(C+2) in the tile.
 // kFwd:  pass 0 = columns, pass 1 = rows   (od_bin_fdctNxN, src/dct.c:151-156)
 // !kFwd: pass 0 = rows,    pass 1 = columns (od_bin_idctNxN, src/dct.c:158-163)
 // `tile` points at the superblock's (0,0) sample inside the shared tile.
 // ---------------------------------------------------------------------------
-template <int L, bool kFwd, class SbCtx>
-__device__ __forceinline__ void transform_pass(int* tile, const unsigned char* leaf,
-                                               const SbCtx& s, bool along_columns) {
-  constexpr int N = 1 << L;
-  constexpr int B = SbCtx::B;
-  constexpr int items = B * (B >> L);
+template <int C, bool kFwd, int P>
+__device__ __forceinline__ void transform_pass(int* tile, const SbLists& L, bool along_columns) {
+  constexpr int LN = C + 2;
+  constexpr int N = 1 << LN;
+  const int items = L.nblk[C] << LN;
   for (int item = threadIdx.x; item < items; item += kThreads) {
-    int a = item % B;        // position across the transform direction
-    int m = item / B;        // which N-segment along the transform direction
-    int px = along_columns ? a : m * N;
-    int py = along_columns ? m * N : a;
-    if (leaf_log(leaf, s, px, py) != L) continue;
-    int* p = tile + py * s.P + px;
-    const int stride = along_columns ? s.P : 1;
+    const int pos = L.blk[blk_base(C) + (item >> LN)];
+    const int k = item & (N - 1);
+    const int px = (pos & 255) + (along_columns ? k : 0);
+    const int py = (pos >> 8) + (along_columns ? 0 : k);
+    int* p = tile + py * P + px;
+    const int stride = along_columns ? P : 1;
     int v[N];
 #pragma unroll
-    for (int k = 0; k < N; k++) v[k] = p[k * stride];
+    for (int q = 0; q < N; q++) v[q] = p[q * stride];
     if (kFwd) Lifting<N>::fwd(v); else Lifting<N>::inv(v);
 #pragma unroll
-    for (int k = 0; k < N; k++) p[k * stride] = v[k];
+    for (int q = 0; q < N; q++) p[q * stride] = v[q];
   }
 }
 
-template <bool kFwd, class SbCtx>
-__device__ __forceinline__ void transform_all_leaves(int* tile, const unsigned char* leaf,
-                                                     const SbCtx& s, unsigned size_mask) {
+template <bool kFwd, int P, int LOGB>
+__device__ __forceinline__ void transform_all_leaves(int* tile, const SbLists& L) {
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
     const bool cols = kFwd ? (pass == 0) : (pass == 1);
-    if (SbCtx::logB >= 6 && (size_mask & (1u << 6))) transform_pass<6, kFwd, SbCtx>(tile, leaf, s, cols);
-    if (size_mask & (1u << 5)) transform_pass<5, kFwd, SbCtx>(tile, leaf, s, cols);
-    if (size_mask & (1u << 4)) transform_pass<4, kFwd, SbCtx>(tile, leaf, s, cols);
-    if (size_mask & (1u << 3)) transform_pass<3, kFwd, SbCtx>(tile, leaf, s, cols);
-    if (size_mask & (1u << 2)) transform_pass<2, kFwd, SbCtx>(tile, leaf, s, cols);
+    if (LOGB >= 6 && L.nblk[4]) transform_pass<4, kFwd, P>(tile, L, cols);
+    if (L.nblk[3]) transform_pass<3, kFwd, P>(tile, L, cols);
+    if (L.nblk[2]) transform_pass<2, kFwd, P>(tile, L, cols);
+    if (L.nblk[1]) transform_pass<1, kFwd, P>(tile, L, cols);
+    if (L.nblk[0]) transform_pass<0, kFwd, P>(tile, L, cols);
     __syncthreads();
   }
 }
 
-// Interior-cross lapping of every split node of edge 2^logS.
+// Interior-cross lapping of every split node of edge 8 << l.
 // Prefilter: horizontal edge (vertical taps) first, then the vertical edge
 // (od_prefilter_split, src/filter.c:1467-1481); postfilter: the reverse
-// (od_postfilter_split, src/filter.c:1510-1525).  A direction is disabled when
-// the node sticks out of the picture; the reference compares PLANE coordinates
-// with the LUMA picture size (src/encode.c:1487-1488) -- reproduced literally.
-template <bool kPost, class SbCtx>
-__device__ __forceinline__ void split_filter_level(int* tile, const unsigned char* leaf,
-                                                   const SbCtx& s, int logS, int pic_w, int pic_h,
-                                                   bool vertical_taps) {
-  const int S = 1 << logS;
-  constexpr int B = SbCtx::B;
-  const int items = B * (B >> logS);
+// (od_postfilter_split, src/filter.c:1510-1525).
+template <bool kPost, int P>
+__device__ __forceinline__ void split_filter_level(int* tile, const SbLists& L, int l, bool vertical_taps) {
+  const int logS = 3 + l, S = 1 << logS;
+  const int items = L.nnode[l] << logS;
+  const unsigned short gate = vertical_taps ? kGateH : kGateV;
   for (int item = threadIdx.x; item < items; item += kThreads) {
-    int a = item % B;   // coordinate along the edge
-    int m = item / B;   // node index across the edge
-    int nx, ny;
-    if (vertical_taps) { nx = a & ~(S - 1); ny = m * S; }
-    else { nx = m * S; ny = a & ~(S - 1); }
-    if (!node_is_split(leaf, s, nx, ny, logS)) continue;
-    if (vertical_taps) {
-      if (s.x0 + nx + S > pic_w) continue;  // hfilter gate
-      lap4_inplace<kPost>(tile + (ny + S / 2 - 2) * s.P + a, s.P);
-    } else {
-      if (s.y0 + ny + S > pic_h) continue;  // vfilter gate
-      lap4_inplace<kPost>(tile + a * s.P + nx + S / 2 - 2, 1);
-    }
+    const int v = L.node[node_base(l) + (item >> logS)];
+    if (!(v & gate)) continue;
+    const int a = item & (S - 1);
+    const int nx = v & 255, ny = (v >> 8) & 63;
+    if (vertical_taps) lap4_inplace<kPost>(tile + (ny + S / 2 - 2) * P + nx + a, P);
+    else lap4_inplace<kPost>(tile + (ny + a) * P + nx + S / 2 - 2, 1);
   }
 }
 
-// DC Haar pyramid over the children of every split node of edge 2^logS
+// DC Haar pyramid over the children of every split node of edge 8 << l
 // (src/encode.c:1497-1510 forward; the inverse applies the same kernel with
 // the two middle terms swapped, cf. od_quantize_haar_dc_level :1651).
-template <bool kInverse, class SbCtx>
-__device__ __forceinline__ void haar_dc_level(int* tile, const unsigned char* leaf, const SbCtx& s,
-                                              int logS) {
-  const int S = 1 << logS;
-  const int per_row = SbCtx::B >> logS;
-  const int items = per_row * per_row;
-  for (int item = threadIdx.x; item < items; item += kThreads) {
-    int nx = (item & (per_row - 1)) * S, ny = (item >> (SbCtx::logB - logS)) * S;
-    if (!node_is_split(leaf, s, nx, ny, logS)) continue;
-    int* p00 = tile + ny * s.P + nx;
+template <bool kInverse, int P>
+__device__ __forceinline__ void haar_dc_level(int* tile, const SbLists& L, int l) {
+  const int S = 8 << l;
+  for (int item = threadIdx.x; item < L.nnode[l]; item += kThreads) {
+    const int v = L.node[node_base(l) + item];
+    int* p00 = tile + ((v >> 8) & 63) * P + (v & 255);
     int* p01 = p00 + S / 2;
-    int* p10 = p00 + (S / 2) * s.P;
+    int* p10 = p00 + (S / 2) * P;
     int* p11 = p10 + S / 2;
     int ll = *p00, hl, lh, hh = *p11;
     // OD_HAAR_KERNEL(ll, lh, hl, hh), src/tf.h:35-46
@@ -238,20 +288,12 @@ __device__ __forceinline__ void haar_dc_level(int* tile, const unsigned char* le
   }
 }
 
-__device__ __forceinline__ unsigned leaf_size_mask(const unsigned char* leaf) {
-  unsigned m = 0;
-  // 64 entries; every thread computes the same mask (broadcast reads).
-#pragma unroll 8
-  for (int i = 0; i < 64; i++) m |= 1u << leaf[i];
-  return m;
-}
-
 // ---------------------------------------------------------------------------
 // Forward kernel.  grid = (nhsb*sb_rows, nplanes, nframes).
 // ---------------------------------------------------------------------------
 template <int XDEC, bool kTma>
 __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, const PlaneXform& pl,
-                                                int* tile_s, unsigned char* leaf, const CUtensorMap* map,
+                                                int* tile_s, SbLists& lists, const CUtensorMap* map,
                                                 unsigned char* raw, uint64_t* bar) {
   constexpr int B = kMaxB >> XDEC;
   constexpr int T = B + 2 * kHalo;
@@ -271,8 +313,10 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
       mbar_expect_tx(bar, RawTile<XDEC>::bytes);
       tma_load_3d(raw, map, s.x0 - RawTile<XDEC>::lead, s.y0 - kHalo, fr, bar);
     }
-    load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, XDEC);
-    __syncthreads();  // barrier initialised before anybody polls it
+    // the work lists are built while the copy is in flight; the __syncthreads inside also
+    // orders the barrier initialisation before anybody polls it
+    build_lists<XDEC>(lists, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, s.x0, s.y0,
+                      prm.pic_w, prm.pic_h);
     mbar_wait(bar, 0);
     for (int i = threadIdx.x; i < T * (T / 4); i += kThreads) {
       int r = i / (T / 4), c4 = (i - r * (T / 4)) * 4;
@@ -286,7 +330,8 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
       t[3] = ((int)(w >> 24) - 128) * 16;
     }
   } else {
-    load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, XDEC);
+    build_lists<XDEC>(lists, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, s.x0, s.y0,
+                      prm.pic_w, prm.pic_h);
     const uint8_t* src = pl.pixels + fr * pl.pixel_frame_pitch;
     for (int i = threadIdx.x; i < T * T; i += kThreads) {
       int r = i / T, c = i - r * T;
@@ -314,20 +359,29 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
     __syncthreads();
   }
   int* tile = tile_s + kHalo * P + kHalo;
-  // Top-down split prefilters.
+  // Top-down split prefilters (levels without split nodes cost nothing).
 #pragma unroll 1
-  for (int logS = Sb::logB; logS >= 3; logS--) {
-    split_filter_level<false>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, true);
+  for (int l = Sb::logB - 3; l >= 0; l--) {
+    if (lists.nnode[l] == 0) continue;
+    split_filter_level<false, P>(tile, lists, l, true);
     __syncthreads();
-    split_filter_level<false>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, false);
+    split_filter_level<false, P>(tile, lists, l, false);
     __syncthreads();
   }
-  const unsigned mask = leaf_size_mask(leaf);
-  transform_all_leaves<true>(tile, leaf, s, mask);
+#ifdef DAALA_DEBUG_LISTS
+  if (threadIdx.x == 0 && XDEC == 1 && sbx == 1 && sby == 1 && blockIdx.y == 1) {
+    printf("chroma lists: nblk %d %d %d %d %d nnode %d %d %d %d\n", lists.nblk[0], lists.nblk[1], lists.nblk[2],
+           lists.nblk[3], lists.nblk[4], lists.nnode[0], lists.nnode[1], lists.nnode[2], lists.nnode[3]);
+    for (int c = 0; c < 4; c++) for (int i = 0; i < lists.nblk[c]; i++) printf("blk c%d (%d,%d)\n", c, lists.blk[blk_base(c) + i] & 255, lists.blk[blk_base(c) + i] >> 8);
+    for (int l = 0; l < 3; l++) for (int i = 0; i < lists.nnode[l]; i++) printf("node l%d (%d,%d) gates %x\n", l, lists.node[node_base(l) + i] & 255, (lists.node[node_base(l) + i] >> 8) & 63, lists.node[node_base(l) + i] >> 14);
+  }
+#endif
+  transform_all_leaves<true, P, Sb::logB>(tile, lists);
   if (prm.haar_dc) {
 #pragma unroll 1
-    for (int logS = 3; logS <= Sb::logB; logS++) {
-      haar_dc_level<false>(tile, leaf, s, logS);
+    for (int l = 0; l <= Sb::logB - 3; l++) {
+      if (lists.nnode[l] == 0) continue;
+      haar_dc_level<false, P>(tile, lists, l);
       __syncthreads();
     }
   }
@@ -341,10 +395,10 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
 __global__ void __launch_bounds__(kThreads, 2)
 k_forward_sb(const __grid_constant__ FrameXformParams prm) {
   __shared__ int tile_s[kMaxT * kMaxPitch];
-  __shared__ unsigned char leaf[64];
+  __shared__ SbLists lists;
   const PlaneXform& pl = prm.plane[blockIdx.y];
-  if (pl.xdec == 0) forward_sb_body<0, false>(prm, pl, tile_s, leaf, nullptr, nullptr, nullptr);
-  else forward_sb_body<1, false>(prm, pl, tile_s, leaf, nullptr, nullptr, nullptr);
+  if (pl.xdec == 0) forward_sb_body<0, false>(prm, pl, tile_s, lists, nullptr, nullptr, nullptr);
+  else forward_sb_body<1, false>(prm, pl, tile_s, lists, nullptr, nullptr, nullptr);
 }
 
 // Same with the input window staged by TMA (the default when the planes meet
@@ -355,13 +409,13 @@ k_forward_sb_tma(const __grid_constant__ FrameXformParams prm, const __grid_cons
   __shared__ int tile_s[kMaxT * kMaxPitch];
   __shared__ __align__(128) unsigned char raw[RawTile<0>::bytes];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ unsigned char leaf[64];
+  __shared__ SbLists lists;
   const PlaneXform& pl = prm.plane[blockIdx.y];
   // the descriptor must stay in parameter space: select between the three
   // kernel parameters, never index an array of them (that would copy to local)
   const CUtensorMap* map = blockIdx.y == 0 ? &map0 : (blockIdx.y == 1 ? &map1 : &map2);
-  if (pl.xdec == 0) forward_sb_body<0, true>(prm, pl, tile_s, leaf, map, raw, &bar);
-  else forward_sb_body<1, true>(prm, pl, tile_s, leaf, map, raw, &bar);
+  if (pl.xdec == 0) forward_sb_body<0, true>(prm, pl, tile_s, lists, map, raw, &bar);
+  else forward_sb_body<1, true>(prm, pl, tile_s, lists, map, raw, &bar);
 }
 
 // ---------------------------------------------------------------------------
@@ -369,7 +423,7 @@ k_forward_sb_tma(const __grid_constant__ FrameXformParams prm, const __grid_cons
 // ---------------------------------------------------------------------------
 template <int XDEC>
 __device__ __forceinline__ void inverse_sb_body(const FrameXformParams& prm, const PlaneXform& pl,
-                                                int* tile, unsigned char* leaf) {
+                                                int* tile, SbLists& lists) {
   constexpr int B = kMaxB >> XDEC;
   constexpr int P = B + 5;
   using Sb = SbCtxT<B, P>;
@@ -378,28 +432,29 @@ __device__ __forceinline__ void inverse_sb_body(const FrameXformParams& prm, con
   Sb s;
   s.x0 = sbx * B;
   s.y0 = sby * B;
-  load_leaf_map(leaf, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, XDEC);
   const int32_t* srcp = pl.coeffs + fr * pl.coeff_frame_pitch + (size_t)s.y0 * pl.coeff_stride + s.x0;
   for (int i = threadIdx.x; i < B * B; i += kThreads) {
     int r = i / B, c = i % B;
     tile[r * P + c] = srcp[(size_t)r * pl.coeff_stride + c];
   }
-  __syncthreads();
+  build_lists<XDEC>(lists, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, s.x0, s.y0,
+                    prm.pic_w, prm.pic_h);  // ends with a CTA barrier: tile and lists are visible
   if (prm.haar_dc) {
 #pragma unroll 1
-    for (int logS = Sb::logB; logS >= 3; logS--) {
-      haar_dc_level<true>(tile, leaf, s, logS);
+    for (int l = Sb::logB - 3; l >= 0; l--) {
+      if (lists.nnode[l] == 0) continue;
+      haar_dc_level<true, P>(tile, lists, l);
       __syncthreads();
     }
   }
-  const unsigned mask = leaf_size_mask(leaf);
-  transform_all_leaves<false>(tile, leaf, s, mask);
+  transform_all_leaves<false, P, Sb::logB>(tile, lists);
   // Bottom-up split postfilters: vertical edge first, then horizontal.
 #pragma unroll 1
-  for (int logS = 3; logS <= Sb::logB; logS++) {
-    split_filter_level<true>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, false);
+  for (int l = 0; l <= Sb::logB - 3; l++) {
+    if (lists.nnode[l] == 0) continue;
+    split_filter_level<true, P>(tile, lists, l, false);
     __syncthreads();
-    split_filter_level<true>(tile, leaf, s, logS, prm.pic_w, prm.pic_h, true);
+    split_filter_level<true, P>(tile, lists, l, true);
     __syncthreads();
   }
   int32_t* dst = pl.lapped + fr * pl.lapped_frame_pitch + (size_t)s.y0 * pl.lapped_stride + s.x0;
@@ -412,10 +467,10 @@ __device__ __forceinline__ void inverse_sb_body(const FrameXformParams& prm, con
 __global__ void __launch_bounds__(kThreads)
 k_inverse_sb(const __grid_constant__ FrameXformParams prm) {
   __shared__ int tile_s[kMaxB * (kMaxB + 5)];
-  __shared__ unsigned char leaf[64];
+  __shared__ SbLists lists;
   const PlaneXform& pl = prm.plane[blockIdx.y];
-  if (pl.xdec == 0) inverse_sb_body<0>(prm, pl, tile_s, leaf);
-  else inverse_sb_body<1>(prm, pl, tile_s, leaf);
+  if (pl.xdec == 0) inverse_sb_body<0>(prm, pl, tile_s, lists);
+  else inverse_sb_body<1>(prm, pl, tile_s, lists);
 }
 
 // ---------------------------------------------------------------------------
