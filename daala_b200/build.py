@@ -24,6 +24,10 @@ FLAGS = [
 ]
 
 
+# extra nvcc flags for tuning experiments, e.g. DAALA_B200_NVCC_FLAGS="-DDAALA_XFORM_THREADS=64"
+FLAGS += os.environ.get("DAALA_B200_NVCC_FLAGS", "").split()
+
+
 def _deps_mtime():
     m = 0.0
     for d, _, files in os.walk(CSRC):

@@ -35,7 +35,16 @@
 
 namespace daala_b200 {
 
-constexpr int kThreads = 256;
+#ifndef DAALA_XFORM_THREADS
+#define DAALA_XFORM_THREADS 64
+#endif
+// Threads per superblock CTA.  Small CTAs win (measured 256 -> 64: forward 2.05 -> 1.05 ms per
+// 16 4K frames): the phases of one superblock are latency chains separated by barriers, so the
+// SM is kept busy by MANY independent superblocks (8 CTAs/SM at 128 registers, 26 KB smem each)
+// rather than by many warps of one.
+constexpr int kThreads = DAALA_XFORM_THREADS;
+constexpr int kPostThreads = 128;               // superblock-edge postfilter kernel
+constexpr int kCtasPerSm = 512 / kThreads;      // 128 registers per thread
 constexpr int kMaxB = 64;            // superblock edge in luma pixels
 constexpr int kHalo = 2;             // lapping reaches 2 samples across an edge
 constexpr int kMaxT = kMaxB + 2 * kHalo;
@@ -121,7 +130,7 @@ struct SbLists {
   unsigned short node[64 + 16 + 4 + 1];
   int nblk[5];
   int nnode[4];
-  unsigned char wcnt[kThreads / 32][9];  // per-warp counts while the lists are being built
+  unsigned char wcnt[8][9];  // per-(virtual-)warp counts while the lists are being built
 };
 __device__ __forceinline__ constexpr int blk_base(int c) { return c == 0 ? 0 : c == 1 ? 256 : c == 2 ? 320 : c == 3 ? 336 : 340; }
 __device__ __forceinline__ constexpr int node_base(int l) { return l == 0 ? 0 : l == 1 ? 64 : l == 2 ? 80 : 84; }
@@ -136,67 +145,82 @@ __device__ __forceinline__ void build_lists(SbLists& L, const unsigned char* bsi
                                             int sby, int x0, int y0, int pic_w, int pic_h) {
   constexpr int B = kMaxB >> XDEC;
   constexpr int U = B / 4;  // 4x4 units per side
-  constexpr int kWarps = kThreads / 32;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  constexpr int kVWarps = 256 / 32;               // the 256 luma units, 32 per (virtual) warp
+  constexpr int kIters = 256 / kThreads;          // unit slices each thread walks
+  const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const bool active = t < U * U;
-  const int ux = t % U, uy = t / U;
-  int c = -1;
-  if (active) {
-    // the 8x8-luma unit covering this 4x4 unit: luma (ux>>1, uy>>1), 4:2:0 chroma (ux, uy)
-    const int bx = XDEC ? ux : ux >> 1, by = XDEC ? uy : uy >> 1;
-    const int obs = bsize[(sby * 8 + by) * bstride + sbx * 8 + bx];
-    c = (obs > XDEC ? obs : XDEC) - XDEC;   // log2(n) - 2
-  }
-  const unsigned short pos = (unsigned short)(((uy * 4) << 8) | (ux * 4));
+  int c_it[kIters];
   // category 0..4: leaf origin of class c; 5..8: split node of edge 8 << (cat - 5)
-  int rank[9];
-  bool flag[9];
+  unsigned short rank_it[kIters][9];
+  unsigned flags_it[kIters];
 #pragma unroll
-  for (int cat = 0; cat < 9; cat++) {
-    bool f = false;
+  for (int it = 0; it < kIters; it++) {
+    const int t = it * kThreads + threadIdx.x, vwarp = t >> 5;
+    const bool active = t < U * U;
+    const int ux = t % U, uy = t / U;
+    int c = -1;
     if (active) {
-      if (cat < 5) {
-        const int n4 = 1 << cat;
-        f = c == cat && !(ux & (n4 - 1)) && !(uy & (n4 - 1));
-      } else {
-        const int l = cat - 5, S = 8 << l, s4 = 2 << l;
-        // a node exists at unit positions aligned to its size and is split iff the leaf at its
-        // corner is smaller (src/encode.c:1466: the block size is read at the corner)
-        f = S <= B && !(ux & (s4 - 1)) && !(uy & (s4 - 1)) && c + 2 < 3 + l;
-      }
+      // the 8x8-luma unit covering this 4x4 unit: luma (ux>>1, uy>>1), 4:2:0 chroma (ux, uy)
+      const int bx = XDEC ? ux : ux >> 1, by = XDEC ? uy : uy >> 1;
+      const int obs = bsize[(sby * 8 + by) * bstride + sbx * 8 + bx];
+      c = (obs > XDEC ? obs : XDEC) - XDEC;   // log2(n) - 2
     }
-    const unsigned b = __ballot_sync(0xffffffffu, f);
-    flag[cat] = f;
-    rank[cat] = __popc(b & lt);
-    if (lane == 0) L.wcnt[warp][cat] = (unsigned char)__popc(b);
+    c_it[it] = c;
+    unsigned fl = 0;
+#pragma unroll
+    for (int cat = 0; cat < 9; cat++) {
+      bool f = false;
+      if (active) {
+        if (cat < 5) {
+          const int n4 = 1 << cat;
+          f = c == cat && !(ux & (n4 - 1)) && !(uy & (n4 - 1));
+        } else {
+          const int l = cat - 5, S = 8 << l, s4 = 2 << l;
+          // a node exists at unit positions aligned to its size and is split iff the leaf at its
+          // corner is smaller (src/encode.c:1466: the block size is read at the corner)
+          f = S <= B && !(ux & (s4 - 1)) && !(uy & (s4 - 1)) && c + 2 < 3 + l;
+        }
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, f);
+      fl |= (unsigned)f << cat;
+      rank_it[it][cat] = (unsigned short)__popc(b & lt);
+      if (lane == 0) L.wcnt[vwarp][cat] = (unsigned char)__popc(b);
+    }
+    flags_it[it] = fl;
   }
   __syncthreads();
 #pragma unroll
-  for (int cat = 0; cat < 9; cat++) {
-    int off = 0, total = 0;
+  for (int it = 0; it < kIters; it++) {
+    const int t = it * kThreads + threadIdx.x, vwarp = t >> 5;
+    const int ux = t % U, uy = t / U;
+    const unsigned short pos = (unsigned short)(((uy * 4) << 8) | (ux * 4));
 #pragma unroll
-    for (int w = 0; w < kWarps; w++) {
-      const int n = L.wcnt[w][cat];
-      if (w < warp) off += n;
-      total += n;
-    }
-    if (t == 0) {
-      if (cat < 5) L.nblk[cat] = total; else L.nnode[cat - 5] = total;
-    }
-    if (flag[cat]) {
-      if (cat < 5) {
-        L.blk[blk_base(cat) + off + rank[cat]] = pos;
-      } else {
-        const int S = 8 << (cat - 5);
-        unsigned short v = pos;
-        // gates compare PLANE coordinates with the LUMA picture size (src/encode.c:1487-1488)
-        if (x0 + ux * 4 + S <= pic_w) v |= kGateH;
-        if (y0 + uy * 4 + S <= pic_h) v |= kGateV;
-        L.node[node_base(cat - 5) + off + rank[cat]] = v;
+    for (int cat = 0; cat < 9; cat++) {
+      int off = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < kVWarps; w++) {
+        const int n = L.wcnt[w][cat];
+        if (w < vwarp) off += n;
+        total += n;
+      }
+      if (t == 0) {
+        if (cat < 5) L.nblk[cat] = total; else L.nnode[cat - 5] = total;
+      }
+      if (flags_it[it] & (1u << cat)) {
+        if (cat < 5) {
+          L.blk[blk_base(cat) + off + rank_it[it][cat]] = pos;
+        } else {
+          const int S = 8 << (cat - 5);
+          unsigned short v = pos;
+          // gates compare PLANE coordinates with the LUMA picture size (src/encode.c:1487-1488)
+          if (x0 + ux * 4 + S <= pic_w) v |= kGateH;
+          if (y0 + uy * 4 + S <= pic_h) v |= kGateV;
+          L.node[node_base(cat - 5) + off + rank_it[it][cat]] = v;
+        }
       }
     }
   }
+  (void)c_it;
   __syncthreads();
 }
 
@@ -392,7 +416,7 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 k_forward_sb(const __grid_constant__ FrameXformParams prm) {
   __shared__ int tile_s[kMaxT * kMaxPitch];
   __shared__ SbLists lists;
@@ -403,7 +427,7 @@ k_forward_sb(const __grid_constant__ FrameXformParams prm) {
 
 // Same with the input window staged by TMA (the default when the planes meet
 // the 16-byte alignment rules of tensor maps).
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 k_forward_sb_tma(const __grid_constant__ FrameXformParams prm, const __grid_constant__ CUtensorMap map0,
                  const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2) {
   __shared__ int tile_s[kMaxT * kMaxPitch];
@@ -464,7 +488,7 @@ __device__ __forceinline__ void inverse_sb_body(const FrameXformParams& prm, con
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 k_inverse_sb(const __grid_constant__ FrameXformParams prm) {
   __shared__ int tile_s[kMaxB * (kMaxB + 5)];
   __shared__ SbLists lists;
@@ -491,7 +515,7 @@ __device__ __forceinline__ void sb_postfilter_store_body(const FrameXformParams&
   const int32_t* lap = pl.lapped + fr * pl.lapped_frame_pitch;
   const int x0 = sbx * B, y0 = sby * B;
   const int pw = prm.nhsb * B, ph = prm.nvsb * B;
-  for (int i = threadIdx.x; i < T * T; i += kThreads) {
+  for (int i = threadIdx.x; i < T * T; i += kPostThreads) {
     int r = i / T, c = i - r * T;
     int gx = x0 + c - kHalo, gy = y0 + r - kHalo;
     int v = 0;
@@ -500,20 +524,20 @@ __device__ __forceinline__ void sb_postfilter_store_body(const FrameXformParams&
   }
   __syncthreads();
   const bool left = sbx > 0, right = sbx + 1 < prm.nhsb;
-  for (int i = threadIdx.x; i < 2 * T; i += kThreads) {
+  for (int i = threadIdx.x; i < 2 * T; i += kPostThreads) {
     int e = i >= T, r = i - e * T;
     if (e == 0 ? left : right) lap4_inplace<true>(tile_s + r * P + (e ? B : 0), 1);
   }
   __syncthreads();
   const bool top = sby > 0, bottom = sby + 1 < prm.nvsb;
-  for (int i = threadIdx.x; i < 2 * B; i += kThreads) {
+  for (int i = threadIdx.x; i < 2 * B; i += kPostThreads) {
     int c = i % B + kHalo, e = i / B;
     if (e == 0 ? top : bottom) lap4_inplace<true>(tile_s + (e ? B : 0) * P + c, P);
   }
   __syncthreads();
   uint8_t* dst = pl.pixels_out + fr * pl.pixel_out_frame_pitch + (size_t)y0 * pl.pixel_out_stride + x0;
   // Four pixels per thread, packed into one 32-bit store.
-  for (int i = threadIdx.x; i < B * B / 4; i += kThreads) {
+  for (int i = threadIdx.x; i < B * B / 4; i += kPostThreads) {
     int r = i / (B / 4), c4 = (i % (B / 4)) * 4;
     const int* p = tile_s + (r + kHalo) * P + c4 + kHalo;
     unsigned w = 0;
@@ -527,7 +551,7 @@ __device__ __forceinline__ void sb_postfilter_store_body(const FrameXformParams&
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPostThreads)
 k_sb_postfilter_store(const __grid_constant__ FrameXformParams prm) {
   __shared__ int tile_s[kMaxT * kMaxPitch];
   const PlaneXform& pl = prm.plane[blockIdx.y];
@@ -676,7 +700,7 @@ int daala_b200_launch_forward_no_tma(const FrameXformParams* prm, int nplanes, c
 int daala_b200_launch_inverse(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
   dim3 grid(prm->nhsb * prm->sb_rows, nplanes, prm->nframes);
   k_inverse_sb<<<grid, kThreads, 0, stream>>>(*prm);
-  k_sb_postfilter_store<<<grid, kThreads, 0, stream>>>(*prm);
+  k_sb_postfilter_store<<<grid, kPostThreads, 0, stream>>>(*prm);
   return (int)cudaGetLastError();
 }
 
@@ -688,7 +712,7 @@ int daala_b200_launch_inverse_lapped_only(const FrameXformParams* prm, int nplan
 
 int daala_b200_launch_sb_postfilter_store(const FrameXformParams* prm, int nplanes, cudaStream_t stream) {
   dim3 grid(prm->nhsb * prm->sb_rows, nplanes, prm->nframes);
-  k_sb_postfilter_store<<<grid, kThreads, 0, stream>>>(*prm);
+  k_sb_postfilter_store<<<grid, kPostThreads, 0, stream>>>(*prm);
   return (int)cudaGetLastError();
 }
 
