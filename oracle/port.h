@@ -44,4 +44,15 @@ int32_t port_mc_compute_sad8(const unsigned char *src, int systride, const unsig
 int32_t port_mc_compute_satd8(int ln, const unsigned char *src, int systride, const unsigned char *ref,
  int rystride);
 
+/* port_tf.c -- src/tf.c, src/intra.c */
+void port_tf_up_h_lp(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int dx, int n);
+void port_tf_up_v_lp(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int dy, int n);
+void port_tf_up_hv_lp(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int dx, int dy, int n);
+void port_tf_up_hv(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int n);
+void port_tf_down_hv(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int n);
+void port_hv_intra_pred(od_coeff *pred, const od_coeff *d, int w, int bx, int by,
+ const unsigned char *bsize, int bstride, int bs);
+void port_resample_luma_coeffs_420(od_coeff *chroma_pred, int cpstride, const od_coeff *decoded_luma,
+ int dlstride, int bs, int luma_is_4x4);
+
 #endif

@@ -13,4 +13,6 @@
 #define X_FROM_CODING(dst, stride, src, n) port_coding_order_to_raster(dst, stride, src, n)
 #define X_PVQ_THETA(out, x0, r0, n, q, y, it, mt, k, beta, sd, kf, pli, qm, qmi, lam) \
   port_pvq_theta(out, x0, r0, n, q, y, it, mt, k, beta, sd, kf, pli, qm, qmi, lam)
+#define X_HV_PRED(pred, d, w, bx, by, bsize, bstride, bs) port_hv_intra_pred(pred, d, w, bx, by, bsize, bstride, bs)
+#define X_CFL_PRED(pred, n, luma, lw, bs, obs) port_resample_luma_coeffs_420(pred, n, luma, lw, bs, (obs) == 0)
 #include "pipeline_driver.inc"

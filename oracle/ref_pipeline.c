@@ -22,4 +22,8 @@ int oracle_ref_pvq_theta(od_coeff *out, const od_coeff *x0, const od_coeff *r0,
 /* speed = 1: the reference's closed-form rate model (src/pvq_encoder.c:252-264) */
 #define X_PVQ_THETA(out, x0, r0, n, q, y, it, mt, k, beta, sd, kf, pli, qm, qmi, lam) \
   oracle_ref_pvq_theta(out, x0, r0, n, q, y, it, mt, k, beta, sd, 1, kf, pli, NULL, qm, qmi, lam, 1)
+#include "intra.h"
+#define X_HV_PRED(pred, d, w, bx, by, bsize, bstride, bs) \
+  od_hv_intra_pred(pred, d, w, bx, by, (unsigned char *)(bsize), bstride, bs)
+#define X_CFL_PRED(pred, n, luma, lw, bs, obs) od_resample_luma_coeffs(pred, n, luma, lw, 1, 1, bs, obs)
 #include "pipeline_driver.inc"

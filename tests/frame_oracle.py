@@ -46,3 +46,19 @@ def pvq_plane(lib, prefix, d, md, geom, pli, bsize, q0, is_keyframe, use_masking
        int(is_keyframe), int(use_masking), ctypes.c_double(lam), addr(np.ascontiguousarray(qm)),
        addr(np.ascontiguousarray(qm_inv)), addr(q4), addr(stats))
     return d, stats
+
+
+def pvq_plane_pred(lib, prefix, d, geom, pli, bsize, q0, use_masking, lam, qm, qm_inv, qm_q4, luma_d=None):
+    """Keyframe quantisation WITH the reference's predictors: luma (pli == 0) uses
+    od_hv_intra_pred from already quantised neighbours, chroma uses CfL from the
+    quantised luma plane `luma_d`.  Returns (d_quantised, stats[5])."""
+    d = np.ascontiguousarray(d, dtype=np.int32).copy()
+    bs = np.ascontiguousarray(bsize, dtype=np.uint8)
+    stats = np.zeros(5, np.float64)
+    q4 = np.ascontiguousarray(qm_q4[pli], dtype=np.uint8)
+    lp = addr(np.ascontiguousarray(luma_d, dtype=np.int32)) if luma_d is not None else None
+    fn = getattr(lib, "oracle_%s_pvq_plane_pred" % prefix)
+    fn(addr(d), None, geom.nhsb, geom.nvsb, geom.xdec[pli], pli, addr(bs), bs.shape[1], int(q0), 1,
+       int(use_masking), ctypes.c_double(lam), addr(np.ascontiguousarray(qm)), addr(np.ascontiguousarray(qm_inv)),
+       addr(q4), addr(stats), 1 if pli == 0 else 0, lp)
+    return d, stats

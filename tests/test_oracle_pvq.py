@@ -116,3 +116,32 @@ def test_frame_pvq_driver_port_matches_reference(port, ref):
             assert np.array_equal(a, b)
             assert np.array_equal(sa, sb)
             assert sa[0] > 0 and not np.array_equal(a, d)
+
+
+def test_keyframe_prediction_driver_port_matches_reference(port, ref):
+    """Luma H/V intra prediction + chroma CfL inside the frame PVQ driver."""
+    from daala_b200 import synth
+    from daala_b200.frame import Geometry
+    from tests import frame_oracle
+    geom = Geometry(192, 128)
+    planes, _ = synth.frame(192, 128, f=1)
+    planes = synth.pad_planes(planes, geom)
+    bsize = synth.block_size_map(geom, "mixed", seed=2)
+    qm, qm_inv = pvq_cases.reference_qm(ref)
+    q4 = np.full((3, 30), 20, np.uint8)
+    luma = {}
+    for lib, prefix in ((ref, "ref"), (port, "port")):
+        d0 = frame_oracle.forward_plane(lib, prefix, planes[0], geom, 0, bsize, 1)
+        luma[prefix] = frame_oracle.pvq_plane_pred(lib, prefix, d0, geom, 0, bsize, 45, 1, 0.147, qm, qm_inv, q4)
+    assert np.array_equal(luma["ref"][0], luma["port"][0]) and np.array_equal(luma["ref"][1], luma["port"][1])
+    nopred = frame_oracle.pvq_plane(ref, "ref", frame_oracle.forward_plane(ref, "ref", planes[0], geom, 0, bsize, 1),
+                                    None, geom, 0, bsize, 45, 1, 1, 0.147, qm, qm_inv, q4)
+    assert not np.array_equal(nopred[0], luma["ref"][0])  # the prediction changes decisions
+    assert luma["ref"][1][2] > -luma["ref"][1][3]  # some bands chose a reference (itheta >= 0)
+    for pli in (1, 2):
+        res = {}
+        for lib, prefix in ((ref, "ref"), (port, "port")):
+            dc = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
+            res[prefix] = frame_oracle.pvq_plane_pred(lib, prefix, dc, geom, pli, bsize, 45, 1, 0.147, qm, qm_inv, q4,
+                                                      luma_d=luma[prefix][0])
+        assert np.array_equal(res["ref"][0], res["port"][0]) and np.array_equal(res["ref"][1], res["port"][1])
