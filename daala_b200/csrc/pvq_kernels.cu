@@ -640,6 +640,165 @@ __global__ void k_coding_order_scatter(const __grid_constant__ daala_b200_pvq_pa
   }
 }
 
+// ---------------------------------------------------------------------------
+// Keyframe luma with the reference's H/V intra prediction (od_hv_intra_pred,
+// src/intra.c:37): the prediction of a block is row 0 / column 0 of the
+// QUANTISED coefficients of its top / left neighbour of the same size, so
+// blocks form dependency chains.  One warp owns one block and
+// runs its whole chain link: wait for the neighbours' done flags, build the
+// prediction, quantise every band (group-cooperative quantiser, 32 lanes),
+// write the reconstruction into the coefficient plane, publish its own flag.
+// Blocks are listed in raster order of their origin, so a block's neighbours
+// always have smaller indices: the lowest unfinished block is resident and
+// never waits on a later one (CTAs are dispatched in index order), hence no
+// deadlock.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(128)
+k_pvq_luma_intra(const __grid_constant__ daala_b200_pvq_params prm, const int32_t* __restrict__ dep_top,
+                 const int32_t* __restrict__ dep_left, int* done, int epoch, int nblocks) {
+  const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blk >= nblocks) return;
+  const Group<32, 4> grp;
+  const daala_b200_pvq_block b = prm.blocks[blk];
+  const int bs = b.bs, ln = bs + 2, n = 1 << ln;
+  const int len = ln >= 5 ? 512 : 1 << (2 * ln);
+  const int stride = prm.plane_stride[0];
+  int32_t* d = prm.coef_plane[0] + b.frame * prm.plane_frame_pitch[0] + (size_t)b.y0 * stride + b.x0;
+  const int top = dep_top[blk], left = dep_left[blk];
+  if (lane == 0) {
+    if (top >= 0) while (ld_acquire(done + top) != epoch) __nanosleep(64);
+    if (left >= 0) while (ld_acquire(done + left) != epoch) __nanosleep(64);
+  }
+  __syncwarp();
+  // g1/g2: energies of the neighbours' first three AC terms decide whether the
+  // low-frequency row or column is predicted (double sums of exact integers)
+  double g1 = 0, g2 = 0;
+  if (top >= 0) for (int i = 1; i < 4; i++) { double v = d[-(ptrdiff_t)n * stride + i]; g1 += v * v; }
+  if (left >= 0) for (int i = 1; i < 4; i++) { double v = d[(ptrdiff_t)i * stride - n]; g2 += v * v; }
+  const bool low_from_top = g1 > g2;
+  int32_t* vin = prm.in + b.coef_off;
+  int32_t* vref = prm.ref + b.coef_off;
+  for (int i = lane; i < len; i += 32) {
+    int r = 0, c = 0;
+    if (i) {
+      int v, sh;
+      if (i < 16) { v = kScan4[i - 1]; sh = 2; }
+      else if (i < 64) { v = kScan8[i - 16]; sh = 3; }
+      else if (i < 256) { v = kScan16[i - 64]; sh = 4; }
+      else { v = kScan32[i - 256]; sh = 5; }
+      r = v >> sh;
+      c = v & ((1 << sh) - 1);
+    }
+    vin[i] = d[(size_t)r * stride + c];
+    int32_t p = 0;
+    if (r == 0 && c > 0 && top >= 0 && (c >= 4 || low_from_top)) p = d[-(ptrdiff_t)n * stride + c];
+    if (c == 0 && r > 0 && left >= 0 && (r >= 4 || !low_from_top)) p = d[(ptrdiff_t)r * stride - n];
+    vref[i] = p;
+  }
+  __syncwarp();
+  const int nb = num_bands(bs);
+  double sd = 0;
+  for (int band = 0; band < nb; band++) {
+    const int start = band_start(band);
+    const int bn = band_start(band + 1) - start;
+    const size_t off = (size_t)b.coef_off + start;
+    int qidx = bs * (bs + 1) + (band + 1) - (band + 1) / 3;
+    int q = (prm.q0 * prm.pvq_qm_q4[0][qidx]) >> 4;
+    if (q < 1) q = 1;
+    const int beta = (prm.use_masking && bs > 0) ? kBeta15 : kBeta1;
+    const int qoff = ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
+    int itheta, max_theta, k;
+    double skip_term;
+    int gain = quantise_band_coop<32, 4, false>(grp, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off,
+                                                &itheta, &max_theta, &k, beta, &skip_term, 1, 0, prm.qm + qoff,
+                                                prm.qm_inv + qoff, prm.pvq_norm_lambda);
+    sd += skip_term;
+    if (lane == 0) {
+      const size_t r = (size_t)blk * 9 + band;
+      prm.res_gain[r] = gain;
+      prm.res_theta[r] = itheta;
+      prm.res_max_theta[r] = max_theta;
+      prm.res_k[r] = k;
+      prm.res_skip_term[r] = skip_term;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    prm.res_skip_diff[blk] = sd;
+    prm.res_flip[blk] = 0;
+    prm.res_dc[blk] = 0;
+    prm.out[b.coef_off] = vin[0];
+  }
+  // od_init_skipped_coeffs + od_coding_order_to_raster (DC untouched on keyframes)
+  const int32_t* vout = prm.out + b.coef_off;
+  if (ln >= 5) {
+    for (int i = lane; i < n * n; i += 32) if (i) d[(size_t)(i >> ln) * stride + (i & (n - 1))] = 0;
+    __syncwarp();
+  }
+  for (int i = lane + 1; i < len; i += 32) {
+    int v, sh;
+    if (i < 16) { v = kScan4[i - 1]; sh = 2; }
+    else if (i < 64) { v = kScan8[i - 16]; sh = 3; }
+    else if (i < 256) { v = kScan16[i - 64]; sh = 4; }
+    else { v = kScan32[i - 256]; sh = 5; }
+    d[(size_t)(v >> sh) * stride + (v & ((1 << sh) - 1))] = vout[i];
+  }
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) st_release(done + blk, epoch);
+}
+
+// Chroma-from-luma prediction of keyframe chroma blocks (od_resample_luma_coeffs,
+// src/intra.c:72, 4:2:0): the low-frequency quarter of the quantised luma block,
+// or -- when the luma area is coded as four 4x4 blocks -- their 2x2 TF merge
+// (od_tf_up_hv_lp, src/tf.c:82) scaled by OD_CFL_SCALING4.  One thread per
+// coefficient; writes an n x n block into the chroma-sized prediction plane.
+__global__ void k_cfl_pred(const __grid_constant__ daala_b200_pvq_params prm, int32_t* pred_plane,
+                           long long pred_frame_pitch, int pred_stride, int nblocks) {
+  const int blk = blockIdx.x;
+  if (blk >= nblocks) return;
+  const daala_b200_pvq_block b = prm.blocks[blk];
+  if (b.pli == 0) return;
+  const int n = 4 << b.bs;
+  const int lstride = prm.plane_stride[0];
+  const int32_t* luma = prm.coef_plane[0] + b.frame * prm.plane_frame_pitch[0] + (size_t)(2 * b.y0) * lstride + 2 * b.x0;
+  int32_t* dst = pred_plane + b.frame * pred_frame_pitch + (size_t)b.y0 * pred_stride + b.x0;
+  if (b.xdec & 0x80) {
+    // four 4x4 luma blocks -> one 4x4 chroma prediction
+    const int scaling4[4][4] = {{128, 128, 100, 36}, {128, 80, 71, 35}, {100, 71, 35, 31}, {36, 35, 31, 18}};
+    if (threadIdx.x < 4) {
+      const int x = threadIdx.x & 1, y = threadIdx.x >> 1;
+      int ll = luma[(size_t)y * lstride + x], lh = luma[(size_t)y * lstride + x + 4];
+      int hl = luma[(size_t)(y + 4) * lstride + x], hh = luma[(size_t)(y + 4) * lstride + x + 4];
+      // OD_HAAR_KERNEL(ll, hl, lh, hh): the reference swaps the middle terms here
+      ll += lh; hh -= hl;
+      int t = (ll - hh) >> 1;
+      hl = t - hl; lh = t - lh;
+      ll -= hl; hh += lh;
+      const int hs = x & 1, vs = y & 1;
+      int r, c;
+      r = 2 * y + vs; c = 2 * x + hs;         dst[(size_t)r * pred_stride + c] = (scaling4[c][r] * ll + 64) >> 7;
+      r = 2 * y + vs; c = 2 * x + 1 - hs;     dst[(size_t)r * pred_stride + c] = (scaling4[c][r] * lh + 64) >> 7;
+      r = 2 * y + 1 - vs; c = 2 * x + hs;     dst[(size_t)r * pred_stride + c] = (scaling4[c][r] * hl + 64) >> 7;
+      r = 2 * y + 1 - vs; c = 2 * x + 1 - hs; dst[(size_t)r * pred_stride + c] = (scaling4[c][r] * hh + 64) >> 7;
+    }
+  } else {
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+      int r = i / n, c = i % n;
+      dst[(size_t)r * pred_stride + c] = luma[(size_t)r * lstride + c];
+    }
+  }
+}
+
 }  // namespace pvq
 }  // namespace daala_b200
 
@@ -703,6 +862,21 @@ int daala_b200_pvq_encode_bands_mode(const daala_b200_pvq_params* prm, const uin
       else launch_coop<4, 32, false>(prm, band_list, count, s);
     }
   }
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_pvq_luma_intra(const daala_b200_pvq_params* prm, const int32_t* dep_top, const int32_t* dep_left,
+                              int32_t* done, int epoch, int nblocks, void* stream) {
+  if (nblocks <= 0) return 0;
+  k_pvq_luma_intra<<<(nblocks * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*prm, dep_top, dep_left, done,
+                                                                                 epoch, nblocks);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_pvq_cfl_pred(const daala_b200_pvq_params* prm, int32_t* pred_plane, long long pred_frame_pitch,
+                            int pred_stride, int nblocks, void* stream) {
+  if (nblocks <= 0) return 0;
+  k_cfl_pred<<<nblocks, 64, 0, (cudaStream_t)stream>>>(*prm, pred_plane, pred_frame_pitch, pred_stride, nblocks);
   return (int)cudaGetLastError();
 }
 

@@ -18,7 +18,7 @@ from .frame import FrameBuffers
 
 class HotPath:
     def __init__(self, geom, nframes=1, device="cuda:0", q0=38, is_keyframe=1, use_masking=1,
-                 lam=pvq.PVQ_LAMBDA, pvq_qm_q4=None, sb_row0=0, sb_rows=None):
+                 lam=pvq.PVQ_LAMBDA, pvq_qm_q4=None, sb_row0=0, sb_rows=None, keyframe_prediction=False):
         self.geom = geom
         self.nframes = nframes
         self.device = torch.device(device)
@@ -30,6 +30,9 @@ class HotPath:
         self.q0, self.is_keyframe, self.use_masking, self.lam = q0, is_keyframe, use_masking, lam
         self.pvq_qm_q4 = pvq_qm_q4 if pvq_qm_q4 is not None else np.full((3, 30), 16, np.uint8)
         self.batch = None
+        # keyframes with the reference's predictors: luma H/V intra (wavefront kernel), chroma CfL
+        self.keyframe_prediction = bool(keyframe_prediction) and bool(is_keyframe)
+        self.batch_luma = self.batch_chroma = self.cfl_plane = None
 
     def set_block_sizes(self, bsizes):
         """bsizes: one map per frame (host numpy).  Builds the block / band
@@ -39,6 +42,20 @@ class HotPath:
             self.fb.bsize[f].copy_(torch.from_numpy(np.ascontiguousarray(b)))
             lists.append(pvq.block_list(b, self.geom, frame=f, sb_row0=self.fb.sb_row0, sb_rows=self.fb.sb_rows))
         blocks = np.concatenate(lists)
+        if self.keyframe_prediction:
+            assert self.fb.sb_row0 == 0 and self.fb.sb_rows == self.geom.nvsb, \
+                "intra prediction chains cross superblock rows: keyframe_prediction needs whole frames per rank"
+            kw = dict(q0=self.q0, is_keyframe=1, use_masking=self.use_masking, lam=self.lam,
+                      pvq_qm_q4=self.pvq_qm_q4, device=self.device)
+            luma = pvq.raster_order(blocks[blocks["pli"] == 0])
+            self.batch_luma = pvq.PvqBatch(luma, self.fb.coeffs, None, **kw)
+            self.batch_luma.setup_intra(list(bsizes), self.geom)
+            chroma = pvq.mark_luma4x4(blocks[blocks["pli"] != 0], list(bsizes))
+            chroma = chroma[np.argsort(chroma["bs"], kind="stable")]
+            self.cfl_plane = torch.zeros_like(self.fb.coeffs[1])
+            self.batch_chroma = pvq.PvqBatch(chroma, self.fb.coeffs, [self.cfl_plane] * 3, **kw)
+            self.batch = self.batch_chroma
+            return
         blocks = blocks[np.argsort(blocks["bs"], kind="stable")]
         self.batch = pvq.PvqBatch(blocks, self.fb.coeffs, self.pred.coeffs if self.pred else None, q0=self.q0,
                                   is_keyframe=self.is_keyframe, use_masking=self.use_masking, lam=self.lam,
@@ -53,7 +70,12 @@ class HotPath:
         """One pass; returns the number of kernel launches.  `exchange` (multi-GPU)
         is called between the two halves of the inverse to trade lapped border rows."""
         self.fb.forward()
-        n = 1 + self.batch.run()
+        if self.keyframe_prediction:
+            n = 1 + self.batch_luma.run_luma_intra()
+            n += self.batch_chroma.cfl_pred(self.cfl_plane)
+            n += self.batch_chroma.run()
+        else:
+            n = 1 + self.batch.run()
         self.fb.inverse(lapped_only=True)
         if exchange is not None:
             exchange()

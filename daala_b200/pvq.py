@@ -51,6 +51,10 @@ def _bind():
     for name in ("daala_b200_pvq_block_finish", "daala_b200_pvq_cfl_flip", "daala_b200_coding_order_scatter"):
         getattr(L, name).argtypes = [pp, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_coding_order_gather.argtypes = [pp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.daala_b200_pvq_luma_intra.argtypes = [pp, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_void_p]
+    L.daala_b200_pvq_cfl_pred.argtypes = [pp, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p]
     L._pvq_bound = True
     return L
 
@@ -97,6 +101,50 @@ def block_list(bsize, geom, frame=0, sb_row0=0, sb_rows=None):
     blocks = np.concatenate(out)
     order = np.argsort(blocks["bs"], kind="stable")
     return blocks[order]
+
+
+def mark_luma4x4(blocks, bsize_maps):
+    """Sets bit 7 of `xdec` on chroma blocks whose luma area is coded as 4x4 blocks
+    (od_resample_luma_coeffs' chroma_bs == 0 case, src/intra.c:78)."""
+    for i in np.nonzero(blocks["pli"] != 0)[0]:
+        b = blocks[i]
+        if b["bs"] == 0 and bsize_maps[int(b["frame"])][int(b["y0"]) >> 2, int(b["x0"]) >> 2] == 0:
+            blocks["xdec"][i] |= 0x80
+    return blocks
+
+
+def intra_dependencies(blocks, bsize_maps, geom):
+    """For luma blocks in raster order of their origin (per frame): index of the top / left
+    neighbour of the same size (od_hv_intra_pred's `top` / `left`, src/intra.c:46-47) or -1."""
+    n = len(blocks)
+    top = np.full(n, -1, np.int32)
+    left = np.full(n, -1, np.int32)
+    h4, w4 = geom.frame_h // 4, geom.frame_w // 4
+    nframes = int(blocks["frame"].max()) + 1 if n else 0
+    index = np.full((nframes, h4, w4), -1, np.int32)
+    index[blocks["frame"], blocks["y0"] >> 2, blocks["x0"] >> 2] = np.arange(n, dtype=np.int32)
+    fr = blocks["frame"].astype(np.int64)
+    x4 = (blocks["x0"] >> 2).astype(np.int64)
+    y4 = (blocks["y0"] >> 2).astype(np.int64)
+    bs = blocks["bs"].astype(np.int64)
+    n4 = 1 << bs
+    maps = np.stack(bsize_maps)
+    has_top = y4 > 0
+    ty = np.maximum(y4 - 1, 0)
+    same_top = has_top & (maps[fr, ty >> 1, x4 >> 1] == bs)
+    top[same_top] = index[fr[same_top], (y4 - n4)[same_top], x4[same_top]]
+    has_left = x4 > 0
+    lx = np.maximum(x4 - 1, 0)
+    same_left = has_left & (maps[fr, y4 >> 1, lx >> 1] == bs)
+    left[same_left] = index[fr[same_left], y4[same_left], (x4 - n4)[same_left]]
+    assert (top[same_top] >= 0).all() and (left[same_left] >= 0).all()
+    assert (top < np.arange(n)).all() and (left < np.arange(n)).all()
+    return top, left
+
+
+def raster_order(blocks):
+    """Sort by (frame, y0, x0): the order the intra wavefront kernel requires."""
+    return blocks[np.lexsort((blocks["x0"], blocks["y0"], blocks["frame"]))]
 
 
 def assign_offsets(blocks):
@@ -204,6 +252,32 @@ class PvqBatch:
         L = _bind()
         _native.check(L.daala_b200_coding_order_scatter(ctypes.byref(self.params), self.nblocks, self._s(stream)),
                       "scatter")
+
+    # --- keyframe predictors -------------------------------------------------
+    def setup_intra(self, bsize_maps, geom):
+        """Luma-only batch in raster order: neighbour indices + done flags for
+        daala_b200_pvq_luma_intra."""
+        top, left = intra_dependencies(self.blocks_np, bsize_maps, geom)
+        self.dep_top = torch.from_numpy(top).to(self.device)
+        self.dep_left = torch.from_numpy(left).to(self.device)
+        self.done = torch.zeros(self.nblocks, dtype=torch.int32, device=self.device)
+        self.epoch = 0
+
+    def run_luma_intra(self, stream=None):
+        L = _bind()
+        self.epoch += 1
+        _native.check(L.daala_b200_pvq_luma_intra(ctypes.byref(self.params), self.dep_top.data_ptr(),
+                                                  self.dep_left.data_ptr(), self.done.data_ptr(), self.epoch,
+                                                  self.nblocks, self._s(stream)), "pvq_luma_intra")
+        return 1
+
+    def cfl_pred(self, pred_plane, stream=None):
+        """Fill the chroma prediction plane ([F, h/2, w/2] int32) from the quantised luma."""
+        L = _bind()
+        _native.check(L.daala_b200_pvq_cfl_pred(ctypes.byref(self.params), pred_plane.data_ptr(),
+                                                pred_plane.stride(0), pred_plane.stride(1), self.nblocks,
+                                                self._s(stream)), "pvq_cfl_pred")
+        return 1
 
     def run(self, stream=None):
         """gather -> quantise -> scatter; returns the number of kernel launches."""

@@ -226,6 +226,20 @@ int daala_b200_pvq_encode_bands(const daala_b200_pvq_params *prm, const uint32_t
    kernels everywhere, 10 + c = alternative lanes-per-band geometries (tuning). */
 int daala_b200_pvq_encode_bands_mode(const daala_b200_pvq_params *prm, const uint32_t *band_list, int count,
                                      int nmax, int mode, void *stream);
+/* Keyframe luma WITH the reference's H/V intra prediction (od_hv_intra_pred,
+   src/intra.c:37; od_encode_compute_pred, src/encode.c:858): one warp per block runs gather,
+   prediction from the quantised neighbours, every band, and the scatter back into
+   coef_plane[0]; blocks wait for their top / left same-size neighbours through `done`
+   (done[i] == epoch once block i is reconstructed).  `blocks` must list luma blocks only, in
+   raster order of their origin per frame; dep_top / dep_left give the neighbour's block index or
+   -1 (daala_b200/pvq.py: intra_dependencies).  Fills the same result arrays as the band kernels. */
+int daala_b200_pvq_luma_intra(const daala_b200_pvq_params *prm, const int32_t *dep_top, const int32_t *dep_left,
+                              int32_t *done, int epoch, int nblocks, void *stream);
+/* Chroma-from-luma prediction planes for keyframe chroma blocks (od_resample_luma_coeffs,
+   src/intra.c:72, 4:2:0) from the quantised luma plane coef_plane[0]; bit 7 of a block's `xdec`
+   field marks "the luma area is coded as 4x4 blocks" (TF merge + OD_CFL_SCALING4). */
+int daala_b200_pvq_cfl_pred(const daala_b200_pvq_params *prm, int32_t *pred_plane, long long pred_frame_pitch,
+                            int pred_stride, int nblocks, void *stream);
 /* Per block: ordered skip_diff sum, DC handling (keyframe: out[0] = in[0];
    inter: scalar quantiser of src/encode.c:1337-1344, 1377-1378). */
 int daala_b200_pvq_block_finish(const daala_b200_pvq_params *prm, int nblocks, void *stream);

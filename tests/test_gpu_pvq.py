@@ -181,3 +181,43 @@ def test_pvq_kernel_variants_agree(is_keyframe, with_pred):
     for other in outs[1:]:
         for a, b in zip(outs[0], other):
             assert torch.equal(a, b)
+
+
+def test_keyframe_with_intra_and_cfl_prediction_matches_frame_oracle():
+    """The complete keyframe chain of the reference on the GPU: forward, luma PVQ
+    with H/V intra prediction (dependency wavefront), chroma PVQ with CfL, inverse."""
+    import torch
+    from daala_b200 import pvq, synth
+    from daala_b200.frame import Geometry
+    from daala_b200.pipeline import HotPath
+    from tests import frame_oracle
+    lib, prefix = _oracle()
+    geom = Geometry(384, 256)
+    q4 = np.full((3, 30), 20, np.uint8)
+    nf = 2
+    hp = HotPath(geom, nframes=nf, q0=45, is_keyframe=1, pvq_qm_q4=q4, keyframe_prediction=True)
+    frames = []
+    for f in range(nf):
+        planes, _ = synth.frame(384, 256, f=5 + f)
+        planes = synth.pad_planes(planes, geom)
+        bsize = synth.block_size_map(geom, "mixed" if f == 0 else "8", seed=31 + f)
+        hp.fb.upload(planes, bsize, frame=f)
+        frames.append((planes, bsize))
+    hp.set_block_sizes([b for _, b in frames])
+    hp.run()
+    torch.cuda.synchronize()
+    qm, qm_inv = pvq.default_qm(True)
+    for f, (planes, bsize) in enumerate(frames):
+        d0 = frame_oracle.forward_plane(lib, prefix, planes[0], geom, 0, bsize, 1)
+        q0, s0 = frame_oracle.pvq_plane_pred(lib, prefix, d0, geom, 0, bsize, 45, 1, 0.147, qm, qm_inv, q4)
+        assert np.array_equal(hp.fb.coeffs[0][f].cpu().numpy(), q0), "luma frame %d" % f
+        assert s0[2] > -s0[3]  # predictions were used
+        for pli in (1, 2):
+            dc = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
+            qc, _ = frame_oracle.pvq_plane_pred(lib, prefix, dc, geom, pli, bsize, 45, 1, 0.147, qm, qm_inv, q4,
+                                                luma_d=q0)
+            assert np.array_equal(hp.fb.coeffs[pli][f].cpu().numpy(), qc), "chroma %d frame %d" % (pli, f)
+            rec = frame_oracle.inverse_plane(lib, prefix, qc, geom, pli, bsize, 1)
+            assert np.array_equal(hp.fb.pixels_out[pli][f].cpu().numpy(), rec)
+        rec0 = frame_oracle.inverse_plane(lib, prefix, q0, geom, 0, bsize, 1)
+        assert np.array_equal(hp.fb.pixels_out[0][f].cpu().numpy(), rec0)
