@@ -33,7 +33,8 @@ METRIC = "encoder Mpixels/s on 4K YUV420 intra"
 UNIT = "Mpixels/s"
 PIC_W, PIC_H = 3840, 2160
 WORKLOAD = ("3840x2160 4:2:0 all-intra hot path: lapped prefilter + fDCT(4..64, quadtree map) + PVQ band "
-            "quantisation (keyframe, zero prediction) + iDCT + lapped postfilter")
+            "quantisation (keyframe: luma H/V intra prediction, chroma CfL) + iDCT + lapped postfilter")
+WORKLOAD_SBROW = WORKLOAD.replace("keyframe: luma H/V intra prediction, chroma CfL", "keyframe, zero prediction")
 FWD_BYTES_PER_PX = 7.5   # SURVEY.md 8(d) K_fwd: 1.5 B in + 6 B out per padded luma pixel (4:2:0)
 
 
@@ -46,6 +47,11 @@ def parse():
     ap.add_argument("--frames", type=int, default=16, help="4K frames per step (whole job)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pvq-mode", type=int, default=0, help="0 cooperative kernels, 2 scalar thread-per-band")
+    ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"],
+                    help="frames: every rank encodes its own --frames frames with the reference's keyframe "
+                         "predictors (weak scaling, no exchange); sbrow: one batch split by superblock row with "
+                         "the NCCL border all-gather (strong scaling; zero-prediction keyframes, because intra "
+                         "prediction chains cross superblock rows)")
     return ap.parse_args()
 
 
@@ -139,15 +145,20 @@ PVQ_QM_Q4 = 16     # flat state->pvq_qm_q4 entries
 
 def cpu_frame(lib, prefix, geom, planes, bsize):
     """The same chain as the GPU step with the reference's own functions:
-    forward transform -> per-block PVQ (pvq_theta, closed-form rate) -> inverse."""
+    forward transform -> per-block PVQ (od_hv_intra_pred / CfL prediction, pvq_theta with the
+    closed-form rate) -> inverse."""
     import numpy as np
     from daala_b200 import pvq
     from tests import frame_oracle
     qm, qm_inv = pvq.default_qm(True)
     q4 = np.full((3, 30), PVQ_QM_Q4, np.uint8)
+    luma_q = None
     for pli in range(3):
         d = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
-        dq, _ = frame_oracle.pvq_plane(lib, prefix, d, None, geom, pli, bsize, Q0, 1, 1, pvq.PVQ_LAMBDA, qm, qm_inv, q4)
+        dq, _ = frame_oracle.pvq_plane_pred(lib, prefix, d, geom, pli, bsize, Q0, 1, pvq.PVQ_LAMBDA, qm, qm_inv, q4,
+                                            luma_d=luma_q)
+        if pli == 0:
+            luma_q = dq
         frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 1)
 
 
@@ -227,11 +238,15 @@ def run_b200(args):
 
     geom = Geometry(PIC_W, PIC_H)
     F = args.frames
-    r0, nrows = geom.shard_rows(rank, world)
+    sbrow = args.shard == "sbrow"
+    if sbrow:
+        r0, nrows = geom.shard_rows(rank, world)
+    else:
+        r0, nrows = 0, geom.nvsb
     host_frames = make_host_frames(geom, F)
     q4 = np.full((3, 30), PVQ_QM_Q4, np.uint8)
     hp = HotPath(geom, nframes=F, device=dev, q0=Q0, is_keyframe=1, use_masking=1, pvq_qm_q4=q4,
-                 sb_row0=r0, sb_rows=nrows)
+                 sb_row0=r0, sb_rows=nrows, keyframe_prediction=not sbrow)
     fb = hp.fb
     hp.set_block_sizes([hf[1] for hf in host_frames])
     hp.batch.mode = args.pvq_mode
@@ -271,12 +286,12 @@ def run_b200(args):
 
     # multi-GPU: one all-gather per step of the 2-row lapped borders (daala_b200/sharding.py)
     from daala_b200.sharding import BorderExchange
-    exchange = BorderExchange(geom, fb.lapped, rank, world)
+    exchange = BorderExchange(geom, fb.lapped, rank, world) if sbrow else None
 
     launches = {"n": 0}
 
     def step():
-        launches["n"] += hp.run(exchange if world > 1 else None)
+        launches["n"] += hp.run(exchange if (sbrow and world > 1) else None)
 
     def barrier():
         if world > 1:
@@ -306,7 +321,7 @@ def run_b200(args):
         a, b = rows(pli, 0)
         err = (fb.pixels_out[pli][:, a:b].float() - fb.pixels[pli][:, a:b].float()).abs().mean().item()
         assert err < 12.0, "reconstruction error too large (%.2f)" % err
-    total_k = int(hp.batch.res_k.sum().item())
+    total_k = int(hp.batch.res_k.sum().item()) + (int(hp.batch_luma.res_k.sum().item()) if hp.batch_luma else 0)
     assert total_k > 0, "PVQ produced no pulses"
 
     sampler = ClockSampler(local)
@@ -331,9 +346,14 @@ def run_b200(args):
     ms_fwd = timed(fb.forward, reps) / reps
     ms_inv = timed(lambda: fb.inverse(lapped_only=True), reps) / reps
     ms_post = timed(fb.sb_postfilter_store, reps) / reps
-    ms_pvq = timed(hp.batch.run, reps) / reps
+    if hp.keyframe_prediction:
+        ms_pvq_luma = timed(hp.batch_luma.run_luma_intra, reps) / reps
+        ms_pvq = ms_pvq_luma + timed(lambda: (hp.batch_chroma.cfl_pred(hp.cfl_plane), hp.batch_chroma.run()), reps) / reps
+    else:
+        ms_pvq_luma = None
+        ms_pvq = timed(hp.batch.run, reps) / reps
 
-    px_job = geom.luma_pixels * F
+    px_job = geom.luma_pixels * F * (1 if sbrow else world)
     value = px_job / (ms / args.steps * 1e-3) / 1e6
     e2e = px_job / (ms_e2e / args.steps * 1e-3) / 1e6
     padded_luma_shard = geom.frame_w * (nrows * 64) * F
@@ -354,9 +374,10 @@ def run_b200(args):
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "frames_per_step": F, "parallelism": "sbrow%d" % world,
+        "scaling": "strong" if sbrow else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_SBROW if sbrow else WORKLOAD,
+                   "frames_per_step": F * (1 if sbrow else world),
+                   "parallelism": ("sbrow%d (NCCL all-gather of lapped border rows)" if sbrow else "frames%d (independent frames per rank)") % world,
                    "l2": "inputs larger than L2 (%.0f MB of planes per step)" % ((geom.padded_samples * F * 9) / 1e6),
                    "block_sizes": "synthetic quadtree map, sizes 4..64", "quantizer": Q0,
                    "pvq_pulses_per_step": total_k},
@@ -368,7 +389,8 @@ def run_b200(args):
                      "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                      "algorithmic_bytes_per_launch": int(algo_bytes), "ms_per_launch": round(ms_fwd, 4)},
         "kernels_ms": {"k_forward_sb": round(ms_fwd, 4), "k_inverse_sb": round(ms_inv, 4),
-                       "k_sb_postfilter_store": round(ms_post, 4), "pvq_stage(gather+bands+scatter)": round(ms_pvq, 4)},
+                       "k_sb_postfilter_store": round(ms_post, 4), "pvq_stage(gather+bands+scatter)": round(ms_pvq, 4),
+                       "k_pvq_luma_intra(wavefront)": None if ms_pvq_luma is None else round(ms_pvq_luma, 4)},
     }
     if world == 1 and not args.no_cpu_baseline:
         cgeom = cpu_sample_geometry()

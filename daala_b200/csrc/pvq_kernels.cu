@@ -663,10 +663,12 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 }
 
 __global__ void __launch_bounds__(128)
-k_pvq_luma_intra(const __grid_constant__ daala_b200_pvq_params prm, const int32_t* __restrict__ dep_top,
-                 const int32_t* __restrict__ dep_left, int* done, int epoch, int nblocks) {
-  const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (blk >= nblocks) return;
+k_pvq_luma_intra(const __grid_constant__ daala_b200_pvq_params prm, const int32_t* __restrict__ ids,
+                 const int32_t* __restrict__ dep_top, const int32_t* __restrict__ dep_left, int* done, int epoch,
+                 int nblocks) {
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (slot >= nblocks) return;
+  const int blk = ids ? ids[slot] : slot;
   const Group<32, 4> grp;
   const daala_b200_pvq_block b = prm.blocks[blk];
   const int bs = b.bs, ln = bs + 2, n = 1 << ln;
@@ -755,6 +757,106 @@ k_pvq_luma_intra(const __grid_constant__ daala_b200_pvq_params prm, const int32_
   __threadfence();
   __syncwarp();
   if (lane == 0) st_release(done + blk, epoch);
+}
+
+// Same chain link with one CTA per block and one WARP PER BAND (NB = bands of
+// this block size): the bands of a block are independent once the prediction
+// is known, so the latency of a link is the slowest band instead of their sum.
+// Dependencies only ever connect blocks of the SAME size (od_hv_intra_pred
+// tests the neighbour's size), so every size class is its own wavefront and
+// gets its own launch; `ids` lists the class's blocks in raster order.
+template <int NB>
+__global__ void __launch_bounds__(32 * NB)
+k_pvq_luma_intra_cta(const __grid_constant__ daala_b200_pvq_params prm, const int32_t* __restrict__ ids,
+                     const int32_t* __restrict__ dep_top, const int32_t* __restrict__ dep_left, int* done,
+                     int epoch) {
+  const int blk = ids[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Group<32, 4> grp;
+  const daala_b200_pvq_block b = prm.blocks[blk];
+  const int bs = b.bs, ln = bs + 2, n = 1 << ln;
+  const int len = ln >= 5 ? 512 : 1 << (2 * ln);
+  const int stride = prm.plane_stride[0];
+  int32_t* d = prm.coef_plane[0] + b.frame * prm.plane_frame_pitch[0] + (size_t)b.y0 * stride + b.x0;
+  const int top = dep_top[blk], left = dep_left[blk];
+  if (threadIdx.x == 0) {
+    if (top >= 0) while (ld_acquire(done + top) != epoch) __nanosleep(32);
+    if (left >= 0) while (ld_acquire(done + left) != epoch) __nanosleep(32);
+  }
+  __syncthreads();
+  double g1 = 0, g2 = 0;
+  if (top >= 0) for (int i = 1; i < 4; i++) { double v = d[-(ptrdiff_t)n * stride + i]; g1 += v * v; }
+  if (left >= 0) for (int i = 1; i < 4; i++) { double v = d[(ptrdiff_t)i * stride - n]; g2 += v * v; }
+  const bool low_from_top = g1 > g2;
+  int32_t* vin = prm.in + b.coef_off;
+  int32_t* vref = prm.ref + b.coef_off;
+  for (int i = threadIdx.x; i < len; i += 32 * NB) {
+    int r = 0, c = 0;
+    if (i) {
+      int v, sh;
+      if (i < 16) { v = kScan4[i - 1]; sh = 2; }
+      else if (i < 64) { v = kScan8[i - 16]; sh = 3; }
+      else if (i < 256) { v = kScan16[i - 64]; sh = 4; }
+      else { v = kScan32[i - 256]; sh = 5; }
+      r = v >> sh;
+      c = v & ((1 << sh) - 1);
+    }
+    vin[i] = d[(size_t)r * stride + c];
+    int32_t p = 0;
+    if (r == 0 && c > 0 && top >= 0 && (c >= 4 || low_from_top)) p = d[-(ptrdiff_t)n * stride + c];
+    if (c == 0 && r > 0 && left >= 0 && (r >= 4 || !low_from_top)) p = d[(ptrdiff_t)r * stride - n];
+    vref[i] = p;
+  }
+  __syncthreads();
+  {
+    const int band = warp;
+    const int start = band_start(band);
+    const int bn = band_start(band + 1) - start;
+    const size_t off = (size_t)b.coef_off + start;
+    int qidx = bs * (bs + 1) + (band + 1) - (band + 1) / 3;
+    int q = (prm.q0 * prm.pvq_qm_q4[0][qidx]) >> 4;
+    if (q < 1) q = 1;
+    const int beta = (prm.use_masking && bs > 0) ? kBeta15 : kBeta1;
+    const int qoff = ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
+    int itheta, max_theta, k;
+    double skip_term;
+    int gain = quantise_band_coop<32, 4, false>(grp, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off,
+                                                &itheta, &max_theta, &k, beta, &skip_term, 1, 0, prm.qm + qoff,
+                                                prm.qm_inv + qoff, prm.pvq_norm_lambda);
+    if (lane == 0) {
+      const size_t r = (size_t)blk * 9 + band;
+      prm.res_gain[r] = gain;
+      prm.res_theta[r] = itheta;
+      prm.res_max_theta[r] = max_theta;
+      prm.res_k[r] = k;
+      prm.res_skip_term[r] = skip_term;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sd = 0;
+    for (int i = 0; i < NB; i++) sd += prm.res_skip_term[(size_t)blk * 9 + i];
+    prm.res_skip_diff[blk] = sd;
+    prm.res_flip[blk] = 0;
+    prm.res_dc[blk] = 0;
+    prm.out[b.coef_off] = vin[0];
+  }
+  const int32_t* vout = prm.out + b.coef_off;
+  if (ln >= 5) {
+    for (int i = threadIdx.x; i < n * n; i += 32 * NB) if (i) d[(size_t)(i >> ln) * stride + (i & (n - 1))] = 0;
+    __syncthreads();
+  }
+  for (int i = threadIdx.x + 1; i < len; i += 32 * NB) {
+    int v, sh;
+    if (i < 16) { v = kScan4[i - 1]; sh = 2; }
+    else if (i < 64) { v = kScan8[i - 16]; sh = 3; }
+    else if (i < 256) { v = kScan16[i - 64]; sh = 4; }
+    else { v = kScan32[i - 256]; sh = 5; }
+    d[(size_t)(v >> sh) * stride + (v & ((1 << sh) - 1))] = vout[i];
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release(done + blk, epoch);
 }
 
 // Chroma-from-luma prediction of keyframe chroma blocks (od_resample_luma_coeffs,
@@ -868,8 +970,31 @@ int daala_b200_pvq_encode_bands_mode(const daala_b200_pvq_params* prm, const uin
 int daala_b200_pvq_luma_intra(const daala_b200_pvq_params* prm, const int32_t* dep_top, const int32_t* dep_left,
                               int32_t* done, int epoch, int nblocks, void* stream) {
   if (nblocks <= 0) return 0;
-  k_pvq_luma_intra<<<(nblocks * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*prm, dep_top, dep_left, done,
-                                                                                 epoch, nblocks);
+  k_pvq_luma_intra<<<(nblocks * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*prm, nullptr, dep_top, dep_left,
+                                                                                 done, epoch, nblocks);
+  return (int)cudaGetLastError();
+}
+
+// Warp-per-block kernel restricted to the blocks listed in `ids` (used for the 4x4 class).
+int daala_b200_pvq_luma_intra_ids(const daala_b200_pvq_params* prm, const int32_t* ids, int count,
+                                  const int32_t* dep_top, const int32_t* dep_left, int32_t* done, int epoch,
+                                  void* stream) {
+  if (count <= 0) return 0;
+  k_pvq_luma_intra<<<(count * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*prm, ids, dep_top, dep_left, done,
+                                                                               epoch, count);
+  return (int)cudaGetLastError();
+}
+
+// One launch for the blocks of one size (`bs` = 1..4) listed in `ids`.
+int daala_b200_pvq_luma_intra_class(const daala_b200_pvq_params* prm, const int32_t* ids, int count, int bs,
+                                    const int32_t* dep_top, const int32_t* dep_left, int32_t* done, int epoch,
+                                    void* stream) {
+  if (count <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (bs == 1) k_pvq_luma_intra_cta<4><<<count, 128, 0, s>>>(*prm, ids, dep_top, dep_left, done, epoch);
+  else if (bs == 2) k_pvq_luma_intra_cta<7><<<count, 224, 0, s>>>(*prm, ids, dep_top, dep_left, done, epoch);
+  else if (bs >= 3) k_pvq_luma_intra_cta<9><<<count, 288, 0, s>>>(*prm, ids, dep_top, dep_left, done, epoch);
+  else return (int)cudaErrorInvalidValue;
   return (int)cudaGetLastError();
 }
 

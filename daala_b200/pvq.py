@@ -53,6 +53,10 @@ def _bind():
     L.daala_b200_coding_order_gather.argtypes = [pp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_pvq_luma_intra.argtypes = [pp, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_void_p]
+    L.daala_b200_pvq_luma_intra_ids.argtypes = [pp, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.daala_b200_pvq_luma_intra_class.argtypes = [pp, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_pvq_cfl_pred.argtypes = [pp, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p]
     L._pvq_bound = True
@@ -262,14 +266,41 @@ class PvqBatch:
         self.dep_left = torch.from_numpy(left).to(self.device)
         self.done = torch.zeros(self.nblocks, dtype=torch.int32, device=self.device)
         self.epoch = 0
+        # per block size: indices in raster order (each size is an independent wavefront)
+        self.class_ids = []
+        self.class_streams = []
+        for bs in range(5):
+            ids = np.nonzero(self.blocks_np["bs"] == bs)[0].astype(np.int32)
+            self.class_ids.append(torch.from_numpy(ids).to(self.device))
+            self.class_streams.append(torch.cuda.Stream(device=self.device))
+        self.intra_by_class = True
 
     def run_luma_intra(self, stream=None):
         L = _bind()
         self.epoch += 1
-        _native.check(L.daala_b200_pvq_luma_intra(ctypes.byref(self.params), self.dep_top.data_ptr(),
-                                                  self.dep_left.data_ptr(), self.done.data_ptr(), self.epoch,
-                                                  self.nblocks, self._s(stream)), "pvq_luma_intra")
-        return 1
+        p = ctypes.byref(self.params)
+        deps = (self.dep_top.data_ptr(), self.dep_left.data_ptr(), self.done.data_ptr(), self.epoch)
+        if not self.intra_by_class:
+            _native.check(L.daala_b200_pvq_luma_intra(p, *deps, self.nblocks, self._s(stream)), "pvq_luma_intra")
+            return 1
+        # one launch per block size, concurrently on side streams that fork from / join the caller's
+        main = stream if stream is not None else torch.cuda.current_stream(self.device)
+        n = 0
+        for bs in (4, 3, 2, 1, 0):
+            ids = self.class_ids[bs]
+            if not ids.numel():
+                continue
+            st = self.class_streams[bs]
+            st.wait_stream(main)
+            sp = ctypes.c_void_p(st.cuda_stream)
+            if bs == 0:
+                _native.check(L.daala_b200_pvq_luma_intra_ids(p, ids.data_ptr(), ids.numel(), *deps, sp), "intra_ids")
+            else:
+                _native.check(L.daala_b200_pvq_luma_intra_class(p, ids.data_ptr(), ids.numel(), bs, *deps, sp),
+                              "intra_class")
+            main.wait_stream(st)
+            n += 1
+        return n
 
     def cfl_pred(self, pred_plane, stream=None):
         """Fill the chroma prediction plane ([F, h/2, w/2] int32) from the quantised luma."""

@@ -235,6 +235,16 @@ int daala_b200_pvq_encode_bands_mode(const daala_b200_pvq_params *prm, const uin
    -1 (daala_b200/pvq.py: intra_dependencies).  Fills the same result arrays as the band kernels. */
 int daala_b200_pvq_luma_intra(const daala_b200_pvq_params *prm, const int32_t *dep_top, const int32_t *dep_left,
                               int32_t *done, int epoch, int nblocks, void *stream);
+/* The same split by block size (chains only connect blocks of equal size): `ids` lists the
+   blocks of one size in raster order.  _ids: one warp per block (used for 4x4 blocks);
+   _class (bs = 1..4): one CTA per block, one warp per band.  The launches of different sizes are
+   independent and may run on different streams. */
+int daala_b200_pvq_luma_intra_ids(const daala_b200_pvq_params *prm, const int32_t *ids, int count,
+                                  const int32_t *dep_top, const int32_t *dep_left, int32_t *done, int epoch,
+                                  void *stream);
+int daala_b200_pvq_luma_intra_class(const daala_b200_pvq_params *prm, const int32_t *ids, int count, int bs,
+                                    const int32_t *dep_top, const int32_t *dep_left, int32_t *done, int epoch,
+                                    void *stream);
 /* Chroma-from-luma prediction planes for keyframe chroma blocks (od_resample_luma_coeffs,
    src/intra.c:72, 4:2:0) from the quantised luma plane coef_plane[0]; bit 7 of a block's `xdec`
    field marks "the luma area is coded as 4x4 blocks" (TF merge + OD_CFL_SCALING4). */
