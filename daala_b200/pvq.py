@@ -146,6 +146,20 @@ def intra_dependencies(blocks, bsize_maps, geom):
     return top, left
 
 
+def dependency_depth(top, left):
+    """Longest chain ending at each block (1 = no dependency): iterated relaxation, one
+    vectorised pass per wavefront (a few dozen for real block-size maps)."""
+    depth = np.ones(len(top), np.int32)
+    ht, hl = top >= 0, left >= 0
+    while True:
+        new = np.ones_like(depth)
+        new[ht] = np.maximum(new[ht], depth[top[ht]] + 1)
+        new[hl] = np.maximum(new[hl], depth[left[hl]] + 1)
+        if np.array_equal(new, depth):
+            return depth
+        depth = new
+
+
 def raster_order(blocks):
     """Sort by (frame, y0, x0): the order the intra wavefront kernel requires."""
     return blocks[np.lexsort((blocks["x0"], blocks["y0"], blocks["frame"]))]
@@ -266,11 +280,17 @@ class PvqBatch:
         self.dep_left = torch.from_numpy(left).to(self.device)
         self.done = torch.zeros(self.nblocks, dtype=torch.int32, device=self.device)
         self.epoch = 0
-        # per block size: indices in raster order (each size is an independent wavefront)
+        # per block size (each size is an independent wavefront): indices ordered by dependency
+        # depth, so that a CTA's neighbours were launched a whole wave earlier and are normally
+        # finished when it starts -- still a topological order, so the in-order dispatch argument
+        # against deadlock holds, but resident CTAs no longer queue up behind their left neighbour
+        depth = dependency_depth(top, left)
+        self.max_depth = int(depth.max()) if len(depth) else 0
         self.class_ids = []
         self.class_streams = []
         for bs in range(5):
             ids = np.nonzero(self.blocks_np["bs"] == bs)[0].astype(np.int32)
+            ids = ids[np.argsort(depth[ids], kind="stable")]
             self.class_ids.append(torch.from_numpy(ids).to(self.device))
             self.class_streams.append(torch.cuda.Stream(device=self.device))
         self.intra_by_class = True
