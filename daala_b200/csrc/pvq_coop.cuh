@@ -86,12 +86,7 @@ struct Group {
   }
 };
 
-__device__ __forceinline__ double rsqrt_small_c(int i) {
-  const double tbl[16] = {1.000000, 0.707107, 0.577350, 0.500000, 0.447214, 0.408248, 0.377964, 0.353553,
-                          0.333333, 0.316228, 0.301511, 0.288675, 0.277350, 0.267261, 0.258199, 0.250000};
-  if (i <= 16) return tbl[i - 1];
-  return 1. / sqrt((double)i);
-}
+__device__ __forceinline__ double rsqrt_small_c(int i) { return rsqrt_small_tbl(i); }
 
 // pvq_search_rdo_double (src/pvq_encoder.c:93) on a distributed vector.
 template <int G, int E, bool kForceScan>

@@ -40,13 +40,7 @@ __device__ __forceinline__ int band_start(int band) {
 
 __device__ __forceinline__ int num_bands(int bs) { return bs == 0 ? 1 : bs == 1 ? 4 : bs == 2 ? 7 : 9; }
 
-__device__ __forceinline__ double rsqrt_small(int i) {
-  // od_rsqrt_table, src/pvq_encoder.c:53 (6-digit constants are normative).
-  const double tbl[16] = {1.000000, 0.707107, 0.577350, 0.500000, 0.447214, 0.408248, 0.377964, 0.353553,
-                          0.333333, 0.316228, 0.301511, 0.288675, 0.277350, 0.267261, 0.258199, 0.250000};
-  if (i <= 16) return tbl[i - 1];
-  return 1. / sqrt((double)i);
-}
+__device__ __forceinline__ double rsqrt_small(int i) { return rsqrt_small_tbl(i); }
 
 // src/pvq_encoder.c:93.  x[] (|xcoeff| as double) is caller scratch of n entries.
 __device__ double search_rdo(const int16_t* xcoeff, int n, int k, int32_t* ypulse, double g2,

@@ -27,6 +27,17 @@ constexpr int kQmInvShift = 12;
 constexpr int kThetaShift = 15;
 constexpr int kMaxN = 128;  // OD_MAX_PVQ_SIZE
 
+// 1/sqrt(i), i = 1..16, with the reference's 6-digit constants (od_rsqrt_table,
+// src/pvq_encoder.c:53); larger arguments use 1./sqrt(i).  Kept in constant memory:
+// a function-local array would be re-materialised on the stack at every call.
+__constant__ double kRsqrtSmall[16] = {1.000000, 0.707107, 0.577350, 0.500000, 0.447214, 0.408248,
+                                       0.377964, 0.353553, 0.333333, 0.316228, 0.301511, 0.288675,
+                                       0.277350, 0.267261, 0.258199, 0.250000};
+__device__ __forceinline__ double rsqrt_small_tbl(int i) {
+  if (i <= 16) return kRsqrtSmall[i - 1];
+  return 1. / sqrt((double)i);
+}
+
 __device__ __forceinline__ int ilog(uint32_t v) { return v ? 32 - __clz((int)v) : 0; }
 __device__ __forceinline__ int32_t shl(int32_t a, int s) { return (int32_t)((uint32_t)a << s); }
 __device__ __forceinline__ int32_t shr_round(int32_t x, int s) { return (x + ((1 << s) >> 1)) >> s; }
