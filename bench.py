@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=16, help="4K frames per step (whole job)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pvq-mode", type=int, default=0, help="0 cooperative kernels, 2 scalar thread-per-band")
+    ap.add_argument("--intra-mode", default="waves", choices=["waves", "chain", "chain_single"])
     ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"],
                     help="frames: every rank encodes its own --frames frames with the reference's keyframe "
                          "predictors (weak scaling, no exchange); sbrow: one batch split by superblock row with "
@@ -250,6 +251,9 @@ def run_b200(args):
     fb = hp.fb
     hp.set_block_sizes([hf[1] for hf in host_frames])
     hp.batch.mode = args.pvq_mode
+    if hp.batch_luma is not None:
+        hp.batch_luma.mode = args.pvq_mode
+        hp.batch_luma.intra_mode = args.intra_mode
 
     # pinned host staging: this rank's rows (+2-sample halo) of every plane, and its output rows
     def rows(pli, halo):

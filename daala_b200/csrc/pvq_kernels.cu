@@ -510,9 +510,10 @@ k_pvq_bands_coop(const __grid_constant__ daala_b200_pvq_params prm, const uint32
 // keyframes keep the Haar-coded DC (scalar_out[0] = dblock[0],
 // src/encode.c:1381); inter frames use the plain scalar quantiser of
 // src/encode.c:1337-1344 and reconstruct it as in :1377-1378.
-__global__ void k_block_finish(const __grid_constant__ daala_b200_pvq_params prm, int nblocks) {
+__global__ void k_block_finish(const __grid_constant__ daala_b200_pvq_params prm, int first, int nblocks) {
   int blk = blockIdx.x * blockDim.x + threadIdx.x;
   if (blk >= nblocks) return;
+  blk += first;
   const daala_b200_pvq_block b = prm.blocks[blk];
   int nb = num_bands(b.bs);
   double sd = 0;
@@ -603,10 +604,10 @@ __global__ void k_coding_order_gather(const __grid_constant__ daala_b200_pvq_par
 // Coding order -> raster, with od_init_skipped_coeffs first (keyframe: zero
 // everything but DC; otherwise copy the prediction), then the coded prefix.
 // DC: the keyframe path keeps the block's (Haar-coded) DC, src/encode.c:1384.
-__global__ void k_coding_order_scatter(const __grid_constant__ daala_b200_pvq_params prm, int nblocks) {
+__global__ void k_coding_order_scatter(const __grid_constant__ daala_b200_pvq_params prm, int first, int nblocks) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= nblocks) return;
-  const daala_b200_pvq_block b = prm.blocks[warp];
+  const daala_b200_pvq_block b = prm.blocks[first + warp];
   const int ln = b.bs + 2, n = 1 << ln;
   const int len = ln >= 5 ? 512 : 1 << (2 * ln);
   const int stride = prm.plane_stride[b.pli];
@@ -751,6 +752,48 @@ k_pvq_luma_intra(const __grid_constant__ daala_b200_pvq_params prm, const int32_
   __threadfence();
   __syncwarp();
   if (lane == 0) st_release(done + blk, epoch);
+}
+
+// Wave-synchronous alternative to the chain kernels: the host sorts luma blocks by
+// dependency depth; every wave (all blocks of one depth, their neighbours finished in
+// earlier waves) runs the ordinary batched kernels.  This kernel is the wave's gather:
+// `in` <- coefficient plane, `ref` <- H/V intra prediction from the quantised neighbours
+// (has_top / has_left: the neighbour of the same size exists, src/intra.c:46-47).
+__global__ void k_intra_pred_gather(const __grid_constant__ daala_b200_pvq_params prm,
+                                    const int32_t* __restrict__ dep_top, const int32_t* __restrict__ dep_left,
+                                    int first, int nblocks) {
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (slot >= nblocks) return;
+  const int blk = first + slot;
+  const daala_b200_pvq_block b = prm.blocks[blk];
+  const int ln = b.bs + 2, n = 1 << ln;
+  const int len = ln >= 5 ? 512 : 1 << (2 * ln);
+  const int stride = prm.plane_stride[0];
+  const int32_t* d = prm.coef_plane[0] + b.frame * prm.plane_frame_pitch[0] + (size_t)b.y0 * stride + b.x0;
+  const bool top = dep_top[blk] >= 0, left = dep_left[blk] >= 0;
+  double g1 = 0, g2 = 0;
+  if (top) for (int i = 1; i < 4; i++) { double v = d[-(ptrdiff_t)n * stride + i]; g1 += v * v; }
+  if (left) for (int i = 1; i < 4; i++) { double v = d[(ptrdiff_t)i * stride - n]; g2 += v * v; }
+  const bool low_from_top = g1 > g2;
+  int32_t* vin = prm.in + b.coef_off;
+  int32_t* vref = prm.ref + b.coef_off;
+  for (int i = lane; i < len; i += 32) {
+    int r = 0, c = 0;
+    if (i) {
+      int v, sh;
+      if (i < 16) { v = kScan4[i - 1]; sh = 2; }
+      else if (i < 64) { v = kScan8[i - 16]; sh = 3; }
+      else if (i < 256) { v = kScan16[i - 64]; sh = 4; }
+      else { v = kScan32[i - 256]; sh = 5; }
+      r = v >> sh;
+      c = v & ((1 << sh) - 1);
+    }
+    vin[i] = d[(size_t)r * stride + c];
+    int32_t p = 0;
+    if (r == 0 && c > 0 && top && (c >= 4 || low_from_top)) p = d[-(ptrdiff_t)n * stride + c];
+    if (c == 0 && r > 0 && left && (r >= 4 || !low_from_top)) p = d[(ptrdiff_t)r * stride - n];
+    vref[i] = p;
+  }
 }
 
 // Same chain link with one CTA per block and one WARP PER BAND (NB = bands of
@@ -969,6 +1012,26 @@ int daala_b200_pvq_luma_intra(const daala_b200_pvq_params* prm, const int32_t* d
   return (int)cudaGetLastError();
 }
 
+int daala_b200_pvq_intra_gather(const daala_b200_pvq_params* prm, const int32_t* dep_top, const int32_t* dep_left,
+                                int first, int count, void* stream) {
+  if (count <= 0) return 0;
+  k_intra_pred_gather<<<(count * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*prm, dep_top, dep_left, first,
+                                                                                  count);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_pvq_block_finish_range(const daala_b200_pvq_params* prm, int first, int count, void* stream) {
+  if (count <= 0) return 0;
+  k_block_finish<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*prm, first, count);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_coding_order_scatter_range(const daala_b200_pvq_params* prm, int first, int count, void* stream) {
+  if (count <= 0) return 0;
+  k_coding_order_scatter<<<(count * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*prm, first, count);
+  return (int)cudaGetLastError();
+}
+
 // Warp-per-block kernel restricted to the blocks listed in `ids` (used for the 4x4 class).
 int daala_b200_pvq_luma_intra_ids(const daala_b200_pvq_params* prm, const int32_t* ids, int count,
                                   const int32_t* dep_top, const int32_t* dep_left, int32_t* done, int epoch,
@@ -1001,7 +1064,7 @@ int daala_b200_pvq_cfl_pred(const daala_b200_pvq_params* prm, int32_t* pred_plan
 
 int daala_b200_pvq_block_finish(const daala_b200_pvq_params* prm, int nblocks, void* stream) {
   if (nblocks <= 0) return 0;
-  k_block_finish<<<(nblocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*prm, nblocks);
+  k_block_finish<<<(nblocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*prm, 0, nblocks);
   return (int)cudaGetLastError();
 }
 
@@ -1019,7 +1082,7 @@ int daala_b200_coding_order_gather(const daala_b200_pvq_params* prm, int nblocks
 
 int daala_b200_coding_order_scatter(const daala_b200_pvq_params* prm, int nblocks, void* stream) {
   if (nblocks <= 0) return 0;
-  k_coding_order_scatter<<<(nblocks * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*prm, nblocks);
+  k_coding_order_scatter<<<(nblocks * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*prm, 0, nblocks);
   return (int)cudaGetLastError();
 }
 

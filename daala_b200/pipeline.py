@@ -47,9 +47,10 @@ class HotPath:
                 "intra prediction chains cross superblock rows: keyframe_prediction needs whole frames per rank"
             kw = dict(q0=self.q0, is_keyframe=1, use_masking=self.use_masking, lam=self.lam,
                       pvq_qm_q4=self.pvq_qm_q4, device=self.device)
-            luma = pvq.raster_order(blocks[blocks["pli"] == 0])
+            luma, top, left, depth = pvq.sort_by_depth(pvq.raster_order(blocks[blocks["pli"] == 0]), list(bsizes),
+                                                       self.geom)
             self.batch_luma = pvq.PvqBatch(luma, self.fb.coeffs, None, **kw)
-            self.batch_luma.setup_intra(list(bsizes), self.geom)
+            self.batch_luma.setup_intra(top, left, depth)
             chroma = pvq.mark_luma4x4(blocks[blocks["pli"] != 0], list(bsizes))
             chroma = chroma[np.argsort(chroma["bs"], kind="stable")]
             self.cfl_plane = torch.zeros_like(self.fb.coeffs[1])

@@ -57,6 +57,10 @@ def _bind():
                                                 ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_pvq_luma_intra_class.argtypes = [pp, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.daala_b200_pvq_intra_gather.argtypes = [pp, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p]
+    L.daala_b200_pvq_block_finish_range.argtypes = [pp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.daala_b200_coding_order_scatter_range.argtypes = [pp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_pvq_cfl_pred.argtypes = [pp, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p]
     L._pvq_bound = True
@@ -158,6 +162,21 @@ def dependency_depth(top, left):
         if np.array_equal(new, depth):
             return depth
         depth = new
+
+
+def sort_by_depth(luma, bsize_maps, geom):
+    """Luma blocks (raster order) -> (blocks sorted by dependency depth, top, left, depth) with the
+    neighbour indices remapped to the new order.  Still a topological order: a neighbour's depth is
+    smaller, so it comes earlier."""
+    top, left = intra_dependencies(luma, bsize_maps, geom)
+    depth = dependency_depth(top, left)
+    order = np.argsort(depth, kind="stable")
+    inv = np.empty(len(order), np.int32)
+    inv[order] = np.arange(len(order), dtype=np.int32)
+    t, l = top[order], left[order]
+    t = np.where(t >= 0, inv[np.maximum(t, 0)], -1).astype(np.int32)
+    l = np.where(l >= 0, inv[np.maximum(l, 0)], -1).astype(np.int32)
+    return luma[order], t, l, depth[order]
 
 
 def raster_order(blocks):
@@ -272,38 +291,61 @@ class PvqBatch:
                       "scatter")
 
     # --- keyframe predictors -------------------------------------------------
-    def setup_intra(self, bsize_maps, geom):
-        """Luma-only batch in raster order: neighbour indices + done flags for
-        daala_b200_pvq_luma_intra."""
-        top, left = intra_dependencies(self.blocks_np, bsize_maps, geom)
-        self.dep_top = torch.from_numpy(top).to(self.device)
-        self.dep_left = torch.from_numpy(left).to(self.device)
-        self.done = torch.zeros(self.nblocks, dtype=torch.int32, device=self.device)
+    def setup_intra(self, top, left, depth):
+        """Luma-only batch whose blocks are sorted by dependency depth (see
+        `sort_by_depth`): neighbour indices for the chain kernels, wave ranges and
+        per-wave band-list slices for the wave-synchronous path."""
+        dev = self.device
+        self.dep_top = torch.from_numpy(np.ascontiguousarray(top)).to(dev)
+        self.dep_left = torch.from_numpy(np.ascontiguousarray(left)).to(dev)
+        self.done = torch.zeros(self.nblocks, dtype=torch.int32, device=dev)
         self.epoch = 0
-        # per block size (each size is an independent wavefront): indices ordered by dependency
-        # depth, so that a CTA's neighbours were launched a whole wave earlier and are normally
-        # finished when it starts -- still a topological order, so the in-order dispatch argument
-        # against deadlock holds, but resident CTAs no longer queue up behind their left neighbour
-        depth = dependency_depth(top, left)
         self.max_depth = int(depth.max()) if len(depth) else 0
-        self.class_ids = []
-        self.class_streams = []
-        for bs in range(5):
-            ids = np.nonzero(self.blocks_np["bs"] == bs)[0].astype(np.int32)
-            ids = ids[np.argsort(depth[ids], kind="stable")]
-            self.class_ids.append(torch.from_numpy(ids).to(self.device))
-            self.class_streams.append(torch.cuda.Stream(device=self.device))
-        self.intra_by_class = True
+        # chain kernels: per block size, indices in (depth, raster) order
+        self.class_ids = [torch.from_numpy(np.nonzero(self.blocks_np["bs"] == bs)[0].astype(np.int32)).to(dev)
+                          for bs in range(5)]
+        self.class_streams = [torch.cuda.Stream(device=dev) for _ in range(5)]
+        # waves: contiguous block ranges of equal depth
+        edges = np.concatenate([[0], np.nonzero(np.diff(depth))[0] + 1, [len(depth)]]) if len(depth) else np.array([0])
+        self.waves = [(int(a), int(b - a)) for a, b in zip(edges[:-1], edges[1:])]
+        # band lists ordered by (wave, band, block) so that a wave is a slice of each class list
+        lists = band_lists(self.blocks_np)
+        self.wave_lists, self.wave_slices = {}, {}
+        for k, v in lists.items():
+            blk, band = (v >> 4).astype(np.int64), (v & 15).astype(np.int64)
+            order = np.lexsort((blk, band, depth[blk]))
+            v = v[order]
+            self.wave_lists[k] = torch.from_numpy(v.view(np.int32)).to(dev)
+            d = depth[(v >> 4).astype(np.int64)]
+            cuts = np.searchsorted(d, np.arange(1, self.max_depth + 2))
+            self.wave_slices[k] = [(int(a), int(b - a)) for a, b in zip(cuts[:-1], cuts[1:])]
+        self.intra_mode = "waves"
 
     def run_luma_intra(self, stream=None):
         L = _bind()
-        self.epoch += 1
         p = ctypes.byref(self.params)
+        if self.intra_mode == "waves":
+            s = self._s(stream)
+            n = 0
+            for w, (first, count) in enumerate(self.waves):
+                _native.check(L.daala_b200_pvq_intra_gather(p, self.dep_top.data_ptr(), self.dep_left.data_ptr(),
+                                                            first, count, s), "intra_gather")
+                for nmax in (128, 32, 16):
+                    a, c = self.wave_slices[nmax][w]
+                    if c:
+                        ptr = self.wave_lists[nmax].data_ptr() + 4 * a
+                        _native.check(L.daala_b200_pvq_encode_bands_mode(p, ptr, c, nmax, self.mode, s), "pvq_bands")
+                        n += 1
+                _native.check(L.daala_b200_pvq_block_finish_range(p, first, count, s), "finish_range")
+                _native.check(L.daala_b200_coding_order_scatter_range(p, first, count, s), "scatter_range")
+                n += 3
+            return n
+        self.epoch += 1
         deps = (self.dep_top.data_ptr(), self.dep_left.data_ptr(), self.done.data_ptr(), self.epoch)
-        if not self.intra_by_class:
+        if self.intra_mode == "chain_single":
             _native.check(L.daala_b200_pvq_luma_intra(p, *deps, self.nblocks, self._s(stream)), "pvq_luma_intra")
             return 1
-        # one launch per block size, concurrently on side streams that fork from / join the caller's
+        # "chain": one launch per block size, concurrently on side streams that fork from / join the caller's
         main = stream if stream is not None else torch.cuda.current_stream(self.device)
         n = 0
         for bs in (4, 3, 2, 1, 0):

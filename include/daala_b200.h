@@ -235,6 +235,14 @@ int daala_b200_pvq_encode_bands_mode(const daala_b200_pvq_params *prm, const uin
    -1 (daala_b200/pvq.py: intra_dependencies).  Fills the same result arrays as the band kernels. */
 int daala_b200_pvq_luma_intra(const daala_b200_pvq_params *prm, const int32_t *dep_top, const int32_t *dep_left,
                               int32_t *done, int epoch, int nblocks, void *stream);
+/* Wave-synchronous form of the same computation: luma blocks sorted by dependency depth; for
+   each wave (blocks [first, first+count) of one depth) the caller runs _intra_gather, the band
+   kernels on the wave's slices of the band lists, _block_finish_range and
+   _coding_order_scatter_range.  dep_top / dep_left only need their sign here. */
+int daala_b200_pvq_intra_gather(const daala_b200_pvq_params *prm, const int32_t *dep_top, const int32_t *dep_left,
+                                int first, int count, void *stream);
+int daala_b200_pvq_block_finish_range(const daala_b200_pvq_params *prm, int first, int count, void *stream);
+int daala_b200_coding_order_scatter_range(const daala_b200_pvq_params *prm, int first, int count, void *stream);
 /* The same split by block size (chains only connect blocks of equal size): `ids` lists the
    blocks of one size in raster order.  _ids: one warp per block (used for 4x4 blocks);
    _class (bs = 1..4): one CTA per block, one warp per band.  The launches of different sizes are

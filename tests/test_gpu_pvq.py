@@ -183,7 +183,8 @@ def test_pvq_kernel_variants_agree(is_keyframe, with_pred):
             assert torch.equal(a, b)
 
 
-def test_keyframe_with_intra_and_cfl_prediction_matches_frame_oracle():
+@pytest.mark.parametrize("intra_mode", ["waves", "chain", "chain_single"])
+def test_keyframe_with_intra_and_cfl_prediction_matches_frame_oracle(intra_mode):
     """The complete keyframe chain of the reference on the GPU: forward, luma PVQ
     with H/V intra prediction (dependency wavefront), chroma PVQ with CfL, inverse."""
     import torch
@@ -204,6 +205,7 @@ def test_keyframe_with_intra_and_cfl_prediction_matches_frame_oracle():
         hp.fb.upload(planes, bsize, frame=f)
         frames.append((planes, bsize))
     hp.set_block_sizes([b for _, b in frames])
+    hp.batch_luma.intra_mode = intra_mode
     hp.run()
     torch.cuda.synchronize()
     qm, qm_inv = pvq.default_qm(True)
