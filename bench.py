@@ -274,19 +274,38 @@ def run_b200(args):
     pin_bsize = torch.empty((F,) + geom.bsize_shape, dtype=torch.uint8).pin_memory()
     for f in range(F):
         pin_bsize[f].copy_(torch.from_numpy(host_frames[f][1]))
-    h2d_bytes = sum(t.numel() for t in pin_in) + pin_bsize.numel()
-    d2h_bytes = sum(t.numel() for t in pin_out)
+    # e2e also moves what the host side of the reference consumes/produces around the hot path:
+    # block descriptors + band lists in (they follow from the block-size decision), and the PVQ
+    # symbols out (per-band indices, flags, 16-bit pulses) for the host entropy coder.
+    batches = [b for b in (hp.batch_luma, hp.batch) if b is not None]
+    desc_dev = []
+    for b in batches:
+        desc_dev.append(b.blocks)
+        desc_dev.extend(b.lists.values())
+        if getattr(b, "wave_lists", None):
+            desc_dev.extend(b.wave_lists.values())
+            desc_dev.extend([b.dep_top, b.dep_left])
+    desc_pin = [t.cpu().pin_memory() for t in desc_dev]
+    sym_dev = [t for b in batches for t in b.symbol_tensors()]
+    sym_pin = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in sym_dev]
+    h2d_bytes = (sum(t.numel() for t in pin_in) + pin_bsize.numel()
+                 + sum(t.numel() * t.element_size() for t in desc_pin))
+    d2h_bytes = sum(t.numel() for t in pin_out) + sum(t.numel() * t.element_size() for t in sym_pin)
 
     def h2d():
         for pli in range(3):
             a, b = rows(pli, 2)
             fb.pixels[pli][:, a:b].copy_(pin_in[pli], non_blocking=True)
         fb.bsize.copy_(pin_bsize, non_blocking=True)
+        for dst, src in zip(desc_dev, desc_pin):
+            dst.copy_(src, non_blocking=True)
 
     def d2h():
         for pli in range(3):
             a, b = rows(pli, 0)
             pin_out[pli].copy_(fb.pixels_out[pli][:, a:b], non_blocking=True)
+        for dst, src in zip(sym_pin, sym_dev):
+            dst.copy_(src, non_blocking=True)
 
     # multi-GPU: one all-gather per step of the 2-row lapped borders (daala_b200/sharding.py)
     from daala_b200.sharding import BorderExchange

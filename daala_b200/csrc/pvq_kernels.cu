@@ -633,6 +633,10 @@ __global__ void k_coding_order_scatter(const __grid_constant__ daala_b200_pvq_pa
       dst[scan_to_raster(i, ln, stride)] = src[i];
     }
   }
+  if (prm.y16) {
+    const int32_t* y = prm.y + b.coef_off;
+    for (int i = lane; i < len; i += 32) prm.y16[b.coef_off + i] = (int16_t)y[i];
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -749,6 +753,7 @@ k_pvq_luma_intra(const __grid_constant__ daala_b200_pvq_params prm, const int32_
     else { v = kScan32[i - 256]; sh = 5; }
     d[(size_t)(v >> sh) * stride + (v & ((1 << sh) - 1))] = vout[i];
   }
+  if (prm.y16) for (int i = lane; i < len; i += 32) prm.y16[b.coef_off + i] = (int16_t)prm.y[b.coef_off + i];
   __threadfence();
   __syncwarp();
   if (lane == 0) st_release(done + blk, epoch);
@@ -891,6 +896,8 @@ k_pvq_luma_intra_cta(const __grid_constant__ daala_b200_pvq_params prm, const in
     else { v = kScan32[i - 256]; sh = 5; }
     d[(size_t)(v >> sh) * stride + (v & ((1 << sh) - 1))] = vout[i];
   }
+  if (prm.y16)
+    for (int i = threadIdx.x; i < len; i += 32 * NB) prm.y16[b.coef_off + i] = (int16_t)prm.y[b.coef_off + i];
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) st_release(done + blk, epoch);

@@ -31,7 +31,7 @@ class PvqParams(ctypes.Structure):
         ("out", ctypes.c_void_p), ("y", ctypes.c_void_p), ("res_gain", ctypes.c_void_p),
         ("res_theta", ctypes.c_void_p), ("res_max_theta", ctypes.c_void_p), ("res_k", ctypes.c_void_p),
         ("res_skip_term", ctypes.c_void_p), ("res_skip_diff", ctypes.c_void_p), ("res_flip", ctypes.c_void_p),
-        ("res_dc", ctypes.c_void_p), ("qm", ctypes.c_void_p), ("qm_inv", ctypes.c_void_p),
+        ("res_dc", ctypes.c_void_p), ("y16", ctypes.c_void_p), ("qm", ctypes.c_void_p), ("qm_inv", ctypes.c_void_p),
         ("coef_plane", ctypes.c_void_p * 3), ("pred_plane", ctypes.c_void_p * 3),
         ("plane_frame_pitch", ctypes.c_longlong * 3), ("plane_stride", ctypes.c_int * 3),
         ("qm_stride", ctypes.c_int), ("q0", ctypes.c_int), ("is_keyframe", ctypes.c_int),
@@ -227,6 +227,7 @@ class PvqBatch:
         self.res_skip_term = z(nb9, torch.float64)
         self.res_skip_diff = z(self.nblocks, torch.float64)
         self.res_flip, self.res_dc = z(self.nblocks), z(self.nblocks)
+        self.y16 = z(self.total, torch.int16)
         if qm is None:
             qm, qm_inv = default_qm(True)
         self.qm = torch.from_numpy(qm).to(dev)
@@ -240,6 +241,7 @@ class PvqBatch:
         p.res_max_theta, p.res_k = self.res_max_theta.data_ptr(), self.res_k.data_ptr()
         p.res_skip_term, p.res_skip_diff = self.res_skip_term.data_ptr(), self.res_skip_diff.data_ptr()
         p.res_flip, p.res_dc = self.res_flip.data_ptr(), self.res_dc.data_ptr()
+        p.y16 = self.y16.data_ptr()
         p.qm, p.qm_inv, p.qm_stride = self.qm.data_ptr(), self.qm_inv.data_ptr(), OD_QM_STRIDE
         for i, t in enumerate(coef_planes):
             p.coef_plane[i] = t.data_ptr()
@@ -257,6 +259,11 @@ class PvqBatch:
         self.is_keyframe = int(is_keyframe)
         # kernel choice of daala_b200_pvq_encode_bands_mode (0 = measured-best mix)
         self.mode = 0
+
+    def symbol_tensors(self):
+        """What the host entropy coder consumes: per-band indices, flags and the packed pulses."""
+        return [self.res_gain, self.res_theta, self.res_max_theta, self.res_k, self.res_skip_diff, self.res_flip,
+                self.res_dc, self.y16]
 
     def _s(self, stream):
         s = stream if stream is not None else torch.cuda.current_stream(self.device)

@@ -198,6 +198,8 @@ typedef struct daala_b200_pvq_params {
   double *res_skip_diff;   /* per block: ordered sum of the terms above */
   int32_t *res_flip;       /* per block: CfL flip flag */
   int32_t *res_dc;         /* per block: scalar-quantised DC index (inter frames) */
+  int16_t *y16;            /* optional (may be NULL): the pulse vectors again, packed to 16 bits by the
+                              scatter kernels -- the form copied back to the host entropy coder */
   const int16_t *qm;       /* state->qm: od_init_qm, src/pvq.c:322 (2*qm_stride entries) */
   const int16_t *qm_inv;
   int32_t *coef_plane[3];  /* `d` planes (raster): gather source / scatter destination */
