@@ -376,6 +376,22 @@ def run_b200(args):
         ms_pvq_luma = None
         ms_pvq = timed(hp.batch.run, reps) / reps
 
+    # dominant kernel by time share (profiles/r1m_launches.csv): the PVQ band search for the
+    # 128-coefficient bands, k_pvq_bands_coop<16,8>; timed alone on the chroma / all-plane batch
+    import ctypes as _ct
+    from daala_b200 import pvq as _pvq, _native as _nat
+    _L = _pvq._bind()
+    _b = hp.batch
+    _lst = _b.lists[128]
+    _b.gather()
+
+    def _dominant():
+        _nat.check(_L.daala_b200_pvq_encode_bands_mode(_ct.byref(_b.params), _lst.data_ptr(), _lst.numel(), 128,
+                                                       _b.mode, _ct.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                   "pvq_bands")
+
+    ms_dom = (timed(_dominant, reps) / reps) if _lst.numel() else 0.0
+    dom_bytes = 20.0 * 128 * _lst.numel()   # K_pvq = 20 B per coded coefficient
     px_job = geom.luma_pixels * F * (1 if sbrow else world)
     value = px_job / (ms / args.steps * 1e-3) / 1e6
     e2e = px_job / (ms_e2e / args.steps * 1e-3) / 1e6
@@ -408,9 +424,22 @@ def run_b200(args):
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": n_launch,
         "clocks": clocks,
-        "roofline": {"kernel": "k_forward_sb", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
-                     "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-                     "algorithmic_bytes_per_launch": int(algo_bytes), "ms_per_launch": round(ms_fwd, 4)},
+        # dominant kernel (40 % of the step): not HBM-bound -- a greedy double-precision search,
+        # issue/latency-bound; its HBM fraction is reported as the contract asks
+        "roofline": {"kernel": "k_pvq_bands_coop<16,8> (PVQ search, 128-coefficient bands)", "bound": "hbm",
+                     "achieved": round(dom_bytes / (ms_dom * 1e-3) / 1e9, 1) if ms_dom else None, "peak": peak,
+                     "peak_source": peak_src, "unit": "GB/s",
+                     "frac": round(dom_bytes / (ms_dom * 1e-3) / 1e9 / peak, 4) if ms_dom else None,
+                     "traffic": None, "algorithmic_bytes_per_launch": int(dom_bytes),
+                     "ms_per_launch": round(ms_dom, 4),
+                     "note": "compute/latency-bound greedy search; see roofline_transform for the HBM-bound kernel"},
+        # the fused lapped-filter + DCT kernel the north star sets its HBM target on
+        "roofline_transform": {"kernel": "k_forward_sb_tma", "bound": "hbm", "achieved": round(achieved, 1),
+                               "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                               "frac": round(achieved / peak, 4),
+                               "traffic": int(974.7e6 * (nrows / geom.nvsb) * (F / 16.0)),
+                               "traffic_source": "ncu dram__bytes_read+write, profiles/r1m_k_forward_sb_tma_ncu_full.txt (16 frames)",
+                               "algorithmic_bytes_per_launch": int(algo_bytes), "ms_per_launch": round(ms_fwd, 4)},
         "kernels_ms": {"k_forward_sb": round(ms_fwd, 4), "k_inverse_sb": round(ms_inv, 4),
                        "k_sb_postfilter_store": round(ms_post, 4), "pvq_stage(gather+bands+scatter)": round(ms_pvq, 4),
                        "k_pvq_luma_intra(wavefront)": None if ms_pvq_luma is None else round(ms_pvq_luma, 4)},

@@ -251,12 +251,14 @@ __device__ __forceinline__ void transform_pass(int* tile, const SbLists& L, bool
   }
 }
 
-template <bool kFwd, int P, int LOGB>
-__device__ __forceinline__ void transform_all_leaves(int* tile, const SbLists& L) {
+// Not inlined on purpose: luma and chroma bodies call ONE copy of the five transform sizes
+// (the 64-point network alone is ~2500 instructions; duplicating it thrashes the i-cache).
+template <bool kFwd, int P>
+__device__ __noinline__ void transform_all_leaves(int* tile, const SbLists& L) {
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
     const bool cols = kFwd ? (pass == 0) : (pass == 1);
-    if (LOGB >= 6 && L.nblk[4]) transform_pass<4, kFwd, P>(tile, L, cols);
+    if (L.nblk[4]) transform_pass<4, kFwd, P>(tile, L, cols);
     if (L.nblk[3]) transform_pass<3, kFwd, P>(tile, L, cols);
     if (L.nblk[2]) transform_pass<2, kFwd, P>(tile, L, cols);
     if (L.nblk[1]) transform_pass<1, kFwd, P>(tile, L, cols);
@@ -321,7 +323,9 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
                                                 unsigned char* raw, uint64_t* bar) {
   constexpr int B = kMaxB >> XDEC;
   constexpr int T = B + 2 * kHalo;
-  constexpr int P = T + 1;
+  // one pitch (69 = 5 mod 32) for luma AND chroma tiles: the transform / filter code is then
+  // instantiated once and shared by both plane types (half the instruction footprint)
+  constexpr int P = kMaxPitch;
   using Sb = SbCtxT<B, P>;
   const int sbx = blockIdx.x % prm.nhsb, sby = prm.sb_row0 + blockIdx.x / prm.nhsb;
   const int fr = blockIdx.z;
@@ -400,7 +404,7 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
     for (int l = 0; l < 3; l++) for (int i = 0; i < lists.nnode[l]; i++) printf("node l%d (%d,%d) gates %x\n", l, lists.node[node_base(l) + i] & 255, (lists.node[node_base(l) + i] >> 8) & 63, lists.node[node_base(l) + i] >> 14);
   }
 #endif
-  transform_all_leaves<true, P, Sb::logB>(tile, lists);
+  transform_all_leaves<true, P>(tile, lists);
   if (prm.haar_dc) {
 #pragma unroll 1
     for (int l = 0; l <= Sb::logB - 3; l++) {
@@ -449,7 +453,7 @@ template <int XDEC>
 __device__ __forceinline__ void inverse_sb_body(const FrameXformParams& prm, const PlaneXform& pl,
                                                 int* tile, SbLists& lists) {
   constexpr int B = kMaxB >> XDEC;
-  constexpr int P = B + 5;
+  constexpr int P = kMaxPitch;  // shared with the forward kernel's instantiations
   using Sb = SbCtxT<B, P>;
   const int sbx = blockIdx.x % prm.nhsb, sby = prm.sb_row0 + blockIdx.x / prm.nhsb;
   const int fr = blockIdx.z;
@@ -471,7 +475,7 @@ __device__ __forceinline__ void inverse_sb_body(const FrameXformParams& prm, con
       __syncthreads();
     }
   }
-  transform_all_leaves<false, P, Sb::logB>(tile, lists);
+  transform_all_leaves<false, P>(tile, lists);
   // Bottom-up split postfilters: vertical edge first, then horizontal.
 #pragma unroll 1
   for (int l = 0; l <= Sb::logB - 3; l++) {
@@ -490,7 +494,7 @@ __device__ __forceinline__ void inverse_sb_body(const FrameXformParams& prm, con
 
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 k_inverse_sb(const __grid_constant__ FrameXformParams prm) {
-  __shared__ int tile_s[kMaxB * (kMaxB + 5)];
+  __shared__ int tile_s[kMaxB * kMaxPitch];
   __shared__ SbLists lists;
   const PlaneXform& pl = prm.plane[blockIdx.y];
   if (pl.xdec == 0) inverse_sb_body<0>(prm, pl, tile_s, lists);
