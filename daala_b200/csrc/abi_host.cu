@@ -32,6 +32,7 @@ int daala_b200_launch_plane_sb_filter(int32_t* c, int stride, int nhsb, int nvsb
                                       int post, cudaStream_t stream);
 int daala_b200_launch_block_transform(int32_t* blocks, int count, int ln, int mode, cudaStream_t stream);
 int daala_b200_launch_filter4(int32_t* v, long count, int post, cudaStream_t stream);
+int daala_b200_launch_lapfilter(int32_t* v, long count, int n, int post, cudaStream_t stream);
 int daala_b200_launch_split_filter(int32_t* blocks, int count, int n, int post, int hfilter, int vfilter,
                                    cudaStream_t stream);
 }
@@ -132,6 +133,17 @@ void filter4(bool post, od_coeff* out, const od_coeff* in) {
   memcpy(out, c.pinned, sizeof(od_coeff) * 4);
 }
 
+void lapfilter_n(int n, bool post, od_coeff* out, const od_coeff* in) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g(c.mu);
+  c.ensure(sizeof(od_coeff) * n);
+  memcpy(c.pinned, in, sizeof(od_coeff) * n);
+  c.h2d(sizeof(od_coeff) * n);
+  check_launch(daala_b200_launch_lapfilter((int32_t*)c.dev, 1, n, post, c.stream), "lapfilter");
+  c.d2h(sizeof(od_coeff) * n);
+  memcpy(out, c.pinned, sizeof(od_coeff) * n);
+}
+
 void split_filter(bool post, od_coeff* c0, int stride, int bs, int hfilter, int vfilter) {
   HostCtx& c = ctx();
   std::lock_guard<std::mutex> g(c.mu);
@@ -188,6 +200,21 @@ const od_dct_func_2d OD_IDCT_2D_CUDA[6] = {od_bin_idct4x4,   od_bin_idct8x8,   o
 
 void od_pre_filter4(od_coeff _y[4], const od_coeff _x[4]) { filter4(false, _y, _x); }
 void od_post_filter4(od_coeff _x[4], const od_coeff _y[4]) { filter4(true, _x, _y); }
+
+void od_pre_filter8(od_coeff _y[8], const od_coeff _x[8]) { lapfilter_n(8, false, _y, _x); }
+void od_post_filter8(od_coeff _x[8], const od_coeff _y[8]) { lapfilter_n(8, true, _x, _y); }
+void od_pre_filter16(od_coeff _y[16], const od_coeff _x[16]) { lapfilter_n(16, false, _y, _x); }
+void od_post_filter16(od_coeff _x[16], const od_coeff _y[16]) { lapfilter_n(16, true, _x, _y); }
+void od_pre_filter32(od_coeff _y[32], const od_coeff _x[32]) { lapfilter_n(32, false, _y, _x); }
+void od_post_filter32(od_coeff _x[32], const od_coeff _y[32]) { lapfilter_n(32, true, _x, _y); }
+
+// reference: OD_PRE_FILTER / OD_POST_FILTER, src/filter.c:115-127
+const od_filter_func OD_PRE_FILTER_CUDA[4] = {od_pre_filter4, od_pre_filter8, od_pre_filter16, od_pre_filter32};
+const od_filter_func OD_POST_FILTER_CUDA[4] = {od_post_filter4, od_post_filter8, od_post_filter16, od_post_filter32};
+
+int daala_b200_lapfilter(int32_t* v, long count, int n, int post, void* stream) {
+  return daala_b200_launch_lapfilter(v, count, n, post, (cudaStream_t)stream);
+}
 
 void od_prefilter_split(od_coeff* c0, int stride, int bs, int f, int hfilter, int vfilter) {
   (void)f;  // OD_FILT_SIZE() == 0: always the 4-point filter (src/filter.h:77)

@@ -625,6 +625,19 @@ __global__ void k_filter4_batch(int32_t* v, long count, int post) {
   }
 }
 
+// Batched N-point lapped filters (N = 8, 16, 32): `count` groups of N ints.
+template <int N>
+__global__ void k_lapfilter_batch(int32_t* v, long count, int post) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < count; i += (long)gridDim.x * blockDim.x) {
+    int t[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) t[k] = v[i * N + k];
+    if (post) LapFilter<N>::post(t); else LapFilter<N>::pre(t);
+#pragma unroll
+    for (int k = 0; k < N; k++) v[i * N + k] = t[k];
+  }
+}
+
 // Interior-cross filter of `count` packed n x n nodes (od_prefilter_split /
 // od_postfilter_split on stand-alone blocks).
 __global__ void k_split_filter_batch(int32_t* blocks, int n, int post, int hfilter, int vfilter) {
@@ -753,6 +766,18 @@ int daala_b200_launch_filter4(int32_t* v, long count, int post, cudaStream_t str
   int blocks = (int)((count + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_filter4_batch<<<blocks, 256, 0, stream>>>(v, count, post);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_launch_lapfilter(int32_t* v, long count, int n, int post, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  int blocks = (int)((count + 127) / 128);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (n == 4) k_filter4_batch<<<blocks, 128, 0, stream>>>(v, count, post);
+  else if (n == 8) k_lapfilter_batch<8><<<blocks, 128, 0, stream>>>(v, count, post);
+  else if (n == 16) k_lapfilter_batch<16><<<blocks, 128, 0, stream>>>(v, count, post);
+  else if (n == 32) k_lapfilter_batch<32><<<blocks, 128, 0, stream>>>(v, count, post);
+  else return (int)cudaErrorInvalidValue;
   return (int)cudaGetLastError();
 }
 

@@ -73,6 +73,17 @@ extern const od_dct_func_2d OD_IDCT_2D_CUDA[6];
    1529,1561. */
 void od_pre_filter4(od_coeff _y[4], const od_coeff _x[4]);
 void od_post_filter4(od_coeff _x[4], const od_coeff _y[4]);
+/* The larger lapping filters (dead in the codec, OD_FILT_SIZE() == 0, but exported by the
+   reference and used by its dcttest / tools): src/filter.c:279,366,519,678,852,1146. */
+void od_pre_filter8(od_coeff _y[8], const od_coeff _x[8]);
+void od_post_filter8(od_coeff _x[8], const od_coeff _y[8]);
+void od_pre_filter16(od_coeff _y[16], const od_coeff _x[16]);
+void od_post_filter16(od_coeff _x[16], const od_coeff _y[16]);
+void od_pre_filter32(od_coeff _y[32], const od_coeff _x[32]);
+void od_post_filter32(od_coeff _x[32], const od_coeff _y[32]);
+typedef void (*od_filter_func)(od_coeff _out[], const od_coeff _in[]);
+extern const od_filter_func OD_PRE_FILTER_CUDA[4];   /* OD_PRE_FILTER, src/filter.c:115 */
+extern const od_filter_func OD_POST_FILTER_CUDA[4];  /* OD_POST_FILTER, src/filter.c:122 */
 void od_prefilter_split(od_coeff *c0, int stride, int bs, int f, int hfilter, int vfilter);
 void od_postfilter_split(od_coeff *c0, int stride, int bs, int f, int q, unsigned char *skip,
                          int skip_stride, int hfilter, int vfilter);
@@ -165,6 +176,9 @@ int daala_b200_sb_postfilter_store_frame(const daala_b200_frame *f, int nplanes,
 int daala_b200_plane_sb_filter(int32_t *c, int stride, int nhsb, int nvsb, int xdec, int ydec,
                                int post, void *stream);
 
+/* `count` contiguous groups of n (4, 8, 16 or 32) ints through the n-point pre (post = 0) or
+   post filter, in place. */
+int daala_b200_lapfilter(int32_t *v, long count, int n, int post, void *stream);
 /* `count` packed (1<<ln)^2 blocks, contiguous, transformed in place.
    mode 0/1: 2-D forward/inverse; mode 2/3: every row as a 1-D forward/inverse. */
 int daala_b200_block_transform(int32_t *blocks, int count, int ln, int mode, void *stream);

@@ -21,6 +21,8 @@ void port_bin_idct2d(int ln, od_coeff *x, int xstride, const od_coeff *y, int ys
 /* port_filter.c -- src/filter.c */
 void port_pre_filter4(od_coeff y[4], const od_coeff x[4]);
 void port_post_filter4(od_coeff x[4], const od_coeff y[4]);
+void port_pre_filter_n(int n, od_coeff *y, const od_coeff *x);
+void port_post_filter_n(int n, od_coeff *x, const od_coeff *y);
 void port_prefilter_split(od_coeff *c0, int stride, int bs, int hfilter, int vfilter);
 void port_postfilter_split(od_coeff *c0, int stride, int bs, int hfilter, int vfilter);
 void port_apply_prefilter_frame_sbs(od_coeff *c0, int stride, int nhsb, int nvsb, int xdec, int ydec);

@@ -48,6 +48,21 @@ void port_post_filter4(od_coeff x[4], const od_coeff y[4]) {
   x[3] = m0 - d3;
 }
 
+/* 8/16/32-point filters (generated from the lifting IR like the DCTs). */
+#include "gen/dct_port.inc"
+void port_pre_filter_n(int n, od_coeff *y, const od_coeff *x) {
+  if (n == 4) port_pre_filter4(y, x);
+  else if (n == 8) port_pre_filter8_impl(y, x);
+  else if (n == 16) port_pre_filter16_impl(y, x);
+  else port_pre_filter32_impl(y, x);
+}
+void port_post_filter_n(int n, od_coeff *x, const od_coeff *y) {
+  if (n == 4) port_post_filter4(x, y);
+  else if (n == 8) port_post_filter8_impl(x, y);
+  else if (n == 16) port_post_filter16_impl(x, y);
+  else port_post_filter32_impl(x, y);
+}
+
 static void filt_col(od_coeff *c, int stride, int post) {
   od_coeff t[4];
   int k;

@@ -133,6 +133,15 @@ def test_dropin_filter_symbols_match_oracle(torch_cuda):
     xg = np.zeros(4, np.int32)
     L.od_post_filter4(a(xg), a(yg))
     assert np.array_equal(xg, x)
+    for n in (8, 16, 32):
+        x = rng.integers(-30000, 30000, size=n, dtype=np.int32)
+        yg, yc = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        getattr(L, "od_pre_filter%d" % n)(a(yg), a(x))
+        port.port_pre_filter_n(n, a(yc), a(x))
+        assert np.array_equal(yg, yc)
+        xg = np.zeros(n, np.int32)
+        getattr(L, "od_post_filter%d" % n)(a(xg), a(yg))
+        assert np.array_equal(xg, x)
     for xdec in (0, 1):
         nhsb, nvsb = 3, 2
         w, h = (nhsb * 64) >> xdec, (nvsb * 64) >> xdec

@@ -111,3 +111,21 @@ def test_split_filters_port_matches_reference(port, ref, bs, hv):
     port.port_postfilter_split(addr(b), stride, bs, hv[0], hv[1])
     assert np.array_equal(a, b)
     assert np.array_equal(a, c)
+
+
+@pytest.mark.parametrize("n", [8, 16, 32])
+def test_large_filters_port_matches_reference_and_inverts(port, ref, n):
+    """od_pre/post_filter8/16/32 (dead in the codec, exported for dcttest/tools)."""
+    rng = np.random.default_rng(n)
+    pre = getattr(ref, "od_pre_filter%d" % n)
+    post = getattr(ref, "od_post_filter%d" % n)
+    for t in range(500):
+        x = rng.integers(-30000, 30000, size=n, dtype=np.int32)
+        ya, yb = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        pre(addr(ya), addr(x))
+        port.port_pre_filter_n(n, addr(yb), addr(x))
+        assert np.array_equal(ya, yb)
+        xa, xb = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        post(addr(xa), addr(ya))
+        port.port_post_filter_n(n, addr(xb), addr(ya))
+        assert np.array_equal(xa, xb) and np.array_equal(xa, x)

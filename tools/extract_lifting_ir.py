@@ -32,6 +32,10 @@ OUT = os.path.join(os.path.dirname(__file__), "..", "daala_b200", "csrc", "gen",
 PRELUDE = """
 #define OD_DCT_OVERFLOW_CHECK(val, scale, offset, idx)
 #define OD_DCT_RSHIFT(a, b) __rshift(a, b)
+#define OD_COEFF_BITS (32)
+#define OD_DISABLE_FILTER (0)
+#define OD_DEBLOCKING (0)
+#define OD_NBSIZES (5)
 """
 
 
@@ -73,6 +77,7 @@ class Flattener:
         self.count = {}
         self.ops = []
         self.regs = []
+        self.local_arrays = {}
 
     def declare(self, name):
         n = self.count.get(name, 0)
@@ -102,6 +107,8 @@ class Flattener:
     def mem_index(self, node):
         """x[k*xstride], *(x + k*xstride), y[k] -> (array, k) or None."""
         if isinstance(node, c_ast.ArrayRef) and isinstance(node.name, c_ast.ID):
+            if node.name.name in self.local_arrays:
+                return None
             return node.name.name, self.const(node.subscript)
         if isinstance(node, c_ast.UnaryOp) and node.op == '*':
             e = node.expr
@@ -123,11 +130,13 @@ class Flattener:
                 arr, k = self.mem_index(node)
                 return ['ld', k]
         if isinstance(node, c_ast.ArrayRef):
+            if node.name.name in self.local_arrays:
+                return self.local_arrays[node.name.name][self.const(node.subscript)]
             arr, k = self.mem_index(node)
             assert arr == self.in_name, arr
             return ['ld', k]
         if isinstance(node, c_ast.BinaryOp):
-            assert node.op in ('+', '-', '*', '>>'), node.op
+            assert node.op in ('+', '-', '*', '>>', '&', '/', '<<'), node.op
             return [node.op, self.expr(node.left), self.expr(node.right)]
         if isinstance(node, c_ast.FuncCall) and node.name.name == '__rshift':
             a, b = node.args.exprs
@@ -145,7 +154,12 @@ class Flattener:
             self.stmt(node.stmt)
         elif isinstance(node, c_ast.Decl):
             assert node.init is None
-            self.declare(node.name)
+            if isinstance(node.type, c_ast.ArrayDecl):
+                # local scratch array int t[N] -> registers t_0 .. t_{N-1}
+                n = int(node.type.dim.value, 0)
+                self.local_arrays[node.name] = [self.declare("%s%d" % (node.name, i)) for i in range(n)]
+            else:
+                self.declare(node.name)
         elif isinstance(node, c_ast.Assignment):
             mem = self.mem_index(node.lvalue)
             if mem is not None:
@@ -153,7 +167,10 @@ class Flattener:
                 assert arr == self.out_name and node.op == '='
                 self.ops.append(['st', k, self.expr(node.rvalue)])
                 return
-            dst = self.lookup(node.lvalue.name)
+            if isinstance(node.lvalue, c_ast.ArrayRef):
+                dst = self.local_arrays[node.lvalue.name.name][self.const(node.lvalue.subscript)]
+            else:
+                dst = self.lookup(node.lvalue.name)
             rhs = self.expr(node.rvalue)
             if node.op == '=':
                 self.ops.append(['set', dst, rhs])
@@ -168,6 +185,7 @@ class Flattener:
 
 def extract(pp, name, in_name, out_name):
     text = function_text(pp, name)
+    text = re.sub(r'\b_([xy])\b', r'\1', text)  # filter.c spells its arguments _x / _y
     text = "typedef int od_coeff;\n" + text
     ast = c_parser.CParser().parse(text)
     fn = [e for e in ast.ext if isinstance(e, c_ast.FuncDef)][0]
@@ -188,6 +206,14 @@ def main():
         print("n=%d: fdct %d ops / %d regs, idct %d ops / %d regs" % (
             n, len(ir["fdct%d" % n]["ops"]), len(ir["fdct%d" % n]["regs"]),
             len(ir["idct%d" % n]["ops"]), len(ir["idct%d" % n]["regs"])), file=sys.stderr)
+    # larger lapping filters of src/filter.c (dead in the codec, kept for ABI completeness):
+    # od_pre_filter8 :279, od_post_filter8 :366, 16 :519/:678, 32 :852/:1146
+    fpp = preprocess(os.path.join(REF, "src", "filter.c"))
+    for n in (8, 16, 32):
+        ir["prefilter%d" % n] = extract(fpp, "od_pre_filter%d" % n, "x", "y")
+        ir["postfilter%d" % n] = extract(fpp, "od_post_filter%d" % n, "y", "x")
+        print("filter n=%d: pre %d ops, post %d ops" % (n, len(ir["prefilter%d" % n]["ops"]),
+                                                        len(ir["postfilter%d" % n]["ops"])), file=sys.stderr)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as f:
         json.dump(ir, f, separators=(",", ":"))
