@@ -32,6 +32,8 @@ int daala_b200_launch_plane_sb_filter(int32_t* c, int stride, int nhsb, int nvsb
                                       int post, cudaStream_t stream);
 int daala_b200_launch_block_transform(int32_t* blocks, int count, int ln, int mode, cudaStream_t stream);
 int daala_b200_launch_filter4(int32_t* v, long count, int post, cudaStream_t stream);
+int daala_b200_pvq_helper_launch(void* buf, int op, void* stream);
+int daala_b200_pvq_helper_bytes(void);
 int daala_b200_launch_lapfilter(int32_t* v, long count, int n, int post, cudaStream_t stream);
 int daala_b200_launch_split_filter(int32_t* blocks, int count, int n, int post, int hfilter, int vfilter,
                                    cudaStream_t stream);
@@ -329,6 +331,113 @@ DAALA_B200_MATCH(8, 3)
 DAALA_B200_MATCH(16, 4)
 DAALA_B200_MATCH(32, 5)
 DAALA_B200_MATCH(64, 6)
+
+// Scalar PVQ helpers with host pointers (src/pvq.h:148-175, src/pvq_encoder.h:46).
+struct PvqHelperBuf {
+  int32_t args[16];
+  int16_t a16[2][128];
+  int32_t a32[2][128];
+  int16_t qmi[128];
+  double dargs[2];
+};
+
+static PvqHelperBuf* helper_begin(HostCtx& c) {
+  if ((size_t)daala_b200_pvq_helper_bytes() != sizeof(PvqHelperBuf)) fatal("pvq helper layout", cudaErrorInvalidValue);
+  c.ensure(sizeof(PvqHelperBuf));
+  PvqHelperBuf* b = (PvqHelperBuf*)c.pinned;
+  memset(b, 0, sizeof(*b));
+  return b;
+}
+
+static void helper_run(HostCtx& c, int op) {
+  c.h2d(sizeof(PvqHelperBuf));
+  check_launch(daala_b200_pvq_helper_launch(c.dev, op, c.stream), "pvq_helper");
+  c.d2h(sizeof(PvqHelperBuf));
+}
+
+#define HELPER_SCALAR(OP, ...)                      \
+  HostCtx& c = ctx();                               \
+  std::lock_guard<std::mutex> g_(c.mu);             \
+  PvqHelperBuf* b = helper_begin(c);                \
+  { int32_t v_[] = {__VA_ARGS__}; memcpy(b->args, v_, sizeof(v_)); } \
+  helper_run(c, OP);
+
+int16_t od_pvq_sin(int32_t x) { HELPER_SCALAR(0, x) return (int16_t)b->args[15]; }
+int16_t od_pvq_cos(int32_t x) { HELPER_SCALAR(1, x) return (int16_t)b->args[15]; }
+int32_t od_gain_expand(int32_t cg, int q0, int16_t beta) { HELPER_SCALAR(6, cg, q0, beta) return b->args[15]; }
+int od_pvq_compute_max_theta(int32_t qcg, int16_t beta) { HELPER_SCALAR(8, qcg, beta) return b->args[15]; }
+int32_t od_pvq_compute_theta(int t, int max_theta) { HELPER_SCALAR(9, t, max_theta) return b->args[15]; }
+int od_pvq_compute_k(int32_t qcg, int itheta, int32_t theta, int noref, int n, int16_t beta, int nodesync) {
+  (void)theta; (void)nodesync;  // robust-stream rule only (OD_ROBUST_STREAM, src/internal.h:118)
+  HELPER_SCALAR(10, qcg, itheta, noref, n, beta)
+  return b->args[15];
+}
+
+int od_vector_log_mag(const od_coeff* x, int n) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g_(c.mu);
+  PvqHelperBuf* b = helper_begin(c);
+  b->args[0] = n;
+  memcpy(b->a32[0], x, sizeof(od_coeff) * n);
+  helper_run(c, 2);
+  return b->args[15];
+}
+
+int od_compute_householder(int16_t* r, int n, int32_t gr, int* sign, int shift) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g_(c.mu);
+  PvqHelperBuf* b = helper_begin(c);
+  b->args[0] = n; b->args[1] = gr; b->args[2] = shift;
+  memcpy(b->a16[0], r, sizeof(int16_t) * n);
+  helper_run(c, 3);
+  memcpy(r, b->a16[0], sizeof(int16_t) * n);
+  *sign = b->args[14];
+  return b->args[15];
+}
+
+void od_apply_householder(int16_t* out, const int16_t* x, const int16_t* r, int n) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g_(c.mu);
+  PvqHelperBuf* b = helper_begin(c);
+  b->args[0] = n;
+  memcpy(b->a16[0], r, sizeof(int16_t) * n);
+  memcpy(b->a16[1], x, sizeof(int16_t) * n);
+  helper_run(c, 4);
+  memcpy(out, b->a16[1], sizeof(int16_t) * n);
+}
+
+void od_pvq_synthesis_partial(od_coeff* xcoeff, const od_coeff* ypulse, const int16_t* r, int n, int noref,
+                              int32_t g, int32_t theta, int m, int s, const int16_t* qm_inv) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g_(c.mu);
+  PvqHelperBuf* b = helper_begin(c);
+  b->args[0] = n; b->args[1] = noref; b->args[2] = g; b->args[3] = theta; b->args[4] = m; b->args[5] = s;
+  memcpy(b->a32[0], ypulse, sizeof(od_coeff) * (n - !noref));
+  if (r) memcpy(b->a16[0], r, sizeof(int16_t) * n);
+  memcpy(b->qmi, qm_inv, sizeof(int16_t) * n);
+  helper_run(c, 5);
+  memcpy(xcoeff, b->a32[1], sizeof(od_coeff) * n);
+}
+
+int32_t od_pvq_compute_gain(const int16_t* x, int n, int q0, int32_t* g, int16_t beta, int bshift) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g_(c.mu);
+  PvqHelperBuf* b = helper_begin(c);
+  b->args[0] = n; b->args[1] = q0; b->args[2] = beta; b->args[3] = bshift;
+  memcpy(b->a16[0], x, sizeof(int16_t) * n);
+  helper_run(c, 7);
+  *g = b->args[14];
+  return b->args[15];
+}
+
+int od_rdo_quant(od_coeff x, int q, double delta0, double pvq_norm_lambda) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g_(c.mu);
+  PvqHelperBuf* b = helper_begin(c);
+  b->args[0] = x; b->args[1] = q; b->dargs[0] = delta0; b->dargs[1] = pvq_norm_lambda;
+  helper_run(c, 11);
+  return b->args[15];
+}
 
 // ---- Section B ------------------------------------------------------------
 int daala_b200_forward_frame(const daala_b200_frame* f, int nplanes, void* stream) {

@@ -945,6 +945,61 @@ __global__ void k_cfl_pred(const __grid_constant__ daala_b200_pvq_params prm, in
   }
 }
 
+// ---------------------------------------------------------------------------
+// Scalar helpers of src/pvq.h:148-175 for the host-pointer ABI: one thread runs
+// the same device functions the batch kernels use.  Marshalling buffer layout
+// (ints): args[16] | a16[2][128] (as int16) | a32[2][128] | qmi[128] (int16) | dargs[2] (double)
+// ---------------------------------------------------------------------------
+struct HelperBuf {
+  int32_t args[16];
+  int16_t a16[2][kMaxN];
+  int32_t a32[2][kMaxN];
+  int16_t qmi[kMaxN];
+  double dargs[2];
+};
+
+__global__ void k_pvq_helper(HelperBuf* b, int op) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int32_t* a = b->args;
+  switch (op) {
+    case 0: a[15] = (int16_t)pvq_sin(a[0]); break;
+    case 1: a[15] = (int16_t)pvq_cos(a[0]); break;
+    case 2: {  // od_vector_log_mag(x, n)
+      int32_t sum = 0;
+      for (int i = 0; i < a[0]; i++) { int16_t t = (int16_t)(b->a32[0][i] >> 8); sum += t * (int32_t)t; }
+      a[15] = 9 + ilog((uint32_t)(a[0] + sum)) / 2;
+      break;
+    }
+    case 3: { int sign; a[15] = householder_setup(b->a16[0], a[0], a[1], &sign, a[2]); a[14] = sign; break; }
+    case 4: householder_apply(b->a16[1], b->a16[1], b->a16[0], a[0]); break;
+    case 5: {  // od_pvq_synthesis_partial(xcoeff, ypulse, r, n, noref, g, theta, m, s, qm_inv)
+      int16_t scratch[kMaxN];
+      synthesis(b->a32[1], b->a32[0], b->a16[0], a[0], a[1], a[2], a[3], a[4], a[5], b->qmi, scratch);
+      break;
+    }
+    case 6: a[15] = gain_expand(a[0], a[1], a[2]); break;
+    case 7: {  // od_pvq_compute_gain(x, n, q0, &g, beta, bshift)
+      int32_t acc = 0, g;
+      for (int i = 0; i < a[0]; i++) acc += b->a16[0][i] * (int32_t)b->a16[0][i];
+      a[15] = compute_gain_from_energy(acc, a[1], &g, a[2], a[3]);
+      a[14] = g;
+      break;
+    }
+    case 8: a[15] = compute_max_theta(a[0], a[1]); break;
+    case 9: a[15] = compute_theta(a[0], a[1]); break;
+    case 10: a[15] = compute_k(a[0], a[1], a[2], a[3], a[4]); break;
+    case 11: {  // od_rdo_quant(x, q, delta0, pvq_norm_lambda), src/pvq_encoder.c:730
+      int t = (int)(256 * b->dargs[1] * b->dargs[0] / 2);
+      t = t < 0 ? 0 : (t > 128 ? 128 : t);  // OD_CLAMPI(0, t, 128)
+      const int threshold = 128 + t, x = a[0], q = a[1];
+      if (abs(x) < q * threshold / 256) a[15] = 0;
+      else { int half = ((q + 1) >> 1) - 1; a[15] = (x + (x < 0 ? -half : half)) / q; }
+      break;
+    }
+    default: a[15] = 0;
+  }
+}
+
 }  // namespace pvq
 }  // namespace daala_b200
 
@@ -1068,6 +1123,12 @@ int daala_b200_pvq_cfl_pred(const daala_b200_pvq_params* prm, int32_t* pred_plan
   k_cfl_pred<<<nblocks, 64, 0, (cudaStream_t)stream>>>(*prm, pred_plane, pred_frame_pitch, pred_stride, nblocks);
   return (int)cudaGetLastError();
 }
+
+int daala_b200_pvq_helper_launch(void* buf, int op, void* stream) {
+  k_pvq_helper<<<1, 32, 0, (cudaStream_t)stream>>>((HelperBuf*)buf, op);
+  return (int)cudaGetLastError();
+}
+int daala_b200_pvq_helper_bytes(void) { return (int)sizeof(HelperBuf); }
 
 int daala_b200_pvq_block_finish(const daala_b200_pvq_params* prm, int nblocks, void* stream) {
   if (nblocks <= 0) return 0;

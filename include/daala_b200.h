@@ -91,6 +91,23 @@ void od_apply_prefilter_frame_sbs(od_coeff *c, int stride, int nhsb, int nvsb, i
 void od_apply_postfilter_frame_sbs(od_coeff *c, int stride, int nhsb, int nvsb, int xdec, int ydec,
                                    int q, unsigned char *skip, int skip_stride);
 
+/* PVQ helpers shared by encoder and decoder (src/pvq.h:148-175; definitions src/pvq.c:428-1115)
+   and the scalar RDO quantiser (src/pvq_encoder.c:730).  Each call is one single-thread launch of
+   the same device functions the batch kernels use: exact, and only meant for ABI completeness. */
+int16_t od_pvq_sin(int32_t x);
+int16_t od_pvq_cos(int32_t x);
+int od_vector_log_mag(const od_coeff *x, int n);
+int od_compute_householder(int16_t *r, int n, int32_t gr, int *sign, int shift);
+void od_apply_householder(int16_t *out, const int16_t *x, const int16_t *r, int n);
+void od_pvq_synthesis_partial(od_coeff *xcoeff, const od_coeff *ypulse, const int16_t *r, int n, int noref,
+                              int32_t g, int32_t theta, int m, int s, const int16_t *qm_inv);
+int32_t od_gain_expand(int32_t cg, int q0, int16_t beta);
+int32_t od_pvq_compute_gain(const int16_t *x, int n, int q0, int32_t *g, int16_t beta, int bshift);
+int od_pvq_compute_max_theta(int32_t qcg, int16_t beta);
+int32_t od_pvq_compute_theta(int t, int max_theta);
+int od_pvq_compute_k(int32_t qcg, int itheta, int32_t theta, int noref, int n, int16_t beta, int nodesync);
+int od_rdo_quant(od_coeff x, int q, double delta0, double pvq_norm_lambda);
+
 /* Motion-compensation and block-matching slots of od_state_opt_vtbl
    (src/state.h:113-121) and od_enc_opt_vtbl (src/encint.h:77-98).  The names
    carry a _cuda suffix because the reference's C kernels keep their _c names in

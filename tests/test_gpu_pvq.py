@@ -223,3 +223,70 @@ def test_keyframe_with_intra_and_cfl_prediction_matches_frame_oracle(intra_mode)
             assert np.array_equal(hp.fb.pixels_out[pli][f].cpu().numpy(), rec)
         rec0 = frame_oracle.inverse_plane(lib, prefix, q0, geom, 0, bsize, 1)
         assert np.array_equal(hp.fb.pixels_out[0][f].cpu().numpy(), rec0)
+
+
+def test_dropin_pvq_helper_symbols_match_oracle():
+    """Host-pointer od_pvq_* helpers and od_rdo_quant against the reference build
+    (or the port when oracle/_ref is absent)."""
+    import ctypes
+    from daala_b200 import _native
+    from tests.oracle_lib import addr
+    L = _native.lib()
+    lib, prefix = _oracle()
+    rng = np.random.default_rng(9)
+    for fn in (L.od_pvq_sin, L.od_pvq_cos):
+        fn.restype = ctypes.c_int16
+    L.od_rdo_quant.restype = ctypes.c_int
+
+    def o(name):
+        return getattr(lib, ("od_" if prefix == "ref" else "port_") + name)
+    if prefix == "ref":
+        lib.od_pvq_sin.restype = lib.od_pvq_cos.restype = ctypes.c_int16
+    for x in (0, 5, 20000, 32768, 40000, 70000, -300):
+        assert L.od_pvq_sin(x) == np.int16(o("pvq_sin")(x)) and L.od_pvq_cos(x) == np.int16(o("pvq_cos")(x))
+    for beta in (4096, 6144):
+        for cg0, q0 in ((300, 64), (1000, 400), (20000, 8)):
+            assert L.od_gain_expand(cg0, q0, beta) == o("gain_expand")(cg0, q0, beta)
+        for qcg in (100, 358, 900, 4000):
+            assert L.od_pvq_compute_max_theta(qcg, beta) == o("pvq_compute_max_theta")(qcg, beta)
+            for n in (15, 8, 32, 128):
+                exp = lib.od_pvq_compute_k(qcg, -1, -1, 1, n, beta, 1) if prefix == "ref" else \
+                    lib.port_pvq_compute_k(qcg, -1, 1, n, beta)
+                assert L.od_pvq_compute_k(qcg, -1, -1, 1, n, beta, 1) == exp
+    for ts in (1, 5, 12):
+        for t in (0, 3, 11):
+            assert L.od_pvq_compute_theta(t, ts) == o("pvq_compute_theta")(t, ts)
+    for n in (15, 8, 32, 128):
+        x = rng.integers(-3000, 3000, size=n).astype(np.int16)
+        r = rng.integers(-3000, 3000, size=n).astype(np.int16)
+        g1, g2 = ctypes.c_int32(0), ctypes.c_int32(0)
+        assert L.od_pvq_compute_gain(addr(x), n, 100, ctypes.byref(g1), 6144, 1) == \
+            o("pvq_compute_gain")(addr(x), n, 100, ctypes.byref(g2), 6144, 1)
+        assert g1.value == g2.value
+        x32 = x.astype(np.int32) * 41
+        assert L.od_vector_log_mag(addr(x32), n) == o("vector_log_mag")(addr(x32), n)
+        ra, rb = r.copy(), r.copy()
+        sa, sb = ctypes.c_int(0), ctypes.c_int(0)
+        gr = int(np.sqrt(float((r.astype(np.int64) ** 2).sum())))
+        assert L.od_compute_householder(addr(ra), n, gr, ctypes.byref(sa), 0) == \
+            o("compute_householder")(addr(rb), n, gr, ctypes.byref(sb), 0)
+        assert sa.value == sb.value and np.array_equal(ra, rb)
+        oa, ob = np.zeros(n, np.int16), np.zeros(n, np.int16)
+        L.od_apply_householder(addr(oa), addr(x), addr(ra), n)
+        o("apply_householder")(addr(ob), addr(x), addr(rb), n)
+        assert np.array_equal(oa, ob)
+        qmi = rng.integers(2000, 6000, size=n).astype(np.int16)
+        for noref in (1, 0):
+            y = np.zeros(n, np.int32)
+            y[rng.integers(0, n - 1, size=5)] = rng.integers(-3, 4, size=5)
+            xa, xb = np.zeros(n, np.int32), np.zeros(n, np.int32)
+            L.od_pvq_synthesis_partial(addr(xa), addr(y), addr(ra), n, noref, 5000, 9000, 3, -1, addr(qmi))
+            o("pvq_synthesis_partial")(addr(xb), addr(y), addr(rb), n, noref, 5000, 9000, 3, -1, addr(qmi))
+            assert np.array_equal(xa, xb)
+    if prefix == "ref":
+        lib.od_rdo_quant.restype = ctypes.c_int
+        for x in (-900, -100, -3, 0, 5, 77, 400, 12345):
+            for q in (7, 64, 300):
+                for d0 in (0.0, 1.3, 7.5):
+                    assert L.od_rdo_quant(x, q, ctypes.c_double(d0), ctypes.c_double(0.147)) == \
+                        lib.od_rdo_quant(x, q, ctypes.c_double(d0), ctypes.c_double(0.147))
