@@ -165,3 +165,60 @@ def test_dropin_mc_symbols_match_oracle():
                 (lib.od_mc_blend_full_split8_c if prefix == "ref" else lib.port_mc_blend_full_split8)(
                     addr(e), n + 2, ptrs, oc, s, ln, ln)
             assert np.array_equal(g, e), (ln, oc, s)
+
+
+def _random_mv_grid(rng, nv, nh, max_mv=200):
+    """Hierarchically consistent validity flags + random MVs (1/8 pel)."""
+    valid = np.zeros((nv + 1, nh + 1), bool)
+    valid[::8, ::8] = True
+
+    def split(vx, vy, l):
+        if l == 0:
+            return
+        h = (1 << l) >> 1
+        if rng.random() < 0.6:
+            valid[vy + h, vx + h] = True
+            for dx, dy in ((h, 0), (0, h), (2 * h, h), (h, 2 * h)):
+                if rng.random() < 0.7:
+                    valid[vy + dy, vx + dx] = True
+            for dx, dy in ((0, 0), (h, 0), (0, h), (h, h)):
+                split(vx + dx, vy + dy, l - 1)
+
+    for vy in range(0, nv, 8):
+        for vx in range(0, nh, 8):
+            split(vx, vy, 3)
+    mv = rng.integers(-max_mv, max_mv + 1, size=(nv + 1, nh + 1, 2)).astype(np.int32)
+    # smooth-ish field plus a few exact full-pel and identical-neighbour vectors
+    mv[::2, ::2] = (mv[::2, ::2] // 8) * 8
+    mv[1::4, :] = mv[0::4, :][:mv[1::4, :].shape[0]]
+    return valid, mv
+
+
+def test_frame_obmc_prediction_matches_reference_state_mc_predict():
+    """MV grid -> block list (daala_b200/mvgrid.py) -> k_obmc_blocks for all three planes against
+    the reference's od_state_mc_predict driven on a real od_state (oracle/ref_hooks_mc.c)."""
+    import torch
+    from daala_b200 import mc, mvgrid
+    lib, prefix = _oracle()
+    if prefix != "ref":
+        pytest.skip("needs the reference build (od_state_mc_predict)")
+    rng = np.random.default_rng(21)
+    W, H = 256, 192
+    cur, ref_y = _frames(seed=6, h=H, w=W)
+    ref_u = np.ascontiguousarray(ref_y[::2, ::2][:, ::-1])
+    ref_v = np.ascontiguousarray(ref_y[1::2, 1::2])
+    nv, nh = H // 8, W // 8
+    valid, mv = _random_mv_grid(rng, nv, nh)
+    outs = [np.zeros((H, W), np.uint8), np.zeros((H // 2, W // 2), np.uint8), np.zeros((H // 2, W // 2), np.uint8)]
+    rc = lib.oracle_ref_state_mc_predict(W, H, addr(ref_y), addr(ref_u), addr(ref_v),
+                                         addr(np.ascontiguousarray(valid.astype(np.uint8))),
+                                         addr(np.ascontiguousarray(mv)), addr(outs[0]), addr(outs[1]), addr(outs[2]))
+    assert rc == 0
+    for pli, refp in enumerate((ref_y, ref_u, ref_v)):
+        xdec = 1 if pli else 0
+        blocks = mvgrid.block_list(valid, mv, xdec=xdec)
+        rp = mc.PaddedPlane(refp)
+        dst = torch.zeros(refp.shape, dtype=torch.uint8, device="cuda:0")
+        mc.predict_blocks(rp, dst, mc.to_device(blocks), len(blocks))
+        got = dst.cpu().numpy()
+        assert np.array_equal(got, outs[pli]), "plane %d: %d mismatches" % (pli, int((got != outs[pli]).sum()))
