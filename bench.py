@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=16, help="4K frames per step (whole job)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pvq-mode", type=int, default=0, help="0 cooperative kernels, 2 scalar thread-per-band")
-    ap.add_argument("--intra-mode", default="waves", choices=["waves", "chain", "chain_single"])
+    ap.add_argument("--intra-mode", default="bands", choices=["bands", "waves", "chain", "chain_single"])
     ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"],
                     help="frames: every rank encodes its own --frames frames with the reference's keyframe "
                          "predictors (weak scaling, no exchange); sbrow: one batch split by superblock row with "

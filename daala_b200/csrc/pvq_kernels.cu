@@ -801,6 +801,48 @@ __global__ void k_intra_pred_gather(const __grid_constant__ daala_b200_pvq_param
   }
 }
 
+// Band-granular form of the same prediction.  od_hv_intra_pred only fills row 0 and column 0 of the
+// block (src/intra.c:53-60), and the neighbour it reads has the SAME size, so coefficient (0, c) /
+// (r, 0) sits at the same coding-order index -- and in the same band -- in both blocks: band b of a
+// block depends on band b of its top / left neighbour only.  Of the bands of OD_BAND_OFFSETS, 1/4/7
+// hold row-0 coefficients (top chain only), 2/5/8 column-0 coefficients (left chain only), 3/6 neither
+// (no dependency at all) and 0 the three low coefficients of each, whose source is chosen by the
+// neighbours' energies (:51-52, :55-60) -- again band-0 values only.  One warp per band-list entry
+// writes that band's slice of `ref` from the neighbours' `out` (coding order, already dequantised).
+__global__ void k_intra_band_ref(const __grid_constant__ daala_b200_pvq_params prm,
+                                 const int32_t* __restrict__ dep_top, const int32_t* __restrict__ dep_left,
+                                 const uint32_t* __restrict__ band_list, int count) {
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (slot >= count) return;
+  const uint32_t e = band_list[slot];
+  const int blk = (int)(e >> 4), band = (int)(e & 15);
+  const int t = dep_top[blk], l = dep_left[blk];
+  const int32_t* ot = t >= 0 ? prm.out + prm.blocks[t].coef_off : nullptr;
+  const int32_t* ol = l >= 0 ? prm.out + prm.blocks[l].coef_off : nullptr;
+  bool low_from_top = false;
+  if (band == 0) {
+    // coding-order indices of (0,1) (0,2) (0,3) and (1,0) (2,0) (3,0) in OD_ZIGZAG4
+    double g1 = 0, g2 = 0;
+    if (ot) { double a = ot[2], b = ot[5], c = ot[9]; g1 += a * a; g1 += b * b; g1 += c * c; }
+    if (ol) { double a = ol[1], b = ol[4], c = ol[7]; g2 += a * a; g2 += b * b; g2 += c * c; }
+    low_from_top = g1 > g2;
+  }
+  const int start = band_start(band), n = band_start(band + 1) - start;
+  int32_t* vref = prm.ref + prm.blocks[blk].coef_off;
+  for (int i = start + lane; i < start + n; i += 32) {
+    int v, sh;
+    if (i < 16) { v = kScan4[i - 1]; sh = 2; }
+    else if (i < 64) { v = kScan8[i - 16]; sh = 3; }
+    else if (i < 256) { v = kScan16[i - 64]; sh = 4; }
+    else { v = kScan32[i - 256]; sh = 5; }
+    const int r = v >> sh, c = v & ((1 << sh) - 1);
+    int32_t p = 0;
+    if (r == 0 && c > 0 && ot && (c >= 4 || low_from_top)) p = ot[i];
+    if (c == 0 && r > 0 && ol && (r >= 4 || !low_from_top)) p = ol[i];
+    vref[i] = p;
+  }
+}
+
 // Same chain link with one CTA per block and one WARP PER BAND (NB = bands of
 // this block size): the bands of a block are independent once the prediction
 // is known, so the latency of a link is the slowest band instead of their sum.
@@ -1079,6 +1121,14 @@ int daala_b200_pvq_intra_gather(const daala_b200_pvq_params* prm, const int32_t*
   if (count <= 0) return 0;
   k_intra_pred_gather<<<(count * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*prm, dep_top, dep_left, first,
                                                                                   count);
+  return (int)cudaGetLastError();
+}
+
+int daala_b200_pvq_intra_band_ref(const daala_b200_pvq_params* prm, const int32_t* dep_top, const int32_t* dep_left,
+                                  const uint32_t* band_list, int count, void* stream) {
+  if (count <= 0) return 0;
+  k_intra_band_ref<<<(count * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*prm, dep_top, dep_left, band_list,
+                                                                               count);
   return (int)cudaGetLastError();
 }
 

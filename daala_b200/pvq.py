@@ -59,6 +59,8 @@ def _bind():
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_pvq_intra_gather.argtypes = [pp, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_void_p]
+    L.daala_b200_pvq_intra_band_ref.argtypes = [pp, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                  ctypes.c_void_p]
     L.daala_b200_pvq_block_finish_range.argtypes = [pp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_coding_order_scatter_range.argtypes = [pp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_pvq_cfl_pred.argtypes = [pp, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
@@ -206,6 +208,34 @@ def band_lists(blocks):
     return {k: (np.concatenate(v) if v else np.zeros(0, np.uint32)) for k, v in cls.items()}
 
 
+def band_wave_lists(blocks, top, left, depth):
+    """Band-granular intra wavefront of a luma block list (see k_intra_band_ref): per size class
+    {16, 32, 128} -> (bulk, chain, slices).  `bulk[k]`: entries of the dependency-free bands 3 / 6;
+    `chain[k]`: the other entries sorted by (wave, band, block), where the wave of band 0 is the
+    block's depth over both neighbour chains, of bands 1/4/7 its depth over the top chain and of
+    2/5/8 over the left chain; `slices[k][w]` = (first, count) of wave w + 1 inside chain[k]."""
+    none = np.full(len(top), -1, np.int32)
+    dh, dv = dependency_depth(top, none), dependency_depth(none, left)
+    per_band = [depth, dh, dv, None, dh, dv, None, dh, dv]
+    bulk, chain, slices = {}, {}, {}
+    for k, v in band_lists(blocks).items():
+        blk, band = (v >> 4).astype(np.int64), (v & 15).astype(np.int64)
+        free = (band == 3) | (band == 6)
+        bulk[k] = v[free]
+        v, blk, band = v[~free], blk[~free], band[~free]
+        d = np.ones(len(v), np.int32)
+        for b in (0, 1, 2, 4, 5, 7, 8):
+            m = band == b
+            d[m] = per_band[b][blk[m]]
+        order = np.lexsort((blk, band, d))
+        v, d = v[order], d[order]
+        chain[k] = v
+        top_d = int(d.max()) if len(d) else 0
+        cuts = np.searchsorted(d, np.arange(1, top_d + 2))
+        slices[k] = [(int(a), int(b - a)) for a, b in zip(cuts[:-1], cuts[1:])]
+    return bulk, chain, slices
+
+
 class PvqBatch:
     """Device state of one PVQ batch: coding-order buffers, result arrays and
     the launch sequence gather -> [CfL flip] -> bands -> finish -> scatter."""
@@ -326,11 +356,56 @@ class PvqBatch:
             d = depth[(v >> 4).astype(np.int64)]
             cuts = np.searchsorted(d, np.arange(1, self.max_depth + 2))
             self.wave_slices[k] = [(int(a), int(b - a)) for a, b in zip(cuts[:-1], cuts[1:])]
-        self.intra_mode = "waves"
+        # band-granular waves (default): band b of a block depends on band b of the same-size top
+        # (bands 1/4/7), left (2/5/8), both (0) or no (3/6) neighbour -- see k_intra_band_ref.  Every
+        # size class is a closed dependency system, so each gets its own stream and wave sequence.
+        bulk, chain, self.chain_slices = band_wave_lists(self.blocks_np, top, left, depth)
+        as_dev = lambda v: torch.from_numpy(np.ascontiguousarray(v).view(np.int32)).to(dev)  # noqa: E731
+        self.bulk_lists = {k: as_dev(v) for k, v in bulk.items()}
+        self.chain_lists = {k: as_dev(v) for k, v in chain.items()}
+        self.chain_streams = {k: torch.cuda.Stream(device=dev, priority=-1) for k in lists}
+        self.bulk_stream = torch.cuda.Stream(device=dev)
+        # waves smaller than this many bands use the group-cooperative kernels (shorter latency)
+        self.small_wave = {16: 0, 32: 0, 128: 0}
+        self.small_mode = 3
+        self.intra_mode = "bands"
 
     def run_luma_intra(self, stream=None):
         L = _bind()
         p = ctypes.byref(self.params)
+        if self.intra_mode == "bands":
+            main = stream if stream is not None else torch.cuda.current_stream(self.device)
+            _native.check(L.daala_b200_coding_order_gather(p, self.nblocks, 0, self._s(main)), "gather(in)")
+            n = 1
+            top, left = self.dep_top.data_ptr(), self.dep_left.data_ptr()
+            # latency-bound chains first (high-priority streams), the dependency-free bands fill the GPU behind
+            for k in (128, 32, 16):
+                st = self.chain_streams[k]
+                st.wait_stream(main)
+                sp = ctypes.c_void_p(st.cuda_stream)
+                for w, (a, c) in enumerate(self.chain_slices[k]):
+                    if not c:
+                        continue
+                    ptr = self.chain_lists[k].data_ptr() + 4 * a
+                    if w > 0:
+                        _native.check(L.daala_b200_pvq_intra_band_ref(p, top, left, ptr, c, sp), "intra_band_ref")
+                        n += 1
+                    mode = self.small_mode if c < self.small_wave[k] else self.mode
+                    _native.check(L.daala_b200_pvq_encode_bands_mode(p, ptr, c, k, mode, sp), "pvq_bands")
+                    n += 1
+            self.bulk_stream.wait_stream(main)
+            sp = ctypes.c_void_p(self.bulk_stream.cuda_stream)
+            for k in (128, 32):
+                lst = self.bulk_lists[k]
+                if lst.numel():
+                    _native.check(L.daala_b200_pvq_encode_bands_mode(p, lst.data_ptr(), lst.numel(), k, self.mode, sp),
+                                  "pvq_bands")
+                    n += 1
+            for st in list(self.chain_streams.values()) + [self.bulk_stream]:
+                main.wait_stream(st)
+            _native.check(L.daala_b200_pvq_block_finish(p, self.nblocks, self._s(main)), "block_finish")
+            _native.check(L.daala_b200_coding_order_scatter(p, self.nblocks, self._s(main)), "scatter")
+            return n + 2
         if self.intra_mode == "waves":
             s = self._s(stream)
             n = 0

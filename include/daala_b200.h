@@ -274,6 +274,14 @@ int daala_b200_pvq_luma_intra(const daala_b200_pvq_params *prm, const int32_t *d
    _coding_order_scatter_range.  dep_top / dep_left only need their sign here. */
 int daala_b200_pvq_intra_gather(const daala_b200_pvq_params *prm, const int32_t *dep_top, const int32_t *dep_left,
                                 int first, int count, void *stream);
+/* Band-granular wavefront (the default): od_hv_intra_pred (src/intra.c:37) couples band b of a block
+   only to band b of the same-size top / left neighbour (row-0 bands 1/4/7: top, column-0 bands 2/5/8:
+   left, bands 3/6: none, band 0: both).  For the entries of `band_list` ((block << 4) | band, all of
+   one dependency depth >= 2) this writes the bands' slices of `ref` from the neighbours' `out`; the
+   caller then runs daala_b200_pvq_encode_bands[_mode] on the same slice.  dep_top / dep_left: index of
+   the neighbour block in prm->blocks or -1. */
+int daala_b200_pvq_intra_band_ref(const daala_b200_pvq_params *prm, const int32_t *dep_top, const int32_t *dep_left,
+                                  const uint32_t *band_list, int count, void *stream);
 int daala_b200_pvq_block_finish_range(const daala_b200_pvq_params *prm, int first, int count, void *stream);
 int daala_b200_coding_order_scatter_range(const daala_b200_pvq_params *prm, int first, int count, void *stream);
 /* The same split by block size (chains only connect blocks of equal size): `ids` lists the

@@ -183,7 +183,7 @@ def test_pvq_kernel_variants_agree(is_keyframe, with_pred):
             assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("intra_mode", ["waves", "chain", "chain_single"])
+@pytest.mark.parametrize("intra_mode", ["bands", "waves", "chain", "chain_single"])
 def test_keyframe_with_intra_and_cfl_prediction_matches_frame_oracle(intra_mode):
     """The complete keyframe chain of the reference on the GPU: forward, luma PVQ
     with H/V intra prediction (dependency wavefront), chroma PVQ with CfL, inverse."""

@@ -51,6 +51,43 @@ def test_block_and_band_lists_cover_every_plane_once(mode):
     assert sum(len(p) for p in parts) == len(blocks)
 
 
+def test_band_wave_lists_respect_the_intra_dependencies():
+    """Every (block, band) entry appears once; an entry of wave w > 1 has the same band of a
+    same-size neighbour in wave w - 1 and none later (od_hv_intra_pred, src/intra.c:37)."""
+    from daala_b200 import pvq, synth
+    from daala_b200.frame import Geometry
+    geom = Geometry(512, 320)
+    maps = [synth.block_size_map(geom, "mixed", seed=s) for s in (3, 4)]
+    blocks = np.concatenate([pvq.block_list(b, geom, frame=f) for f, b in enumerate(maps)])
+    luma, top, left, depth = pvq.sort_by_depth(pvq.raster_order(blocks[blocks["pli"] == 0]), maps, geom)
+    bulk, chain, slices = pvq.band_wave_lists(luma, top, left, depth)
+    wave = {}
+    for k in (16, 32, 128):
+        assert set((bulk[k] & 15).tolist()) <= {3, 6}
+        for e in bulk[k].tolist():
+            wave[e] = 0
+        assert sum(c for _, c in slices[k]) == len(chain[k])
+        for w, (a, c) in enumerate(slices[k]):
+            assert c > 0
+            for e in chain[k][a:a + c].tolist():
+                assert e not in wave
+                wave[e] = w + 1
+    total = sum(pvq.NBANDS[int(b)] for b in luma["bs"])
+    assert len(wave) == total
+    for e, w in wave.items():
+        blk, band = e >> 4, e & 15
+        need = []
+        if band in (0, 1, 4, 7) and top[blk] >= 0:
+            need.append((int(top[blk]) << 4) | band)
+        if band in (0, 2, 5, 8) and left[blk] >= 0:
+            need.append((int(left[blk]) << 4) | band)
+        if band in (3, 6):
+            assert w == 0
+            continue
+        assert luma["bs"][blk] == luma["bs"][top[blk]] if top[blk] >= 0 else True
+        assert w == 1 + max([wave[x] for x in need], default=0)
+
+
 def test_library_exports_every_declared_symbol():
     """The built library must export everything include/daala_b200.h declares
     (no compute calls here: the build container has no GPU)."""
