@@ -281,9 +281,12 @@ def run_b200(args):
     desc_dev = []
     for b in batches:
         desc_dev.append(b.blocks)
-        desc_dev.extend(b.lists.values())
-        if getattr(b, "wave_lists", None):
-            desc_dev.extend(b.wave_lists.values())
+        if getattr(b, "chain_lists", None) is None:
+            desc_dev.extend(b.lists.values())
+        else:
+            desc_dev.extend(b.chain_lists.values())
+            desc_dev.extend(b.bulk_lists.values())
+            desc_dev.extend(b.chain_waves.values())
             desc_dev.extend([b.dep_top, b.dep_left])
     desc_pin = [t.cpu().pin_memory() for t in desc_dev]
     sym_dev = [t for b in batches for t in b.symbol_tensors()]

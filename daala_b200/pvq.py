@@ -61,6 +61,8 @@ def _bind():
                                               ctypes.c_void_p]
     L.daala_b200_pvq_intra_band_ref.argtypes = [pp, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                   ctypes.c_void_p]
+    L.daala_b200_pvq_order_by_work.argtypes = [pp, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.daala_b200_pvq_block_finish_range.argtypes = [pp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_coding_order_scatter_range.argtypes = [pp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.daala_b200_pvq_cfl_pred.argtypes = [pp, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
@@ -289,6 +291,12 @@ class PvqBatch:
         self.is_keyframe = int(is_keyframe)
         # kernel choice of daala_b200_pvq_encode_bands_mode (0 = measured-best mix)
         self.mode = 0
+        # bucket every launch's entries by expected search work (daala_b200_pvq_order_by_work)
+        self.order_by_work = True
+        self._order_bins = torch.zeros(_bind().daala_b200_pvq_order_bins(), dtype=torch.int32, device=dev)
+        self._order_keys = torch.zeros(max(1, max(v.numel() for v in self.lists.values())), dtype=torch.int16,
+                                       device=dev)
+        self.ordered = {k: torch.empty_like(v) for k, v in self.lists.items()}
 
     def symbol_tensors(self):
         """What the host entropy coder consumes: per-band indices, flags and the packed pulses."""
@@ -305,6 +313,16 @@ class PvqBatch:
         _native.check(L.daala_b200_coding_order_gather(p, self.nblocks, 0, self._s(stream)), "gather(in)")
         _native.check(L.daala_b200_coding_order_gather(p, self.nblocks, 1, self._s(stream)), "gather(ref)")
 
+    def _order(self, src, dst, nmax, s, waves=None, nwaves=1):
+        """dst <- src bucketed by (wave, work); 3 launches.  Needs `in` gathered."""
+        if not src.numel():
+            return 0
+        assert src.numel() <= self._order_keys.numel()
+        _native.check(_bind().daala_b200_pvq_order_by_work(
+            ctypes.byref(self.params), src.data_ptr(), waves.data_ptr() if waves is not None else None, src.numel(),
+            nwaves, nmax, dst.data_ptr(), self._order_keys.data_ptr(), self._order_bins.data_ptr(), s), "order_by_work")
+        return 3
+
     def quantise(self, stream=None):
         L = _bind()
         p = ctypes.byref(self.params)
@@ -315,6 +333,9 @@ class PvqBatch:
             n += 1
         for nmax in (128, 32, 16):
             lst = self.lists[nmax]
+            if self.order_by_work and lst.numel():
+                n += self._order(lst, self.ordered[nmax], nmax, s)
+                lst = self.ordered[nmax]
             if lst.numel():
                 _native.check(L.daala_b200_pvq_encode_bands_mode(p, lst.data_ptr(), lst.numel(), nmax, self.mode, s),
                               "pvq_bands")
@@ -363,6 +384,13 @@ class PvqBatch:
         as_dev = lambda v: torch.from_numpy(np.ascontiguousarray(v).view(np.int32)).to(dev)  # noqa: E731
         self.bulk_lists = {k: as_dev(v) for k, v in bulk.items()}
         self.chain_lists = {k: as_dev(v) for k, v in chain.items()}
+        self.chain_waves, self.chain_ordered, self.bulk_ordered = {}, {}, {}
+        for k, sl in self.chain_slices.items():
+            assert len(sl) < 65536
+            w = np.repeat(np.arange(len(sl), dtype=np.uint16), [c for _, c in sl])
+            self.chain_waves[k] = torch.from_numpy(w.view(np.int16)).to(dev)
+            self.chain_ordered[k] = torch.empty_like(self.chain_lists[k])
+            self.bulk_ordered[k] = torch.empty_like(self.bulk_lists[k])
         self.chain_streams = {k: torch.cuda.Stream(device=dev, priority=-1) for k in lists}
         self.bulk_stream = torch.cuda.Stream(device=dev)
         # waves smaller than this many bands use the group-cooperative kernels (shorter latency)
@@ -378,6 +406,13 @@ class PvqBatch:
             _native.check(L.daala_b200_coding_order_gather(p, self.nblocks, 0, self._s(main)), "gather(in)")
             n = 1
             top, left = self.dep_top.data_ptr(), self.dep_left.data_ptr()
+            chain_lists, bulk_lists = self.chain_lists, self.bulk_lists
+            if self.order_by_work:
+                for k in (128, 32, 16):
+                    n += self._order(self.chain_lists[k], self.chain_ordered[k], k, self._s(main),
+                                     self.chain_waves[k], max(1, len(self.chain_slices[k])))
+                    n += self._order(self.bulk_lists[k], self.bulk_ordered[k], k, self._s(main))
+                chain_lists, bulk_lists = self.chain_ordered, self.bulk_ordered
             # latency-bound chains first (high-priority streams), the dependency-free bands fill the GPU behind
             for k in (128, 32, 16):
                 st = self.chain_streams[k]
@@ -386,7 +421,7 @@ class PvqBatch:
                 for w, (a, c) in enumerate(self.chain_slices[k]):
                     if not c:
                         continue
-                    ptr = self.chain_lists[k].data_ptr() + 4 * a
+                    ptr = chain_lists[k].data_ptr() + 4 * a
                     if w > 0:
                         _native.check(L.daala_b200_pvq_intra_band_ref(p, top, left, ptr, c, sp), "intra_band_ref")
                         n += 1
@@ -396,7 +431,7 @@ class PvqBatch:
             self.bulk_stream.wait_stream(main)
             sp = ctypes.c_void_p(self.bulk_stream.cuda_stream)
             for k in (128, 32):
-                lst = self.bulk_lists[k]
+                lst = bulk_lists[k]
                 if lst.numel():
                     _native.check(L.daala_b200_pvq_encode_bands_mode(p, lst.data_ptr(), lst.numel(), k, self.mode, sp),
                                   "pvq_bands")

@@ -274,6 +274,17 @@ int daala_b200_pvq_luma_intra(const daala_b200_pvq_params *prm, const int32_t *d
    _coding_order_scatter_range.  dep_top / dep_left only need their sign here. */
 int daala_b200_pvq_intra_gather(const daala_b200_pvq_params *prm, const int32_t *dep_top, const int32_t *dep_left,
                                 int first, int count, void *stream);
+/* Work ordering of a band list (3 kernel launches): `ordered` receives the entries of `band_list`
+   bucketed by (wave, expected search work), heaviest first inside each wave.  The lanes of a warp of
+   the band kernels then run similar trip counts (1.3-2x on real data); results do not depend on the
+   order.  entry_wave[i] (NULL = all 0) is the wave of entry i, entries of a wave stay inside that
+   wave's range, so a caller's per-wave (first, count) slices remain valid.  Reads prm->in (run
+   _coding_order_gather first).  Scratch: keys[count], bins[daala_b200_pvq_order_bins()]. */
+int daala_b200_pvq_order_by_work(const daala_b200_pvq_params *prm, const uint32_t *band_list,
+                                 const uint16_t *entry_wave, int count, int nwaves, int nmax, uint32_t *ordered,
+                                 uint16_t *keys, int32_t *bins, void *stream);
+int daala_b200_pvq_order_bins(void);
+
 /* Band-granular wavefront (the default): od_hv_intra_pred (src/intra.c:37) couples band b of a block
    only to band b of the same-size top / left neighbour (row-0 bands 1/4/7: top, column-0 bands 2/5/8:
    left, bands 3/6: none, band 0: both).  For the entries of `band_list` ((block << 4) | band, all of

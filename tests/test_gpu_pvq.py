@@ -225,6 +225,48 @@ def test_keyframe_with_intra_and_cfl_prediction_matches_frame_oracle(intra_mode)
         assert np.array_equal(hp.fb.pixels_out[0][f].cpu().numpy(), rec0)
 
 
+def test_work_ordering_is_a_wave_preserving_permutation_and_does_not_change_results():
+    """daala_b200_pvq_order_by_work only reorders a launch: same entries, every entry stays inside its
+    wave's slice, heavier bins first; symbols with and without ordering are identical."""
+    import torch
+    from daala_b200 import synth
+    from daala_b200.frame import Geometry
+    from daala_b200.pipeline import HotPath
+    geom = Geometry(384, 256)
+    q4 = np.full((3, 30), 20, np.uint8)
+    outs = []
+    for order in (True, False):
+        hp = HotPath(geom, nframes=1, q0=45, is_keyframe=1, pvq_qm_q4=q4, keyframe_prediction=True)
+        planes, _ = synth.frame(384, 256, f=9)
+        bsize = synth.block_size_map(geom, "mixed", seed=77)
+        hp.fb.upload(synth.pad_planes(planes, geom), bsize, frame=0)
+        hp.set_block_sizes([bsize])
+        hp.batch_luma.order_by_work = hp.batch_chroma.order_by_work = order
+        hp.run()
+        torch.cuda.synchronize()
+        outs.append([t.clone() for b in (hp.batch_luma, hp.batch_chroma) for t in b.symbol_tensors()])
+        if order:
+            bl = hp.batch_luma
+            for k in (16, 32, 128):
+                src, dst = bl.chain_lists[k].cpu().numpy(), bl.chain_ordered[k].cpu().numpy()
+                for a, c in bl.chain_slices[k]:
+                    assert np.array_equal(np.sort(src[a:a + c]), np.sort(dst[a:a + c]))
+                assert np.array_equal(np.sort(bl.bulk_lists[k].cpu().numpy()), np.sort(bl.bulk_ordered[k].cpu().numpy()))
+                bc = hp.batch_chroma
+                assert np.array_equal(np.sort(bc.lists[k].cpu().numpy()), np.sort(bc.ordered[k].cpu().numpy()))
+            # heaviest first: the energy of the first tenth of a chroma launch exceeds that of the last tenth
+            lst = hp.batch_chroma.ordered[16].cpu().numpy().view(np.uint32)
+            blk, band = (lst >> 4).astype(np.int64), (lst & 15).astype(np.int64)
+            off = hp.batch_chroma.blocks_np["coef_off"].astype(np.int64)[blk]
+            x = hp.batch_chroma.in_.cpu().numpy().astype(np.float64)
+            from daala_b200.pvq import BAND_EDGES
+            e = np.array([np.sum(x[o + BAND_EDGES[b]:o + BAND_EDGES[b + 1]] ** 2) for o, b in zip(off, band)])
+            m = max(1, len(e) // 10)
+            assert e[:m].mean() > e[-m:].mean()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def test_dropin_pvq_helper_symbols_match_oracle():
     """Host-pointer od_pvq_* helpers and od_rdo_quant against the reference build
     (or the port when oracle/_ref is absent)."""
