@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=16, help="4K frames per step (whole job)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pvq-mode", type=int, default=0, help="0 cooperative kernels, 2 scalar thread-per-band")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="e2e: serial copy-in / compute / copy-out instead of the double-buffered pipeline")
     ap.add_argument("--intra-mode", default="bands", choices=["bands", "waves", "chain", "chain_single"])
     ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"],
                     help="frames: every rank encodes its own --frames frames with the reference's keyframe "
@@ -163,23 +165,43 @@ def cpu_frame(lib, prefix, geom, planes, bsize):
         frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 1)
 
 
-def cpu_throughput(geom, host_frames, nframes, threads):
-    """Mpx/s of the CPU pipeline over `nframes` frames on `threads` threads
-    (ctypes releases the GIL inside the C calls)."""
-    from concurrent.futures import ThreadPoolExecutor
+_CPU_JOB = {}
+
+
+def _cpu_worker(i):
+    """Runs in a forked worker process: one frame of the CPU pipeline."""
+    if "lib" not in _CPU_JOB:
+        _CPU_JOB["lib"] = cpu_pipeline_lib()
+    lib, prefix, _ = _CPU_JOB["lib"]
+    frames = _CPU_JOB["frames"]
+    planes, bsize = frames[i % len(frames)]
+    cpu_frame(lib, prefix, _CPU_JOB["geom"], planes, bsize)
+    return i
+
+
+def cpu_pool(geom, host_frames, workers):
+    """Worker processes (fork: they inherit the frames) -- the reference has no threading of its own,
+    so its all-core throughput is N independent encoders, one per host core."""
+    import multiprocessing
+    _CPU_JOB.update(geom=geom, frames=host_frames)
+    return multiprocessing.get_context("fork").Pool(workers)
+
+
+def cpu_throughput(geom, host_frames, nframes, threads, pool=None):
+    """Mpx/s of the CPU pipeline over `nframes` frames on `threads` worker processes (1: in-process)."""
     lib, prefix, kind = cpu_pipeline_lib()
-    jobs = [host_frames[i % len(host_frames)] for i in range(nframes)]
     t0 = time.perf_counter()
-    if threads == 1:
-        for planes, bsize in jobs:
+    if threads == 1 or pool is None:
+        for i in range(nframes):
+            planes, bsize = host_frames[i % len(host_frames)]
             cpu_frame(lib, prefix, geom, planes, bsize)
     else:
-        with ThreadPoolExecutor(max_workers=threads) as ex:
-            list(ex.map(lambda j: cpu_frame(lib, prefix, geom, j[0], j[1]), jobs))
+        pool.map(_cpu_worker, range(nframes), chunksize=1)
     dt = time.perf_counter() - t0
     return geom.luma_pixels * nframes / dt / 1e6, dt, kind
 
 
+CPU_SAMPLE_FRAMES = 48  # ~12 s of single-core CPU work
 CPU_SAMPLE_ROWS = 512   # bounded CPU sample: a 3840x512 band (8 superblock rows) of the 4K frame
 
 
@@ -195,17 +217,20 @@ def run_reference(args):
     geom = cpu_sample_geometry()
     cores = len(os.sched_getaffinity(0))
     host_frames = make_host_frames(geom, 2, distinct=2)
-    per_step = max(1, cores)
-    for _ in range(min(args.warmup, 1)):
-        cpu_throughput(geom, host_frames, per_step, cores)
+    per_step = 2 * max(1, cores)
+    pool = cpu_pool(geom, host_frames, cores) if cores > 1 else None
+    for _ in range(max(args.warmup, 1)):
+        cpu_throughput(geom, host_frames, per_step, cores, pool)
     times = []
     kind = "port"
     for _ in range(args.steps):
-        _, dt, kind = cpu_throughput(geom, host_frames, per_step, cores)
+        _, dt, kind = cpu_throughput(geom, host_frames, per_step, cores, pool)
         times.append(dt)
+    if pool is not None:
+        pool.close()
     total = sum(times)
     value = geom.luma_pixels * per_step * args.steps / total / 1e6
-    sample = ("%d x 3840x%d 4:2:0 bands (8 superblock rows of the 4K frame) per step on %d host threads; "
+    sample = ("%d x 3840x%d 4:2:0 bands (8 superblock rows of the 4K frame) per step on %d worker processes (one per host core); "
               "reference functions: prefilter + fDCT + pvq_theta(speed=1) + iDCT + postfilter" % (per_step, CPU_SAMPLE_ROWS, cores))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
@@ -246,69 +271,82 @@ def run_b200(args):
         r0, nrows = 0, geom.nvsb
     host_frames = make_host_frames(geom, F)
     q4 = np.full((3, 30), PVQ_QM_Q4, np.uint8)
-    hp = HotPath(geom, nframes=F, device=dev, q0=Q0, is_keyframe=1, use_masking=1, pvq_qm_q4=q4,
-                 sb_row0=r0, sb_rows=nrows, keyframe_prediction=not sbrow)
-    fb = hp.fb
-    hp.set_block_sizes([hf[1] for hf in host_frames])
-    hp.batch.mode = args.pvq_mode
-    if hp.batch_luma is not None:
-        hp.batch_luma.mode = args.pvq_mode
-        hp.batch_luma.intra_mode = args.intra_mode
+    use_graph = not args.no_graph and not (sbrow and world > 1)   # the NCCL exchange stays host-launched
+    overlap = use_graph and not args.no_overlap
 
-    # pinned host staging: this rank's rows (+2-sample halo) of every plane, and its output rows
     def rows(pli, halo):
         sb = 64 >> geom.xdec[pli]
         ph = geom.plane_shape(pli)[0]
         return max(0, r0 * sb - halo), min(ph, (r0 + nrows) * sb + halo)
 
+    # pinned host input: this rank's rows (+2-sample halo) of every plane, block-size maps
     pin_in = []
-    pin_out = []
     for pli in range(3):
         a, b = rows(pli, 2)
         t = torch.empty((F, b - a, geom.plane_shape(pli)[1]), dtype=torch.uint8).pin_memory()
         for f in range(F):
             t[f].copy_(torch.from_numpy(host_frames[f][0][pli][a:b]))
         pin_in.append(t)
-        a, b = rows(pli, 0)
-        pin_out.append(torch.empty((F, b - a, geom.plane_shape(pli)[1]), dtype=torch.uint8).pin_memory())
     pin_bsize = torch.empty((F,) + geom.bsize_shape, dtype=torch.uint8).pin_memory()
     for f in range(F):
         pin_bsize[f].copy_(torch.from_numpy(host_frames[f][1]))
-    # e2e also moves what the host side of the reference consumes/produces around the hot path:
-    # block descriptors + band lists in (they follow from the block-size decision), and the PVQ
-    # symbols out (per-band indices, flags, 16-bit pulses) for the host entropy coder.
-    batches = [b for b in (hp.batch_luma, hp.batch) if b is not None]
-    desc_dev = []
-    for b in batches:
-        desc_dev.append(b.blocks)
-        if getattr(b, "chain_lists", None) is None:
-            desc_dev.extend(b.lists.values())
-        else:
-            desc_dev.extend(b.chain_lists.values())
-            desc_dev.extend(b.bulk_lists.values())
-            desc_dev.extend(b.chain_waves.values())
-            desc_dev.extend([b.dep_top, b.dep_left])
-    desc_pin = [t.cpu().pin_memory() for t in desc_dev]
-    sym_dev = [t for b in batches for t in b.symbol_tensors()]
-    sym_pin = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in sym_dev]
+
+    class Slot:
+        """One set of device buffers (+ its CUDA graph) and the pinned host buffers its results land in."""
+
+        def __init__(self):
+            hp = HotPath(geom, nframes=F, device=dev, q0=Q0, is_keyframe=1, use_masking=1, pvq_qm_q4=q4,
+                         sb_row0=r0, sb_rows=nrows, keyframe_prediction=not sbrow)
+            hp.set_block_sizes([hf[1] for hf in host_frames])
+            hp.batch.mode = args.pvq_mode
+            if hp.batch_luma is not None:
+                hp.batch_luma.mode = args.pvq_mode
+                hp.batch_luma.intra_mode = args.intra_mode
+            self.hp, self.fb = hp, hp.fb
+            self.pin_out = []
+            for pli in range(3):
+                a, b = rows(pli, 0)
+                self.pin_out.append(torch.empty((F, b - a, geom.plane_shape(pli)[1]), dtype=torch.uint8).pin_memory())
+            # e2e also moves what the host side of the reference consumes/produces around the hot path:
+            # block descriptors + band lists in (they follow from the block-size decision), and the PVQ
+            # symbols out (per-band indices, flags, 16-bit pulses) for the host entropy coder.
+            batches = [b for b in (hp.batch_luma, hp.batch) if b is not None]
+            self.desc_dev = []
+            for b in batches:
+                self.desc_dev.append(b.blocks)
+                if getattr(b, "chain_lists", None) is None:
+                    self.desc_dev.extend(b.lists.values())
+                else:
+                    self.desc_dev.extend(b.chain_lists.values())
+                    self.desc_dev.extend(b.bulk_lists.values())
+                    self.desc_dev.extend(b.chain_waves.values())
+                    self.desc_dev.extend([b.dep_top, b.dep_left])
+            self.desc_pin = [t.cpu().pin_memory() for t in self.desc_dev]
+            self.sym_dev = [t for b in batches for t in b.symbol_tensors()]
+            self.sym_pin = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self.sym_dev]
+            self.ev_in, self.ev_comp, self.ev_out = (torch.cuda.Event() for _ in range(3))
+
+        def h2d(self):
+            for pli in range(3):
+                a, b = rows(pli, 2)
+                self.fb.pixels[pli][:, a:b].copy_(pin_in[pli], non_blocking=True)
+            self.fb.bsize.copy_(pin_bsize, non_blocking=True)
+            for dst, src in zip(self.desc_dev, self.desc_pin):
+                dst.copy_(src, non_blocking=True)
+
+        def d2h(self):
+            for pli in range(3):
+                a, b = rows(pli, 0)
+                self.pin_out[pli].copy_(self.fb.pixels_out[pli][:, a:b], non_blocking=True)
+            for dst, src in zip(self.sym_pin, self.sym_dev):
+                dst.copy_(src, non_blocking=True)
+
+    slots = [Slot() for _ in range(2 if overlap else 1)]
+    hp, fb = slots[0].hp, slots[0].fb
     h2d_bytes = (sum(t.numel() for t in pin_in) + pin_bsize.numel()
-                 + sum(t.numel() * t.element_size() for t in desc_pin))
-    d2h_bytes = sum(t.numel() for t in pin_out) + sum(t.numel() * t.element_size() for t in sym_pin)
-
-    def h2d():
-        for pli in range(3):
-            a, b = rows(pli, 2)
-            fb.pixels[pli][:, a:b].copy_(pin_in[pli], non_blocking=True)
-        fb.bsize.copy_(pin_bsize, non_blocking=True)
-        for dst, src in zip(desc_dev, desc_pin):
-            dst.copy_(src, non_blocking=True)
-
-    def d2h():
-        for pli in range(3):
-            a, b = rows(pli, 0)
-            pin_out[pli].copy_(fb.pixels_out[pli][:, a:b], non_blocking=True)
-        for dst, src in zip(sym_pin, sym_dev):
-            dst.copy_(src, non_blocking=True)
+                 + sum(t.numel() * t.element_size() for t in slots[0].desc_pin))
+    d2h_bytes = (sum(t.numel() for t in slots[0].pin_out)
+                 + sum(t.numel() * t.element_size() for t in slots[0].sym_pin))
 
     # multi-GPU: one all-gather per step of the 2-row lapped borders (daala_b200/sharding.py)
     from daala_b200.sharding import BorderExchange
@@ -316,20 +354,27 @@ def run_b200(args):
 
     launches = {"n": 0}
 
-    def step():
-        launches["n"] += hp.run(exchange if (sbrow and world > 1) else None)
+    def step(sl=slots[0]):
+        if use_graph:
+            launches["n"] += sl.hp.replay()
+        else:
+            launches["n"] += sl.hp.run(exchange if (sbrow and world > 1) else None)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, before=None, after=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if before:
+            before()
         for _ in range(steps):
             fn()
+        if after:
+            after()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -337,8 +382,11 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # upload once, warm up
-    h2d()
+    # upload once, warm up (and record the graphs)
+    for sl in slots:
+        sl.h2d()
+        if use_graph:
+            sl.hp.capture()
     for _ in range(max(args.warmup, 3)):
         step()
     # sanity guard: the quantised reconstruction stays close to the source on my rows
@@ -357,14 +405,53 @@ def run_b200(args):
     ms = timed(step, args.steps)
     n_launch = launches["n"]
 
-    def e2e_step():
-        h2d()
-        step()
-        d2h()
+    # end to end: every step copies its inputs in from pinned host memory and its results out.
+    if overlap:
+        # double-buffered: copy-in of step i+1 and copy-out of step i-1 run on their own streams
+        # (both copy engines) under the compute of step i; events carry the buffer hazards.
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_comp, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        counter = {"i": 0}
 
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+        def fork():
+            for st in (s_in, s_comp, s_out):
+                st.wait_stream(cur)
+
+        def join():
+            for st in (s_in, s_comp, s_out):
+                cur.wait_stream(st)
+
+        def e2e_step():
+            sl = slots[counter["i"] % 2]
+            counter["i"] += 1
+            s_in.wait_event(sl.ev_comp)            # inputs of this slot were consumed (step i-2)
+            with torch.cuda.stream(s_in):
+                sl.h2d()
+                sl.ev_in.record(s_in)
+            s_comp.wait_event(sl.ev_in)
+            s_comp.wait_event(sl.ev_out)           # results of step i-2 have left the device
+            with torch.cuda.stream(s_comp):
+                step(sl)
+                sl.ev_comp.record(s_comp)
+            s_out.wait_event(sl.ev_comp)
+            with torch.cuda.stream(s_out):
+                sl.d2h()
+                sl.ev_out.record(s_out)
+
+        for sl in slots:
+            for ev in (sl.ev_in, sl.ev_comp, sl.ev_out):
+                ev.record(cur)
+        timed(e2e_step, 4, fork, join)
+        ms_e2e = timed(e2e_step, args.steps, fork, join)
+    else:
+        def e2e_step():
+            slots[0].h2d()
+            step()
+            slots[0].d2h()
+
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     # dominant kernel alone (forward), CUDA events on the launching stream
@@ -424,7 +511,10 @@ def run_b200(args):
                    "block_sizes": "synthetic quadtree map, sizes 4..64", "quantizer": Q0,
                    "pvq_pulses_per_step": total_k},
         "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 4),
+                "pipeline": ("double-buffered: copy-in / CUDA-graph compute / copy-out of consecutive steps overlap on three streams"
+                             if overlap else "serial copy-in, compute, copy-out")},
+        "cuda_graph": bool(use_graph),
         "gpu_launches": n_launch,
         "clocks": clocks,
         # dominant kernel (40 % of the step): not HBM-bound -- a greedy double-precision search,
@@ -450,10 +540,10 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cgeom = cpu_sample_geometry()
         cpu_frames = make_host_frames(cgeom, 2, distinct=2)
-        v, dt, kind = cpu_throughput(cgeom, cpu_frames, 2, 1)
+        v, dt, kind = cpu_throughput(cgeom, cpu_frames, CPU_SAMPLE_FRAMES, 1)
         out["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": 1, "kind": kind,
-                               "sample": "2 x 3840x%d bands (8 superblock rows of the 4K frame), same chain "
-                                         "(reference functions, pvq_theta speed=1), 1 thread, %.1f s" % (CPU_SAMPLE_ROWS, dt)}
+                               "sample": "%d x 3840x%d bands (8 superblock rows of the 4K frame), same chain "
+                                         "(reference functions, pvq_theta speed=1), 1 thread, %.1f s" % (CPU_SAMPLE_FRAMES, CPU_SAMPLE_ROWS, dt)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

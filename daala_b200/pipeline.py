@@ -67,6 +67,23 @@ class HotPath:
         prediction (the reference's mdtmp planes)."""
         self.pred = pred_fb
 
+    def capture(self):
+        """Record one whole pass (all streams, ~10^2-10^3 launches, many of them latency-bound wave
+        kernels) into a CUDA graph; `replay()` then costs one launch on the host.  Pointers, lists and
+        tensor maps are baked in: call again after set_block_sizes()."""
+        torch.cuda.synchronize(self.device)
+        self.run()                       # loads modules, creates streams outside the capture
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.graph_launches = self.run()
+        self.graph = graph
+        return graph
+
+    def replay(self):
+        self.graph.replay()
+        return self.graph_launches
+
     def run(self, exchange=None):
         """One pass; returns the number of kernel launches.  `exchange` (multi-GPU)
         is called between the two halves of the inverse to trade lapped border rows."""
