@@ -511,11 +511,14 @@ k_pvq_bands_coop(const __grid_constant__ daala_b200_pvq_params prm, const uint32
 // stored per (block, band), so the order inside a launch is free.  Three small kernels bucket a band
 // list by (wave, work bin), heaviest first: keys + histogram, exclusive scan, scatter.
 // ---------------------------------------------------------------------------
-constexpr int kWorkBins = 64;
-constexpr int kMaxOrderBins = 8192;
+constexpr int kMaxOrderBins = 8192;   // bins of one ordering call: waves x bins per wave
+constexpr int kMaxWaveBins = 2048;
 
 // G lanes per entry.  Work proxy: energy of the band relative to its quantiser, scaled by n^2
-// (K grows with gain / q, the search costs K x n): half-octave bins.
+// (K grows with gain / q, the search costs K x n), binned on a log scale: bins_per_wave / 32 bins per
+// octave.  The bins must be fine: K steps with the quantised gain, and a launch only runs at the
+// speed of a fully sorted one when neighbouring entries share K (measured: 64 half-octave bins gave
+// none of the gain of a full sort on the CfL chroma bands, whose energies cluster within an octave).
 template <int G>
 __global__ void __launch_bounds__(256)
 k_band_work_keys(const __grid_constant__ daala_b200_pvq_params prm, const uint32_t* __restrict__ band_list,
@@ -544,10 +547,10 @@ k_band_work_keys(const __grid_constant__ daala_b200_pvq_params prm, const uint32
   for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
   if (valid && lane == 0) {
     const float w = acc * (float)(n * n) / ((float)q * (float)q);
-    int bin = (int)(2.f * log2f(w + 1.f));
-    bin = bin < 0 ? 0 : bin > kWorkBins - 1 ? kWorkBins - 1 : bin;
+    int bin = (int)(log2f(w + 1.f) * (float)bins_per_wave * (1.f / 32.f));
+    bin = bin < 0 ? 0 : bin > bins_per_wave - 1 ? bins_per_wave - 1 : bin;
     const int wave = entry_wave ? entry_wave[slot] : 0;
-    const int key = wave * bins_per_wave + (((kWorkBins - 1 - bin) * bins_per_wave) >> 6);
+    const int key = wave * bins_per_wave + (bins_per_wave - 1 - bin);
     keys[slot] = (uint16_t)key;
     atomicAdd(&hist[key], 1);
   }
@@ -1223,7 +1226,7 @@ int daala_b200_pvq_order_by_work(const daala_b200_pvq_params* prm, const uint32_
   if (count <= 0) return 0;
   if (nwaves < 1 || nwaves > kMaxOrderBins) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
-  int bpw = kWorkBins;
+  int bpw = kMaxWaveBins;
   while (bpw > 1 && nwaves * bpw > kMaxOrderBins) bpw >>= 1;
   const int nbins = nwaves * bpw;
   cudaError_t err = cudaMemsetAsync(bins, 0, sizeof(int32_t) * nbins, s);

@@ -289,8 +289,11 @@ class PvqBatch:
                 p.pvq_qm_q4[pli][i] = int(pvq_qm_q4[pli][i])
         self.params = p
         self.is_keyframe = int(is_keyframe)
-        # kernel choice of daala_b200_pvq_encode_bands_mode (0 = measured-best mix)
+        # kernel choice of daala_b200_pvq_encode_bands_mode (0 = measured-best mix); per size class
+        # override (None = self.mode): e.g. the CfL chroma batch, whose 128-coefficient bands all run the
+        # with-reference search, is 25 % faster on 32 lanes x 4 registers (mode 3)
         self.mode = 0
+        self.class_mode = {16: None, 32: None, 128: None}
         # bucket every launch's entries by expected search work (daala_b200_pvq_order_by_work)
         self.order_by_work = True
         self._order_bins = torch.zeros(_bind().daala_b200_pvq_order_bins(), dtype=torch.int32, device=dev)
@@ -337,7 +340,8 @@ class PvqBatch:
                 n += self._order(lst, self.ordered[nmax], nmax, s)
                 lst = self.ordered[nmax]
             if lst.numel():
-                _native.check(L.daala_b200_pvq_encode_bands_mode(p, lst.data_ptr(), lst.numel(), nmax, self.mode, s),
+                mode = self.mode if self.class_mode[nmax] is None else self.class_mode[nmax]
+                _native.check(L.daala_b200_pvq_encode_bands_mode(p, lst.data_ptr(), lst.numel(), nmax, mode, s),
                               "pvq_bands")
                 n += 1
         _native.check(L.daala_b200_pvq_block_finish(p, self.nblocks, s), "block_finish")
@@ -394,7 +398,8 @@ class PvqBatch:
         self.chain_streams = {k: torch.cuda.Stream(device=dev, priority=-1) for k in lists}
         self.bulk_stream = torch.cuda.Stream(device=dev)
         # waves smaller than this many bands use the group-cooperative kernels (shorter latency)
-        self.small_wave = {16: 0, 32: 0, 128: 0}
+        # (tools/probe/time_bandwaves.py, time_modes_ref.py: crossover of the scalar / 16-lane kernels)
+        self.small_wave = {16: 8192, 32: 16384, 128: 4096}
         self.small_mode = 3
         self.intra_mode = "bands"
 
