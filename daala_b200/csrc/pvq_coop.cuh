@@ -304,6 +304,7 @@ __device__ void householder_apply_coop(const Group<G, E>& grp, int16_t (&out)[E]
 struct CandC {
   int gain, k, theta, ts;
   int32_t qtheta, qcg;
+  int noref;
 };
 
 // One band by G lanes.  x0/r0/out/y/qm/qm_inv point at the band's first entry.
@@ -396,12 +397,14 @@ __device__ int quantise_band_coop(const Group<G, E>& grp, int32_t* out, const in
     noref = 0;
   }
   const double dist0 = best_dist;
+  // One candidate list and ONE search / rate call site for both passes of pvq_theta (with-reference
+  // candidates in (k, gain) order, src/pvq_encoder.c:504-560, then the no-reference gains, :573-606):
+  // the search is most of this kernel's code, and its instruction footprint is what the warps stall on
+  // (profiles/r1p_pvq_chroma_ncu.txt), so it is instantiated once.
+  CandC items[22];
+  int nitems = 0;
   if (r_nonnull && corr > 0) {
-    CandC items[20];
-    int nitems = 0;
     int gain_bound = (cg - gain_offset) >> kCgainShift;
-    int prev_k = 0;
-    double cos_dist = 0;
     theta = round32(theta_scale * acos(corr));
     // od_compute_householder, src/pvq.c:498: first largest |r|
     {
@@ -447,6 +450,7 @@ __device__ int quantise_band_coop(const Group<G, E>& grp, int32_t* out, const in
         c.k = compute_k(qcg, j, 0, n, beta);
         c.qcg = qcg;
         c.ts = ts;
+        c.noref = 0;
         int p = nitems++;
         while (p > 0 && (items[p - 1].k > c.k || (items[p - 1].k == c.k && items[p - 1].gain > c.gain))) {
           items[p] = items[p - 1];
@@ -455,68 +459,76 @@ __device__ int quantise_band_coop(const Group<G, E>& grp, int32_t* out, const in
         items[p] = c;
       }
     }
+  }
+  const int first_noref = nitems;
+  if ((is_keyframe && pli == 0) || corr < .5 || cg < (int32_t)shl(2, kCgainShift)) {
+    int gain_bound = cg >> kCgainShift;
+    for (int i = gain_bound > 1 ? gain_bound : 1; i <= gain_bound + 1; i++) {
+      CandC c;
+      c.gain = i;
+      c.theta = -1;
+      c.qtheta = 0;
+      c.qcg = shl(i, kCgainShift);
+      c.k = compute_k(c.qcg, -1, 1, n, beta);
+      c.ts = 0;
+      c.noref = 1;
+      items[nitems++] = c;
+    }
+  }
+  {
+    int prev_k = 0;
+    double cos_dist = 0;
+    const double sin_theta = pvq_sin(theta) * trig_1;
     for (int idx = 0; idx < nitems; idx++) {
       const CandC c = items[idx];
       const int32_t qcg = c.qcg, qtheta = c.qtheta;
       const int k = c.k;
-      double dist_theta = 2 - 2. * pvq_cos(theta - qtheta) * trig_1;
-      dist = gain_weight * (qcg - cg) * (qcg - cg) + qcg * (double)cg * dist_theta;
-      dist *= cgain_2;
-      if (dist > dist0 + 1.0 * pvq_norm_lambda && k != 0) continue;
-      double sin_prod = pvq_sin(theta) * trig_1 * pvq_sin(qtheta) * trig_1;
-      if (k == 0) {
+      if (idx == first_noref) prev_k = 0;
+      double sin_prod = 0;
+      if (c.noref) {
+        dist = gain_weight * (qcg - cg) * (qcg - cg);
+        dist *= cgain_2;
+        if (dist > dist0 && k != 0) continue;
+      } else {
+        double dist_theta = 2 - 2. * pvq_cos(theta - qtheta) * trig_1;
+        dist = gain_weight * (qcg - cg) * (qcg - cg) + qcg * (double)cg * dist_theta;
+        dist *= cgain_2;
+        if (dist > dist0 + 1.0 * pvq_norm_lambda && k != 0) continue;
+        sin_prod = sin_theta * pvq_sin(qtheta) * trig_1;
+      }
+      if (!c.noref && k == 0) {
         cos_dist = 0;
 #pragma unroll
         for (int e = 0; e < E; e++) y_tmp[e] = 0;
-      } else if (k != prev_k) {
-        cos_dist = search_rdo_coop<G, E, kForceScan>(grp, xr, n - 1, k, y_tmp, qcg * (double)cg * sin_prod * cgain_2,
-                                                     pvq_norm_lambda, prev_k);
+      } else if (c.noref || k != prev_k) {
+        int16_t xin[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) xin[e] = c.noref ? x16[e] : xr[e];
+        const double g2 = c.noref ? qcg * (double)cg * cgain_2 : qcg * (double)cg * sin_prod * cgain_2;
+        cos_dist = search_rdo_coop<G, E, kForceScan>(grp, xin, c.noref ? n : n - 1, k, y_tmp, g2, pvq_norm_lambda,
+                                                     prev_k);
       }
       prev_k = k;
-      dist_theta = 2 - 2. * pvq_cos(theta - qtheta) * trig_1 + sin_prod * (2 - 2 * cos_dist);
-      dist = gain_weight * (qcg - cg) * (qcg - cg) + qcg * (double)cg * dist_theta;
+      if (c.noref) {
+        dist = gain_weight * (qcg - cg) * (qcg - cg) + qcg * (double)cg * (2 - 2 * cos_dist);
+      } else {
+        double dist_theta = 2 - 2. * pvq_cos(theta - qtheta) * trig_1 + sin_prod * (2 - 2 * cos_dist);
+        dist = gain_weight * (qcg - cg) * (qcg - cg) + qcg * (double)cg * dist_theta;
+      }
       dist *= cgain_2;
-      double cost = dist + pvq_norm_lambda * band_rate_coop(grp, c.gain, icgr, c.theta, c.ts, y_tmp, k, n,
-                                                            is_keyframe, pli);
-      if (cost < best_cost) {
+      const double cost = dist + pvq_norm_lambda * band_rate_coop(grp, c.gain, c.noref ? 0 : icgr, c.theta, c.ts,
+                                                                  y_tmp, k, n, is_keyframe, pli);
+      if (c.noref ? cost <= best_cost : cost < best_cost) {
         best_cost = cost;
         best_dist = dist;
         qg = c.gain;
         best_k = k;
-        best_qtheta = qtheta;
+        noref = c.noref;
+        best_qtheta = c.noref ? best_qtheta : qtheta;
         *itheta = c.theta;
         *max_theta = c.ts;
-        noref = 0;
 #pragma unroll
-        for (int e = 0; e < E; e++) y[e] = grp.idx(e) < n - 1 ? y_tmp[e] : 0;
-      }
-    }
-  }
-  if ((is_keyframe && pli == 0) || corr < .5 || cg < (int32_t)shl(2, kCgainShift)) {
-    int gain_bound = cg >> kCgainShift;
-    int prev_k = 0;
-    for (int i = gain_bound > 1 ? gain_bound : 1; i <= gain_bound + 1; i++) {
-      int32_t qcg = shl(i, kCgainShift);
-      int k = compute_k(qcg, -1, 1, n, beta);
-      dist = gain_weight * (qcg - cg) * (qcg - cg);
-      dist *= cgain_2;
-      if (dist > dist0 && k != 0) continue;
-      double cos_dist = search_rdo_coop<G, E, kForceScan>(grp, x16, n, k, y_tmp, qcg * (double)cg * cgain_2,
-                                                          pvq_norm_lambda, prev_k);
-      prev_k = k;
-      dist = gain_weight * (qcg - cg) * (qcg - cg) + qcg * (double)cg * (2 - 2 * cos_dist);
-      dist *= cgain_2;
-      double cost = dist + pvq_norm_lambda * band_rate_coop(grp, i, 0, -1, 0, y_tmp, k, n, is_keyframe, pli);
-      if (cost <= best_cost) {
-        best_cost = cost;
-        best_dist = dist;
-        qg = i;
-        noref = 1;
-        best_k = k;
-        *itheta = -1;
-        *max_theta = 0;
-#pragma unroll
-        for (int e = 0; e < E; e++) y[e] = y_tmp[e];
+        for (int e = 0; e < E; e++) y[e] = (c.noref || grp.idx(e) < n - 1) ? y_tmp[e] : 0;
       }
     }
   }

@@ -43,7 +43,7 @@ __device__ __forceinline__ int num_bands(int bs) { return bs == 0 ? 1 : bs == 1 
 __device__ __forceinline__ double rsqrt_small(int i) { return rsqrt_small_tbl(i); }
 
 // src/pvq_encoder.c:93.  x[] (|xcoeff| as double) is caller scratch of n entries.
-__device__ double search_rdo(const int16_t* xcoeff, int n, int k, int32_t* ypulse, double g2,
+__device__ __noinline__ double search_rdo(const int16_t* xcoeff, int n, int k, int32_t* ypulse, double g2,
                              double pvq_norm_lambda, int prev_k, double* x) {
   double xx = 0, xy = 0, yy = 0;
   for (int j = 0; j < n; j++) {
@@ -130,7 +130,7 @@ __device__ double search_rdo(const int16_t* xcoeff, int n, int k, int32_t* ypuls
 }
 
 // src/pvq_encoder.c:247, closed-form branch.
-__device__ double band_rate(int qg, int icgr, int theta, int ts, const int32_t* y0, int k, int n,
+__device__ __noinline__ double band_rate(int qg, int icgr, int theta, int ts, const int32_t* y0, int k, int n,
                             int is_keyframe, int pli) {
   double rate;
   if (k == 0) {
@@ -156,7 +156,7 @@ __device__ __forceinline__ int neg_interleave(int x, int ref) {
   return x - 1;
 }
 
-__device__ int householder_setup(int16_t* r, int n, int32_t gr, int* sign, int shift) {
+__device__ __noinline__ int householder_setup(int16_t* r, int n, int32_t gr, int* sign, int shift) {
   int m = 0;
   int16_t maxr = 0;
   for (int i = 0; i < n; i++) {
@@ -172,7 +172,7 @@ __device__ int householder_setup(int16_t* r, int n, int32_t gr, int* sign, int s
   return m;
 }
 
-__device__ void householder_apply(int16_t* out, const int16_t* x, const int16_t* r, int n) {
+__device__ __noinline__ void householder_apply(int16_t* out, const int16_t* x, const int16_t* r, int n) {
   int32_t l2r = 0, proj = 0;
   for (int i = 0; i < n; i++) l2r += mul16(r[i], r[i]);
   for (int i = 0; i < n; i++) proj += mul16(r[i], x[i]);
@@ -191,7 +191,7 @@ __device__ void householder_apply(int16_t* out, const int16_t* x, const int16_t*
   }
 }
 
-__device__ void synthesis(int32_t* xcoeff, const int32_t* ypulse, const int16_t* r16, int n, int noref,
+__device__ __noinline__ void synthesis(int32_t* xcoeff, const int32_t* ypulse, const int16_t* r16, int n, int noref,
                           int32_t g, int32_t theta, int m, int s, const int16_t* qm_inv, int16_t* xs) {
   int nn = n - !noref;
   int yy = 0;
@@ -431,8 +431,8 @@ __device__ int quantise_band(int32_t* out, const int32_t* x0, const int32_t* r0,
 // ---------------------------------------------------------------------------
 
 // band_list entries: (block index << 4) | band index.
-template <int NMAX>
-__global__ void __launch_bounds__(128)
+template <int NMAX, int kMinCtas = 4>
+__global__ void __launch_bounds__(128, kMinCtas)
 k_pvq_bands(const __grid_constant__ daala_b200_pvq_params prm, const uint32_t* __restrict__ band_list,
             int count) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -467,8 +467,8 @@ k_pvq_bands(const __grid_constant__ daala_b200_pvq_params prm, const uint32_t* _
 }
 
 // Group-cooperative variant (pvq_coop.cuh): G lanes per band, registers only.
-template <int G, int E, bool kForceScan>
-__global__ void __launch_bounds__(128)
+template <int G, int E, bool kForceScan, int kMinCtas = 4>
+__global__ void __launch_bounds__(128, kMinCtas)
 k_pvq_bands_coop(const __grid_constant__ daala_b200_pvq_params prm, const uint32_t* __restrict__ band_list,
                  int count) {
   const Group<G, E> grp;
@@ -1143,10 +1143,10 @@ __global__ void k_pvq_helper(HelperBuf* b, int op) {
 
 using namespace daala_b200::pvq;
 
-template <int G, int E, bool kForceScan>
+template <int G, int E, bool kForceScan, int kMinCtas = 4>
 static void launch_coop(const daala_b200_pvq_params* prm, const uint32_t* band_list, int count, cudaStream_t s) {
   const int per = 128 / G, blocks = (count + per - 1) / per;
-  k_pvq_bands_coop<G, E, kForceScan><<<blocks, 128, 0, s>>>(*prm, band_list, count);
+  k_pvq_bands_coop<G, E, kForceScan, kMinCtas><<<blocks, 128, 0, s>>>(*prm, band_list, count);
 }
 
 
@@ -1158,9 +1158,10 @@ int daala_b200_pvq_encode_bands(const daala_b200_pvq_params* prm, const uint32_t
   cudaStream_t s = (cudaStream_t)stream;
   const int threads = 128;
   const int blocks = (count + threads - 1) / threads;
-  if (nmax <= 16) k_pvq_bands<16><<<blocks, threads, 0, s>>>(*prm, band_list, count);
-  else if (nmax <= 32) k_pvq_bands<32><<<blocks, threads, 0, s>>>(*prm, band_list, count);
-  else k_pvq_bands<128><<<blocks, threads, 0, s>>>(*prm, band_list, count);
+  // 64 registers (8 CTAs per SM): the search is latency-bound at 16 warps per SM, the spills stay in L1
+  if (nmax <= 16) k_pvq_bands<16, 8><<<blocks, threads, 0, s>>>(*prm, band_list, count);
+  else if (nmax <= 32) k_pvq_bands<32, 8><<<blocks, threads, 0, s>>>(*prm, band_list, count);
+  else k_pvq_bands<128, 4><<<blocks, threads, 0, s>>>(*prm, band_list, count);
   return (int)cudaGetLastError();
 }
 
@@ -1173,11 +1174,37 @@ int daala_b200_pvq_encode_bands_mode(const daala_b200_pvq_params* prm, const uin
   cudaStream_t s = (cudaStream_t)stream;
   if (mode == 2) return daala_b200_pvq_encode_bands(prm, band_list, count, nmax, stream);
   const int cls = nmax <= 16 ? 0 : nmax <= 32 ? 1 : 2;
+  if (mode >= 20 && mode < 40) {
+    // occupancy experiments (tools/probe/time_modes_ref.py): 20/21 scalar kernels capped at 80 / 64
+    // registers (mode 2 = 64), 30/31 default cooperative geometry capped at 96 / 80 registers
+    const int blocks = (count + 127) / 128;
+    if (mode == 20) {
+      if (cls == 0) k_pvq_bands<16, 6><<<blocks, 128, 0, s>>>(*prm, band_list, count);
+      else if (cls == 1) k_pvq_bands<32, 6><<<blocks, 128, 0, s>>>(*prm, band_list, count);
+      else k_pvq_bands<128, 6><<<blocks, 128, 0, s>>>(*prm, band_list, count);
+    } else if (mode == 21) {
+      if (cls == 0) k_pvq_bands<16, 8><<<blocks, 128, 0, s>>>(*prm, band_list, count);
+      else if (cls == 1) k_pvq_bands<32, 8><<<blocks, 128, 0, s>>>(*prm, band_list, count);
+      else k_pvq_bands<128, 8><<<blocks, 128, 0, s>>>(*prm, band_list, count);
+    } else if (mode == 30) {
+      if (cls == 0) launch_coop<4, 4, false, 5>(prm, band_list, count, s);
+      else if (cls == 1) launch_coop<8, 4, false, 5>(prm, band_list, count, s);
+      else launch_coop<32, 4, false, 5>(prm, band_list, count, s);
+    } else if (mode == 31) {
+      if (cls == 0) launch_coop<4, 4, false, 6>(prm, band_list, count, s);
+      else if (cls == 1) launch_coop<8, 4, false, 6>(prm, band_list, count, s);
+      else launch_coop<32, 4, false, 6>(prm, band_list, count, s);
+    } else {
+      return (int)cudaErrorInvalidValue;
+    }
+    return (int)cudaGetLastError();
+  }
   if (mode == 0) {
-    // measured best on B200 (tools/tune_pvq.py): scalar threads for the short
-    // bands, 16 lanes x 8 registers for the 128-coefficient bands
+    // measured best on B200 (tools/probe/time_modes_ref.py, real with-reference data): scalar threads
+    // for the short bands, a whole warp (32 lanes x 4 registers, capped at 80 registers = 6 CTAs per
+    // SM) for the 128-coefficient bands
     if (cls < 2) return daala_b200_pvq_encode_bands(prm, band_list, count, nmax, stream);
-    launch_coop<16, 8, false>(prm, band_list, count, s);
+    launch_coop<32, 4, false, 6>(prm, band_list, count, s);
     return (int)cudaGetLastError();
   }
   if (mode == 1) {

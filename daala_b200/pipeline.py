@@ -55,7 +55,6 @@ class HotPath:
             chroma = chroma[np.argsort(chroma["bs"], kind="stable")]
             self.cfl_plane = torch.zeros_like(self.fb.coeffs[1])
             self.batch_chroma = pvq.PvqBatch(chroma, self.fb.coeffs, [self.cfl_plane] * 3, **kw)
-            self.batch_chroma.class_mode[128] = 3
             self.batch = self.batch_chroma
             return
         blocks = blocks[np.argsort(blocks["bs"], kind="stable")]

@@ -290,8 +290,7 @@ class PvqBatch:
         self.params = p
         self.is_keyframe = int(is_keyframe)
         # kernel choice of daala_b200_pvq_encode_bands_mode (0 = measured-best mix); per size class
-        # override (None = self.mode): e.g. the CfL chroma batch, whose 128-coefficient bands all run the
-        # with-reference search, is 25 % faster on 32 lanes x 4 registers (mode 3)
+        # override (None = self.mode) for tuning
         self.mode = 0
         self.class_mode = {16: None, 32: None, 128: None}
         # bucket every launch's entries by expected search work (daala_b200_pvq_order_by_work)
@@ -399,7 +398,7 @@ class PvqBatch:
         self.bulk_stream = torch.cuda.Stream(device=dev)
         # waves smaller than this many bands use the group-cooperative kernels (shorter latency)
         # (tools/probe/time_bandwaves.py, time_modes_ref.py: crossover of the scalar / 16-lane kernels)
-        self.small_wave = {16: 8192, 32: 16384, 128: 4096}
+        self.small_wave = {16: 8192, 32: 16384, 128: 0}
         self.small_mode = 3
         self.intra_mode = "bands"
 

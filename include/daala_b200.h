@@ -252,11 +252,12 @@ typedef struct daala_b200_pvq_params {
 int daala_b200_pvq_encode_bands(const daala_b200_pvq_params *prm, const uint32_t *band_list, int count,
                                 int nmax, void *stream);
 /* Same with an explicit kernel choice: mode 0 = the measured-best mix (scalar
-   thread-per-band kernels for n <= 32, 16 lanes x 8 registers per band for
-   n = 128), 1 = group-cooperative kernels with the literal sequential arg-max
-   scan forced (test hook for the rare inexact-product regime), 2 = scalar
+   thread-per-band kernels for n <= 32, one warp = 32 lanes x 4 registers per
+   band for n = 128), 1 = group-cooperative kernels with the literal sequential
+   arg-max scan forced (test hook for the rare inexact-product regime), 2 = scalar
    kernels everywhere (what _encode_bands launches), 3 = group-cooperative
-   kernels everywhere, 10 + c = alternative lanes-per-band geometries (tuning). */
+   kernels everywhere, 10 + c = alternative lanes-per-band geometries, 20/21/30/31 =
+   register-cap (occupancy) variants (tuning). */
 int daala_b200_pvq_encode_bands_mode(const daala_b200_pvq_params *prm, const uint32_t *band_list, int count,
                                      int nmax, int mode, void *stream);
 /* Keyframe luma WITH the reference's H/V intra prediction (od_hv_intra_pred,

@@ -25,7 +25,7 @@ def t(fn, reps=3):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
     return best
 
-MODES = {16: [2, 3, 11, 12], 32: [2, 3, 11, 12], 128: [2, 3, 11, 12, 13]}
+MODES = {16: [2, 20, 21, 3, 30, 31], 32: [2, 20, 21, 3, 30, 31], 128: [2, 3, 30, 31, 11]}
 b = hp.batch_luma
 p = ctypes.byref(b.params)
 for k in (128, 32, 16):
