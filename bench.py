@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--pvq-mode", type=int, default=0, help="0 cooperative kernels, 2 scalar thread-per-band")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="e2e: serial copy-in / compute / copy-out instead of the double-buffered pipeline")
+    ap.add_argument("--pvq-groups", type=int, default=2, help="frame groups whose PVQ stages run on separate streams")
     ap.add_argument("--intra-mode", default="bands", choices=["bands", "waves", "chain", "chain_single"])
     ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"],
                     help="frames: every rank encodes its own --frames frames with the reference's keyframe "
@@ -296,12 +297,12 @@ def run_b200(args):
 
         def __init__(self):
             hp = HotPath(geom, nframes=F, device=dev, q0=Q0, is_keyframe=1, use_masking=1, pvq_qm_q4=q4,
-                         sb_row0=r0, sb_rows=nrows, keyframe_prediction=not sbrow)
+                         sb_row0=r0, sb_rows=nrows, keyframe_prediction=not sbrow, pvq_groups=args.pvq_groups)
             hp.set_block_sizes([hf[1] for hf in host_frames])
-            hp.batch.mode = args.pvq_mode
-            if hp.batch_luma is not None:
-                hp.batch_luma.mode = args.pvq_mode
-                hp.batch_luma.intra_mode = args.intra_mode
+            for b in hp.pvq_batches():
+                b.mode = args.pvq_mode
+                if getattr(b, "chain_lists", None) is not None:
+                    b.intra_mode = args.intra_mode
             self.hp, self.fb = hp, hp.fb
             self.pin_out = []
             for pli in range(3):
@@ -310,7 +311,7 @@ def run_b200(args):
             # e2e also moves what the host side of the reference consumes/produces around the hot path:
             # block descriptors + band lists in (they follow from the block-size decision), and the PVQ
             # symbols out (per-band indices, flags, 16-bit pulses) for the host entropy coder.
-            batches = [b for b in (hp.batch_luma, hp.batch) if b is not None]
+            batches = hp.pvq_batches()
             self.desc_dev = []
             for b in batches:
                 self.desc_dev.append(b.blocks)
@@ -395,7 +396,7 @@ def run_b200(args):
         a, b = rows(pli, 0)
         err = (fb.pixels_out[pli][:, a:b].float() - fb.pixels[pli][:, a:b].float()).abs().mean().item()
         assert err < 12.0, "reconstruction error too large (%.2f)" % err
-    total_k = int(hp.batch.res_k.sum().item()) + (int(hp.batch_luma.res_k.sum().item()) if hp.batch_luma else 0)
+    total_k = sum(int(b.res_k.sum().item()) for b in hp.pvq_batches())
     assert total_k > 0, "PVQ produced no pulses"
 
     sampler = ClockSampler(local)
@@ -461,29 +462,28 @@ def run_b200(args):
     ms_post = timed(fb.sb_postfilter_store, reps) / reps
     # PVQ stages on fresh transform output every repetition (re-quantising the already quantised
     # planes of the previous pass would be a different, lighter workload)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    acc_luma = acc_rest = 0.0
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    acc_luma = acc_all = 0.0
     barrier()
     for _ in range(reps):
         fb.forward()
         evs[0].record()
         if hp.keyframe_prediction:
-            hp.batch_luma.run_luma_intra()
-            evs[1].record()
-            hp.batch_chroma.cfl_pred(hp.cfl_plane)
-            hp.batch_chroma.run()
-        else:
-            evs[1].record()
-            hp.batch.run()
+            for bl, _, _ in hp.groups:      # the luma wavefronts alone, one group after the other
+                bl.run_luma_intra()
+        evs[1].record()
+        fb.forward()
         evs[2].record()
+        hp.run_pvq()                        # the stage as the step runs it (groups on their streams)
+        evs[3].record()
         torch.cuda.synchronize()
         acc_luma += evs[0].elapsed_time(evs[1])
-        acc_rest += evs[1].elapsed_time(evs[2])
+        acc_all += evs[2].elapsed_time(evs[3])
     ms_pvq_luma = acc_luma / reps if hp.keyframe_prediction else None
-    ms_pvq = (acc_luma + acc_rest) / reps
+    ms_pvq = acc_all / reps
 
-    # dominant kernel by time share (profiles/r1m_launches.csv): the PVQ band search for the
-    # 128-coefficient bands, k_pvq_bands_coop<16,8>; timed alone on the chroma / all-plane batch
+    # dominant kernel by time share (profiles/r1q_launches.csv: 42 % of the step): the PVQ band search for
+    # the 128-coefficient bands, k_pvq_bands_coop<32,4>; timed alone on the first chroma / all-plane batch
     import ctypes as _ct
     from daala_b200 import pvq as _pvq, _native as _nat
     _L = _pvq._bind()
@@ -539,7 +539,7 @@ def run_b200(args):
         "clocks": clocks,
         # dominant kernel (40 % of the step): not HBM-bound -- a greedy double-precision search,
         # issue/latency-bound; its HBM fraction is reported as the contract asks
-        "roofline": {"kernel": "k_pvq_bands_coop<16,8> (PVQ search, 128-coefficient bands)", "bound": "hbm",
+        "roofline": {"kernel": "k_pvq_bands_coop<32,4> (PVQ search, 128-coefficient bands)", "bound": "hbm",
                      "achieved": round(dom_bytes / (ms_dom * 1e-3) / 1e9, 1) if ms_dom else None, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s",
                      "frac": round(dom_bytes / (ms_dom * 1e-3) / 1e9 / peak, 4) if ms_dom else None,

@@ -18,7 +18,8 @@ from .frame import FrameBuffers
 
 class HotPath:
     def __init__(self, geom, nframes=1, device="cuda:0", q0=38, is_keyframe=1, use_masking=1,
-                 lam=pvq.PVQ_LAMBDA, pvq_qm_q4=None, sb_row0=0, sb_rows=None, keyframe_prediction=False):
+                 lam=pvq.PVQ_LAMBDA, pvq_qm_q4=None, sb_row0=0, sb_rows=None, keyframe_prediction=False,
+                 pvq_groups=1):
         self.geom = geom
         self.nframes = nframes
         self.device = torch.device(device)
@@ -33,6 +34,11 @@ class HotPath:
         # keyframes with the reference's predictors: luma H/V intra (wavefront kernel), chroma CfL
         self.keyframe_prediction = bool(keyframe_prediction) and bool(is_keyframe)
         self.batch_luma = self.batch_chroma = self.cfl_plane = None
+        # keyframe prediction: the frames of the batch are split into `pvq_groups` groups, each with its
+        # own luma / chroma PVQ batches on its own stream, so that the latency-bound tail of one group's
+        # luma wavefront overlaps the throughput-bound chroma / early-wave work of another
+        self.pvq_groups = max(1, min(int(pvq_groups), nframes))
+        self.groups = []
 
     def set_block_sizes(self, bsizes):
         """bsizes: one map per frame (host numpy).  Builds the block / band
@@ -47,20 +53,33 @@ class HotPath:
                 "intra prediction chains cross superblock rows: keyframe_prediction needs whole frames per rank"
             kw = dict(q0=self.q0, is_keyframe=1, use_masking=self.use_masking, lam=self.lam,
                       pvq_qm_q4=self.pvq_qm_q4, device=self.device)
-            luma, top, left, depth = pvq.sort_by_depth(pvq.raster_order(blocks[blocks["pli"] == 0]), list(bsizes),
-                                                       self.geom)
-            self.batch_luma = pvq.PvqBatch(luma, self.fb.coeffs, None, **kw)
-            self.batch_luma.setup_intra(top, left, depth)
-            chroma = pvq.mark_luma4x4(blocks[blocks["pli"] != 0], list(bsizes))
-            chroma = chroma[np.argsort(chroma["bs"], kind="stable")]
             self.cfl_plane = torch.zeros_like(self.fb.coeffs[1])
-            self.batch_chroma = pvq.PvqBatch(chroma, self.fb.coeffs, [self.cfl_plane] * 3, **kw)
+            self.groups = []
+            bounds = np.linspace(0, self.nframes, self.pvq_groups + 1).astype(int)
+            for g in range(self.pvq_groups):
+                sel = blocks[(blocks["frame"] >= bounds[g]) & (blocks["frame"] < bounds[g + 1])]
+                luma, top, left, depth = pvq.sort_by_depth(pvq.raster_order(sel[sel["pli"] == 0]), list(bsizes),
+                                                           self.geom)
+                bl = pvq.PvqBatch(luma, self.fb.coeffs, None, **kw)
+                bl.setup_intra(top, left, depth)
+                chroma = pvq.mark_luma4x4(sel[sel["pli"] != 0], list(bsizes))
+                chroma = chroma[np.argsort(chroma["bs"], kind="stable")]
+                bc = pvq.PvqBatch(chroma, self.fb.coeffs, [self.cfl_plane] * 3, **kw)
+                stream = torch.cuda.Stream(device=self.device) if self.pvq_groups > 1 else None
+                self.groups.append((bl, bc, stream))
+            self.batch_luma, self.batch_chroma = self.groups[0][0], self.groups[0][1]
             self.batch = self.batch_chroma
             return
         blocks = blocks[np.argsort(blocks["bs"], kind="stable")]
         self.batch = pvq.PvqBatch(blocks, self.fb.coeffs, self.pred.coeffs if self.pred else None, q0=self.q0,
                                   is_keyframe=self.is_keyframe, use_masking=self.use_masking, lam=self.lam,
                                   pvq_qm_q4=self.pvq_qm_q4, device=self.device)
+
+    def pvq_batches(self):
+        """Every PVQ batch of this pass (what produces symbols for the host entropy coder)."""
+        if self.groups:
+            return [b for bl, bc, _ in self.groups for b in (bl, bc)]
+        return [self.batch]
 
     def use_prediction(self, pred_fb):
         """Inter frames: `pred_fb.coeffs` hold the transformed motion-compensated
@@ -84,16 +103,28 @@ class HotPath:
         self.graph.replay()
         return self.graph_launches
 
+    def run_pvq(self):
+        """The PVQ stage of one pass (after forward()); returns the number of kernel launches."""
+        if not self.keyframe_prediction:
+            return self.batch.run()
+        n = 0
+        main = torch.cuda.current_stream(self.device)
+        for bl, bc, st in self.groups:
+            if st is not None:
+                st.wait_stream(main)
+            n += bl.run_luma_intra(st)
+            n += bc.cfl_pred(self.cfl_plane, st)
+            n += bc.run(st)
+        for _, _, st in self.groups:
+            if st is not None:
+                main.wait_stream(st)
+        return n
+
     def run(self, exchange=None):
         """One pass; returns the number of kernel launches.  `exchange` (multi-GPU)
         is called between the two halves of the inverse to trade lapped border rows."""
         self.fb.forward()
-        if self.keyframe_prediction:
-            n = 1 + self.batch_luma.run_luma_intra()
-            n += self.batch_chroma.cfl_pred(self.cfl_plane)
-            n += self.batch_chroma.run()
-        else:
-            n = 1 + self.batch.run()
+        n = 1 + self.run_pvq()
         self.fb.inverse(lapped_only=True)
         if exchange is not None:
             exchange()

@@ -267,6 +267,41 @@ def test_work_ordering_is_a_wave_preserving_permutation_and_does_not_change_resu
         assert torch.equal(a, b)
 
 
+def test_frame_groups_and_graph_replay_give_the_same_planes():
+    """pvq_groups only changes scheduling (per-group batches on their own streams) and a CUDA-graph
+    replay re-issues the identical launches: coefficient and pixel planes are bit-identical."""
+    import torch
+    from daala_b200 import synth
+    from daala_b200.frame import Geometry
+    from daala_b200.pipeline import HotPath
+    geom = Geometry(320, 192)
+    q4 = np.full((3, 30), 18, np.uint8)
+    frames = []
+    for f in range(3):
+        planes, _ = synth.frame(320, 192, f=20 + f)
+        frames.append((synth.pad_planes(planes, geom), synth.block_size_map(geom, "mixed", seed=50 + f)))
+    outs = []
+    for groups, graph in ((1, False), (2, False), (3, True)):
+        hp = HotPath(geom, nframes=3, q0=40, is_keyframe=1, pvq_qm_q4=q4, keyframe_prediction=True,
+                     pvq_groups=groups)
+        for f, (planes, bsize) in enumerate(frames):
+            hp.fb.upload(planes, bsize, frame=f)
+        hp.set_block_sizes([b for _, b in frames])
+        if graph:
+            hp.capture()
+            for t in hp.fb.coeffs + hp.fb.pixels_out:
+                t.zero_()
+            assert hp.replay() == hp.graph_launches > 0
+        else:
+            hp.run()
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in hp.fb.coeffs + hp.fb.pixels_out])
+        assert int(sum(b.res_k.sum().item() for b in hp.pvq_batches())) > 0
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
+
+
 def test_dropin_pvq_helper_symbols_match_oracle():
     """Host-pointer od_pvq_* helpers and od_rdo_quant against the reference build
     (or the port when oracle/_ref is absent)."""
