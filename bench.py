@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--pvq-mode", type=int, default=0, help="0 cooperative kernels, 2 scalar thread-per-band")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="e2e: serial copy-in / compute / copy-out instead of the double-buffered pipeline")
-    ap.add_argument("--pvq-groups", type=int, default=2, help="frame groups whose PVQ stages run on separate streams")
+    ap.add_argument("--pvq-groups", type=int, default=1, help="frame groups whose PVQ stages run on separate streams")
     ap.add_argument("--intra-mode", default="bands", choices=["bands", "waves", "chain", "chain_single"])
     ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"],
                     help="frames: every rank encodes its own --frames frames with the reference's keyframe "
