@@ -398,8 +398,14 @@ class PvqBatch:
         self.bulk_stream = torch.cuda.Stream(device=dev)
         # waves smaller than this many bands use the group-cooperative kernels (shorter latency)
         # (tools/probe/time_bandwaves.py, time_modes_ref.py: crossover of the scalar / 16-lane kernels)
-        self.small_wave = {16: 8192, 32: 16384, 128: 0}
+        self.small_wave = {16: 32768, 32: 65536, 128: 0}
         self.small_mode = 3
+        if os.environ.get("DAALA_B200_SMALL_WAVE"):          # tuning hook: "n16,n32,n128"
+            self.small_wave = dict(zip((16, 32, 128), map(int, os.environ["DAALA_B200_SMALL_WAVE"].split(","))))
+        if os.environ.get("DAALA_B200_ONE_CHAIN_STREAM"):     # tuning hook: all chains on one stream
+            one = self.chain_streams[128]
+            self.chain_streams = {k: one for k in self.chain_streams}
+            self.bulk_stream = one
         self.intra_mode = "bands"
 
     def run_luma_intra(self, stream=None):
