@@ -222,3 +222,64 @@ def test_frame_obmc_prediction_matches_reference_state_mc_predict():
         mc.predict_blocks(rp, dst, mc.to_device(blocks), len(blocks))
         got = dst.cpu().numpy()
         assert np.array_equal(got, outs[pli]), "plane %d: %d mismatches" % (pli, int((got != outs[pli]).sum()))
+
+
+def test_inter_frame_chain_mv_grid_to_pvq_matches_reference():
+    """The inter-frame hot path end to end on the device: MV grid -> OBMC prediction of all planes
+    (k_obmc_blocks) -> forward transform of the prediction (the reference's mdtmp planes,
+    src/encode.c:2566-2573) -> forward transform of the source -> PVQ against that prediction ->
+    inverse.  Oracle: od_state_mc_predict on a real od_state, then the reference's own transform /
+    pvq_theta / inverse functions on the predicted planes."""
+    import torch
+    from daala_b200 import mc, mvgrid, pvq, synth
+    from daala_b200.frame import FrameBuffers, Geometry
+    from daala_b200.pipeline import HotPath
+    from tests import frame_oracle
+    lib, prefix = _oracle()
+    if prefix != "ref":
+        pytest.skip("needs the reference build (od_state_mc_predict)")
+    rng = np.random.default_rng(33)
+    W, H = 256, 192
+    geom = Geometry(W, H)
+    cur_y, ref_y = _frames(seed=9, h=H, w=W)
+    ref_u = np.ascontiguousarray(ref_y[::2, ::2][:, ::-1])
+    ref_v = np.ascontiguousarray(ref_y[1::2, 1::2])
+    cur = [cur_y, np.ascontiguousarray(cur_y[::2, ::2][:, ::-1]), np.ascontiguousarray(cur_y[1::2, 1::2])]
+    valid, mv = _random_mv_grid(rng, H // 8, W // 8)
+    # reference prediction
+    pred_ref = [np.zeros((H, W), np.uint8), np.zeros((H // 2, W // 2), np.uint8), np.zeros((H // 2, W // 2), np.uint8)]
+    rc = lib.oracle_ref_state_mc_predict(W, H, addr(ref_y), addr(ref_u), addr(ref_v),
+                                         addr(np.ascontiguousarray(valid.astype(np.uint8))),
+                                         addr(np.ascontiguousarray(mv)), addr(pred_ref[0]), addr(pred_ref[1]),
+                                         addr(pred_ref[2]))
+    assert rc == 0
+    # device chain
+    bsize = synth.block_size_map(geom, "mixed", seed=12)
+    q4 = np.full((3, 30), 20, np.uint8)
+    hp = HotPath(geom, q0=45, is_keyframe=0, pvq_qm_q4=q4)
+    hp.fb.upload(cur, bsize)
+    pred = FrameBuffers(geom)
+    pred.upload(cur, bsize)      # block-size map; the pixel planes are overwritten by the prediction below
+    pred.haar_dc = 0
+    for pli, refp in enumerate((ref_y, ref_u, ref_v)):
+        blocks = mvgrid.block_list(valid, mv, xdec=1 if pli else 0)
+        dst = torch.zeros(refp.shape, dtype=torch.uint8, device="cuda:0")
+        mc.predict_blocks(mc.PaddedPlane(refp), dst, mc.to_device(blocks), len(blocks))
+        pred.pixels[pli][0].copy_(dst)
+    pred.forward()
+    hp.use_prediction(pred)
+    hp.set_block_sizes([bsize])
+    hp.run()
+    torch.cuda.synchronize()
+    qm, qm_inv = pvq.default_qm(True)
+    coded = 0
+    for pli in range(3):
+        assert np.array_equal(pred.pixels[pli][0].cpu().numpy(), pred_ref[pli]), "prediction plane %d" % pli
+        d = frame_oracle.forward_plane(lib, prefix, cur[pli], geom, pli, bsize, 0)
+        md = frame_oracle.forward_plane(lib, prefix, pred_ref[pli], geom, pli, bsize, 0)
+        dq, stats = frame_oracle.pvq_plane(lib, prefix, d, md, geom, pli, bsize, 45, 0, 1, 0.147, qm, qm_inv, q4)
+        coded += int(stats[0])
+        assert np.array_equal(hp.fb.coeffs[pli][0].cpu().numpy(), dq), "quantised plane %d" % pli
+        rec = frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 0)
+        assert np.array_equal(hp.fb.pixels_out[pli][0].cpu().numpy(), rec), "recon plane %d" % pli
+    assert coded > 0
