@@ -32,6 +32,7 @@ int daala_b200_launch_plane_sb_filter(int32_t* c, int stride, int nhsb, int nvsb
                                       int post, cudaStream_t stream);
 int daala_b200_launch_block_transform(int32_t* blocks, int count, int ln, int mode, cudaStream_t stream);
 int daala_b200_launch_filter4(int32_t* v, long count, int post, cudaStream_t stream);
+int daala_b200_launch_haar_blocks(int32_t* blocks, int count, int ln, int inverse, cudaStream_t stream);
 int daala_b200_pvq_helper_launch(void* buf, int op, void* stream);
 int daala_b200_pvq_helper_bytes(void);
 int daala_b200_launch_lapfilter(int32_t* v, long count, int n, int post, cudaStream_t stream);
@@ -108,6 +109,19 @@ void dct1d(int ln, bool inverse, od_coeff* out, int out_stride, const od_coeff* 
                "block_transform(1d)");
   c.d2h(sizeof(od_coeff) * n);
   for (int i = 0; i < n; i++) out[i * out_stride] = p[i];
+}
+
+void haar2d(int ln, bool inverse, od_coeff* out, int out_stride, const od_coeff* in, int in_stride) {
+  HostCtx& c = ctx();
+  std::lock_guard<std::mutex> g(c.mu);
+  const int n = 1 << ln;
+  c.ensure(sizeof(od_coeff) * n * n);
+  od_coeff* p = (od_coeff*)c.pinned;
+  for (int i = 0; i < n; i++) memcpy(p + i * n, in + (size_t)i * in_stride, sizeof(od_coeff) * n);
+  c.h2d(sizeof(od_coeff) * n * n);
+  check_launch(daala_b200_launch_haar_blocks((int32_t*)c.dev, 1, ln, inverse ? 1 : 0, c.stream), "haar_blocks");
+  c.d2h(sizeof(od_coeff) * n * n);
+  for (int i = 0; i < n; i++) memcpy(out + (size_t)i * out_stride, p + i * n, sizeof(od_coeff) * n);
 }
 
 void dct2d(int ln, bool inverse, od_coeff* out, int out_stride, const od_coeff* in, int in_stride) {
@@ -194,6 +208,10 @@ DAALA_B200_DCT(8, 3)
 DAALA_B200_DCT(16, 4)
 DAALA_B200_DCT(32, 5)
 DAALA_B200_DCT(64, 6)
+
+/* src/dct.c:4822 / :4861 */
+void od_haar(od_coeff* y, int ystride, const od_coeff* x, int xstride, int ln) { haar2d(ln, false, y, ystride, x, xstride); }
+void od_haar_inv(od_coeff* x, int xstride, const od_coeff* y, int ystride, int ln) { haar2d(ln, true, x, xstride, y, ystride); }
 
 const od_dct_func_2d OD_FDCT_2D_CUDA[6] = {od_bin_fdct4x4,   od_bin_fdct8x8,   od_bin_fdct16x16,
                                            od_bin_fdct32x32, od_bin_fdct64x64, nullptr};
@@ -459,6 +477,10 @@ int daala_b200_plane_sb_filter(int32_t* c, int stride, int nhsb, int nvsb, int x
                                void* stream) {
   return daala_b200_launch_plane_sb_filter(c, stride, nhsb, nvsb, xdec, ydec, post, (cudaStream_t)stream);
 }
+int daala_b200_haar_blocks(int32_t* blocks, int count, int ln, int inverse, void* stream) {
+  return daala_b200_launch_haar_blocks(blocks, count, ln, inverse, (cudaStream_t)stream);
+}
+
 int daala_b200_block_transform(int32_t* blocks, int count, int ln, int mode, void* stream) {
   return daala_b200_launch_block_transform(blocks, count, ln, mode, (cudaStream_t)stream);
 }

@@ -62,6 +62,9 @@ void od_bin_fdct32x32(od_coeff *y, int ystride, const od_coeff *x, int xstride);
 void od_bin_idct32x32(od_coeff *x, int xstride, const od_coeff *y, int ystride);
 void od_bin_fdct64x64(od_coeff *y, int ystride, const od_coeff *x, int xstride);
 void od_bin_idct64x64(od_coeff *x, int xstride, const od_coeff *y, int ystride);
+/* src/dct.c:4822 / :4861 (prototypes src/dct.h): the multi-level Haar wavelet of the lossless path, n = 1 << ln */
+void od_haar(od_coeff *y, int ystride, const od_coeff *x, int xstride, int ln);
+void od_haar_inv(od_coeff *x, int xstride, const od_coeff *y, int ystride, int ln);
 
 typedef void (*od_dct_func_2d)(od_coeff *out, int out_stride, const od_coeff *in, int in_stride);
 /* reference: OD_FDCT_2D_C / OD_IDCT_2D_C, src/dct.c:54-68 (last entry NULL). */
@@ -196,6 +199,8 @@ int daala_b200_plane_sb_filter(int32_t *c, int stride, int nhsb, int nvsb, int x
 /* `count` contiguous groups of n (4, 8, 16 or 32) ints through the n-point pre (post = 0) or
    post filter, in place. */
 int daala_b200_lapfilter(int32_t *v, long count, int n, int post, void *stream);
+/* `count` packed (1<<ln)^2 blocks (ln = 1..6) through od_haar (inverse = 0) or od_haar_inv (1), in place. */
+int daala_b200_haar_blocks(int32_t *blocks, int count, int ln, int inverse, void *stream);
 /* `count` packed (1<<ln)^2 blocks, contiguous, transformed in place.
    mode 0/1: 2-D forward/inverse; mode 2/3: every row as a 1-D forward/inverse. */
 int daala_b200_block_transform(int32_t *blocks, int count, int ln, int mode, void *stream);

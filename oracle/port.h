@@ -16,6 +16,8 @@ typedef int32_t od_coeff;
 void port_bin_fdct(int ln, od_coeff *y, const od_coeff *x, int xstride);
 void port_bin_idct(int ln, od_coeff *x, int xstride, const od_coeff *y);
 void port_bin_fdct2d(int ln, od_coeff *y, int ystride, const od_coeff *x, int xstride);
+void port_haar(od_coeff *y, int ystride, const od_coeff *x, int xstride, int ln);
+void port_haar_inv(od_coeff *x, int xstride, const od_coeff *y, int ystride, int ln);
 void port_bin_idct2d(int ln, od_coeff *x, int xstride, const od_coeff *y, int ystride);
 
 /* port_filter.c -- src/filter.c */

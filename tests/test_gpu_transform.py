@@ -119,6 +119,50 @@ def test_dropin_dct_symbols_match_oracle(torch_cuda, ln):
         assert np.array_equal(v2, v)
 
 
+@pytest.mark.parametrize("ln", [1, 2, 3, 4, 5, 6])
+def test_haar_wavelet_matches_oracle(torch_cuda, ln):
+    """od_haar / od_haar_inv drop-in symbols (host pointers, strided) and the batched device entry point
+    daala_b200_haar_blocks against the reference build / the port (src/dct.c:4822, :4861)."""
+    torch = torch_cuda
+    from daala_b200 import _native
+    L = _native.lib()
+    L.daala_b200_haar_blocks.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.daala_b200_haar_blocks.restype = ctypes.c_int
+    a = oracle_lib.addr
+    n = 1 << ln
+    rng = np.random.default_rng(40 + ln)
+    for name, lib, prefix in checkers():
+        fwd = lib.od_haar if prefix == "ref" else lib.port_haar
+        inv = lib.od_haar_inv if prefix == "ref" else lib.port_haar_inv
+        for t in range(3):
+            x = np.zeros((n, n + 3), np.int32)
+            x[:, :n] = rng.integers(-(1 << 14), 1 << 14, size=(n, n))
+            y_gpu = np.zeros((n, n + 1), np.int32)
+            y_cpu = np.zeros((n, n + 1), np.int32)
+            L.od_haar(a(y_gpu), n + 1, a(x), n + 3, ln)
+            fwd(a(y_cpu), n + 1, a(x), n + 3, ln)
+            assert np.array_equal(y_gpu, y_cpu), name
+            x_gpu = np.zeros((n, n + 2), np.int32)
+            x_cpu = np.zeros((n, n + 2), np.int32)
+            L.od_haar_inv(a(x_gpu), n + 2, a(y_gpu), n + 1, ln)
+            inv(a(x_cpu), n + 2, a(y_cpu), n + 1, ln)
+            assert np.array_equal(x_gpu, x_cpu), name
+            assert np.array_equal(x_gpu[:, :n], x[:, :n])
+    # batch of packed blocks on the device, in place: forward equals the per-block oracle, inverse restores
+    port = oracle_lib.load_port()
+    blocks = rng.integers(-(1 << 14), 1 << 14, size=(37, n, n)).astype(np.int32)
+    dev = torch.from_numpy(blocks.copy()).cuda()
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert L.daala_b200_haar_blocks(dev.data_ptr(), len(blocks), ln, 0, s) == 0
+    got = dev.cpu().numpy()
+    for i in (0, 17, 36):
+        exp = np.zeros((n, n), np.int32)
+        port.port_haar(a(exp), n, a(np.ascontiguousarray(blocks[i])), n, ln)
+        assert np.array_equal(got[i], exp)
+    assert L.daala_b200_haar_blocks(dev.data_ptr(), len(blocks), ln, 1, s) == 0
+    assert np.array_equal(dev.cpu().numpy(), blocks)
+
+
 def test_dropin_filter_symbols_match_oracle(torch_cuda):
     from daala_b200 import _native
     L = _native.lib()

@@ -62,6 +62,27 @@ def test_dct_2d_port_matches_reference(port, ref, ln):
         assert np.array_equal(x_ref, x)
 
 
+@pytest.mark.parametrize("ln", [1, 2, 3, 4, 5, 6])
+def test_haar_port_matches_reference_and_is_lossless(port, ref, ln):
+    """od_haar / od_haar_inv (src/dct.c:4822/:4861), strided in and out; the wavelet is exactly invertible."""
+    n = 1 << ln
+    rng = np.random.default_rng(300 + ln)
+    for t in range(10):
+        x = np.zeros((n, n + 3), np.int32)
+        x[:, :n] = rng.integers(-(1 << 14), 1 << 14, size=(n, n))
+        y_ref = np.zeros((n, n + 1), np.int32)
+        y_port = np.zeros((n, n + 1), np.int32)
+        ref.od_haar(addr(y_ref), n + 1, addr(x), n + 3, ln)
+        port.port_haar(addr(y_port), n + 1, addr(x), n + 3, ln)
+        assert np.array_equal(y_ref, y_port)
+        x_ref = np.zeros((n, n + 2), np.int32)
+        x_port = np.zeros((n, n + 2), np.int32)
+        ref.od_haar_inv(addr(x_ref), n + 2, addr(y_ref), n + 1, ln)
+        port.port_haar_inv(addr(x_port), n + 2, addr(y_ref), n + 1, ln)
+        assert np.array_equal(x_ref, x_port)
+        assert np.array_equal(x_ref[:, :n], x[:, :n])
+
+
 def test_filter4_port_matches_reference_and_inverts(port, ref):
     rng = np.random.default_rng(7)
     for t in range(2000):
