@@ -302,6 +302,49 @@ def test_frame_groups_and_graph_replay_give_the_same_planes():
             assert torch.equal(a, b)
 
 
+def test_hot_path_matches_recorded_reference_checksums():
+    """The device chain against tests/golden/reference_vectors.npz (plane CRC-32s recorded from the real
+    reference build by tests/golden/make_golden.py): forward, keyframe / inter PVQ + inverse, and the
+    keyframe chain with intra + CfL prediction.  Needs neither oracle/_ref nor the port."""
+    import os
+    import torch
+    from daala_b200.frame import FrameBuffers
+    from daala_b200.pipeline import HotPath
+    from tests.golden import make_golden
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
+    want = dict(zip(gold["frame_keys"].tolist(), gold["frame_crc"].tolist()))
+    F = make_golden.FRAME
+    geom, planes, prev, bsize = make_golden.frame_inputs()
+    q4 = np.full((3, 30), F["q4"], np.uint8)
+    crc = make_golden.crc
+    for key in (1, 0):
+        hp = HotPath(geom, q0=F["q0"], is_keyframe=key, pvq_qm_q4=q4)
+        hp.fb.upload(planes, bsize)
+        if not key:
+            pred = FrameBuffers(geom)
+            pred.upload(prev, bsize)
+            pred.haar_dc = 0
+            pred.forward()
+            hp.use_prediction(pred)
+        hp.set_block_sizes([bsize])
+        hp.fb.forward()
+        torch.cuda.synchronize()
+        for pli in range(3):
+            assert crc(hp.fb.coeffs[pli][0].cpu().numpy()) == want["fwd_p%d_k%d" % (pli, key)], (pli, key)
+        hp.run()
+        torch.cuda.synchronize()
+        for pli in range(3):
+            assert crc(hp.fb.coeffs[pli][0].cpu().numpy()) == want["pvq_p%d_k%d" % (pli, key)], (pli, key)
+            assert crc(hp.fb.pixels_out[pli][0].cpu().numpy()) == want["inv_p%d_k%d" % (pli, key)], (pli, key)
+    hp = HotPath(geom, q0=F["q0"], is_keyframe=1, pvq_qm_q4=q4, keyframe_prediction=True)
+    hp.fb.upload(planes, bsize)
+    hp.set_block_sizes([bsize])
+    hp.run()
+    torch.cuda.synchronize()
+    for pli in range(3):
+        assert crc(hp.fb.coeffs[pli][0].cpu().numpy()) == want["pred_p%d" % pli], pli
+
+
 def test_dropin_pvq_helper_symbols_match_oracle():
     """Host-pointer od_pvq_* helpers and od_rdo_quant against the reference build
     (or the port when oracle/_ref is absent)."""
