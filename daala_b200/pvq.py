@@ -238,6 +238,65 @@ def band_wave_lists(blocks, top, left, depth):
     return bulk, chain, slices
 
 
+class _KeyframeLists(ctypes.Structure):
+    """struct daala_b200_keyframe_lists"""
+    _fields_ = [
+        ("n_luma", ctypes.c_int), ("n_chroma", ctypes.c_int),
+        ("luma", ctypes.c_void_p), ("chroma", ctypes.c_void_p),
+        ("dep_top", ctypes.c_void_p), ("dep_left", ctypes.c_void_p), ("depth", ctypes.c_void_p),
+        ("luma_total", ctypes.c_longlong), ("chroma_total", ctypes.c_longlong),
+        ("chain", ctypes.c_void_p * 3), ("chain_wave", ctypes.c_void_p * 3),
+        ("wave_first", ctypes.c_void_p * 3), ("wave_count", ctypes.c_void_p * 3),
+        ("bulk", ctypes.c_void_p * 3), ("chroma_list", ctypes.c_void_p * 3),
+        ("n_chain", ctypes.c_int * 3), ("n_waves", ctypes.c_int * 3), ("n_bulk", ctypes.c_int * 3),
+        ("n_chroma_list", ctypes.c_int * 3),
+    ]
+
+
+def native_keyframe_lists(bsize_maps, geom, nthreads=8):
+    """The work lists of a keyframe batch built by the library's host code
+    (daala_b200_host_keyframe_lists, csrc/host_lists.cu): the same arrays, in the same order, as
+    block_list + raster_order + sort_by_depth + band_wave_lists (luma) and mark_luma4x4 + the stable
+    size sort + band_lists (chroma) produce in numpy -- about two orders of magnitude faster, which
+    matters because a real encoder rebuilds them for every frame.  No GPU involved."""
+    L = _native.lib()
+    fn = L.daala_b200_host_keyframe_lists
+    fn.restype = ctypes.POINTER(_KeyframeLists)
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                   ctypes.c_int]
+    L.daala_b200_host_keyframe_lists_free.argtypes = [ctypes.POINTER(_KeyframeLists)]
+    maps = np.ascontiguousarray(np.stack([np.asarray(b, np.uint8) for b in bsize_maps]))
+    assert maps.shape[1:] == tuple(geom.bsize_shape)
+    p = fn(maps.ctypes.data, len(maps), maps.strides[0], maps.strides[1], geom.nhsb, geom.nvsb, nthreads)
+    if not p:
+        raise RuntimeError("daala_b200_host_keyframe_lists failed")
+    k = p.contents
+
+    def arr(ptr, count, dtype):
+        if count == 0:
+            return np.zeros(0, dtype)
+        nbytes = count * np.dtype(dtype).itemsize
+        return np.frombuffer((ctypes.c_char * nbytes).from_address(ptr), dtype=dtype).copy()
+
+    try:
+        out = dict(
+            luma=arr(k.luma, k.n_luma, BLOCK_DTYPE), chroma=arr(k.chroma, k.n_chroma, BLOCK_DTYPE),
+            dep_top=arr(k.dep_top, k.n_luma, np.int32), dep_left=arr(k.dep_left, k.n_luma, np.int32),
+            depth=arr(k.depth, k.n_luma, np.int32), luma_total=int(k.luma_total), chroma_total=int(k.chroma_total),
+            chain={}, chain_wave={}, chain_slices={}, bulk={}, chroma_lists={})
+        for c, key in enumerate((16, 32, 128)):
+            out["chain"][key] = arr(k.chain[c], k.n_chain[c], np.uint32)
+            out["chain_wave"][key] = arr(k.chain_wave[c], k.n_chain[c], np.uint16)
+            first = arr(k.wave_first[c], k.n_waves[c], np.int32)
+            count = arr(k.wave_count[c], k.n_waves[c], np.int32)
+            out["chain_slices"][key] = [(int(a), int(b)) for a, b in zip(first, count)]
+            out["bulk"][key] = arr(k.bulk[c], k.n_bulk[c], np.uint32)
+            out["chroma_lists"][key] = arr(k.chroma_list[c], k.n_chroma_list[c], np.uint32)
+    finally:
+        L.daala_b200_host_keyframe_lists_free(p)
+    return out
+
+
 class PvqBatch:
     """Device state of one PVQ batch: coding-order buffers, result arrays and
     the launch sequence gather -> [CfL flip] -> bands -> finish -> scatter."""

@@ -328,6 +328,39 @@ int daala_b200_coding_order_gather(const daala_b200_pvq_params *prm, int nblocks
    (src/partition.c:157): out -> coef_plane. */
 int daala_b200_coding_order_scatter(const daala_b200_pvq_params *prm, int nblocks, void *stream);
 
+/* ---- Host-side work-list construction (no GPU involved) -------------------- */
+
+/* Everything the keyframe PVQ stage consumes besides pixels, derived from the block-size maps of a
+   batch (state->bsize of every frame: one byte per 8x8 luma unit = log2(block size) - 2; 4:2:0):
+   luma blocks sorted by (dependency depth, frame, y0, x0) with coef_off assigned, the same-size top /
+   left neighbour of each (od_hv_intra_pred, src/intra.c:46-47) as indices into that array, and per
+   size class c (0: n <= 16, 1: n = 32, 2: n = 128) the band-granular wave lists -- chain[c] sorted by
+   (wave, band, block) with wave w occupying [wave_first[c][w], + wave_count[c][w]), chain_wave[c][i]
+   the wave of entry i, bulk[c] the dependency-free bands 3 / 6 -- ready for
+   daala_b200_pvq_intra_band_ref / _pvq_encode_bands / _pvq_order_by_work; chroma blocks of both
+   planes sorted by (size, frame, plane, y0, x0), bit 7 of xdec set where the co-located luma is coded
+   as 4x4 blocks (od_resample_luma_coeffs, src/intra.c:78), with their per-class band lists.
+   Linear passes and counting sorts, frames in parallel on up to `nthreads` host threads.  All
+   arrays are malloc'd and owned by the returned object; free with _host_keyframe_lists_free.
+   NULL on bad arguments / out of memory.  nframes <= 255. */
+typedef struct daala_b200_keyframe_lists {
+  int n_luma, n_chroma;
+  daala_b200_pvq_block *luma, *chroma;
+  int32_t *dep_top, *dep_left, *depth;             /* [n_luma] */
+  long long luma_total, chroma_total;              /* coefficients in the coding-order buffers */
+  uint32_t *chain[3];
+  uint16_t *chain_wave[3];
+  int32_t *wave_first[3], *wave_count[3];
+  uint32_t *bulk[3];
+  uint32_t *chroma_list[3];
+  int n_chain[3], n_waves[3], n_bulk[3], n_chroma_list[3];
+} daala_b200_keyframe_lists;
+
+daala_b200_keyframe_lists *daala_b200_host_keyframe_lists(const uint8_t *bsize, int nframes,
+                                                          long long bsize_frame_pitch, int bstride, int nhsb,
+                                                          int nvsb, int nthreads);
+void daala_b200_host_keyframe_lists_free(daala_b200_keyframe_lists *lists);
+
 /* ---- Motion compensation / block matching (8-bit references) ------------- */
 
 /* One OBMC block: four corner motion vectors in 1/8 pel (rotational order:

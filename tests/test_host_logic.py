@@ -88,6 +88,44 @@ def test_band_wave_lists_respect_the_intra_dependencies():
         assert w == 1 + max([wave[x] for x in need], default=0)
 
 
+@pytest.mark.parametrize("mode", ["mixed", "4", "8", "64"])
+def test_native_list_builder_equals_the_numpy_construction(mode):
+    """daala_b200_host_keyframe_lists (C++, csrc/host_lists.cu) against the numpy builders HotPath uses:
+    identical arrays in identical order (host code only -- no GPU)."""
+    import time
+    from daala_b200 import pvq, synth
+    from daala_b200.frame import Geometry
+    geom = Geometry(704, 448)
+    maps = [synth.block_size_map(geom, mode, seed=s) for s in (3, 4, 5)]
+    t0 = time.perf_counter()
+    nat = pvq.native_keyframe_lists(maps, geom)
+    t_native = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    blocks = np.concatenate([pvq.block_list(b, geom, frame=f) for f, b in enumerate(maps)])
+    luma, top, left, depth = pvq.sort_by_depth(pvq.raster_order(blocks[blocks["pli"] == 0]), maps, geom)
+    luma = luma.copy()
+    luma_total = pvq.assign_offsets(luma)
+    bulk, chain, slices = pvq.band_wave_lists(luma, top, left, depth)
+    chroma = pvq.mark_luma4x4(blocks[blocks["pli"] != 0].copy(), maps)
+    chroma = chroma[np.argsort(chroma["bs"], kind="stable")].copy()
+    chroma_total = pvq.assign_offsets(chroma)
+    chroma_lists = pvq.band_lists(chroma)
+    t_numpy = time.perf_counter() - t0
+    assert np.array_equal(nat["luma"], luma)
+    assert np.array_equal(nat["dep_top"], top) and np.array_equal(nat["dep_left"], left)
+    assert np.array_equal(nat["depth"], depth)
+    assert nat["luma_total"] == luma_total and nat["chroma_total"] == chroma_total
+    assert np.array_equal(nat["chroma"], chroma)
+    for k in (16, 32, 128):
+        assert np.array_equal(nat["chain"][k], chain[k]), k
+        assert nat["chain_slices"][k] == slices[k], k
+        assert np.array_equal(nat["bulk"][k], bulk[k]), k
+        assert np.array_equal(nat["chroma_lists"][k], chroma_lists[k]), k
+        waves = np.repeat(np.arange(len(slices[k]), dtype=np.uint16), [c for _, c in slices[k]])
+        assert np.array_equal(nat["chain_wave"][k], waves), k
+    assert t_native < t_numpy
+
+
 def test_library_exports_every_declared_symbol():
     """The built library must export everything include/daala_b200.h declares
     (no compute calls here: the build container has no GPU)."""
