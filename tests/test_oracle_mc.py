@@ -75,3 +75,36 @@ def test_sad_satd_port_matches_reference(port, ref, ln):
         assert sad_ref == ref.od_mc_compute_sad8_c(addr(a), n + 8, addr(b), n + 8, n, n)
         satd_ref = getattr(ref, "od_mc_compute_satd8_%dx%d_c" % (n, n))(addr(a), n + 8, addr(b), n + 8)
         assert satd_ref == port.port_mc_compute_satd8(ln, addr(a), n + 8, addr(b), n + 8)
+
+
+def test_mv_grid_block_list_reproduces_reference_frame_prediction(port, ref):
+    """Host logic of daala_b200/mvgrid.py (leaf walk, corner / split state, vertex selection, chroma MV
+    scaling) checked on the CPU: predicting its block list with the plain-C OBMC port must give the planes
+    od_state_mc_predict (src/state.c:932) produces on a real od_state."""
+    from daala_b200 import mc, mvgrid
+    from tests.test_gpu_mc import _frames, _random_mv_grid
+    rng = np.random.default_rng(77)
+    W, H = 192, 128
+    _, ref_y = _frames(seed=3, h=H, w=W)
+    ref_u = np.ascontiguousarray(ref_y[::2, ::2][:, ::-1])
+    ref_v = np.ascontiguousarray(ref_y[1::2, 1::2])
+    valid, mv = _random_mv_grid(rng, H // 8, W // 8)
+    want = [np.zeros((H, W), np.uint8), np.zeros((H // 2, W // 2), np.uint8), np.zeros((H // 2, W // 2), np.uint8)]
+    rc = ref.oracle_ref_state_mc_predict(W, H, addr(ref_y), addr(ref_u), addr(ref_v),
+                                         addr(np.ascontiguousarray(valid.astype(np.uint8))),
+                                         addr(np.ascontiguousarray(mv)), addr(want[0]), addr(want[1]), addr(want[2]))
+    assert rc == 0
+    I4 = ctypes.c_int32 * 4
+    pad = mc.OD_BUFFER_PADDING
+    for pli, plane in enumerate((ref_y, ref_u, ref_v)):
+        blocks = mvgrid.block_list(valid, mv, xdec=1 if pli else 0)
+        src = np.pad(plane, pad, mode="edge")
+        stride = src.shape[1]
+        got = np.zeros_like(plane)
+        w = plane.shape[1]
+        for b in blocks:
+            x0, y0 = int(b["x0"]), int(b["y0"])
+            port.port_mc_predict(addr(got, y0 * w + x0), w, addr(src, (y0 + pad) * stride + x0 + pad), stride,
+                                 I4(*[int(v) for v in b["mvx"]]), I4(*[int(v) for v in b["mvy"]]), int(b["oc"]),
+                                 int(b["s"]), int(b["log_xblk"]), int(b["log_yblk"]))
+        assert np.array_equal(got, want[pli]), "plane %d" % pli
