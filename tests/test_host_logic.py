@@ -126,6 +126,28 @@ def test_native_list_builder_equals_the_numpy_construction(mode):
     assert t_native < t_numpy
 
 
+def test_header_is_plain_c_and_reference_arm_prints_the_contract_line(tmp_path):
+    """include/daala_b200.h must compile as C99 (the reference is C and binds to it directly), and
+    `bench.py --impl reference` must print one JSON line with the contract's keys (CPU only)."""
+    import json
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "daala_b200.h"\nint main(void) { daala_b200_pvq_params p; (void)p; return 0; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                   check=True)
+    root = os.path.dirname(inc)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
 def test_library_exports_every_declared_symbol():
     """The built library must export everything include/daala_b200.h declares
     (no compute calls here: the build container has no GPU)."""
