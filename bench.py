@@ -211,6 +211,22 @@ def cpu_sample_geometry():
     return Geometry(PIC_W, CPU_SAMPLE_ROWS)
 
 
+def cgroup_cpu_quota():
+    """CPU quota of this container in cores (cgroup v2 cpu.max / v1 cfs), or None when unlimited/unknown:
+    sched_getaffinity can list far more CPUs than the container may actually use."""
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if quota == "max" else round(int(quota) / int(period), 2)
+    except (OSError, ValueError):
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else round(q / p, 2)
+    except (OSError, ValueError):
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -233,6 +249,8 @@ def run_reference(args):
     value = geom.luma_pixels * per_step * args.steps / total / 1e6
     sample = ("%d x 3840x%d 4:2:0 bands (8 superblock rows of the 4K frame) per step on %d worker processes (one per host core); "
               "reference functions: prefilter + fDCT + pvq_theta(speed=1) + iDCT + postfilter" % (per_step, CPU_SAMPLE_ROWS, cores))
+    quota = cgroup_cpu_quota()
+    sample += "; container CPU quota: %s" % ("none" if quota is None else "%.2f cores" % quota)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3),
