@@ -69,6 +69,44 @@ def frame_crcs(lib, prefix, qm, qm_inv):
     return out
 
 
+def dering_image(nvsb, nhsb, sb, seed):
+    rng = np.random.default_rng(seed)
+    h, w = nvsb * sb, nhsb * sb
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = 900 * np.sign(np.sin((xx * 0.9 + yy * 0.4) / 6.0)) + 300 * np.sin(yy / 3.0) + rng.integers(-40, 41, size=(h, w))
+    return np.clip(np.round(img), -2048, 2047).astype(np.int16)
+
+
+def dering_cases(fn):
+    """fn(y, ystride, x, xstride, nhb, nvb, sbx, sby, nhsb, nvsb, xdec, dir, pli, bskip, skip_stride, threshold,
+    overlap, coeff_shift) -- od_dering without the vtable.  Returns (case rows, CRC of output + directions)."""
+    rows, crcs = [], []
+    nhsb, nvsb = 3, 2
+    Dir = (ctypes.c_int * 8) * 8
+    for xdec in (0, 1):
+        sb = 64 >> xdec
+        img = dering_image(nvsb, nhsb, sb, 31 + xdec)
+        w = img.shape[1]
+        rng = np.random.default_rng(17 + xdec)
+        skip_stride = nhsb * 16
+        for threshold, overlap in ((19, 0), (64, 1), (200, 1)):
+            bskip = (rng.random((nvsb * 16, skip_stride)) < 0.4).astype(np.uint8)
+            for sby in range(nvsb):
+                for sbx in range(nhsb):
+                    d = Dir()
+                    vals = rng.integers(0, 8, size=(8, 8))
+                    for r in range(8):
+                        for c in range(8):
+                            d[r][c] = int(vals[r, c])
+                    y = np.zeros((sb, sb), np.int16)
+                    fn(addr(y), sb, addr(img, sby * sb * w + sbx * sb), w, 8, 8, sbx, sby, nhsb, nvsb, xdec, d,
+                       1 if xdec else 0, addr(bskip, (sby * 16) * skip_stride + sbx * 16), skip_stride, threshold,
+                       overlap, 4)
+                    rows.append([xdec, threshold, overlap, sbx, sby])
+                    crcs.append(crc(y) ^ crc(np.array([list(r) for r in d], np.int32)))
+    return rows, crcs
+
+
 def main():
     ref = oracle_lib.load_ref()
     assert ref is not None, "needs oracle/_ref (make -C oracle ref, with /root/reference present)"
@@ -156,6 +194,10 @@ def main():
     fc = frame_crcs(ref, "ref", qm, qm_inv)
     g["frame_keys"] = np.array(sorted(fc))
     g["frame_crc"] = np.array([fc[k] for k in sorted(fc)], np.uint32)
+    # deringing of whole superblocks (oracle of the next hot-path row)
+    drows, dcrc = dering_cases(lambda *a: ref.od_dering(
+        ctypes.c_void_p(ctypes.addressof(ctypes.c_void_p.in_dll(ref, "OD_DERING_VTBL_C"))), *a))
+    g["dering_rows"], g["dering_crc"] = np.array(drows, np.int64), np.array(dcrc, np.uint32)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.npz")
     np.savez_compressed(path, **g)
     print("wrote %s (%d arrays, %d bytes)" % (path, len(g), os.path.getsize(path)))

@@ -95,3 +95,9 @@ def test_frame_drivers_match_recorded_reference_plane_checksums(port, gold):
     got = make_golden.frame_crcs(port, "port", gold["qm"], gold["qm_inv"])
     want = dict(zip(gold["frame_keys"].tolist(), gold["frame_crc"].tolist()))
     assert got == want
+
+
+def test_dering_port_matches_recorded_reference_outputs(port, gold):
+    rows, crcs = make_golden.dering_cases(port.port_dering)
+    assert rows == gold["dering_rows"].tolist()
+    assert crcs == gold["dering_crc"].tolist()

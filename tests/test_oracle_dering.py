@@ -1,0 +1,77 @@
+"""Pins oracle/port_dering.c (the oracle of the NEXT hot-path row, SURVEY.md 8(f) rank 1 -- no CUDA
+twin yet) against the reference's od_dering with its C vtable (src/dering.c:252)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests.oracle_lib import addr
+
+
+def _image(rng, nvsb, nhsb, sb, kind):
+    h, w = nvsb * sb, nhsb * sb
+    yy, xx = np.mgrid[0:h, 0:w]
+    if kind == "edges":
+        img = 900 * np.sign(np.sin((xx * 0.9 + yy * 0.4) / 6.0)) + 300 * np.sin(yy / 3.0)
+    elif kind == "noise":
+        img = rng.integers(-1500, 1500, size=(h, w))
+    else:
+        img = 1200 * np.sin(xx / 9.0) * np.cos(yy / 7.0)
+    img = img + rng.integers(-40, 41, size=(h, w))
+    return np.clip(np.round(img), -2048, 2047).astype(np.int16)
+
+
+@pytest.mark.parametrize("kind", ["edges", "noise", "smooth"])
+def test_direction_search_matches_reference(port, ref, kind):
+    rng = np.random.default_rng(5)
+    img = _image(rng, 2, 2, 64, kind)
+    stride = img.shape[1]
+    # od_dir_find8 is static: reach it through od_dering's `dir` output below; here the port's own
+    # invariances: a constant block has no direction contrast, a pure horizontal ramp picks direction 2
+    flat = np.full((8, 8), 100 << 4, np.int16)
+    var = ctypes.c_int32(-1)
+    assert port.port_dering_find_direction(addr(flat), 8, ctypes.byref(var), 4) == 0 and var.value == 0
+    rows = (np.arange(8)[:, None] * np.ones((1, 8)) * 160).astype(np.int16)   # constant along each row
+    assert port.port_dering_find_direction(addr(rows), 8, ctypes.byref(var), 4) == 2 and var.value > 0
+    cols = np.ascontiguousarray(rows.T)
+    assert port.port_dering_find_direction(addr(cols), 8, ctypes.byref(var), 4) == 6 and var.value > 0
+    assert img.shape[1] == stride
+
+
+@pytest.mark.parametrize("kind", ["edges", "noise", "smooth"])
+@pytest.mark.parametrize("xdec", [0, 1])
+def test_superblock_dering_port_matches_reference(port, ref, kind, xdec):
+    rng = np.random.default_rng(11 + xdec)
+    nhsb, nvsb = 3, 2
+    sb = 64 >> xdec
+    img = _image(rng, nvsb, nhsb, sb, kind)
+    h, w = img.shape
+    vtbl = ctypes.c_void_p.in_dll(ref, "OD_DERING_VTBL_C")
+    vt = ctypes.addressof(vtbl)
+    Dir = (ctypes.c_int * 8) * 8
+    skip_stride = nhsb * 16
+    for threshold in (0, 19, 64, 200):
+        for overlap in (0, 1):
+            bskip = (rng.random((nvsb * 16, skip_stride)) < 0.5).astype(np.uint8)
+            if threshold == 64:
+                bskip[:] = 0
+            for sby in range(nvsb):
+                for sbx in range(nhsb):
+                    da, db = Dir(), Dir()
+                    if xdec:   # chroma reads the directions luma found
+                        vals = rng.integers(0, 8, size=(8, 8))
+                        for r in range(8):
+                            for c in range(8):
+                                da[r][c] = db[r][c] = int(vals[r, c])
+                    ya = np.zeros((sb, sb), np.int16)
+                    yb = np.zeros((sb, sb), np.int16)
+                    x0 = addr(img, sby * sb * w + sbx * sb)
+                    s0 = addr(bskip, (sby * 16) * skip_stride + sbx * 16)
+                    ref.od_dering(ctypes.c_void_p(vt), addr(ya), sb, x0, w, 8, 8, sbx, sby, nhsb, nvsb, xdec, da,
+                                  1 if xdec else 0, s0, skip_stride, threshold, overlap, 4)
+                    port.port_dering(addr(yb), sb, x0, w, 8, 8, sbx, sby, nhsb, nvsb, xdec, db,
+                                     1 if xdec else 0, s0, skip_stride, threshold, overlap, 4)
+                    assert np.array_equal(ya, yb), (threshold, overlap, sbx, sby)
+                    assert [list(r) for r in da] == [list(r) for r in db]
+                    if threshold == 64 and kind != "smooth":
+                        assert not np.array_equal(ya, img[sby * sb:(sby + 1) * sb, sbx * sb:(sbx + 1) * sb])
