@@ -17,6 +17,9 @@ void port_bin_fdct(int ln, od_coeff *y, const od_coeff *x, int xstride);
 void port_bin_idct(int ln, od_coeff *x, int xstride, const od_coeff *y);
 void port_bin_fdct2d(int ln, od_coeff *y, int ystride, const od_coeff *x, int xstride);
 void port_haar(od_coeff *y, int ystride, const od_coeff *x, int xstride, int ln);
+/* perceptual block distortion of the RDO loops (reference src/encode.c:1180) */
+double port_compute_dist(const od_coeff *x, const od_coeff *y, int n, int qm_is_flat, int use_activity_masking,
+ int coded_quantizer);
 /* deringing of one superblock (oracle for the next hot-path row; reference src/dering.c) */
 int port_dering_find_direction(const int16_t *img, int stride, int32_t *var, int coeff_shift);
 void port_dering(int16_t *y, int ystride, const int16_t *x, int xstride, int nhb, int nvb, int sbx, int sby,

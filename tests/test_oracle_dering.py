@@ -75,3 +75,22 @@ def test_superblock_dering_port_matches_reference(port, ref, kind, xdec):
                     assert [list(r) for r in da] == [list(r) for r in db]
                     if threshold == 64 and kind != "smooth":
                         assert not np.array_equal(ya, img[sby * sb:(sby + 1) * sb, sbx * sb:(sbx + 1) * sb])
+
+
+@pytest.mark.parametrize("n", [8, 16, 32, 64])
+def test_distortion_metric_port_matches_reference(port, ref, n):
+    """od_compute_dist (static, reached through oracle/ref_hooks_encode.c): bit-identical doubles -- same
+    libm, same operation order."""
+    rng = np.random.default_rng(n)
+    ref.oracle_ref_compute_dist.restype = ctypes.c_double
+    port.port_compute_dist.restype = ctypes.c_double
+    for t in range(12):
+        x = (rng.integers(-128, 128, size=(n, n)) * 16 + rng.integers(-8, 9, size=(n, n))).astype(np.int32)
+        if t % 3 == 0:
+            x[:] = (x // 64) * 64                       # flat-ish regions: small window variances
+        y = (x + rng.integers(-60, 61, size=(n, n)) * (1 + t % 4)).astype(np.int32)
+        for qm, masking, cq in ((1, 1, 20), (1, 0, 40), (1, 1, 60), (0, 1, 20)):
+            a = ref.oracle_ref_compute_dist(addr(x), addr(y), n, qm, masking, cq)
+            b = port.port_compute_dist(addr(x), addr(y), n, 1 if qm == 0 else 0, masking, cq)
+            assert a == b and a > 0, (t, qm, masking, cq)
+    assert port.port_compute_dist(addr(x), addr(x), n, 0, 1, 20) == 0.0
