@@ -328,6 +328,28 @@ int daala_b200_coding_order_gather(const daala_b200_pvq_params *prm, int nblocks
    (src/partition.c:157): out -> coef_plane. */
 int daala_b200_coding_order_scatter(const daala_b200_pvq_params *prm, int nblocks, void *stream);
 
+/* ---- Deringing (NOT yet verified on a GPU, see csrc/dering_kernels.cu) ---- */
+
+/* One plane through od_dering (reference src/dering.c:252, DAALA_ODINTRIN form) for every superblock:
+   y <- dering(x), both int16 planes of (nhsb*64 >> xdec) x (nvsb*64 >> xdec) samples (device
+   pointers; x is state->etmp[pli], y the filtered copy).  dir: one int32 per 8x8 luma block,
+   [nvsb*8][dir_stride]; written when pli == 0, read for the chroma planes (run luma first).
+   bskip: this plane's skip flags, one byte per 4x4 block (state->bskip[pli]).  threshold: the
+   level's threshold (OD_DERING_GAIN_TABLE[level] * base, times 0.6 for chroma, call site
+   src/encode.c:2822); sb_threshold (nullable) overrides it per superblock, [nvsb*nhsb].
+   overlap: OD_DERING_CHECK_OVERLAP; coeff_shift: OD_COEFF_SHIFT. */
+typedef struct daala_b200_dering_params {
+  int16_t *y;
+  const int16_t *x;
+  int32_t *dir;
+  const uint8_t *bskip;
+  const int32_t *sb_threshold;
+  int ystride, xstride, dir_stride, skip_stride;
+  int nhsb, nvsb, xdec, pli;
+  int threshold, overlap, coeff_shift, pad_;
+} daala_b200_dering_params;
+int daala_b200_dering_plane(const daala_b200_dering_params *prm, void *stream);
+
 /* ---- Host-side work-list construction (no GPU involved) -------------------- */
 
 /* Everything the keyframe PVQ stage consumes besides pixels, derived from the block-size maps of a

@@ -175,6 +175,26 @@ def test_native_struct_layouts_match_the_header():
     assert ctypes.sizeof(pvq.PvqParams) % 8 == 0
 
 
+def test_ctypes_mirrors_have_the_sizes_the_c_compiler_gives(tmp_path):
+    """sizeof() of every ABI struct as gcc lays it out vs the ctypes / numpy mirrors on the Python side."""
+    import ctypes
+    from daala_b200 import _native, mc, pvq
+    from tests.test_gpu_dering import DeringParams
+    names = ["daala_b200_plane", "daala_b200_frame", "daala_b200_pvq_block", "daala_b200_pvq_params",
+             "daala_b200_mc_block", "daala_b200_match_job", "daala_b200_dering_params", "daala_b200_keyframe_lists"]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "daala_b200.h"\nint main(void) {\n'
+                   + "".join('  printf("%%zu\\n", sizeof(%s));\n' % n for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_native.Plane), ctypes.sizeof(_native.Frame), pvq.BLOCK_DTYPE.itemsize,
+            ctypes.sizeof(pvq.PvqParams), mc.MC_BLOCK_DTYPE.itemsize, mc.MATCH_JOB_DTYPE.itemsize,
+            ctypes.sizeof(DeringParams), ctypes.sizeof(pvq._KeyframeLists)]
+    assert got == want, list(zip(names, got, want))
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, %r)
