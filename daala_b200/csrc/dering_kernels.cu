@@ -2,10 +2,9 @@
 // od_dir_find8 :61, od_filter_dering_direction_c :132, od_filter_dering_orthogonal_c :172,
 // od_compute_thresh :237) -- SURVEY.md 8(f) rank 1, the row after the transform / PVQ / MC path.
 //
-// STATUS: written against the pinned CPU oracle (oracle/port_dering.c) at the end of round 1, when the
-// round's GPU budget was spent: it compiles for sm_100a but has NOT run on a GPU yet.  Its parity test
-// (tests/test_gpu_dering.py) is skipped until DAALA_B200_UNVERIFIED=1; nothing in the measured hot path
-// launches it.
+// Parity: bit-exact against oracle/port_dering.c (pinned against od_dering) in tests/test_gpu_dering.py.
+// Not yet part of HotPath / bench.py: the level search around it (src/encode.c:2680-2842) needs
+// od_compute_dist on the device (oracle: oracle/port_dist.c) -- next round.
 //
 // Mapping: one 256-thread CTA per superblock.  The (B+6)^2 int16 window (3-sample apron, 30000 where the
 // frame ends) is staged once in shared memory; one thread per 8x8 block finds the direction (8 x 64

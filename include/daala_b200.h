@@ -328,7 +328,7 @@ int daala_b200_coding_order_gather(const daala_b200_pvq_params *prm, int nblocks
    (src/partition.c:157): out -> coef_plane. */
 int daala_b200_coding_order_scatter(const daala_b200_pvq_params *prm, int nblocks, void *stream);
 
-/* ---- Deringing (NOT yet verified on a GPU, see csrc/dering_kernels.cu) ---- */
+/* ---- Deringing ------------------------------------ */
 
 /* One plane through od_dering (reference src/dering.c:252, DAALA_ODINTRIN form) for every superblock:
    y <- dering(x), both int16 planes of (nhsb*64 >> xdec) x (nvsb*64 >> xdec) samples (device

@@ -1,10 +1,8 @@
 """GPU parity of the deringing kernel (csrc/dering_kernels.cu) against the pinned CPU oracle
-(oracle/port_dering.c, itself checked against od_dering by tests/test_oracle_dering.py).
-
-The kernel was written after round 1's GPU budget was spent and has not run on a device yet: the test
-is skipped unless DAALA_B200_UNVERIFIED=1 (first GPU call of the next round)."""
+(oracle/port_dering.c, itself checked against od_dering by tests/test_oracle_dering.py): bit-exact
+int16 planes and direction maps, luma and 4:2:0 chroma, every superblock position (frame edges,
+interior), skip flags with and without the lapping ring."""
 import ctypes
-import os
 
 import numpy as np
 import pytest
@@ -12,9 +10,7 @@ import pytest
 from tests import oracle_lib
 from tests.oracle_lib import addr
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DAALA_B200_UNVERIFIED") != "1",
-                                 reason="dering kernel not yet run on a GPU (set DAALA_B200_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 class DeringParams(ctypes.Structure):
