@@ -350,6 +350,12 @@ typedef struct daala_b200_dering_params {
 } daala_b200_dering_params;
 int daala_b200_dering_plane(const daala_b200_dering_params *prm, void *stream);
 
+/* Perceptual distortion od_compute_dist (static, reference src/encode.c:1180) of `count` packed
+   n x n block pairs (n = 8, 16, 32 or 64; device pointers), one double per pair.  qm_is_flat:
+   enc->qm == OD_FLAT_QM (plain squared error).  NOT yet verified on a GPU (csrc/dist_kernels.cu). */
+int daala_b200_compute_dist(const int32_t *x, const int32_t *y, int count, int n, int qm_is_flat,
+                            int use_activity_masking, int coded_quantizer, double *out, void *stream);
+
 /* ---- Host-side work-list construction (no GPU involved) -------------------- */
 
 /* Everything the keyframe PVQ stage consumes besides pixels, derived from the block-size maps of a
