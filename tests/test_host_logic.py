@@ -126,6 +126,30 @@ def test_native_list_builder_equals_the_numpy_construction(mode):
     assert t_native < t_numpy
 
 
+@pytest.mark.parametrize("mode", ["mixed", "4", "16", "64"])
+def test_tensor_op_list_builder_equals_the_native_builder(mode):
+    """daala_b200/lists_torch.py (device-agnostic tensor ops, meant to run where the block-size maps
+    already live) against the C++ host builder: identical arrays (run here on CPU tensors)."""
+    import torch
+    from daala_b200 import lists_torch, pvq, synth
+    from daala_b200.frame import Geometry
+    geom = Geometry(576, 320)
+    maps = [synth.block_size_map(geom, mode, seed=s) for s in (7, 8, 9)]
+    nat = pvq.native_keyframe_lists(maps, geom)
+    got = lists_torch.keyframe_lists(torch.from_numpy(np.stack(maps)), geom.nhsb, geom.nvsb)
+    assert np.array_equal(got["luma"].numpy().reshape(-1).view(pvq.BLOCK_DTYPE), nat["luma"])
+    assert np.array_equal(got["chroma"].numpy().reshape(-1).view(pvq.BLOCK_DTYPE), nat["chroma"])
+    for k in ("dep_top", "dep_left", "depth"):
+        assert np.array_equal(got[k].numpy(), nat[k]), k
+    assert got["luma_total"] == nat["luma_total"] and got["chroma_total"] == nat["chroma_total"]
+    for k in (16, 32, 128):
+        assert np.array_equal(got["chain"][k].numpy().view(np.uint32), nat["chain"][k]), k
+        assert np.array_equal(got["chain_wave"][k].numpy().view(np.uint16), nat["chain_wave"][k]), k
+        assert got["chain_slices"][k] == nat["chain_slices"][k], k
+        assert np.array_equal(got["bulk"][k].numpy().view(np.uint32), nat["bulk"][k]), k
+        assert np.array_equal(got["chroma_lists"][k].numpy().view(np.uint32), nat["chroma_lists"][k]), k
+
+
 def test_header_is_plain_c_and_reference_arm_prints_the_contract_line(tmp_path):
     """include/daala_b200.h must compile as C99 (the reference is C and binds to it directly), and
     `bench.py --impl reference` must print one JSON line with the contract's keys (CPU only)."""
