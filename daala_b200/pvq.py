@@ -118,10 +118,11 @@ def block_list(bsize, geom, frame=0, sb_row0=0, sb_rows=None):
 def mark_luma4x4(blocks, bsize_maps):
     """Sets bit 7 of `xdec` on chroma blocks whose luma area is coded as 4x4 blocks
     (od_resample_luma_coeffs' chroma_bs == 0 case, src/intra.c:78)."""
-    for i in np.nonzero(blocks["pli"] != 0)[0]:
-        b = blocks[i]
-        if b["bs"] == 0 and bsize_maps[int(b["frame"])][int(b["y0"]) >> 2, int(b["x0"]) >> 2] == 0:
-            blocks["xdec"][i] |= 0x80
+    maps = np.stack([np.asarray(m) for m in bsize_maps])
+    cand = np.nonzero((blocks["pli"] != 0) & (blocks["bs"] == 0))[0]
+    b = blocks[cand]
+    hit = maps[b["frame"].astype(np.int64), b["y0"].astype(np.int64) >> 2, b["x0"].astype(np.int64) >> 2] == 0
+    blocks["xdec"][cand[hit]] |= 0x80
     return blocks
 
 
