@@ -547,6 +547,8 @@ def run_b200(args):
                    "parallelism": ("sbrow%d (NCCL all-gather of lapped border rows)" if sbrow else "frames%d (independent frames per rank)") % world,
                    "l2": "inputs larger than L2 (%.0f MB of planes per step)" % ((geom.padded_samples * F * 9) / 1e6),
                    "block_sizes": "synthetic quadtree map, sizes 4..64", "quantizer": Q0,
+                   "work_lists": "block / band / wave lists derived from the block-size maps once at setup (maps are "
+                                 "fixed across steps); e2e re-uploads them every step but does not rebuild them",
                    "pvq_pulses_per_step": total_k},
         "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 4),
