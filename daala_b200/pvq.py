@@ -78,6 +78,56 @@ def default_qm(hvs=True):
     return a[0].copy(), a[1].copy()
 
 
+def qm_inputs():
+    """The data od_init_qm starts from, exported from the reference build by tools/extract_tables.py:
+    basis magnitudes OD_BASIS_MAG per decimation and size, the 8x8 base matrices, the scan tables."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "qm_inputs.npz")
+    return dict(np.load(path))
+
+
+def raster_to_coding_order(block, scans):
+    """od_raster_to_coding_order (src/partition.c:123) of a full n x n block: DC, then for every nested
+    size m = 4, 8, .. n the m-size stage's scan (entries are raster indices y*m + x)."""
+    n = block.shape[0]
+    out = [block[0:1, 0]]
+    m = 4
+    while m <= n:
+        idx = scans[m]
+        out.append(block[idx // m, idx % m])
+        m *= 2
+    return np.concatenate(out)
+
+
+def init_qm(qm8, inputs=None):
+    """Host restatement of od_init_qm (src/pvq.c:322, fixed-point branch): magnitude-compensated
+    quantisation matrix and its inverse for every block size and both decimations, in coding order,
+    Q11 / Q12 int16.  qm8: the 64 entries of an 8x8 base matrix in Q4 (OD_QM8_Q4_HVS / _FLAT)."""
+    inputs = qm_inputs() if inputs is None else inputs
+    scans = {m: inputs["scan%d" % m].astype(np.int64) for m in (4, 8, 16, 32, 64)}
+    qm8 = np.asarray(qm8, np.int64)
+    qm = np.zeros(2 * OD_QM_STRIDE, np.int16)
+    qm_inv = np.zeros(2 * OD_QM_STRIDE, np.int16)
+    for bs in range(5):
+        n = 4 << bs
+        off0 = (((1 << (2 * bs)) - 1) << 4) // 3           # OD_QM_OFFSET(bs), src/pvq.h:71
+        i, j = np.mgrid[0:n, 0:n]
+        qmv = qm8[((i << 1) >> bs) * 8 + ((j << 1) >> bs)]
+        for xydec in range(2):
+            bm = inputs["mag_%d_%d" % (xydec, bs)]
+            mag = np.floor(.5 + (2048. * bm[i]) * bm[j]).astype(np.int64)     # OD_ROUND32(OD_QM_SCALE * m_i * m_j)
+            mag = (mag * 16 + (qmv >> 1)) // qmv
+            mag[0, 0] = 2048
+            y = np.minimum(32767, mag)
+            y_inv = (2048 * 4096 + (y >> 1)) // y
+            off = xydec * OD_QM_STRIDE + off0
+            # od_raster_to_coding_order_16 writes the coded prefix only: 512 entries for 32x32 / 64x64
+            # (src/partition.c:216); the rest of the table stays zero
+            ncoded = min(n * n, 512)
+            qm[off:off + ncoded] = raster_to_coding_order(y, scans)[:ncoded].astype(np.int16)
+            qm_inv[off:off + ncoded] = raster_to_coding_order(y_inv, scans)[:ncoded].astype(np.int16)
+    return qm, qm_inv
+
+
 def block_list(bsize, geom, frame=0, sb_row0=0, sb_rows=None):
     """Leaf transform blocks of one frame for every plane, from the block-size
     map (one byte per 8x8 luma unit).  Returns a BLOCK_DTYPE array (coef_off

@@ -150,6 +150,25 @@ def test_tensor_op_list_builder_equals_the_native_builder(mode):
         assert np.array_equal(got["chroma_lists"][k].numpy().view(np.uint32), nat["chroma_lists"][k]), k
 
 
+@pytest.mark.parametrize("name", ["hvs", "flat"])
+def test_host_init_qm_reproduces_the_reference_tables(name):
+    """daala_b200.pvq.init_qm (restatement of od_init_qm, src/pvq.c:322) against the tables exported from the
+    reference build (daala_b200/data/qm_*.npy) and, when oracle/_ref is present, against od_init_qm itself."""
+    from daala_b200 import pvq
+    from tests import oracle_lib, pvq_cases
+    inputs = pvq.qm_inputs()
+    qm, qm_inv = pvq.init_qm(inputs["qm8_" + name], inputs)
+    want, want_inv = pvq.default_qm(name == "hvs")
+    assert np.array_equal(qm, want) and np.array_equal(qm_inv, want_inv)
+    ref = oracle_lib.load_ref()
+    if ref is not None:
+        a, b = pvq_cases.reference_qm(ref, name == "hvs")
+        assert np.array_equal(qm, a) and np.array_equal(qm_inv, b)
+    # a custom matrix goes through the same path: doubling every entry halves the (non-DC) scale
+    q2, _ = pvq.init_qm(inputs["qm8_" + name] * 2, inputs)
+    assert q2[0] == 2048 and abs(int(q2[5]) * 2 - int(qm[5])) <= 1
+
+
 def test_header_is_plain_c_and_reference_arm_prints_the_contract_line(tmp_path):
     """include/daala_b200.h must compile as C99 (the reference is C and binds to it directly), and
     `bench.py --impl reference` must print one JSON line with the contract's keys (CPU only)."""
