@@ -145,3 +145,33 @@ def test_keyframe_prediction_driver_port_matches_reference(port, ref):
             res[prefix] = frame_oracle.pvq_plane_pred(lib, prefix, dc, geom, pli, bsize, 45, 1, 0.147, qm, qm_inv, q4,
                                                       luma_d=luma[prefix][0])
         assert np.array_equal(res["ref"][0], res["port"][0]) and np.array_equal(res["ref"][1], res["port"][1])
+
+
+def test_full_4k_frame_port_matches_reference(port, ref):
+    """BASELINE.json's frame size (3840x2160, padded to 3840x2176): the whole keyframe chain of the frame
+    drivers -- forward, PVQ with intra / CfL prediction, inverse -- port vs reference, all three planes."""
+    import zlib
+    from daala_b200 import synth
+    from daala_b200.frame import Geometry
+    from tests import frame_oracle
+    geom = Geometry(3840, 2160)
+    planes, _ = synth.frame(3840, 2160, f=1)
+    planes = synth.pad_planes(planes, geom)
+    bsize = synth.block_size_map(geom, "mixed", seed=21)
+    qm, qm_inv = pvq_cases.reference_qm(ref)
+    q4 = np.full((3, 30), 16, np.uint8)
+    crcs = {}
+    for lib, prefix in ((ref, "ref"), (port, "port")):
+        luma_q = None
+        out = []
+        for pli in range(3):
+            d = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
+            dq, stats = frame_oracle.pvq_plane_pred(lib, prefix, d, geom, pli, bsize, 72, 1, 0.147, qm, qm_inv, q4,
+                                                    luma_d=luma_q)
+            if pli == 0:
+                luma_q = dq
+            rec = frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 1)
+            out += [zlib.crc32(d.tobytes()), zlib.crc32(dq.tobytes()), zlib.crc32(rec.tobytes()), int(stats[0])]
+        crcs[prefix] = out
+    assert crcs["ref"] == crcs["port"]
+    assert crcs["ref"][3] > 100000     # coded pulses on the luma plane
