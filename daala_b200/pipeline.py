@@ -40,12 +40,31 @@ class HotPath:
         self.pvq_groups = max(1, min(int(pvq_groups), nframes))
         self.groups = []
 
-    def set_block_sizes(self, bsizes):
+    def set_block_sizes(self, bsizes, device_lists=False):
         """bsizes: one map per frame (host numpy).  Builds the block / band
-        lists of this rank's superblock rows and uploads them."""
-        lists = []
+        lists of this rank's superblock rows and uploads them.  device_lists (keyframe prediction only):
+        derive every list from the uploaded maps with tensor ops on the device (daala_b200/lists_torch.py,
+        identical arrays) instead of numpy on the host."""
         for f, b in enumerate(bsizes):
             self.fb.bsize[f].copy_(torch.from_numpy(np.ascontiguousarray(b)))
+        if device_lists:
+            assert self.keyframe_prediction and self.pvq_groups == 1
+            assert self.fb.sb_row0 == 0 and self.fb.sb_rows == self.geom.nvsb
+            from . import lists_torch
+            kw = dict(q0=self.q0, is_keyframe=1, use_masking=self.use_masking, lam=self.lam,
+                      pvq_qm_q4=self.pvq_qm_q4, device=self.device)
+            L = lists_torch.keyframe_lists(self.fb.bsize, self.geom.nhsb, self.geom.nvsb)
+            self.cfl_plane = torch.zeros_like(self.fb.coeffs[1])
+            bl = pvq.PvqBatch(dict(records=L["luma"], total=L["luma_total"], lists=L["chain"]), self.fb.coeffs, None,
+                              **kw)
+            bl.setup_intra_device(L)
+            bc = pvq.PvqBatch(dict(records=L["chroma"], total=L["chroma_total"], lists=L["chroma_lists"]),
+                              self.fb.coeffs, [self.cfl_plane] * 3, **kw)
+            self.groups = [(bl, bc, None)]
+            self.batch_luma, self.batch_chroma, self.batch = bl, bc, bc
+            return
+        lists = []
+        for f, b in enumerate(bsizes):
             lists.append(pvq.block_list(b, self.geom, frame=f, sb_row0=self.fb.sb_row0, sb_rows=self.fb.sb_rows))
         blocks = np.concatenate(lists)
         if self.keyframe_prediction:

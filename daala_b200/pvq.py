@@ -356,12 +356,21 @@ class PvqBatch:
                  lam=PVQ_LAMBDA, qm=None, qm_inv=None, pvq_qm_q4=None, device="cuda:0"):
         self.device = torch.device(device)
         dev = self.device
-        self.blocks_np = blocks.copy()
-        self.total = assign_offsets(self.blocks_np)
-        self.nblocks = len(blocks)
-        self.blocks = torch.from_numpy(self.blocks_np.view(np.uint8).reshape(-1)).to(dev)
-        lists = band_lists(self.blocks_np)
-        self.lists = {k: torch.from_numpy(v.view(np.int32)).to(dev) for k, v in lists.items()}
+        if isinstance(blocks, dict):
+            # descriptors and band lists already on the device (daala_b200/lists_torch.py):
+            # {"records": [n, 12] uint8, "total": coefficients, "lists": {16 / 32 / 128: int32 entries}}
+            self.blocks_np = None
+            self.total = int(blocks["total"])
+            self.nblocks = int(blocks["records"].shape[0])
+            self.blocks = blocks["records"].reshape(-1).to(dev)
+            self.lists = {k: v.to(dev) for k, v in blocks["lists"].items()}
+        else:
+            self.blocks_np = blocks.copy()
+            self.total = assign_offsets(self.blocks_np)
+            self.nblocks = len(blocks)
+            self.blocks = torch.from_numpy(self.blocks_np.view(np.uint8).reshape(-1)).to(dev)
+            lists = band_lists(self.blocks_np)
+            self.lists = {k: torch.from_numpy(v.view(np.int32)).to(dev) for k, v in lists.items()}
         z = lambda n, dt=torch.int32: torch.zeros(max(n, 1), dtype=dt, device=dev)  # noqa: E731
         self.in_, self.ref, self.out, self.y = z(self.total), z(self.total), z(self.total), z(self.total)
         nb9 = self.nblocks * 9
@@ -462,6 +471,42 @@ class PvqBatch:
                       "scatter")
 
     # --- keyframe predictors -------------------------------------------------
+    def _intra_streams_and_tuning(self):
+        dev = self.device
+        if dev.type == "cuda":
+            self.chain_streams = {k: torch.cuda.Stream(device=dev, priority=-1) for k in (16, 32, 128)}
+            self.bulk_stream = torch.cuda.Stream(device=dev)
+        else:                       # host-side dry runs of the list plumbing (tests)
+            self.chain_streams, self.bulk_stream = {}, None
+        # waves smaller than this many bands use the group-cooperative kernels (shorter latency)
+        # (tools/probe/time_bandwaves.py, time_modes_ref.py: crossover of the scalar / 16-lane kernels)
+        self.small_wave = {16: 32768, 32: 65536, 128: 0}
+        self.small_mode = 3
+        if os.environ.get("DAALA_B200_SMALL_WAVE"):          # tuning hook: "n16,n32,n128"
+            self.small_wave = dict(zip((16, 32, 128), map(int, os.environ["DAALA_B200_SMALL_WAVE"].split(","))))
+        if os.environ.get("DAALA_B200_ONE_CHAIN_STREAM") and self.chain_streams:     # tuning hook
+            one = self.chain_streams[128]
+            self.chain_streams = {k: one for k in self.chain_streams}
+            self.bulk_stream = one
+        self.intra_mode = "bands"
+
+    def setup_intra_device(self, lists):
+        """setup_intra for descriptors built on the device (lists_torch.keyframe_lists output): only the
+        band-granular wavefront ("bands") is available, the block-granular alternatives need host arrays."""
+        dev = self.device
+        self.dep_top, self.dep_left = lists["dep_top"].to(dev), lists["dep_left"].to(dev)
+        self.max_depth = int(lists["depth"].max().item()) if self.nblocks else 0
+        self.chain_lists = {k: lists["chain"][k].to(dev) for k in (16, 32, 128)}
+        self.bulk_lists = {k: lists["bulk"][k].to(dev) for k in (16, 32, 128)}
+        self.chain_waves = {k: lists["chain_wave"][k].to(dev) for k in (16, 32, 128)}
+        self.chain_slices = {k: list(lists["chain_slices"][k]) for k in (16, 32, 128)}
+        self.chain_ordered = {k: torch.empty_like(v) for k, v in self.chain_lists.items()}
+        self.bulk_ordered = {k: torch.empty_like(v) for k, v in self.bulk_lists.items()}
+        need = max([v.numel() for v in self.chain_lists.values()] + [v.numel() for v in self.bulk_lists.values()] + [1])
+        if need > self._order_keys.numel():
+            self._order_keys = torch.zeros(need, dtype=torch.int16, device=dev)
+        self._intra_streams_and_tuning()
+
     def setup_intra(self, top, left, depth):
         """Luma-only batch whose blocks are sorted by dependency depth (see
         `sort_by_depth`): neighbour indices for the chain kernels, wave ranges and
@@ -475,7 +520,7 @@ class PvqBatch:
         # chain kernels: per block size, indices in (depth, raster) order
         self.class_ids = [torch.from_numpy(np.nonzero(self.blocks_np["bs"] == bs)[0].astype(np.int32)).to(dev)
                           for bs in range(5)]
-        self.class_streams = [torch.cuda.Stream(device=dev) for _ in range(5)]
+        self.class_streams = [torch.cuda.Stream(device=dev) for _ in range(5)] if dev.type == "cuda" else []
         # waves: contiguous block ranges of equal depth
         edges = np.concatenate([[0], np.nonzero(np.diff(depth))[0] + 1, [len(depth)]]) if len(depth) else np.array([0])
         self.waves = [(int(a), int(b - a)) for a, b in zip(edges[:-1], edges[1:])]
@@ -504,19 +549,7 @@ class PvqBatch:
             self.chain_waves[k] = torch.from_numpy(w.view(np.int16)).to(dev)
             self.chain_ordered[k] = torch.empty_like(self.chain_lists[k])
             self.bulk_ordered[k] = torch.empty_like(self.bulk_lists[k])
-        self.chain_streams = {k: torch.cuda.Stream(device=dev, priority=-1) for k in lists}
-        self.bulk_stream = torch.cuda.Stream(device=dev)
-        # waves smaller than this many bands use the group-cooperative kernels (shorter latency)
-        # (tools/probe/time_bandwaves.py, time_modes_ref.py: crossover of the scalar / 16-lane kernels)
-        self.small_wave = {16: 32768, 32: 65536, 128: 0}
-        self.small_mode = 3
-        if os.environ.get("DAALA_B200_SMALL_WAVE"):          # tuning hook: "n16,n32,n128"
-            self.small_wave = dict(zip((16, 32, 128), map(int, os.environ["DAALA_B200_SMALL_WAVE"].split(","))))
-        if os.environ.get("DAALA_B200_ONE_CHAIN_STREAM"):     # tuning hook: all chains on one stream
-            one = self.chain_streams[128]
-            self.chain_streams = {k: one for k in self.chain_streams}
-            self.bulk_stream = one
-        self.intra_mode = "bands"
+        self._intra_streams_and_tuning()
 
     def run_luma_intra(self, stream=None):
         L = _bind()

@@ -169,6 +169,40 @@ def test_host_init_qm_reproduces_the_reference_tables(name):
     assert q2[0] == 2048 and abs(int(q2[5]) * 2 - int(qm[5])) <= 1
 
 
+def test_hot_path_plumbing_is_identical_with_device_built_lists():
+    """HotPath.set_block_sizes(device_lists=True) (tensor-op construction where the maps live) must hand the
+    kernels byte-identical descriptors, lists, neighbour indices and wave slices as the numpy path.  Dry run on
+    CPU tensors: buffers are allocated, no kernel is launched."""
+    import torch
+    from daala_b200 import synth
+    from daala_b200.frame import Geometry
+    from daala_b200.pipeline import HotPath
+    geom = Geometry(448, 320)
+    maps = [synth.block_size_map(geom, "mixed", seed=s) for s in (11, 12)]
+    hps = []
+    for device_lists in (False, True):
+        hp = HotPath(geom, nframes=2, device="cpu", q0=40, is_keyframe=1, keyframe_prediction=True)
+        hp.set_block_sizes(maps, device_lists=device_lists)
+        hps.append(hp)
+    a, b = hps
+    for x, y in ((a.batch_luma, b.batch_luma), (a.batch_chroma, b.batch_chroma)):
+        assert torch.equal(x.blocks, y.blocks) and (x.total, x.nblocks) == (y.total, y.nblocks)
+        assert x.in_.shape == y.in_.shape and x.res_k.shape == y.res_k.shape and x.y16.shape == y.y16.shape
+        assert (x.params.q0, x.params.is_keyframe, x.params.use_masking) == (y.params.q0, y.params.is_keyframe,
+                                                                               y.params.use_masking)
+    for k in (16, 32, 128):
+        assert torch.equal(a.batch_chroma.lists[k], b.batch_chroma.lists[k])
+        assert torch.equal(a.batch_luma.chain_lists[k], b.batch_luma.chain_lists[k])
+        assert torch.equal(a.batch_luma.bulk_lists[k], b.batch_luma.bulk_lists[k])
+        assert torch.equal(a.batch_luma.chain_waves[k], b.batch_luma.chain_waves[k])
+        assert a.batch_luma.chain_slices[k] == b.batch_luma.chain_slices[k]
+        assert b.batch_luma._order_keys.numel() >= max(b.batch_luma.chain_lists[k].numel(),
+                                                       b.batch_luma.bulk_lists[k].numel())
+    assert torch.equal(a.batch_luma.dep_top, b.batch_luma.dep_top)
+    assert torch.equal(a.batch_luma.dep_left, b.batch_luma.dep_left)
+    assert a.batch_luma.max_depth == b.batch_luma.max_depth and b.batch_luma.intra_mode == "bands"
+
+
 def test_header_is_plain_c_and_reference_arm_prints_the_contract_line(tmp_path):
     """include/daala_b200.h must compile as C99 (the reference is C and binds to it directly), and
     `bench.py --impl reference` must print one JSON line with the contract's keys (CPU only)."""
