@@ -1,0 +1,50 @@
+"""Edge-case pictures (flat-128, pure noise; plus saturated black / white) through the
+device keyframe chain against the oracle.  Added after round 1's GPU budget was spent: same kernels as
+the verified tests, new inputs -- skipped unless DAALA_B200_UNVERIFIED=1 until it has run once."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import frame_oracle, oracle_lib
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("DAALA_B200_UNVERIFIED") != "1",
+                                 reason="not yet run on a GPU (set DAALA_B200_UNVERIFIED=1)")]
+
+
+@pytest.mark.parametrize("content", ["flat128", "noise", "black", "white"])
+def test_edge_content_keyframe_chain_matches_oracle(content):
+    import torch
+    from daala_b200 import pvq, synth
+    from daala_b200.frame import Geometry
+    from daala_b200.pipeline import HotPath
+    ref = oracle_lib.load_ref()
+    lib, prefix = (ref, "ref") if ref is not None else (oracle_lib.load_port(), "port")
+    geom = Geometry(200, 136)
+    rng = np.random.default_rng(3)
+    planes = []
+    for pli in range(3):
+        h, w = (136, 200) if pli == 0 else (68, 100)
+        value = {"flat128": 128, "black": 0, "white": 255}.get(content)
+        planes.append(np.full((h, w), value, np.uint8) if value is not None
+                      else rng.integers(0, 256, size=(h, w), dtype=np.uint8))
+    planes = synth.pad_planes(planes, geom)
+    bsize = synth.block_size_map(geom, "mixed", seed=8)
+    q4 = np.full((3, 30), 16, np.uint8)
+    hp = HotPath(geom, q0=30, is_keyframe=1, pvq_qm_q4=q4, keyframe_prediction=True)
+    hp.fb.upload(planes, bsize)
+    hp.set_block_sizes([bsize])
+    hp.run()
+    torch.cuda.synchronize()
+    qm, qm_inv = pvq.default_qm(True)
+    luma_q = None
+    for pli in range(3):
+        d = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
+        dq, _ = frame_oracle.pvq_plane_pred(lib, prefix, d, geom, pli, bsize, 30, 1, 0.147, qm, qm_inv, q4,
+                                            luma_d=luma_q)
+        if pli == 0:
+            luma_q = dq
+        assert np.array_equal(hp.fb.coeffs[pli][0].cpu().numpy(), dq), pli
+        rec = frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 1)
+        assert np.array_equal(hp.fb.pixels_out[pli][0].cpu().numpy(), rec), pli

@@ -4,6 +4,7 @@ oracle/ref_hooks_pvq.c, and the exported src/pvq.c functions)."""
 import ctypes
 
 import numpy as np
+import pytest
 
 from tests import pvq_cases
 from tests.oracle_lib import addr
@@ -175,3 +176,59 @@ def test_full_4k_frame_port_matches_reference(port, ref):
         crcs[prefix] = out
     assert crcs["ref"] == crcs["port"]
     assert crcs["ref"][3] > 100000     # coded pulses on the luma plane
+
+
+@pytest.mark.parametrize("content", ["flat128", "noise", "black", "white"])
+def test_edge_content_frames_port_matches_reference(port, ref, content):
+    """SURVEY.md 8(d) edge cases: a flat-128 frame (every AC coefficient zero: all-skip paths), saturated
+    frames and a pure-noise frame (large K everywhere) through the whole keyframe chain."""
+    from daala_b200 import synth
+    from daala_b200.frame import Geometry
+    from tests import frame_oracle
+    geom = Geometry(200, 136)
+    rng = np.random.default_rng(3)
+    planes = []
+    for pli in range(3):
+        h, w = (136, 200) if pli == 0 else (68, 100)
+        if content == "flat128":
+            p = np.full((h, w), 128, np.uint8)
+        elif content == "black":
+            p = np.zeros((h, w), np.uint8)
+        elif content == "white":
+            p = np.full((h, w), 255, np.uint8)
+        else:
+            p = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+        planes.append(p)
+    planes = synth.pad_planes(planes, geom)
+    bsize = synth.block_size_map(geom, "mixed", seed=8)
+    qm, qm_inv = pvq_cases.reference_qm(ref)
+    q4 = np.full((3, 30), 16, np.uint8)
+    res = {}
+    for lib, prefix in ((ref, "ref"), (port, "port")):
+        luma_q = None
+        out = []
+        for pli in range(3):
+            d = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
+            dq, stats = frame_oracle.pvq_plane_pred(lib, prefix, d, geom, pli, bsize, 30, 1, 0.147, qm, qm_inv, q4,
+                                                    luma_d=luma_q)
+            if pli == 0:
+                luma_q = dq
+            rec = frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 1)
+            out.append((d, dq, rec, stats))
+        res[prefix] = out
+    for a, b in zip(res["ref"], res["port"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    pulses = sum(int(o[3][0]) for o in res["ref"])
+    if content == "noise":
+        assert pulses > 20000
+    elif content == "flat128":
+        assert pulses == 0
+        for pli in range(3):        # mid-grey is the transform's zero: it survives the lossy chain exactly
+            assert np.array_equal(res["ref"][pli][2], planes[pli])
+    else:
+        # saturated constants: the lapping filters are gated at the picture edge (src/filter.c:1459), which
+        # leaves a little AC there; the reconstruction stays within the quantiser's reach
+        assert pulses < 500
+        for pli in range(3):
+            assert np.abs(res["ref"][pli][2].astype(int) - planes[pli].astype(int)).max() <= 8
