@@ -563,7 +563,11 @@ def run_b200(args):
                      "achieved": round(dom_bytes / (ms_dom * 1e-3) / 1e9, 1) if ms_dom else None, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s",
                      "frac": round(dom_bytes / (ms_dom * 1e-3) / 1e9 / peak, 4) if ms_dom else None,
-                     "traffic": None, "algorithmic_bytes_per_launch": int(dom_bytes),
+                     # ncu dram__bytes_read+write of this kernel, 146.2 MB for 38208 bands (profiles/r1q_pvq_chroma_ncu.txt);
+                     # writes are 2.6x the algorithmic 8 B/coefficient: local-memory scratch evictions
+                     "traffic": int(146.2e6 / 38208 * _lst.numel()),
+                     "traffic_source": "ncu dram bytes per band of profiles/r1q_pvq_chroma_ncu.txt (4-frame capture) x bands of this launch",
+                     "algorithmic_bytes_per_launch": int(dom_bytes),
                      "ms_per_launch": round(ms_dom, 4),
                      "note": "compute/latency-bound greedy search; see roofline_transform for the HBM-bound kernel"},
         # the fused lapped-filter + DCT kernel the north star sets its HBM target on
