@@ -107,6 +107,22 @@ def dering_cases(fn):
     return rows, crcs
 
 
+def real_map_crcs(lib, prefix, qm, qm_inv, bsize):
+    """Keyframe chain with prediction on the golden picture with an externally decided block-size map."""
+    geom, planes, _, _ = frame_inputs()
+    q4 = np.full((3, 30), FRAME["q4"], np.uint8)
+    out, luma_q = {}, None
+    for pli in range(3):
+        d = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
+        dq, _ = frame_oracle.pvq_plane_pred(lib, prefix, d, geom, pli, bsize, FRAME["q0"], 1, FRAME["lam"], qm, qm_inv,
+                                            q4, luma_d=luma_q)
+        if pli == 0:
+            luma_q = dq
+        out["fwd_p%d" % pli], out["pred_p%d" % pli] = crc(d), crc(dq)
+        out["inv_p%d" % pli] = crc(frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 1))
+    return out
+
+
 def main():
     ref = oracle_lib.load_ref()
     assert ref is not None, "needs oracle/_ref (make -C oracle ref, with /root/reference present)"
@@ -198,6 +214,22 @@ def main():
     drows, dcrc = dering_cases(lambda *a: ref.od_dering(
         ctypes.c_void_p(ctypes.addressof(ctypes.c_void_p.in_dll(ref, "OD_DERING_VTBL_C"))), *a))
     g["dering_rows"], g["dering_crc"] = np.array(drows, np.int64), np.array(dcrc, np.uint32)
+    # the same picture with the block sizes the whole reference encoder decides (public API, complexity 7)
+    from daala_b200 import synth
+    src, _ = synth.frame(FRAME["w"], FRAME["h"], f=FRAME["f"])
+    geom = frame_inputs()[0]
+    real = np.zeros(geom.bsize_shape, np.uint8)
+    dering = np.zeros((geom.nvsb, geom.nhsb), np.uint8)
+    nbytes, csum = ctypes.c_long(0), ctypes.c_uint(0)
+    rc = ref.oracle_ref_encode_keyframe(FRAME["w"], FRAME["h"], addr(np.ascontiguousarray(src[0])),
+                                        addr(np.ascontiguousarray(src[1])), addr(np.ascontiguousarray(src[2])), 20, 7,
+                                        addr(real), addr(dering), ctypes.byref(nbytes), ctypes.byref(csum))
+    assert rc == 0
+    g["real_bsize"], g["real_dering_levels"] = real, dering
+    g["real_packet"] = np.array([nbytes.value, csum.value], np.int64)
+    rc_crc = real_map_crcs(ref, "ref", qm, qm_inv, real)
+    g["real_keys"] = np.array(sorted(rc_crc))
+    g["real_crc"] = np.array([rc_crc[k] for k in sorted(rc_crc)], np.uint32)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.npz")
     np.savez_compressed(path, **g)
     print("wrote %s (%d arrays, %d bytes)" % (path, len(g), os.path.getsize(path)))

@@ -101,3 +101,10 @@ def test_dering_port_matches_recorded_reference_outputs(port, gold):
     rows, crcs = make_golden.dering_cases(port.port_dering)
     assert rows == gold["dering_rows"].tolist()
     assert crcs == gold["dering_crc"].tolist()
+
+
+def test_frame_drivers_with_the_reference_encoders_block_sizes(port, gold):
+    """Same picture, block sizes decided by the whole reference encoder (recorded in the fixture)."""
+    got = make_golden.real_map_crcs(port, "port", gold["qm"], gold["qm_inv"], gold["real_bsize"])
+    assert got == dict(zip(gold["real_keys"].tolist(), gold["real_crc"].tolist()))
+    assert gold["real_bsize"].max() <= 4 and gold["real_packet"][0] > 500

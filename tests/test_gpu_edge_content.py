@@ -48,3 +48,29 @@ def test_edge_content_keyframe_chain_matches_oracle(content):
         assert np.array_equal(hp.fb.coeffs[pli][0].cpu().numpy(), dq), pli
         rec = frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 1)
         assert np.array_equal(hp.fb.pixels_out[pli][0].cpu().numpy(), rec), pli
+
+
+def test_real_encoder_block_sizes_match_recorded_reference_checksums():
+    """The golden picture with the block-size map the whole reference encoder decided
+    (tests/golden/reference_vectors.npz: real_bsize) -- plane CRCs recorded from the reference build."""
+    import torch
+    from daala_b200.pipeline import HotPath
+    from tests.golden import make_golden
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
+    want = dict(zip(gold["real_keys"].tolist(), gold["real_crc"].tolist()))
+    F = make_golden.FRAME
+    geom, planes, _, _ = make_golden.frame_inputs()
+    bsize = np.ascontiguousarray(gold["real_bsize"])
+    q4 = np.full((3, 30), F["q4"], np.uint8)
+    hp = HotPath(geom, q0=F["q0"], is_keyframe=1, pvq_qm_q4=q4, keyframe_prediction=True)
+    hp.fb.upload(planes, bsize)
+    hp.set_block_sizes([bsize])
+    hp.fb.forward()
+    torch.cuda.synchronize()
+    for pli in range(3):
+        assert make_golden.crc(hp.fb.coeffs[pli][0].cpu().numpy()) == want["fwd_p%d" % pli], pli
+    hp.run()
+    torch.cuda.synchronize()
+    for pli in range(3):
+        assert make_golden.crc(hp.fb.coeffs[pli][0].cpu().numpy()) == want["pred_p%d" % pli], pli
+        assert make_golden.crc(hp.fb.pixels_out[pli][0].cpu().numpy()) == want["inv_p%d" % pli], pli

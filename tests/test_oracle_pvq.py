@@ -232,3 +232,52 @@ def test_edge_content_frames_port_matches_reference(port, ref, content):
         assert pulses < 500
         for pli in range(3):
             assert np.abs(res["ref"][pli][2].astype(int) - planes[pli].astype(int)).max() <= 8
+
+
+def test_real_encoder_block_sizes_through_the_frame_drivers(port, ref):
+    """Block sizes decided by the WHOLE reference encoder (oracle_ref_encode_keyframe: public API, complexity 7
+    RDO) instead of a synthetic quadtree: the list builders agree on that map and the frame drivers of the
+    port and of the reference produce identical planes with it."""
+    from daala_b200 import pvq, synth
+    from daala_b200.frame import Geometry
+    from tests import frame_oracle
+    w, h = 960, 540
+    geom = Geometry(w, h)
+    src, _ = synth.frame(w, h, f=4)
+    bsize = np.zeros(geom.bsize_shape, np.uint8)
+    dering = np.zeros((geom.nvsb, geom.nhsb), np.uint8)
+    nbytes, csum = ctypes.c_long(0), ctypes.c_uint(0)
+    quant = 20
+    rc = ref.oracle_ref_encode_keyframe(w, h, addr(np.ascontiguousarray(src[0])), addr(np.ascontiguousarray(src[1])),
+                                        addr(np.ascontiguousarray(src[2])), quant, 7, addr(bsize), addr(dering),
+                                        ctypes.byref(nbytes), ctypes.byref(csum))
+    assert rc == 0 and nbytes.value > 1000
+    assert bsize.max() <= 4 and len(np.unique(bsize)) >= 2
+    # quadtree consistency of the decided map: a block of size L covers units that all carry L
+    blocks = pvq.block_list(bsize, geom)
+    for pli in range(3):
+        cover = np.zeros(geom.plane_shape(pli), np.int32)
+        for b in blocks[blocks["pli"] == pli]:
+            n = 4 << int(b["bs"])
+            cover[b["y0"]:b["y0"] + n, b["x0"]:b["x0"] + n] += 1
+        assert (cover == 1).all()
+    nat = pvq.native_keyframe_lists([bsize], geom)
+    luma, top, left, depth = pvq.sort_by_depth(pvq.raster_order(blocks[blocks["pli"] == 0]), [bsize], geom)
+    assert np.array_equal(nat["dep_top"], top) and np.array_equal(nat["depth"], depth)
+    planes = synth.pad_planes(src, geom)
+    qm, qm_inv = pvq_cases.reference_qm(ref)
+    q4 = np.full((3, 30), 16, np.uint8)
+    out = {}
+    for lib, prefix in ((ref, "ref"), (port, "port")):
+        luma_q = None
+        res = []
+        for pli in range(3):
+            d = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
+            dq, stats = frame_oracle.pvq_plane_pred(lib, prefix, d, geom, pli, bsize, 72, 1, 0.147, qm, qm_inv, q4,
+                                                    luma_d=luma_q)
+            if pli == 0:
+                luma_q = dq
+            res += [d, dq, frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 1)]
+        out[prefix] = res
+    for a, b in zip(out["ref"], out["port"]):
+        assert np.array_equal(a, b)
