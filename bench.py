@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="e2e: serial copy-in / compute / copy-out instead of the double-buffered pipeline")
     ap.add_argument("--pvq-groups", type=int, default=1, help="frame groups whose PVQ stages run on separate streams")
+    ap.add_argument("--block-sizes", default="synthetic", choices=["synthetic", "reference"],
+                    help="synthetic: seeded quadtree maps with every size 4..64 (default, the measured configuration); "
+                         "reference: the maps the whole reference encoder decides for these frames at OD_SET_QUANT 20, "
+                         "complexity 7 (daala_b200/data/bench_bsize_4k.npz)")
     ap.add_argument("--intra-mode", default="bands", choices=["bands", "waves", "chain", "chain_single"])
     ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"],
                     help="frames: every rank encodes its own --frames frames with the reference's keyframe "
@@ -62,15 +66,28 @@ def parse():
 # --------------------------------------------------------------------------
 # synthetic workload (host side)
 # --------------------------------------------------------------------------
+BLOCK_SIZES = "synthetic"   # --block-sizes: "synthetic" quadtree maps, or the "reference" encoder's decisions
+
+
 def make_host_frames(geom, nframes, distinct=4):
     """`distinct` different synthetic frames, cycled to `nframes`; padded planes + bsize maps."""
     import numpy as np
     from daala_b200 import synth
     frames = []
     seed = 12345
+    real = None
+    if BLOCK_SIZES == "reference":
+        # maps the whole reference encoder decided for these frames (tools/make_real_bsize.py); a band
+        # geometry (CPU sample) takes the top superblock rows of the same maps
+        real = np.load(os.path.join(ROOT, "daala_b200", "data", "bench_bsize_4k.npz"))
+        assert geom.pic_w == PIC_W and geom.bsize_shape[0] <= real["bsize_0"].shape[0]
     for f in range(min(distinct, nframes)):
         planes, seed = synth.frame(geom.pic_w, geom.pic_h, f=f, seed=seed)
-        frames.append((synth.pad_planes(planes, geom), synth.block_size_map(geom, "mixed", seed=100 + f)))
+        if real is not None:
+            bsize = np.ascontiguousarray(real["bsize_%d" % (f % 4)][:geom.bsize_shape[0]])
+        else:
+            bsize = synth.block_size_map(geom, "mixed", seed=100 + f)
+        frames.append((synth.pad_planes(planes, geom), bsize))
     return [frames[i % len(frames)] for i in range(nframes)]
 
 
@@ -546,7 +563,8 @@ def run_b200(args):
                    "frames_per_step": F * (1 if sbrow else world),
                    "parallelism": ("sbrow%d (NCCL all-gather of lapped border rows)" if sbrow else "frames%d (independent frames per rank)") % world,
                    "l2": "inputs larger than L2 (%.0f MB of planes per step)" % ((geom.padded_samples * F * 9) / 1e6),
-                   "block_sizes": "synthetic quadtree map, sizes 4..64", "quantizer": Q0,
+                   "block_sizes": ("synthetic quadtree map, sizes 4..64" if BLOCK_SIZES == "synthetic" else
+                                   "decided by the reference encoder (quant 20, complexity 7)"), "quantizer": Q0,
                    "work_lists": "block / band / wave lists derived from the block-size maps once at setup (maps are "
                                  "fixed across steps); e2e re-uploads them every step but does not rebuild them",
                    "pvq_pulses_per_step": total_k},
@@ -594,7 +612,9 @@ def run_b200(args):
 
 
 def main():
+    global BLOCK_SIZES
     args = parse()
+    BLOCK_SIZES = args.block_sizes
     if args.impl == "reference":
         run_reference(args)
     else:
