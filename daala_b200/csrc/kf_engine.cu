@@ -1,0 +1,1036 @@
+// Keyframe engine: the whole per-block encode hot path of a batch of keyframes as ONE device-resident,
+// CUDA-graph-captured step behind a C ABI that takes HOST buffers (include/daala_b200.h, "Keyframe
+// engine").  It is the batched equivalent of od_encode_coefficients (reference src/encode.c:2539) for
+// keyframes minus the serial entropy coder:
+//
+//   u8 planes + state->bsize maps
+//     -> work lists built ON THE DEVICE from the block-size maps (every step; a live encoder changes
+//        block sizes every frame): leaf-block descriptors by a prefix scan over the 8x8 units, same-size
+//        top / left neighbours of od_hv_intra_pred (src/intra.c:46-47), per size class the (block, band)
+//        items counting-sorted by their position along the intra-prediction dependency chains
+//     -> fused lapped prefilter + fDCT (frame_transform.cu)
+//     -> luma PVQ with the H/V intra predictor: ONE persistent kernel, warps pull items by ticket in
+//        dependency order and wait on per-(block, band) flags of the neighbours they read
+//        (acquire / release) -- no per-wave launches
+//     -> chroma-from-luma prediction + CfL flip + chroma PVQ (same persistent kernel, no dependencies)
+//     -> iDCT + lapped postfilters -> u8 reconstruction, packed symbols for the host entropy coder.
+//
+// Nothing returns to the host between the H2D of the inputs and the D2H of the results; list sizes
+// live in device memory (`cnt`), every kernel is launched with a fixed grid and loops / pulls tickets
+// up to the device-side counts, so the step is captured once into a CUDA graph.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "daala_b200.h"
+#include "gen/coding_order.inc"
+#include "pvq_math.cuh"
+#include "pvq_coop.cuh"
+#include "pvq_common.cuh"
+
+namespace daala_b200 {
+namespace kf {
+
+using namespace daala_b200::pvq;
+
+// ---- device-side counters ----------------------------------------------------------------------
+enum Cnt {
+  kNLuma = 0, kNChroma, kLumaCoefs, kChromaCoefs,
+  kNItemsL = 4,      // [3] luma items per class (n <= 16, 32, 128)
+  kNItemsC = 7,      // [3] chroma items per class
+  kTicketL = 10,     // [3]
+  kTicketC = 13,     // [3]
+  kEpoch = 16,
+  kError = 17,
+  kCntWords = 32
+};
+
+constexpr int kKeyBins = 4096;     // dependency-position bins of one class
+constexpr int kTile = 1024;        // units per scan tile
+
+struct Lists {
+  const uint8_t* bsize;            // [F][UH][bstride]
+  int bstride;
+  long long bsize_pitch;
+  int F, UW, UH;                   // 8x8-luma units per frame
+  int u_row0, u_rows;              // unit rows of this rank's shard
+  int ntiles;
+  int4* tile_sum;                  // [ntiles] then exclusive prefixes in place
+  int32_t* unit_lbase;             // [F*UH*UW] index of the first luma block whose origin is in the unit
+  daala_b200_pvq_block* luma;
+  daala_b200_pvq_block* chroma;
+  int32_t* dep_top;
+  int32_t* dep_left;
+  uint32_t* items_l[3];
+  uint32_t* items_c[3];
+  int32_t* hist;                   // [3][kKeyBins]
+  int32_t* cnt;                    // [kCntWords]
+  int key_scale[3];                // band 0 (x+y), top chains (y), left chains (x): key = pos * scale
+  int max_luma, max_chroma;        // capacities (blocks)
+};
+
+__device__ __forceinline__ int4 add4(int4 a, int4 b) { return make_int4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// (luma blocks, luma coefficients, chroma blocks per plane, chroma coefficients per plane) whose
+// origin lies in unit (ux, uy): leaf rule of od_compute_dcts / od_encode_recursive
+// (src/encode.c:1466-1470: the size is read at the block's top-left unit; bs = max(obs, xdec)).
+__device__ __forceinline__ int4 unit_counts(int b, int ux, int uy) {
+  if (b == 0) return make_int4(4, 64, 1, 16);
+  const int span = 1 << (b - 1);
+  if ((ux & (span - 1)) | (uy & (span - 1))) return make_int4(0, 0, 0, 0);
+  const int lc = b == 1 ? 64 : b == 2 ? 256 : 512;
+  const int cc = b == 1 ? 16 : b == 2 ? 64 : b == 3 ? 256 : 512;
+  return make_int4(1, lc, 1, cc);
+}
+
+__device__ __forceinline__ bool unit_of(const Lists& L, long long i, int* f, int* uy, int* ux, int* b) {
+  const long long per = (long long)L.u_rows * L.UW;
+  if (i >= per * L.F) return false;
+  *f = (int)(i / per);
+  const int r = (int)(i - (long long)*f * per);
+  *uy = L.u_row0 + r / L.UW;
+  *ux = r % L.UW;
+  *b = L.bsize[*f * L.bsize_pitch + (long long)*uy * L.bstride + *ux];
+  return true;
+}
+
+__global__ void __launch_bounds__(kTile) k_unit_tile_sums(const __grid_constant__ Lists L) {
+  __shared__ int4 part[32];
+  const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
+  int f, uy, ux, b;
+  int4 v = make_int4(0, 0, 0, 0);
+  if (unit_of(L, i, &f, &uy, &ux, &b)) v = unit_counts(b, ux, uy);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+    v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+  }
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int4 s = make_int4(0, 0, 0, 0);
+    for (int w = 0; w < kTile / 32; w++) s = add4(s, part[w]);
+    L.tile_sum[blockIdx.x] = s;
+  }
+}
+
+// One CTA: exclusive scan of the tile sums, totals, reset of the per-step counters, new epoch.
+__global__ void __launch_bounds__(1024) k_tile_scan(const __grid_constant__ Lists L) {
+  __shared__ int4 part[1024];
+  __shared__ int4 carry;
+  const int t = threadIdx.x;
+  if (t == 0) carry = make_int4(0, 0, 0, 0);
+  for (int i = t; i < 3 * kKeyBins; i += 1024) L.hist[i] = 0;
+  __syncthreads();
+  for (int base = 0; base < L.ntiles; base += 1024) {
+    const int i = base + t;
+    const int4 v = i < L.ntiles ? L.tile_sum[i] : make_int4(0, 0, 0, 0);
+    part[t] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int4 a = t >= o ? part[t - o] : make_int4(0, 0, 0, 0);
+      __syncthreads();
+      part[t] = add4(part[t], a);
+      __syncthreads();
+    }
+    const int4 incl = part[t], c = carry;
+    if (i < L.ntiles) L.tile_sum[i] = make_int4(c.x + incl.x - v.x, c.y + incl.y - v.y, c.z + incl.z - v.z, c.w + incl.w - v.w);
+    __syncthreads();
+    if (t == 1023) carry = add4(c, incl);
+    __syncthreads();
+  }
+  if (t == 0) {
+    const int4 tot = carry;
+    L.cnt[kNLuma] = tot.x;
+    L.cnt[kLumaCoefs] = tot.y;
+    L.cnt[kNChroma] = 2 * tot.z;
+    L.cnt[kChromaCoefs] = 2 * tot.w;
+    for (int c = 0; c < 3; c++) {
+      L.cnt[kNItemsL + c] = 0;
+      L.cnt[kNItemsC + c] = 0;
+    }
+    if (tot.x > L.max_luma || 2 * tot.z > L.max_chroma) L.cnt[kError] = 1;
+  }
+}
+
+__device__ __forceinline__ void put_block(daala_b200_pvq_block* dst, int coef_off, int x0, int y0, int bs, int pli,
+                                          int xdec, int frame) {
+  // one 12-byte record = three 32-bit stores
+  int32_t* w = reinterpret_cast<int32_t*>(dst);
+  w[0] = coef_off;
+  w[1] = (x0 & 0xffff) | (y0 << 16);
+  w[2] = bs | (pli << 8) | (xdec << 16) | (frame << 24);
+}
+
+__global__ void __launch_bounds__(kTile) k_unit_emit(const __grid_constant__ Lists L) {
+  __shared__ int4 wsum[32];
+  const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int f = 0, uy = 0, ux = 0, b = 0;
+  const bool valid = unit_of(L, i, &f, &uy, &ux, &b);
+  const int4 v = valid ? unit_counts(b, ux, uy) : make_int4(0, 0, 0, 0);
+  int4 s = v;  // inclusive warp scan
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int4 a;
+    a.x = __shfl_up_sync(0xffffffffu, s.x, o);
+    a.y = __shfl_up_sync(0xffffffffu, s.y, o);
+    a.z = __shfl_up_sync(0xffffffffu, s.z, o);
+    a.w = __shfl_up_sync(0xffffffffu, s.w, o);
+    if (lane >= o) s = add4(s, a);
+  }
+  if (lane == 31) wsum[warp] = s;
+  __syncthreads();
+  int4 pre = L.tile_sum[blockIdx.x];
+  for (int w = 0; w < warp; w++) pre = add4(pre, wsum[w]);
+  pre = make_int4(pre.x + s.x - v.x, pre.y + s.y - v.y, pre.z + s.z - v.z, pre.w + s.w - v.w);
+  if (!valid) return;
+  L.unit_lbase[((long long)f * L.UH + uy) * L.UW + ux] = pre.x;
+  if (v.x == 0) return;
+  if (pre.x + v.x > L.max_luma || 2 * (pre.z + v.z) > L.max_chroma) return;   // flagged by k_tile_scan
+  if (b == 0) {
+    for (int q = 0; q < 4; q++)
+      put_block(L.luma + pre.x + q, pre.y + 16 * q, ux * 8 + (q & 1) * 4, uy * 8 + (q >> 1) * 4, 0, 0, 0, f);
+  } else {
+    put_block(L.luma + pre.x, pre.y, ux * 8, uy * 8, b, 0, 0, f);
+  }
+  // 4:2:0 chroma: bs = max(obs, 1) - 1; bit 7 of xdec: the co-located luma is coded as 4x4 blocks
+  // (od_resample_luma_coeffs' chroma_bs == 0 case, src/intra.c:78)
+  const int cbs = (b > 1 ? b : 1) - 1;
+  const int xd = 1 | (b == 0 ? 0x80 : 0);
+  put_block(L.chroma + 2 * pre.z, 2 * pre.w, ux * 4, uy * 4, cbs, 1, xd, f);
+  put_block(L.chroma + 2 * pre.z + 1, 2 * pre.w + v.w, ux * 4, uy * 4, cbs, 2, xd, f);
+}
+
+// Position of (block, band) along its dependency chain, scaled into [0, kKeyBins): strictly larger
+// than the key of every item it depends on (od_hv_intra_pred reads the same-size TOP neighbour for
+// row-0 bands 1/4/7, the LEFT one for column-0 bands 2/5/8, both for band 0, none for 3/6), so the
+// sorted item list is a topological order.  Dependency-free bands are spread over the whole range
+// (they fill the machine while chain links wait).
+__device__ __forceinline__ int item_key(const Lists& L, int blk, int band, int x0, int y0) {
+  const int x4 = x0 >> 2, y4 = (y0 >> 2) - L.u_row0 * 2;
+  if (band == 0) return (x4 + y4) * L.key_scale[0];
+  if (band == 3 || band == 6) return (int)(((unsigned)blk * 2654435761u) >> 20);   // 12 bits
+  const int r = band % 3;
+  return r == 1 ? y4 * L.key_scale[1] : x4 * L.key_scale[2];
+}
+
+__device__ __forceinline__ int band_class(int band) { return band < 3 ? 0 : band < 6 ? 1 : 2; }
+
+// pass 0: neighbours + key histogram; pass 1: scatter into the sorted lists (hist holds the cursors).
+template <int kPass>
+__global__ void __launch_bounds__(256) k_luma_items(const __grid_constant__ Lists L) {
+  const int n = min(L.cnt[kNLuma], L.max_luma);
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < n; blk += gridDim.x * blockDim.x) {
+    const daala_b200_pvq_block b = L.luma[blk];
+    const int bs = b.bs, x0 = b.x0, y0 = b.y0, f = b.frame;
+    if (kPass == 0) {
+      const int nn = 4 << bs;
+      const uint8_t* map = L.bsize + f * L.bsize_pitch;
+      int top = -1, left = -1;
+      if (y0 - nn >= L.u_row0 * 8 && map[(long long)((y0 - 1) >> 3) * L.bstride + (x0 >> 3)] == bs) {
+        const int ty = y0 - nn;
+        top = L.unit_lbase[((long long)f * L.UH + (ty >> 3)) * L.UW + (x0 >> 3)] +
+              (bs == 0 ? ((ty >> 2) & 1) * 2 + ((x0 >> 2) & 1) : 0);
+      }
+      if (x0 > 0 && map[(long long)(y0 >> 3) * L.bstride + ((x0 - 1) >> 3)] == bs) {
+        const int lx = x0 - nn;
+        left = L.unit_lbase[((long long)f * L.UH + (y0 >> 3)) * L.UW + (lx >> 3)] +
+               (bs == 0 ? ((y0 >> 2) & 1) * 2 + ((lx >> 2) & 1) : 0);
+      }
+      L.dep_top[blk] = top;
+      L.dep_left[blk] = left;
+    }
+    const int nb = num_bands(bs);
+    for (int band = 0; band < nb; band++) {
+      const int c = band_class(band);
+      int key = item_key(L, blk, band, x0, y0);
+      key = key < kKeyBins ? key : kKeyBins - 1;
+      if (kPass == 0) {
+        atomicAdd(&L.hist[c * kKeyBins + key], 1);
+      } else {
+        const int pos = atomicAdd(&L.hist[c * kKeyBins + key], 1);
+        L.items_l[c][pos] = ((uint32_t)blk << 4) | band;
+      }
+    }
+  }
+}
+
+// 3 CTAs: exclusive scan of each class's histogram in place; totals into cnt.
+__global__ void __launch_bounds__(1024) k_hist_scan(const __grid_constant__ Lists L) {
+  __shared__ int part[1024];
+  constexpr int kPer = kKeyBins / 1024;
+  int* hist = L.hist + blockIdx.x * kKeyBins;
+  const int t = threadIdx.x;
+  int v[kPer], sum = 0;
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    v[i] = hist[t * kPer + i];
+    sum += v[i];
+  }
+  part[t] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int add = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += add;
+    __syncthreads();
+  }
+  int run = part[t] - sum;
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    hist[t * kPer + i] = run;
+    run += v[i];
+  }
+  if (t == 1023) L.cnt[kNItemsL + blockIdx.x] = part[1023];
+}
+
+// Chroma items: no dependencies between blocks; compaction per class (order is free).
+__global__ void __launch_bounds__(256) k_chroma_items(const __grid_constant__ Lists L) {
+  const int n = min(L.cnt[kNChroma], L.max_chroma);
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < n; blk += gridDim.x * blockDim.x) {
+    const int bs = L.chroma[blk].bs;
+    const int nb = num_bands(bs);
+    for (int band = 0; band < nb; band++) {
+      const int c = band_class(band);
+      // warp-aggregated append
+      const unsigned m = __activemask();
+      const unsigned same = __match_any_sync(m, c);
+      const int leader = __ffs(same) - 1, lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&L.cnt[kNItemsC + c], __popc(same));
+      base = __shfl_sync(same, base, leader);
+      L.items_c[c][base + __popc(same & ((1u << lane) - 1u))] = ((uint32_t)blk << 4) | band;
+    }
+  }
+}
+
+// ---- PVQ stage -----------------------------------------------------------------------------------
+struct Stage {
+  daala_b200_pvq_params prm;
+  const uint32_t* items[3];
+  const int32_t* dep_top;          // luma: neighbours (NULL for chroma)
+  const int32_t* dep_left;
+  int32_t* flags;                  // [nblocks*9] == epoch once that band's `out` is final
+  int32_t* cnt;
+  int n_items_at, ticket_at, n_blocks_at;
+  int max_blocks;
+  int16_t* res_pack;               // [nblocks*9][4]: gain, itheta, max_theta, k (what the coder reads)
+  const int32_t* cfl_plane;        // chroma: prediction plane (chroma geometry), else NULL
+  long long cfl_pitch;
+  int cfl_stride;
+};
+
+// raster -> coding order of every block (od_raster_to_coding_order, src/partition.c:123); chroma:
+// also the CfL prediction and its sign flip (src/pvq_encoder.c:847-871).  One warp per block.
+template <bool kChroma>
+__global__ void __launch_bounds__(256) k_gather(const __grid_constant__ Stage S) {
+  const daala_b200_pvq_params& prm = S.prm;
+  const int n = min(S.cnt[S.n_blocks_at], S.max_blocks);
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < n; blk += nwarps) {
+    const daala_b200_pvq_block b = prm.blocks[blk];
+    const int ln = b.bs + 2;
+    const int len = ln >= 5 ? 512 : 1 << (2 * ln);
+    const int stride = prm.plane_stride[b.pli];
+    const int32_t* src = prm.coef_plane[b.pli] + b.frame * prm.plane_frame_pitch[b.pli] + (size_t)b.y0 * stride + b.x0;
+    int32_t* vin = prm.in + b.coef_off;
+    if (!kChroma) {
+      for (int i = lane; i < len; i += 32) vin[i] = i == 0 ? src[0] : src[scan_to_raster(i, ln, stride)];
+    } else {
+      const int32_t* psrc = S.cfl_plane + b.frame * S.cfl_pitch + (size_t)b.y0 * S.cfl_stride + b.x0;
+      int32_t* vref = prm.ref + b.coef_off;
+      const int qoff = prm.qm_stride + ((((1 << (2 * b.bs)) - 1) << 4) / 3);
+      int32_t xy = 0;
+      for (int i = lane; i < len; i += 32) {
+        const int32_t vi = i == 0 ? src[0] : src[scan_to_raster(i, ln, stride)];
+        const int32_t vr = i == 0 ? psrc[0] : psrc[scan_to_raster(i, ln, S.cfl_stride)];
+        vin[i] = vi;
+        vref[i] = vr;
+        if (i >= 1 && i < 16) {
+          const int32_t rq = vr * prm.qm[qoff + i], inq = vi * prm.qm[qoff + i];
+          xy += (int32_t)((rq * (int64_t)inq) >> ((kQmShift + 4) << 1));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) xy += __shfl_xor_sync(0xffffffffu, xy, o);
+      const int flip = xy < 0;
+      __syncwarp();
+      if (flip) {
+        const int end = band_start(num_bands(b.bs));
+        for (int i = 1 + lane; i < end; i += 32) vref[i] = -vref[i];
+      }
+      if (lane == 0) prm.res_flip[blk] = flip;
+    }
+  }
+}
+
+// Chroma-from-luma prediction planes (od_resample_luma_coeffs, src/intra.c:72): see k_cfl_pred of
+// pvq_kernels.cu; here with the block count on the device.  One warp per chroma block of plane 1
+// (plane 2 shares the prediction).
+__global__ void __launch_bounds__(256) k_cfl_plane(const __grid_constant__ Stage S, int32_t* pred_plane) {
+  const daala_b200_pvq_params& prm = S.prm;
+  const int n = min(S.cnt[S.n_blocks_at], S.max_blocks);
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < n; blk += nwarps) {
+    const daala_b200_pvq_block b = prm.blocks[blk];
+    if (b.pli != 1) continue;
+    const int nn = 4 << b.bs;
+    const int lstride = prm.plane_stride[0];
+    const int32_t* luma = prm.coef_plane[0] + b.frame * prm.plane_frame_pitch[0] + (size_t)(2 * b.y0) * lstride + 2 * b.x0;
+    int32_t* dst = pred_plane + b.frame * S.cfl_pitch + (size_t)b.y0 * S.cfl_stride + b.x0;
+    if (b.xdec & 0x80) {
+      // four 4x4 luma blocks -> one 4x4 chroma prediction: od_tf_up_hv_lp (src/tf.c:82) + OD_CFL_SCALING4
+      const int scaling4[4][4] = {{128, 128, 100, 36}, {128, 80, 71, 35}, {100, 71, 35, 31}, {36, 35, 31, 18}};
+      if (lane < 4) {
+        const int x = lane & 1, y = lane >> 1;
+        int ll = luma[(size_t)y * lstride + x], lh = luma[(size_t)y * lstride + x + 4];
+        int hl = luma[(size_t)(y + 4) * lstride + x], hh = luma[(size_t)(y + 4) * lstride + x + 4];
+        ll += lh; hh -= hl;
+        const int t = (ll - hh) >> 1;
+        hl = t - hl; lh = t - lh;
+        ll -= hl; hh += lh;
+        const int hs = x & 1, vs = y & 1;
+        int r, c;
+        r = 2 * y + vs; c = 2 * x + hs;         dst[(size_t)r * S.cfl_stride + c] = (scaling4[c][r] * ll + 64) >> 7;
+        r = 2 * y + vs; c = 2 * x + 1 - hs;     dst[(size_t)r * S.cfl_stride + c] = (scaling4[c][r] * lh + 64) >> 7;
+        r = 2 * y + 1 - vs; c = 2 * x + hs;     dst[(size_t)r * S.cfl_stride + c] = (scaling4[c][r] * hl + 64) >> 7;
+        r = 2 * y + 1 - vs; c = 2 * x + 1 - hs; dst[(size_t)r * S.cfl_stride + c] = (scaling4[c][r] * hh + 64) >> 7;
+      }
+    } else {
+      // only the coded prefix is ever read; copying the whole low-frequency quarter keeps this simple
+      const int lim = nn > 32 ? 32 : nn;
+      for (int i = lane; i < lim * lim; i += 32) {
+        const int r = i / lim, c = i % lim;
+        dst[(size_t)r * S.cfl_stride + c] = luma[(size_t)r * lstride + c];
+      }
+    }
+  }
+}
+
+// One (block, band) item by a G-lane group; kIntra: build the band's prediction from the quantised
+// neighbours first (k_intra_band_ref of pvq_kernels.cu) after waiting for their flags.
+template <int G, int E, bool kIntra>
+__device__ __forceinline__ void run_items(const Stage& S, int cls, int epoch) {
+  const daala_b200_pvq_params& prm = S.prm;
+  const Group<G, E> grp;
+  constexpr int kPerWarp = 32 / G;
+  const int n = S.cnt[S.n_items_at + cls];
+  const uint32_t* items = S.items[cls];
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&S.cnt[S.ticket_at + cls], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    const int base = t * kPerWarp;
+    if (base >= n) return;
+    const int idx = base + lane / G;
+    const bool valid = idx < n;
+    const uint32_t e = items[valid ? idx : n - 1];
+    const int blk = (int)(e >> 4), band = (int)(e & 15);
+    const daala_b200_pvq_block b = prm.blocks[blk];
+    const int bs = b.bs, pli = b.pli;
+    const int start = band_start(band);
+    const int bn = band_start(band + 1) - start;
+    const size_t off = (size_t)b.coef_off + start;
+    int top = -1, left = -1;
+    if (kIntra) {
+      const int r = band % 3;
+      if (band == 0 || r == 1) top = S.dep_top[blk];
+      if (band == 0 || r == 2) left = S.dep_left[blk];
+      if (band == 3 || band == 6) top = left = -1;
+      // every lane polls its own group's flags; the warp leaves together
+      const int* ft = top >= 0 ? S.flags + (size_t)top * 9 + band : nullptr;
+      const int* fl = left >= 0 ? S.flags + (size_t)left * 9 + band : nullptr;
+      for (;;) {
+        const bool ready = (!ft || ld_acquire(ft) == epoch) && (!fl || ld_acquire(fl) == epoch);
+        if (__all_sync(0xffffffffu, ready)) break;
+        __nanosleep(200);
+      }
+      const int32_t* ot = top >= 0 ? prm.out + prm.blocks[top].coef_off : nullptr;
+      const int32_t* ol = left >= 0 ? prm.out + prm.blocks[left].coef_off : nullptr;
+      bool low_from_top = false;
+      if (band == 0) {
+        // coding-order indices of (0,1) (0,2) (0,3) and (1,0) (2,0) (3,0) in the 4x4 stage; double
+        // sums of exact integers as in od_hv_intra_pred (src/intra.c:51-52)
+        double g1 = 0, g2 = 0;
+        if (ot) { double a = ot[2], bb = ot[5], c = ot[9]; g1 += a * a; g1 += bb * bb; g1 += c * c; }
+        if (ol) { double a = ol[1], bb = ol[4], c = ol[7]; g2 += a * a; g2 += bb * bb; g2 += c * c; }
+        low_from_top = g1 > g2;
+      }
+      int32_t* vref = prm.ref + b.coef_off;
+      // element j of the band is owned by lane j % G: the lane that writes ref[j] is the one that reads it
+      for (int i = start + grp.lane; i < start + bn; i += G) {
+        int r2, c2;
+        scan_rc(i, &r2, &c2);
+        int32_t p = 0;
+        if (r2 == 0 && c2 > 0 && ot && (c2 >= 4 || low_from_top)) p = ot[i];
+        if (c2 == 0 && r2 > 0 && ol && (r2 >= 4 || !low_from_top)) p = ol[i];
+        vref[i] = p;
+      }
+    }
+    int qidx = bs * (bs + 1) + (band + 1) - (band + 1) / 3;
+    int q = (prm.q0 * prm.pvq_qm_q4[pli][qidx]) >> 4;
+    if (q < 1) q = 1;
+    const int beta = (prm.use_masking && pli == 0 && bs > 0) ? kBeta15 : kBeta1;
+    const int qoff = (b.xdec & 1 ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
+    int itheta, max_theta, k;
+    double skip_term;
+    const int gain = quantise_band_coop<G, E, false>(grp, prm.out + off, prm.in + off, prm.ref + off, bn, q,
+                                                     prm.y + off, &itheta, &max_theta, &k, beta, &skip_term,
+                                                     prm.is_keyframe, pli, prm.qm + qoff, prm.qm_inv + qoff,
+                                                     prm.pvq_norm_lambda);
+    if (valid && grp.lane == 0) {
+      const size_t r = (size_t)blk * 9 + band;
+      prm.res_skip_term[r] = skip_term;
+      short4 pk;
+      pk.x = (short)gain; pk.y = (short)itheta; pk.z = (short)max_theta; pk.w = (short)k;
+      reinterpret_cast<short4*>(S.res_pack)[r] = pk;
+    }
+    if (kIntra) {
+      __threadfence();
+      __syncwarp();
+      if (valid && grp.lane == 0) st_release(S.flags + (size_t)blk * 9 + band, epoch);
+    }
+  }
+}
+
+// Persistent PVQ kernel: every warp serves the three size classes, starting with `warp % 3` so that
+// all classes progress concurrently (each class is its own dependency system), and moves on when a
+// class is exhausted.  Tickets are handed out in sorted (= dependency) order to running warps only,
+// so the holder of the lowest unfinished ticket never waits on a later one: no deadlock.
+template <bool kIntra>
+__global__ void __launch_bounds__(128, 5) k_pvq_persist(const __grid_constant__ Stage S) {
+  const int epoch = S.cnt[kEpoch];
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (int r = 0; r < 3; r++) {
+    const int cls = (w + r) % 3;
+    if (cls == 0) run_items<4, 4, kIntra>(S, 0, epoch);
+    else if (cls == 1) run_items<8, 4, kIntra>(S, 1, epoch);
+    else run_items<32, 4, kIntra>(S, 2, epoch);
+  }
+}
+
+// Start of a PVQ stage: fresh tickets, new epoch for the dependency flags.
+__global__ void k_begin_pvq(int32_t* cnt) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int c = 0; c < 3; c++) cnt[kTicketL + c] = cnt[kTicketC + c] = 0;
+    cnt[kEpoch] += 1;
+  }
+}
+
+// Per block, after all its bands: ordered skip_diff sum (src/pvq_encoder.c:875-880), keyframe DC
+// (scalar_out[0] = dblock[0], src/encode.c:1381), od_init_skipped_coeffs (src/state.c:1347) +
+// od_coding_order_to_raster (src/partition.c:157) back into the coefficient plane, pulses packed to
+// 16 bits for the host entropy coder.  One warp per block.
+__global__ void __launch_bounds__(256) k_finish_scatter(const __grid_constant__ Stage S) {
+  const daala_b200_pvq_params& prm = S.prm;
+  const int n = min(S.cnt[S.n_blocks_at], S.max_blocks);
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < n; blk += nwarps) {
+    const daala_b200_pvq_block b = prm.blocks[blk];
+    const int ln = b.bs + 2, nn = 1 << ln;
+    const int len = ln >= 5 ? 512 : 1 << (2 * ln);
+    const int stride = prm.plane_stride[b.pli];
+    int32_t* dst = prm.coef_plane[b.pli] + b.frame * prm.plane_frame_pitch[b.pli] + (size_t)b.y0 * stride + b.x0;
+    const int32_t* src = prm.out + b.coef_off;
+    if (lane == 0) {
+      const int nb = num_bands(b.bs);
+      double sd = 0;
+      for (int i = 0; i < nb; i++) sd += prm.res_skip_term[(size_t)blk * 9 + i];
+      prm.res_skip_diff[blk] = sd;
+      prm.out[b.coef_off] = prm.in[b.coef_off];
+    }
+    if (ln >= 5) {
+      for (int i = lane; i < nn * nn; i += 32) if (i) dst[(size_t)(i >> ln) * stride + (i & (nn - 1))] = 0;
+      __syncwarp();
+    }
+    for (int i = lane + 1; i < len; i += 32) dst[scan_to_raster(i, ln, stride)] = src[i];
+    const int32_t* y = prm.y + b.coef_off;
+    for (int i = lane; i < len; i += 32) prm.y16[b.coef_off + i] = i ? (int16_t)y[i] : (int16_t)0;
+  }
+}
+
+}  // namespace kf
+}  // namespace daala_b200
+
+// =====================================================================================================
+// Host side of the engine
+// =====================================================================================================
+using namespace daala_b200::kf;
+
+extern "C" int daala_b200_launch_forward(const daala_b200_frame* prm, int nplanes, cudaStream_t stream);
+extern "C" int daala_b200_launch_inverse(const daala_b200_frame* prm, int nplanes, cudaStream_t stream);
+
+struct daala_b200_kf {
+  daala_b200_kf_config cfg;
+  int nhsb, nvsb, F;
+  int plane_w[3], plane_h[3];
+  cudaStream_t stream;
+  bool own_stream;
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  bool captured;
+  // device buffers
+  uint8_t* pixels[3];
+  int32_t* coeffs[3];
+  int32_t* lapped[3];
+  uint8_t* pixels_out[3];
+  uint8_t* bsize;
+  int32_t* cfl_plane;
+  int16_t *qm, *qm_inv;
+  Lists lists;
+  Stage luma, chroma;
+  daala_b200_frame frame;
+  size_t bytes_allocated;
+  int sms;
+  char err[256];
+};
+
+#define KF_CHECK(x)                                                                       \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess) {                                                              \
+      snprintf(kf->err, sizeof(kf->err), "%s: %s", #x, cudaGetErrorString(e_));           \
+      return (int)e_;                                                                     \
+    }                                                                                     \
+  } while (0)
+
+template <class T>
+static cudaError_t dalloc(daala_b200_kf* kf, T** p, size_t n) {
+  const size_t bytes = (n ? n : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void**)p, bytes);
+  if (e == cudaSuccess) {
+    kf->bytes_allocated += bytes;
+    e = cudaMemset(*p, 0, bytes);
+  }
+  return e;
+}
+
+static int kf_alloc(daala_b200_kf* kf) {
+  const int F = kf->F;
+  const long long luma_px = (long long)kf->plane_w[0] * kf->plane_h[0];
+  for (int p = 0; p < 3; p++) {
+    const size_t n = (size_t)kf->plane_w[p] * kf->plane_h[p] * F;
+    KF_CHECK(dalloc(kf, &kf->pixels[p], n));
+    KF_CHECK(dalloc(kf, &kf->coeffs[p], n));
+    KF_CHECK(dalloc(kf, &kf->lapped[p], n));
+    KF_CHECK(dalloc(kf, &kf->pixels_out[p], n));
+  }
+  const int UW = kf->nhsb * 8, UH = kf->nvsb * 8;
+  KF_CHECK(dalloc(kf, &kf->bsize, (size_t)F * UW * UH));
+  KF_CHECK(dalloc(kf, &kf->cfl_plane, (size_t)kf->plane_w[1] * kf->plane_h[1] * F));
+  KF_CHECK(dalloc(kf, &kf->qm, (size_t)2 * kf->cfg.qm_stride));
+  KF_CHECK(dalloc(kf, &kf->qm_inv, (size_t)2 * kf->cfg.qm_stride));
+  KF_CHECK(cudaMemcpy(kf->qm, kf->cfg.qm, sizeof(int16_t) * 2 * kf->cfg.qm_stride, cudaMemcpyHostToDevice));
+  KF_CHECK(cudaMemcpy(kf->qm_inv, kf->cfg.qm_inv, sizeof(int16_t) * 2 * kf->cfg.qm_stride, cudaMemcpyHostToDevice));
+
+  Lists& L = kf->lists;
+  memset(&L, 0, sizeof(L));
+  L.bsize = kf->bsize;
+  L.bstride = UW;
+  L.bsize_pitch = (long long)UW * UH;
+  L.F = F;
+  L.UW = UW;
+  L.UH = UH;
+  L.u_row0 = kf->cfg.sb_row0 * 8;
+  L.u_rows = kf->cfg.sb_rows * 8;
+  const long long nunits = (long long)F * L.u_rows * UW;
+  L.ntiles = (int)((nunits + kTile - 1) / kTile);
+  // capacities: every unit coded as four 4x4 luma blocks / one 4x4 chroma block per plane, unless the
+  // caller bounds the smallest block size it will ever submit
+  const int div = kf->cfg.max_blocks_div > 0 ? kf->cfg.max_blocks_div : 1;
+  L.max_luma = (int)(nunits * 4 / div) + 64;
+  L.max_chroma = (int)(nunits * 2 / div) + 64;
+  KF_CHECK(dalloc(kf, &L.tile_sum, (size_t)L.ntiles));
+  KF_CHECK(dalloc(kf, &L.unit_lbase, (size_t)F * UW * UH));
+  KF_CHECK(dalloc(kf, &L.luma, (size_t)L.max_luma));
+  KF_CHECK(dalloc(kf, &L.chroma, (size_t)L.max_chroma));
+  KF_CHECK(dalloc(kf, &L.dep_top, (size_t)L.max_luma));
+  KF_CHECK(dalloc(kf, &L.dep_left, (size_t)L.max_luma));
+  // items per class: class 0 (bands 0-2) <= max(blocks) [all 4x4: one band each; 8x8: 3 per 4 units]
+  const size_t luma_shard_px = (size_t)F * L.u_rows * UW * 64;
+  const size_t cap_l[3] = {(size_t)L.max_luma, luma_shard_px * 3 / 64 + 64, luma_shard_px * 3 / 256 + 64};
+  const size_t cap_c[3] = {(size_t)L.max_chroma * 3 / 2 + 64, luma_shard_px / 4 * 2 * 3 / 64 + 64,
+                           luma_shard_px / 4 * 2 * 3 / 256 + 64};
+  for (int c = 0; c < 3; c++) {
+    KF_CHECK(dalloc(kf, &L.items_l[c], cap_l[c]));
+    KF_CHECK(dalloc(kf, &L.items_c[c], cap_c[c]));
+  }
+  KF_CHECK(dalloc(kf, &L.hist, (size_t)3 * kKeyBins));
+  KF_CHECK(dalloc(kf, &L.cnt, (size_t)kCntWords));
+  // chain-position scales: strictly monotonic, filling [0, kKeyBins)
+  const int x4max = kf->plane_w[0] / 4, y4max = L.u_rows * 2;
+  L.key_scale[0] = (kKeyBins - 1) / (x4max + y4max);
+  L.key_scale[1] = (kKeyBins - 1) / y4max;
+  L.key_scale[2] = (kKeyBins - 1) / x4max;
+  for (int i = 0; i < 3; i++) if (L.key_scale[i] < 1) return (int)cudaErrorInvalidValue;   // frame too large for the key range
+
+  auto setup_stage = [&](Stage& S, bool chroma) -> int {
+    memset(&S, 0, sizeof(S));
+    daala_b200_pvq_params& p = S.prm;
+    const size_t ncoef = chroma ? luma_shard_px / 2 + 1024 : luma_shard_px + 1024;
+    const size_t nblk = chroma ? L.max_chroma : L.max_luma;
+    p.blocks = chroma ? L.chroma : L.luma;
+    KF_CHECK(dalloc(kf, &p.in, ncoef));
+    KF_CHECK(dalloc(kf, &p.ref, ncoef));
+    KF_CHECK(dalloc(kf, &p.out, ncoef));
+    KF_CHECK(dalloc(kf, &p.y, ncoef));
+    KF_CHECK(dalloc(kf, &p.y16, ncoef));
+    KF_CHECK(dalloc(kf, &p.res_skip_term, nblk * 9));
+    KF_CHECK(dalloc(kf, &p.res_skip_diff, nblk));
+    KF_CHECK(dalloc(kf, &p.res_flip, nblk));
+    KF_CHECK(dalloc(kf, &S.res_pack, nblk * 9 * 4));
+    p.res_gain = p.res_theta = p.res_max_theta = p.res_k = nullptr;   // packed into res_pack here
+    p.res_dc = nullptr;
+    p.qm = kf->qm;
+    p.qm_inv = kf->qm_inv;
+    for (int i = 0; i < 3; i++) {
+      p.coef_plane[i] = kf->coeffs[i];
+      p.pred_plane[i] = nullptr;
+      p.plane_frame_pitch[i] = (long long)kf->plane_w[i] * kf->plane_h[i];
+      p.plane_stride[i] = kf->plane_w[i];
+    }
+    p.qm_stride = kf->cfg.qm_stride;
+    p.q0 = kf->cfg.q0 > 1 ? kf->cfg.q0 : 1;
+    p.is_keyframe = 1;
+    p.use_masking = kf->cfg.use_masking;
+    p.pvq_norm_lambda = kf->cfg.pvq_norm_lambda;
+    memcpy(p.pvq_qm_q4, kf->cfg.pvq_qm_q4, sizeof(p.pvq_qm_q4));
+    for (int c = 0; c < 3; c++) S.items[c] = chroma ? L.items_c[c] : L.items_l[c];
+    S.cnt = L.cnt;
+    S.n_items_at = chroma ? kNItemsC : kNItemsL;
+    S.ticket_at = chroma ? kTicketC : kTicketL;
+    S.n_blocks_at = chroma ? kNChroma : kNLuma;
+    S.max_blocks = (int)nblk;
+    if (!chroma) {
+      S.dep_top = L.dep_top;
+      S.dep_left = L.dep_left;
+      KF_CHECK(dalloc(kf, &S.flags, nblk * 9));
+    } else {
+      S.cfl_plane = kf->cfl_plane;
+      S.cfl_pitch = (long long)kf->plane_w[1] * kf->plane_h[1];
+      S.cfl_stride = kf->plane_w[1];
+    }
+    return 0;
+  };
+  int rc = setup_stage(kf->luma, false);
+  if (rc) return rc;
+  rc = setup_stage(kf->chroma, true);
+  if (rc) return rc;
+  (void)luma_px;
+
+  daala_b200_frame& f = kf->frame;
+  memset(&f, 0, sizeof(f));
+  for (int p = 0; p < 3; p++) {
+    daala_b200_plane& pl = f.plane[p];
+    pl.pixels = kf->pixels[p];
+    pl.coeffs = kf->coeffs[p];
+    pl.lapped = kf->lapped[p];
+    pl.pixels_out = kf->pixels_out[p];
+    pl.pixel_stride = pl.coeff_stride = pl.lapped_stride = pl.pixel_out_stride = kf->plane_w[p];
+    pl.xdec = p ? 1 : 0;
+    pl.pixel_frame_pitch = pl.coeff_frame_pitch = pl.lapped_frame_pitch = pl.pixel_out_frame_pitch =
+        (long long)kf->plane_w[p] * kf->plane_h[p];
+  }
+  f.bsize = kf->bsize;
+  f.bstride = UW;
+  f.bsize_frame_pitch = (long long)UW * UH;
+  f.nhsb = kf->nhsb;
+  f.nvsb = kf->nvsb;
+  f.pic_w = kf->cfg.pic_w;
+  f.pic_h = kf->cfg.pic_h;
+  f.haar_dc = 1;
+  f.nframes = F;
+  f.sb_row0 = kf->cfg.sb_row0;
+  f.sb_rows = kf->cfg.sb_rows;
+  return 0;
+}
+
+// Everything between "inputs are in HBM" and "results are in HBM", on kf->stream.
+static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
+  cudaStream_t s = kf->stream;
+  const Lists& L = kf->lists;
+  const int wide = kf->sms * 8;
+  if (phases & DAALA_B200_KF_LISTS) {
+    k_unit_tile_sums<<<L.ntiles, kTile, 0, s>>>(L);
+    k_tile_scan<<<1, 1024, 0, s>>>(L);
+    k_unit_emit<<<L.ntiles, kTile, 0, s>>>(L);
+    k_luma_items<0><<<wide, 256, 0, s>>>(L);
+    k_hist_scan<<<3, 1024, 0, s>>>(L);
+    k_luma_items<1><<<wide, 256, 0, s>>>(L);
+    k_chroma_items<<<wide, 256, 0, s>>>(L);
+  }
+  if (phases & DAALA_B200_KF_FORWARD) {
+    int rc = daala_b200_launch_forward(&kf->frame, 3, s);
+    if (rc) return rc;
+  }
+  if (phases & DAALA_B200_KF_PVQ) {
+    const int persist = kf->sms * (kf->cfg.persist_ctas_per_sm > 0 ? kf->cfg.persist_ctas_per_sm : 5);
+    k_begin_pvq<<<1, 32, 0, s>>>(kf->lists.cnt);
+    k_gather<false><<<wide, 256, 0, s>>>(kf->luma);
+    k_pvq_persist<true><<<persist, 128, 0, s>>>(kf->luma);
+    k_finish_scatter<<<wide, 256, 0, s>>>(kf->luma);
+    k_cfl_plane<<<wide, 256, 0, s>>>(kf->chroma, kf->cfl_plane);
+    k_gather<true><<<wide, 256, 0, s>>>(kf->chroma);
+    k_pvq_persist<false><<<persist, 128, 0, s>>>(kf->chroma);
+    k_finish_scatter<<<wide, 256, 0, s>>>(kf->chroma);
+  }
+  if (phases & DAALA_B200_KF_INVERSE) {
+    int rc = daala_b200_launch_inverse(&kf->frame, 3, s);
+    if (rc) return rc;
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" {
+
+daala_b200_kf* daala_b200_kf_create(const daala_b200_kf_config* cfg) {
+  if (!cfg || cfg->pic_w <= 0 || cfg->pic_h <= 0 || cfg->nframes <= 0 || cfg->nframes > 255 || !cfg->qm ||
+      !cfg->qm_inv || cfg->qm_stride <= 0)
+    return nullptr;
+  daala_b200_kf* kf = (daala_b200_kf*)calloc(1, sizeof(daala_b200_kf));
+  if (!kf) return nullptr;
+  kf->cfg = *cfg;
+  kf->nhsb = (cfg->pic_w + 63) / 64;
+  kf->nvsb = (cfg->pic_h + 63) / 64;
+  kf->F = cfg->nframes;
+  if (kf->cfg.sb_rows <= 0) {
+    kf->cfg.sb_row0 = 0;
+    kf->cfg.sb_rows = kf->nvsb;
+  }
+  for (int p = 0; p < 3; p++) {
+    kf->plane_w[p] = (kf->nhsb * 64) >> (p ? 1 : 0);
+    kf->plane_h[p] = (kf->nvsb * 64) >> (p ? 1 : 0);
+  }
+  // coefficient offsets are 32-bit: the whole batch must stay below 2^31 coded coefficients
+  if ((long long)kf->plane_w[0] * kf->plane_h[0] * kf->F >= (1ll << 31)) {
+    free(kf);
+    return nullptr;
+  }
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    free(kf);
+    return nullptr;
+  }
+  kf->sms = prop.multiProcessorCount;
+  if (cfg->stream) {
+    kf->stream = (cudaStream_t)cfg->stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&kf->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      free(kf);
+      return nullptr;
+    }
+    kf->own_stream = true;
+  }
+  if (kf_alloc(kf) != 0) {
+    fprintf(stderr, "daala_b200_kf_create: %s\n", kf->err);
+    // leak-free teardown is the destroy function's job
+    daala_b200_kf_destroy(kf);
+    return nullptr;
+  }
+  return kf;
+}
+
+void daala_b200_kf_destroy(daala_b200_kf* kf) {
+  if (!kf) return;
+  cudaStreamSynchronize(kf->stream);
+  if (kf->exec) cudaGraphExecDestroy(kf->exec);
+  if (kf->graph) cudaGraphDestroy(kf->graph);
+  for (int p = 0; p < 3; p++) {
+    cudaFree(kf->pixels[p]);
+    cudaFree(kf->coeffs[p]);
+    cudaFree(kf->lapped[p]);
+    cudaFree(kf->pixels_out[p]);
+  }
+  cudaFree(kf->bsize);
+  cudaFree(kf->cfl_plane);
+  cudaFree(kf->qm);
+  cudaFree(kf->qm_inv);
+  Lists& L = kf->lists;
+  cudaFree(L.tile_sum);
+  cudaFree(L.unit_lbase);
+  cudaFree(L.luma);
+  cudaFree(L.chroma);
+  cudaFree(L.dep_top);
+  cudaFree(L.dep_left);
+  for (int c = 0; c < 3; c++) {
+    cudaFree(L.items_l[c]);
+    cudaFree(L.items_c[c]);
+  }
+  cudaFree(L.hist);
+  cudaFree(L.cnt);
+  for (Stage* S : {&kf->luma, &kf->chroma}) {
+    cudaFree(S->prm.in);
+    cudaFree(S->prm.ref);
+    cudaFree(S->prm.out);
+    cudaFree(S->prm.y);
+    cudaFree(S->prm.y16);
+    cudaFree(S->prm.res_skip_term);
+    cudaFree(S->prm.res_skip_diff);
+    cudaFree(S->prm.res_flip);
+    cudaFree(S->res_pack);
+    cudaFree(S->flags);
+  }
+  if (kf->own_stream) cudaStreamDestroy(kf->stream);
+  free(kf);
+}
+
+const char* daala_b200_kf_error(const daala_b200_kf* kf) { return kf ? kf->err : "null engine"; }
+
+int daala_b200_kf_device_buffers(daala_b200_kf* kf, daala_b200_kf_buffers* out) {
+  if (!kf || !out) return (int)cudaErrorInvalidValue;
+  memset(out, 0, sizeof(*out));
+  for (int p = 0; p < 3; p++) {
+    out->pixels[p] = kf->pixels[p];
+    out->coeffs[p] = kf->coeffs[p];
+    out->lapped[p] = kf->lapped[p];
+    out->pixels_out[p] = kf->pixels_out[p];
+    out->plane_w[p] = kf->plane_w[p];
+    out->plane_h[p] = kf->plane_h[p];
+  }
+  out->bsize = kf->bsize;
+  out->counts = kf->lists.cnt;
+  out->luma_blocks = kf->lists.luma;
+  out->chroma_blocks = kf->lists.chroma;
+  out->dep_top = kf->lists.dep_top;
+  out->dep_left = kf->lists.dep_left;
+  for (int c = 0; c < 3; c++) {
+    out->luma_items[c] = kf->lists.items_l[c];
+    out->chroma_items[c] = kf->lists.items_c[c];
+  }
+  out->luma_res = kf->luma.res_pack;
+  out->chroma_res = kf->chroma.res_pack;
+  out->luma_y16 = kf->luma.prm.y16;
+  out->chroma_y16 = kf->chroma.prm.y16;
+  out->luma_skip_diff = kf->luma.prm.res_skip_diff;
+  out->chroma_skip_diff = kf->chroma.prm.res_skip_diff;
+  out->chroma_flip = kf->chroma.prm.res_flip;
+  out->max_luma_blocks = kf->lists.max_luma;
+  out->max_chroma_blocks = kf->lists.max_chroma;
+  out->stream = kf->stream;
+  out->bytes_allocated = (long long)kf->bytes_allocated;
+  return 0;
+}
+
+int daala_b200_kf_run_device(daala_b200_kf* kf, int phases, int use_graph) {
+  if (!kf) return (int)cudaErrorInvalidValue;
+  if (!use_graph || phases != DAALA_B200_KF_ALL) return kf_enqueue_step(kf, phases);
+  if (!kf->captured) {
+    // warm-up outside the capture: module loading and the TMA descriptor encode are not capturable
+    int rc = kf_enqueue_step(kf, phases);
+    if (rc) return rc;
+    KF_CHECK(cudaStreamSynchronize(kf->stream));
+    KF_CHECK(cudaStreamBeginCapture(kf->stream, cudaStreamCaptureModeThreadLocal));
+    rc = kf_enqueue_step(kf, phases);
+    cudaError_t e = cudaStreamEndCapture(kf->stream, &kf->graph);
+    if (rc) return rc;
+    KF_CHECK(e);
+    KF_CHECK(cudaGraphInstantiate(&kf->exec, kf->graph, 0));
+    kf->captured = true;
+  }
+  KF_CHECK(cudaGraphLaunch(kf->exec, kf->stream));
+  return 0;
+}
+
+// Totals that follow from the block-size maps (what the host needs to size its result buffers):
+// the same leaf rule as unit_counts above, on the host.
+int daala_b200_kf_count_blocks(const uint8_t* bsize, int nframes, long long frame_pitch, int bstride, int nhsb,
+                               int nvsb, int sb_row0, int sb_rows, daala_b200_kf_totals* out) {
+  if (!bsize || !out) return (int)cudaErrorInvalidValue;
+  long long nl = 0, cl = 0, nc = 0, cc = 0;
+  if (sb_rows <= 0) { sb_row0 = 0; sb_rows = nvsb; }
+  for (int f = 0; f < nframes; f++) {
+    for (int uy = sb_row0 * 8; uy < (sb_row0 + sb_rows) * 8; uy++) {
+      const uint8_t* row = bsize + f * frame_pitch + (long long)uy * bstride;
+      for (int ux = 0; ux < nhsb * 8; ux++) {
+        const int b = row[ux];
+        if (b == 0) { nl += 4; cl += 64; nc += 1; cc += 16; continue; }
+        const int span = 1 << (b - 1);
+        if ((ux & (span - 1)) | (uy & (span - 1))) continue;
+        nl += 1;
+        cl += b == 1 ? 64 : b == 2 ? 256 : 512;
+        nc += 1;
+        cc += b == 1 ? 16 : b == 2 ? 64 : b == 3 ? 256 : 512;
+      }
+    }
+  }
+  out->n_luma = nl;
+  out->luma_coefs = cl;
+  out->n_chroma = 2 * nc;
+  out->chroma_coefs = 2 * cc;
+  return 0;
+}
+
+int daala_b200_kf_submit(daala_b200_kf* kf, const daala_b200_kf_io* io) {
+  if (!kf || !io) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = kf->stream;
+  const int F = kf->F;
+  for (int p = 0; p < 3; p++) {
+    if (!io->pixels[p]) return (int)cudaErrorInvalidValue;
+    KF_CHECK(cudaMemcpyAsync(kf->pixels[p], io->pixels[p], (size_t)kf->plane_w[p] * kf->plane_h[p] * F,
+                             cudaMemcpyHostToDevice, s));
+  }
+  const size_t map_bytes = (size_t)kf->nhsb * 8 * kf->nvsb * 8 * F;
+  KF_CHECK(cudaMemcpyAsync(kf->bsize, io->bsize, map_bytes, cudaMemcpyHostToDevice, s));
+  int rc = daala_b200_kf_run_device(kf, DAALA_B200_KF_ALL, 1);
+  if (rc) return rc;
+  daala_b200_kf_totals tot;
+  if (io->totals) tot = *io->totals;
+  else daala_b200_kf_count_blocks(io->bsize, F, (long long)kf->nhsb * 8 * kf->nvsb * 8, kf->nhsb * 8, kf->nhsb, kf->nvsb,
+                                  kf->cfg.sb_row0, kf->cfg.sb_rows, &tot);
+  if (tot.n_luma > kf->lists.max_luma || tot.n_chroma > kf->lists.max_chroma) return (int)cudaErrorInvalidValue;
+  for (int p = 0; p < 3; p++)
+    if (io->pixels_out[p])
+      KF_CHECK(cudaMemcpyAsync(io->pixels_out[p], kf->pixels_out[p], (size_t)kf->plane_w[p] * kf->plane_h[p] * F,
+                               cudaMemcpyDeviceToHost, s));
+  if (io->luma_blocks) KF_CHECK(cudaMemcpyAsync(io->luma_blocks, kf->lists.luma, sizeof(daala_b200_pvq_block) * tot.n_luma, cudaMemcpyDeviceToHost, s));
+  if (io->chroma_blocks) KF_CHECK(cudaMemcpyAsync(io->chroma_blocks, kf->lists.chroma, sizeof(daala_b200_pvq_block) * tot.n_chroma, cudaMemcpyDeviceToHost, s));
+  if (io->luma_res) KF_CHECK(cudaMemcpyAsync(io->luma_res, kf->luma.res_pack, 8 * 9 * (size_t)tot.n_luma, cudaMemcpyDeviceToHost, s));
+  if (io->chroma_res) KF_CHECK(cudaMemcpyAsync(io->chroma_res, kf->chroma.res_pack, 8 * 9 * (size_t)tot.n_chroma, cudaMemcpyDeviceToHost, s));
+  if (io->luma_y16) KF_CHECK(cudaMemcpyAsync(io->luma_y16, kf->luma.prm.y16, 2 * (size_t)tot.luma_coefs, cudaMemcpyDeviceToHost, s));
+  if (io->chroma_y16) KF_CHECK(cudaMemcpyAsync(io->chroma_y16, kf->chroma.prm.y16, 2 * (size_t)tot.chroma_coefs, cudaMemcpyDeviceToHost, s));
+  if (io->luma_skip_diff) KF_CHECK(cudaMemcpyAsync(io->luma_skip_diff, kf->luma.prm.res_skip_diff, 8 * (size_t)tot.n_luma, cudaMemcpyDeviceToHost, s));
+  if (io->chroma_skip_diff) KF_CHECK(cudaMemcpyAsync(io->chroma_skip_diff, kf->chroma.prm.res_skip_diff, 8 * (size_t)tot.n_chroma, cudaMemcpyDeviceToHost, s));
+  if (io->chroma_flip) KF_CHECK(cudaMemcpyAsync(io->chroma_flip, kf->chroma.prm.res_flip, 4 * (size_t)tot.n_chroma, cudaMemcpyDeviceToHost, s));
+  if (io->counts) KF_CHECK(cudaMemcpyAsync(io->counts, kf->lists.cnt, sizeof(int32_t) * kCntWords, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+int daala_b200_kf_wait(daala_b200_kf* kf) {
+  if (!kf) return (int)cudaErrorInvalidValue;
+  KF_CHECK(cudaStreamSynchronize(kf->stream));
+  return 0;
+}
+
+int daala_b200_kf_encode(daala_b200_kf* kf, const daala_b200_kf_io* io) {
+  int rc = daala_b200_kf_submit(kf, io);
+  if (rc) return rc;
+  return daala_b200_kf_wait(kf);
+}
+
+// Synchronous copy helper for tests / device-resident callers without a CUDA binding of their own:
+// kind 0 = host -> device, 1 = device -> host, 2 = device -> device.
+int daala_b200_device_copy(void* dst, const void* src, size_t bytes, int kind) {
+  const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  cudaError_t e = cudaMemcpy(dst, src, bytes, k);
+  return (int)e;
+}
+
+void* daala_b200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void daala_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -24,21 +24,13 @@
 #include "gen/coding_order.inc"
 #include "pvq_math.cuh"
 #include "pvq_coop.cuh"
+#include "pvq_common.cuh"
 
 namespace daala_b200 {
 namespace pvq {
 
 constexpr int kSkipZero = 1;
 constexpr int kSkipCopy = 2;
-
-// Band boundaries in coding order (OD_BAND_OFFSETS, src/partition.c:85-91).
-__device__ __forceinline__ int band_start(int band) {
-  // 1,16,24,32,64,96,128,256,384,512
-  const int t[10] = {1, 16, 24, 32, 64, 96, 128, 256, 384, 512};
-  return t[band];
-}
-
-__device__ __forceinline__ int num_bands(int bs) { return bs == 0 ? 1 : bs == 1 ? 4 : bs == 2 ? 7 : 9; }
 
 __device__ __forceinline__ double rsqrt_small(int i) { return rsqrt_small_tbl(i); }
 
@@ -667,17 +659,6 @@ __global__ void k_cfl_flip(const __grid_constant__ daala_b200_pvq_params prm, in
 // Raster (block inside a coefficient plane) -> coding order, one warp per block.
 // Only the coded prefix is produced: n^2 for n <= 16, 512 for 32 and 64
 // (OD_LAYOUT32/64 in src/partition.c:40-55 cover nothing beyond it).
-__device__ __forceinline__ int scan_to_raster(int i, int ln, int stride) {
-  // i in [1, coded length)
-  int v, n;
-  if (i < 16) { v = kScan4[i - 1]; n = 2; }
-  else if (i < 64) { v = kScan8[i - 16]; n = 3; }
-  else if (i < 256) { v = kScan16[i - 64]; n = 4; }
-  else { v = kScan32[i - 256]; n = 5; }
-  (void)ln;
-  return (v >> n) * stride + (v & ((1 << n) - 1));
-}
-
 __global__ void k_coding_order_gather(const __grid_constant__ daala_b200_pvq_params prm, int nblocks,
                                       int which /*0: in <- coeffs, 1: ref <- pred*/) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -748,15 +729,6 @@ __global__ void k_coding_order_scatter(const __grid_constant__ daala_b200_pvq_pa
 // never waits on a later one (CTAs are dispatched in index order), hence no
 // deadlock.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 __global__ void __launch_bounds__(128)
 k_pvq_luma_intra(const __grid_constant__ daala_b200_pvq_params prm, const int32_t* __restrict__ ids,
                  const int32_t* __restrict__ dep_top, const int32_t* __restrict__ dep_left, int* done, int epoch,

@@ -24,6 +24,7 @@
 #ifndef DAALA_B200_H
 #define DAALA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -388,6 +389,101 @@ daala_b200_keyframe_lists *daala_b200_host_keyframe_lists(const uint8_t *bsize, 
                                                           long long bsize_frame_pitch, int bstride, int nhsb,
                                                           int nvsb, int nthreads);
 void daala_b200_host_keyframe_lists_free(daala_b200_keyframe_lists *lists);
+
+/* ---- Keyframe engine: the whole hot path of a batch of keyframes, host buffers in / out --------- */
+
+/* The batched, GPU-resident equivalent of od_encode_coefficients (reference src/encode.c:2539) for
+   keyframes, minus the serial entropy coder: per frame u8 planes + the block-size map state->bsize in,
+   reconstruction + PVQ symbols out.  Inside (csrc/kf_engine.cu): work lists built on the device from
+   the block-size maps EVERY step (leaf descriptors by prefix scan, od_hv_intra_pred neighbours,
+   dependency-ordered band items), fused lapped prefilter + fDCT, luma PVQ with H/V intra prediction as
+   one persistent kernel with per-band acquire / release flags, chroma CfL + PVQ, iDCT + postfilters;
+   one CUDA graph per engine.  Two engines give a double-buffered pipeline (submit one, wait for the
+   other). */
+typedef struct daala_b200_kf daala_b200_kf;
+
+typedef struct daala_b200_kf_config {
+  int pic_w, pic_h;            /* luma picture size; frames are padded to whole 64x64 superblocks */
+  int nframes;                 /* frames per batch (1..255), independent keyframes of one geometry */
+  int q0;                      /* state->quantizer */
+  int use_masking;             /* activity masking (OD_PVQ_BETA, src/pvq.c:205) */
+  int qm_stride;               /* OD_QM_STRIDE = 5456 */
+  double pvq_norm_lambda;      /* enc->pvq_norm_lambda */
+  uint8_t pvq_qm_q4[3][32];    /* state->pvq_qm_q4 */
+  const int16_t *qm, *qm_inv;  /* HOST: state->qm / qm_inv, 2*qm_stride entries each (copied) */
+  int sb_row0, sb_rows;        /* superblock rows of this rank's shard (sb_rows <= 0: whole frames) */
+  int max_blocks_div;          /* 0/1: capacity for all-4x4 maps; d > 1: 1/d of that (saves HBM) */
+  int persist_ctas_per_sm;     /* 0 = default (5) */
+  void *stream;                /* cudaStream_t to run on, or NULL: the engine creates its own */
+} daala_b200_kf_config;
+
+typedef struct daala_b200_kf_totals {
+  long long n_luma, luma_coefs, n_chroma, chroma_coefs;
+} daala_b200_kf_totals;
+
+/* Host buffers of one batch.  Inputs: padded planes [nframes][plane_h][plane_w] u8 and block-size
+   maps [nframes][nvsb*8][nhsb*8] (one byte per 8x8 luma unit = log2(size) - 2).  Outputs (each may be
+   NULL = not copied back): reconstruction planes; block descriptors in scan order of the 8x8 units
+   (frame, row, column; the four 4x4 blocks of a unit in raster order; chroma: plane 1 then plane 2 per
+   unit); per block 9 band records {coded gain index (pvq_theta's return value), itheta, max_theta, K}
+   as int16[4]; the pulse vectors in coding order (16 bit) at each block's coef_off; per block
+   skip_diff; per chroma block the CfL flip flag.  Sized by daala_b200_kf_count_blocks.  Pinned memory
+   (daala_b200_host_alloc) makes the copies asynchronous. */
+typedef struct daala_b200_kf_io {
+  const uint8_t *pixels[3];
+  const uint8_t *bsize;
+  const daala_b200_kf_totals *totals;   /* optional: result of _count_blocks for `bsize` */
+  uint8_t *pixels_out[3];
+  daala_b200_pvq_block *luma_blocks, *chroma_blocks;
+  int16_t *luma_res, *chroma_res;       /* [n_blocks][9][4] */
+  int16_t *luma_y16, *chroma_y16;       /* [coefs] */
+  double *luma_skip_diff, *chroma_skip_diff;
+  int32_t *chroma_flip;
+  int32_t *counts;                      /* 32 ints of device-side counters (diagnostics) */
+} daala_b200_kf_io;
+
+typedef struct daala_b200_kf_buffers {  /* device pointers of an engine (tests, device-resident callers) */
+  uint8_t *pixels[3];
+  int32_t *coeffs[3];
+  int32_t *lapped[3];
+  uint8_t *pixels_out[3];
+  int plane_w[3], plane_h[3];
+  uint8_t *bsize;
+  int32_t *counts;
+  daala_b200_pvq_block *luma_blocks, *chroma_blocks;
+  int32_t *dep_top, *dep_left;
+  uint32_t *luma_items[3], *chroma_items[3];
+  int16_t *luma_res, *chroma_res, *luma_y16, *chroma_y16;
+  double *luma_skip_diff, *chroma_skip_diff;
+  int32_t *chroma_flip;
+  int max_luma_blocks, max_chroma_blocks;
+  void *stream;
+  long long bytes_allocated;
+} daala_b200_kf_buffers;
+
+#define DAALA_B200_KF_LISTS 1
+#define DAALA_B200_KF_FORWARD 2
+#define DAALA_B200_KF_PVQ 4
+#define DAALA_B200_KF_INVERSE 8
+#define DAALA_B200_KF_ALL 15
+
+daala_b200_kf *daala_b200_kf_create(const daala_b200_kf_config *cfg);   /* NULL on failure */
+void daala_b200_kf_destroy(daala_b200_kf *kf);
+const char *daala_b200_kf_error(const daala_b200_kf *kf);
+int daala_b200_kf_device_buffers(daala_b200_kf *kf, daala_b200_kf_buffers *out);
+/* Runs the selected phases on the engine's stream with inputs already in HBM (asynchronous);
+   use_graph: replay the captured CUDA graph (DAALA_B200_KF_ALL only). */
+int daala_b200_kf_run_device(daala_b200_kf *kf, int phases, int use_graph);
+/* Host-side totals implied by block-size maps (sizes of the result arrays). */
+int daala_b200_kf_count_blocks(const uint8_t *bsize, int nframes, long long frame_pitch, int bstride, int nhsb,
+                               int nvsb, int sb_row0, int sb_rows, daala_b200_kf_totals *out);
+/* H2D of the inputs, the whole step, D2H of the requested outputs: enqueued, not waited for. */
+int daala_b200_kf_submit(daala_b200_kf *kf, const daala_b200_kf_io *io);
+int daala_b200_kf_wait(daala_b200_kf *kf);
+int daala_b200_kf_encode(daala_b200_kf *kf, const daala_b200_kf_io *io);   /* submit + wait */
+int daala_b200_device_copy(void *dst, const void *src, size_t bytes, int kind);  /* 0 H2D, 1 D2H, 2 D2D; synchronous */
+void *daala_b200_host_alloc(size_t bytes);   /* pinned host memory */
+void daala_b200_host_free(void *p);
 
 /* ---- Motion compensation / block matching (8-bit references) ------------- */
 

@@ -62,3 +62,36 @@ def pvq_plane_pred(lib, prefix, d, geom, pli, bsize, q0, use_masking, lam, qm, q
        int(use_masking), ctypes.c_double(lam), addr(np.ascontiguousarray(qm)), addr(np.ascontiguousarray(qm_inv)),
        addr(q4), addr(stats), 1 if pli == 0 else 0, lp)
     return d, stats
+
+
+def keyframe_chain(lib, prefix, planes, geom, bsize, q0, qm_q4, use_masking=1, lam=0.147, qm=None, qm_inv=None,
+                   record=True):
+    """One keyframe through the oracle's whole chain (forward -> PVQ with luma H/V intra prediction and
+    chroma CfL -> inverse).  Returns per plane a dict: dq (quantised coefficient plane), recon (u8),
+    stats, and with record=True rec ([h/4, w/4, 9, 4] int16 band decisions at each block's origin,
+    -32768 where no band) and yplane (pulse vectors in raster order)."""
+    from daala_b200 import pvq
+    if qm is None:
+        qm, qm_inv = pvq.default_qm(True)
+    out = []
+    luma_q = None
+    for pli in range(3):
+        ph, pw = geom.plane_shape(pli)
+        d = forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
+        d = np.ascontiguousarray(d, dtype=np.int32).copy()
+        bs = np.ascontiguousarray(bsize, dtype=np.uint8)
+        stats = np.zeros(5, np.float64)
+        q4 = np.ascontiguousarray(qm_q4[pli], dtype=np.uint8)
+        rec = np.full((ph // 4, pw // 4, 9, 4), -32768, np.int16) if record else None
+        yplane = np.zeros((ph, pw), np.int32) if record else None
+        lp = addr(np.ascontiguousarray(luma_q, dtype=np.int32)) if pli else None
+        fn = getattr(lib, "oracle_%s_pvq_plane_rec" % prefix)
+        fn(addr(d), None, geom.nhsb, geom.nvsb, geom.xdec[pli], pli, addr(bs), bs.shape[1], int(q0), 1,
+           int(use_masking), ctypes.c_double(lam), addr(np.ascontiguousarray(qm)),
+           addr(np.ascontiguousarray(qm_inv)), addr(q4), addr(stats), 1 if pli == 0 else 0, lp,
+           addr(rec) if record else None, addr(yplane) if record else None)
+        if pli == 0:
+            luma_q = d
+        recon = inverse_plane(lib, prefix, d, geom, pli, bsize, 1)
+        out.append(dict(dq=d, recon=recon, stats=stats, rec=rec, yplane=yplane))
+    return out

@@ -1,15 +1,13 @@
 """HotPath with the work lists built on the device (daala_b200/lists_torch.py) against the numpy-built
 lists: identical planes.  The tensor-op construction is verified on CPU tensors
 (tests/test_host_logic.py); its CUDA execution has not been exercised yet (round 1 ran out of GPU
-budget), so this test is skipped unless DAALA_B200_UNVERIFIED=1."""
+budget), first ran on a B200 in round 2."""
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DAALA_B200_UNVERIFIED") != "1",
-                                 reason="device-side list construction not yet run on a GPU (set DAALA_B200_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_device_built_lists_give_the_same_planes():

@@ -2,7 +2,7 @@
 (oracle/port_dist.c, bit-identical to od_compute_dist by tests/test_oracle_dering.py).
 
 The kernel was written after round 1's GPU budget was spent and has not run on a device yet: the test
-is skipped unless DAALA_B200_UNVERIFIED=1 (first GPU call of the next round)."""
+first ran on a B200 in round 2."""
 import ctypes
 import os
 
@@ -12,9 +12,7 @@ import pytest
 from tests import oracle_lib
 from tests.oracle_lib import addr
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DAALA_B200_UNVERIFIED") != "1",
-                                 reason="distortion kernel not yet run on a GPU (set DAALA_B200_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("n", [8, 16, 32, 64])

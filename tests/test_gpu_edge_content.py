@@ -1,6 +1,6 @@
 """Edge-case pictures (flat-128, pure noise; plus saturated black / white) through the
 device keyframe chain against the oracle.  Added after round 1's GPU budget was spent: same kernels as
-the verified tests, new inputs -- skipped unless DAALA_B200_UNVERIFIED=1 until it has run once."""
+the verified tests, new inputs. First run on a B200 in round 2."""
 import os
 
 import numpy as np
@@ -8,9 +8,7 @@ import pytest
 
 from tests import frame_oracle, oracle_lib
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DAALA_B200_UNVERIFIED") != "1",
-                                 reason="not yet run on a GPU (set DAALA_B200_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("content", ["flat128", "noise", "black", "white"])

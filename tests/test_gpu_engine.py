@@ -1,0 +1,219 @@
+"""The keyframe engine (csrc/kf_engine.cu) through its host-buffer C ABI against the oracle: device-side
+work lists, persistent intra wavefront, chroma CfL, reconstruction and every per-band decision."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import frame_oracle, oracle_lib
+
+pytestmark = [pytest.mark.gpu]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle():
+    ref = oracle_lib.load_ref()
+    return (ref, "ref") if ref is not None else (oracle_lib.load_port(), "port")
+
+
+def _coding_tables():
+    """Per block size: (rows, cols) of the coded prefix in coding order."""
+    from daala_b200 import pvq
+    inp = pvq.qm_inputs()
+    scans = {m: inp["scan%d" % m].astype(np.int64) for m in (4, 8, 16, 32, 64)}
+    tabs = {}
+    for bs in range(5):
+        n = 4 << bs
+        idx = np.arange(n * n).reshape(n, n)
+        order = pvq.raster_to_coding_order(idx, scans)[:min(n * n, 512)]
+        tabs[bs] = (order // n, order % n)
+    return tabs
+
+
+def _y_plane(blocks, y16, geom, pli, frame, tabs):
+    h, w = geom.plane_shape(pli)
+    out = np.zeros((h, w), np.int32)
+    sel = np.nonzero((blocks["pli"] == pli) & (blocks["frame"] == frame))[0]
+    for bs in range(5):
+        ids = sel[blocks["bs"][sel] == bs]
+        if not len(ids):
+            continue
+        r, c = tabs[bs]
+        off = blocks["coef_off"][ids].astype(np.int64)[:, None] + np.arange(len(r))[None, :]
+        rows = blocks["y0"][ids].astype(np.int64)[:, None] + r[None, :]
+        cols = blocks["x0"][ids].astype(np.int64)[:, None] + c[None, :]
+        out[rows, cols] = y16[off]
+    return out
+
+
+def _check_batch(eng, geom, frames, q0, q4, use_masking=1, planes_checked=(0, 1, 2)):
+    """frames: list of (padded planes, bsize).  Runs the engine end to end and compares everything."""
+    from daala_b200 import engine
+    lib, prefix = _oracle()
+    F = len(frames)
+    planes = [np.stack([f[0][p] for f in frames]) for p in range(3)]
+    bsize = np.stack([f[1] for f in frames])
+    out = eng.encode(planes, bsize)
+    tabs = _coding_tables()
+    for f in range(F):
+        want = frame_oracle.keyframe_chain(lib, prefix, frames[f][0], geom, frames[f][1], q0, q4, use_masking)
+        for pli in planes_checked:
+            assert np.array_equal(out["recon%d" % pli][f], want[pli]["recon"]), ("recon", f, pli)
+            blocks = out["luma_blocks"] if pli == 0 else out["chroma_blocks"]
+            res = out["luma_res"] if pli == 0 else out["chroma_res"]
+            y16 = out["luma_y16"] if pli == 0 else out["chroma_y16"]
+            got = engine.band_records(blocks, res, geom, pli, f)
+            bad = np.argwhere(got != want[pli]["rec"])
+            assert len(bad) == 0, ("band decisions", f, pli, len(bad), bad[:5], got[tuple(bad[0][:3])], want[pli]["rec"][tuple(bad[0][:3])])
+            assert np.array_equal(_y_plane(blocks, y16, geom, pli, f, tabs), want[pli]["yplane"]), ("pulses", f, pli)
+        dq = [eng.coeff_plane(p)[f] for p in range(3)]
+        for pli in planes_checked:
+            assert np.array_equal(dq[pli], want[pli]["dq"]), ("quantised plane", f, pli)
+    return out
+
+
+def _frames(geom, n, q_seed=0, mode="mixed", pic=None):
+    from daala_b200 import synth
+    frames = []
+    seed = 12345 + q_seed
+    for f in range(n):
+        planes, seed = synth.frame(geom.pic_w, geom.pic_h, f=f, seed=seed)
+        frames.append((synth.pad_planes(planes, geom), synth.block_size_map(geom, mode, seed=50 + f + q_seed)))
+    return frames
+
+
+def test_engine_lists_are_consistent():
+    """Descriptors partition the coding-order buffers; neighbours are the same-size top / left blocks;
+    the item lists hold every (block, band) once, in an order in which dependencies come first."""
+    from daala_b200 import engine
+    from daala_b200.frame import Geometry
+    geom = Geometry(328, 200)
+    frames = _frames(geom, 3)
+    eng = engine.KeyframeEngine(geom, nframes=3, q0=40)
+    eng.upload([np.stack([f[0][p] for f in frames]) for p in range(3)], np.stack([f[1] for f in frames]))
+    eng.run_device(engine.PH_LISTS, graph=False)
+    cnt = eng.counts()
+    tot = eng.count_blocks(np.stack([f[1] for f in frames]))
+    assert cnt[0] == tot.n_luma and cnt[1] == tot.n_chroma and cnt[2] == tot.luma_coefs and cnt[3] == tot.chroma_coefs
+    from daala_b200 import pvq
+    nl = int(cnt[0])
+    luma = eng.download(eng.buf.luma_blocks, (nl,), pvq.BLOCK_DTYPE)
+    top = eng.download(eng.buf.dep_top, (nl,), np.int32)
+    left = eng.download(eng.buf.dep_left, (nl,), np.int32)
+    # same set of blocks as the numpy builder
+    want = np.concatenate([pvq.block_list(frames[f][1], geom, frame=f) for f in range(3)])
+    key = lambda b: (b["frame"].astype(np.int64) << 40) | (b["pli"].astype(np.int64) << 36) | (b["y0"].astype(np.int64) << 18) | b["x0"]  # noqa: E731
+    wl = want[want["pli"] == 0]
+    assert np.array_equal(np.sort(key(luma)), np.sort(key(wl)))
+    o1, o2 = np.argsort(key(luma)), np.argsort(key(wl))
+    assert np.array_equal(luma["bs"][o1], wl["bs"][o2])
+    # coefficient ranges tile [0, total)
+    length = np.minimum(16 << (2 * luma["bs"].astype(np.int64)), 512)
+    o = np.argsort(luma["coef_off"])
+    assert luma["coef_off"][o][0] == 0 and np.array_equal(luma["coef_off"][o][1:], np.cumsum(length[o])[:-1])
+    # neighbours
+    maps = np.stack([f[1] for f in frames])
+    index = {}
+    for i, b in enumerate(luma):
+        index[(int(b["frame"]), int(b["y0"]), int(b["x0"]))] = i
+    for i, b in enumerate(luma):
+        n = 4 << int(b["bs"])
+        f, y0, x0 = int(b["frame"]), int(b["y0"]), int(b["x0"])
+        et = index[(f, y0 - n, x0)] if y0 > 0 and maps[f, (y0 - 1) >> 3, x0 >> 3] == b["bs"] else -1
+        el = index[(f, y0, x0 - n)] if x0 > 0 and maps[f, y0 >> 3, (x0 - 1) >> 3] == b["bs"] else -1
+        assert (top[i], left[i]) == (et, el), (i, b, top[i], left[i], et, el)
+    # chroma descriptors
+    nc = int(cnt[1])
+    chroma = eng.download(eng.buf.chroma_blocks, (nc,), pvq.BLOCK_DTYPE)
+    wc = pvq.mark_luma4x4(want[want["pli"] != 0].copy(), [f[1] for f in frames])
+    assert np.array_equal(np.sort(key(chroma)), np.sort(key(wc)))
+    o1, o2 = np.argsort(key(chroma)), np.argsort(key(wc))
+    assert np.array_equal(chroma["bs"][o1], wc["bs"][o2]) and np.array_equal(chroma["xdec"][o1], wc["xdec"][o2])
+    # items
+    nbands = np.array([1, 4, 7, 9, 9])
+    for c in range(3):
+        n = int(cnt[4 + c])
+        items = eng.download(eng.buf.luma_items[c], (n,), np.uint32)
+        blk, band = (items >> 4).astype(np.int64), (items & 15).astype(np.int64)
+        assert (band // 3 == c).all() and (band < nbands[luma["bs"][blk]]).all()
+        assert len(np.unique(items)) == n == int((np.clip(nbands[luma["bs"]] - 3 * c, 0, 3)).sum())
+        pos = {int(e): i for i, e in enumerate(items)}
+        for i, (b, bd) in enumerate(zip(blk, band)):
+            r = bd % 3
+            if bd in (3, 6):
+                continue
+            if (bd == 0 or r == 1) and top[b] >= 0:
+                assert pos[(int(top[b]) << 4) | int(bd)] < i
+            if (bd == 0 or r == 2) and left[b] >= 0:
+                assert pos[(int(left[b]) << 4) | int(bd)] < i
+        n = int(cnt[7 + c])
+        items = eng.download(eng.buf.chroma_items[c], (n,), np.uint32)
+        assert len(np.unique(items)) == n == int((np.clip(nbands[chroma["bs"]] - 3 * c, 0, 3)).sum())
+    eng.close()
+
+
+@pytest.mark.parametrize("size,q0,nf", [((200, 130), 45, 1), ((384, 256), 38, 2), ((328, 200), 72, 3)])
+def test_engine_keyframe_chain_matches_oracle(size, q0, nf):
+    from daala_b200 import engine
+    from daala_b200.frame import Geometry
+    geom = Geometry(*size)
+    q4 = np.full((3, 30), 16 if q0 != 45 else 20, np.uint8)
+    eng = engine.KeyframeEngine(geom, nframes=nf, q0=q0, pvq_qm_q4=q4)
+    frames = _frames(geom, nf)
+    _check_batch(eng, geom, frames, q0, q4)
+    # block sizes change every step: second batch with different maps and content on the same engine
+    frames = _frames(geom, nf, q_seed=7)
+    _check_batch(eng, geom, frames, q0, q4)
+    eng.close()
+
+
+@pytest.mark.parametrize("mode", ["4", "8", "16", "32", "64"])
+def test_engine_uniform_block_sizes(mode):
+    from daala_b200 import engine
+    from daala_b200.frame import Geometry
+    geom = Geometry(256, 192)
+    q4 = np.full((3, 30), 16, np.uint8)
+    eng = engine.KeyframeEngine(geom, nframes=1, q0=50, pvq_qm_q4=q4)
+    _check_batch(eng, geom, _frames(geom, 1, mode=mode), 50, q4)
+    eng.close()
+
+
+@pytest.mark.parametrize("content", ["flat128", "noise", "black", "white"])
+def test_engine_edge_content(content):
+    from daala_b200 import engine, synth
+    from daala_b200.frame import Geometry
+    geom = Geometry(200, 136)
+    rng = np.random.default_rng(3)
+    planes = []
+    for pli in range(3):
+        h, w = (136, 200) if pli == 0 else (68, 100)
+        value = {"flat128": 128, "black": 0, "white": 255}.get(content)
+        planes.append(np.full((h, w), value, np.uint8) if value is not None
+                      else rng.integers(0, 256, size=(h, w), dtype=np.uint8))
+    planes = synth.pad_planes(planes, geom)
+    bsize = synth.block_size_map(geom, "mixed", seed=8)
+    q4 = np.full((3, 30), 16, np.uint8)
+    eng = engine.KeyframeEngine(geom, nframes=1, q0=30, pvq_qm_q4=q4)
+    _check_batch(eng, geom, [(planes, bsize)], 30, q4)
+    eng.close()
+
+
+@pytest.mark.parametrize("size,maps", [((1920, 1080), "synthetic"), ((3840, 2160), "synthetic"),
+                                       ((3840, 2160), "reference")])
+def test_engine_baseline_sizes_q72_match_oracle(size, maps):
+    """BASELINE.json's configurations at the bench's quantiser (q0 = 72): whole keyframe chain, every
+    per-band index, against the reference build."""
+    from daala_b200 import engine, synth
+    from daala_b200.frame import Geometry
+    geom = Geometry(*size)
+    q4 = np.full((3, 30), 16, np.uint8)
+    planes, _ = synth.frame(geom.pic_w, geom.pic_h, f=1, seed=4242)
+    planes = synth.pad_planes(planes, geom)
+    if maps == "reference":
+        real = np.load(os.path.join(ROOT, "daala_b200", "data", "bench_bsize_4k.npz"))
+        bsize = np.ascontiguousarray(real["bsize_1"])
+    else:
+        bsize = synth.block_size_map(geom, "mixed", seed=101)
+    eng = engine.KeyframeEngine(geom, nframes=1, q0=72, pvq_qm_q4=q4)
+    _check_batch(eng, geom, [(planes, bsize)], 72, q4)
+    eng.close()
