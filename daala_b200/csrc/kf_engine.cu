@@ -261,17 +261,28 @@ __global__ void __launch_bounds__(256) k_luma_items(const __grid_constant__ List
   }
 }
 
-// 3 CTAs: exclusive scan of each class's histogram in place; totals into cnt.
+// Items one warp of the persistent kernel takes per ticket, by class (32 / lanes per band).
+__host__ __device__ constexpr int items_per_warp(int cls) { return cls == 0 ? 8 : cls == 1 ? 4 : 1; }
+constexpr uint32_t kNoItem = 0xffffffffu;
+
+// 3 CTAs: exclusive scan of each class's histogram in place; totals into cnt.  Every key bin is
+// padded to a whole number of warp chunks (pad entries = kNoItem): the items one warp processes
+// together then all share one key, so none of them depends on another one of the same warp (a warp
+// waiting on itself would never finish).
 __global__ void __launch_bounds__(1024) k_hist_scan(const __grid_constant__ Lists L) {
   __shared__ int part[1024];
   constexpr int kPer = kKeyBins / 1024;
-  int* hist = L.hist + blockIdx.x * kKeyBins;
+  const int cls = blockIdx.x;
+  const int P = items_per_warp(cls);
+  int* hist = L.hist + cls * kKeyBins;
+  uint32_t* items = L.items_l[cls];
   const int t = threadIdx.x;
-  int v[kPer], sum = 0;
+  int v[kPer], pv[kPer], sum = 0;
 #pragma unroll
   for (int i = 0; i < kPer; i++) {
     v[i] = hist[t * kPer + i];
-    sum += v[i];
+    pv[i] = (v[i] + P - 1) / P * P;
+    sum += pv[i];
   }
   part[t] = sum;
   __syncthreads();
@@ -285,9 +296,10 @@ __global__ void __launch_bounds__(1024) k_hist_scan(const __grid_constant__ List
 #pragma unroll
   for (int i = 0; i < kPer; i++) {
     hist[t * kPer + i] = run;
-    run += v[i];
+    for (int j = v[i]; j < pv[i]; j++) items[run + j] = kNoItem;
+    run += pv[i];
   }
-  if (t == 1023) L.cnt[kNItemsL + blockIdx.x] = part[1023];
+  if (t == 1023) L.cnt[kNItemsL + cls] = part[1023];
 }
 
 // Chroma items: no dependencies between blocks; compaction per class (order is free).
@@ -432,19 +444,19 @@ __device__ __forceinline__ void run_items(const Stage& S, int cls, int epoch) {
     const int base = t * kPerWarp;
     if (base >= n) return;
     const int idx = base + lane / G;
-    const bool valid = idx < n;
-    const uint32_t e = items[valid ? idx : n - 1];
-    const int blk = (int)(e >> 4), band = (int)(e & 15);
+    const uint32_t e = idx < n ? items[idx] : kNoItem;
+    const bool valid = e != kNoItem;
+    const int blk = valid ? (int)(e >> 4) : 0, band = valid ? (int)(e & 15) : 3;
     const daala_b200_pvq_block b = prm.blocks[blk];
     const int bs = b.bs, pli = b.pli;
     const int start = band_start(band);
     const int bn = band_start(band + 1) - start;
     const size_t off = (size_t)b.coef_off + start;
-    int top = -1, left = -1;
     if (kIntra) {
+      int top = -1, left = -1;
       const int r = band % 3;
-      if (band == 0 || r == 1) top = S.dep_top[blk];
-      if (band == 0 || r == 2) left = S.dep_left[blk];
+      if (valid && (band == 0 || r == 1)) top = S.dep_top[blk];
+      if (valid && (band == 0 || r == 2)) left = S.dep_left[blk];
       if (band == 3 || band == 6) top = left = -1;
       // every lane polls its own group's flags; the warp leaves together
       const int* ft = top >= 0 ? S.flags + (size_t)top * 9 + band : nullptr;
@@ -454,45 +466,49 @@ __device__ __forceinline__ void run_items(const Stage& S, int cls, int epoch) {
         if (__all_sync(0xffffffffu, ready)) break;
         __nanosleep(200);
       }
-      const int32_t* ot = top >= 0 ? prm.out + prm.blocks[top].coef_off : nullptr;
-      const int32_t* ol = left >= 0 ? prm.out + prm.blocks[left].coef_off : nullptr;
-      bool low_from_top = false;
-      if (band == 0) {
-        // coding-order indices of (0,1) (0,2) (0,3) and (1,0) (2,0) (3,0) in the 4x4 stage; double
-        // sums of exact integers as in od_hv_intra_pred (src/intra.c:51-52)
-        double g1 = 0, g2 = 0;
-        if (ot) { double a = ot[2], bb = ot[5], c = ot[9]; g1 += a * a; g1 += bb * bb; g1 += c * c; }
-        if (ol) { double a = ol[1], bb = ol[4], c = ol[7]; g2 += a * a; g2 += bb * bb; g2 += c * c; }
-        low_from_top = g1 > g2;
-      }
-      int32_t* vref = prm.ref + b.coef_off;
-      // element j of the band is owned by lane j % G: the lane that writes ref[j] is the one that reads it
-      for (int i = start + grp.lane; i < start + bn; i += G) {
-        int r2, c2;
-        scan_rc(i, &r2, &c2);
-        int32_t p = 0;
-        if (r2 == 0 && c2 > 0 && ot && (c2 >= 4 || low_from_top)) p = ot[i];
-        if (c2 == 0 && r2 > 0 && ol && (r2 >= 4 || !low_from_top)) p = ol[i];
-        vref[i] = p;
+      if (valid) {
+        const int32_t* ot = top >= 0 ? prm.out + prm.blocks[top].coef_off : nullptr;
+        const int32_t* ol = left >= 0 ? prm.out + prm.blocks[left].coef_off : nullptr;
+        bool low_from_top = false;
+        if (band == 0) {
+          // coding-order indices of (0,1) (0,2) (0,3) and (1,0) (2,0) (3,0) in the 4x4 stage; double
+          // sums of exact integers as in od_hv_intra_pred (src/intra.c:51-52)
+          double g1 = 0, g2 = 0;
+          if (ot) { double a = ot[2], bb = ot[5], c = ot[9]; g1 += a * a; g1 += bb * bb; g1 += c * c; }
+          if (ol) { double a = ol[1], bb = ol[4], c = ol[7]; g2 += a * a; g2 += bb * bb; g2 += c * c; }
+          low_from_top = g1 > g2;
+        }
+        int32_t* vref = prm.ref + b.coef_off;
+        // element j of the band is owned by lane j % G: the lane that writes ref[j] is the one that reads it
+        for (int i = start + grp.lane; i < start + bn; i += G) {
+          int r2, c2;
+          scan_rc(i, &r2, &c2);
+          int32_t p = 0;
+          if (r2 == 0 && c2 > 0 && ot && (c2 >= 4 || low_from_top)) p = ot[i];
+          if (c2 == 0 && r2 > 0 && ol && (r2 >= 4 || !low_from_top)) p = ol[i];
+          vref[i] = p;
+        }
       }
     }
-    int qidx = bs * (bs + 1) + (band + 1) - (band + 1) / 3;
-    int q = (prm.q0 * prm.pvq_qm_q4[pli][qidx]) >> 4;
-    if (q < 1) q = 1;
-    const int beta = (prm.use_masking && pli == 0 && bs > 0) ? kBeta15 : kBeta1;
-    const int qoff = (b.xdec & 1 ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
-    int itheta, max_theta, k;
-    double skip_term;
-    const int gain = quantise_band_coop<G, E, false>(grp, prm.out + off, prm.in + off, prm.ref + off, bn, q,
-                                                     prm.y + off, &itheta, &max_theta, &k, beta, &skip_term,
-                                                     prm.is_keyframe, pli, prm.qm + qoff, prm.qm_inv + qoff,
-                                                     prm.pvq_norm_lambda);
-    if (valid && grp.lane == 0) {
-      const size_t r = (size_t)blk * 9 + band;
-      prm.res_skip_term[r] = skip_term;
-      short4 pk;
-      pk.x = (short)gain; pk.y = (short)itheta; pk.z = (short)max_theta; pk.w = (short)k;
-      reinterpret_cast<short4*>(S.res_pack)[r] = pk;
+    if (valid) {
+      int qidx = bs * (bs + 1) + (band + 1) - (band + 1) / 3;
+      int q = (prm.q0 * prm.pvq_qm_q4[pli][qidx]) >> 4;
+      if (q < 1) q = 1;
+      const int beta = (prm.use_masking && pli == 0 && bs > 0) ? kBeta15 : kBeta1;
+      const int qoff = (b.xdec & 1 ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
+      int itheta, max_theta, k;
+      double skip_term;
+      const int gain = quantise_band_coop<G, E, false>(grp, prm.out + off, prm.in + off, prm.ref + off, bn, q,
+                                                       prm.y + off, &itheta, &max_theta, &k, beta, &skip_term,
+                                                       prm.is_keyframe, pli, prm.qm + qoff, prm.qm_inv + qoff,
+                                                       prm.pvq_norm_lambda);
+      if (grp.lane == 0) {
+        const size_t r = (size_t)blk * 9 + band;
+        prm.res_skip_term[r] = skip_term;
+        short4 pk;
+        pk.x = (short)gain; pk.y = (short)itheta; pk.z = (short)max_theta; pk.w = (short)k;
+        reinterpret_cast<short4*>(S.res_pack)[r] = pk;
+      }
     }
     if (kIntra) {
       __threadfence();
@@ -658,7 +674,8 @@ static int kf_alloc(daala_b200_kf* kf) {
   KF_CHECK(dalloc(kf, &L.dep_left, (size_t)L.max_luma));
   // items per class: class 0 (bands 0-2) <= max(blocks) [all 4x4: one band each; 8x8: 3 per 4 units]
   const size_t luma_shard_px = (size_t)F * L.u_rows * UW * 64;
-  const size_t cap_l[3] = {(size_t)L.max_luma, luma_shard_px * 3 / 64 + 64, luma_shard_px * 3 / 256 + 64};
+  const size_t pad = (size_t)kKeyBins * 8;   // per-bin padding to whole warp chunks
+  const size_t cap_l[3] = {(size_t)L.max_luma + pad, luma_shard_px * 3 / 64 + 64 + pad, luma_shard_px * 3 / 256 + 64 + pad};
   const size_t cap_c[3] = {(size_t)L.max_chroma * 3 / 2 + 64, luma_shard_px / 4 * 2 * 3 / 64 + 64,
                            luma_shard_px / 4 * 2 * 3 / 256 + 64};
   for (int c = 0; c < 3; c++) {

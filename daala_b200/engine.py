@@ -124,6 +124,7 @@ class KeyframeEngine:
         self.pinned = pinned
         self._host = {}
         self._io = None
+        self._out = None
         self.totals = None
 
     def close(self):
