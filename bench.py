@@ -1,18 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- Daala per-block encode hot path on B200: Mpixels/s on 4K 4:2:0 intra.
 
-A "step" = one pass of the hot path over a batch of `--frames` synthetic
-3840x2160 4:2:0 frames (SURVEY.md 8(d) content, seeded):
-    u8 planes -> lapped prefilter + fDCT (block sizes 4..64 by a quadtree map)
-              -> [PVQ band quantisation when built] -> iDCT + lapped postfilter -> u8
-Frames shard by superblock row over the ranks (one process per GPU); the only
-exchange is one NCCL all-gather per step of the 2-row lapped borders.
+A "step" = one pass of the keyframe hot path over a batch of `--frames` synthetic
+3840x2160 4:2:0 frames (SURVEY.md 8(d) content, seeded) through the keyframe engine
+(include/daala_b200.h, csrc/kf_engine.cu):
+    u8 planes + block-size maps -> work lists built on the device (every step)
+      -> lapped prefilter + fDCT (4..64) -> PVQ (luma H/V intra wavefront, chroma CfL)
+      -> iDCT + lapped postfilter -> u8 reconstruction + PVQ symbols
 
-  value : luma picture pixels x frames / device time, inputs resident in HBM
-  e2e   : same, with pinned-host inputs copied H2D and the reconstruction
-          copied D2H inside the timed region
-  --impl reference : the reference's own CPU code (oracle/_ref, all host
-          threads) on a bounded sample of the same workload
+  value : luma picture pixels x frames / device time (CUDA events), inputs resident in HBM,
+          one CUDA-graph replay per step
+  e2e   : the same through the host-buffer C ABI (daala_b200_kf_submit / _wait): pinned host
+          planes + block-size maps copied H2D, reconstruction + symbols copied D2H every step,
+          two engines double-buffered, block-size maps differ from step to step
+  --impl reference : the reference's own CPU code (oracle/_ref, SIMD build, one process per
+          usable host core) on whole 4K frames of the same workload
 
 Prints ONE JSON line (rank 0).
 """
@@ -34,7 +36,6 @@ UNIT = "Mpixels/s"
 PIC_W, PIC_H = 3840, 2160
 WORKLOAD = ("3840x2160 4:2:0 all-intra hot path: lapped prefilter + fDCT(4..64, quadtree map) + PVQ band "
             "quantisation (keyframe: luma H/V intra prediction, chroma CfL) + iDCT + lapped postfilter")
-WORKLOAD_SBROW = WORKLOAD.replace("keyframe: luma H/V intra prediction, chroma CfL", "keyframe, zero prediction")
 FWD_BYTES_PER_PX = 7.5   # SURVEY.md 8(d) K_fwd: 1.5 B in + 6 B out per padded luma pixel (4:2:0)
 
 
@@ -44,33 +45,28 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=16, help="4K frames per step (whole job)")
+    ap.add_argument("--frames", type=int, default=16, help="4K frames per step per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pvq-mode", type=int, default=0, help="0 cooperative kernels, 2 scalar thread-per-band")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
-    ap.add_argument("--no-overlap", action="store_true", help="e2e: serial copy-in / compute / copy-out instead of the double-buffered pipeline")
-    ap.add_argument("--pvq-groups", type=int, default=1, help="frame groups whose PVQ stages run on separate streams")
-    ap.add_argument("--block-sizes", default="synthetic", choices=["synthetic", "reference"],
-                    help="synthetic: seeded quadtree maps with every size 4..64 (default, the measured configuration); "
-                         "reference: the maps the whole reference encoder decides for these frames at OD_SET_QUANT 20, "
-                         "complexity 7 (daala_b200/data/bench_bsize_4k.npz)")
-    ap.add_argument("--intra-mode", default="bands", choices=["bands", "waves", "chain", "chain_single"])
-    ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"],
-                    help="frames: every rank encodes its own --frames frames with the reference's keyframe "
-                         "predictors (weak scaling, no exchange); sbrow: one batch split by superblock row with "
-                         "the NCCL border all-gather (strong scaling; zero-prediction keyframes, because intra "
-                         "prediction chains cross superblock rows)")
+    ap.add_argument("--no-overlap", action="store_true", help="e2e: one engine, submit + wait per step")
+    ap.add_argument("--block-sizes", default="reference", choices=["synthetic", "reference"],
+                    help="reference (default): the maps the whole reference encoder decides for these frames at "
+                         "OD_SET_QUANT 20, complexity 7 (daala_b200/data/bench_bsize_4k.npz); synthetic: seeded "
+                         "quadtree maps with every size 4..64")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="persistent PVQ kernel CTAs per SM (0 = default)")
+    ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"])
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------
 # synthetic workload (host side)
 # --------------------------------------------------------------------------
-BLOCK_SIZES = "synthetic"   # --block-sizes: "synthetic" quadtree maps, or the "reference" encoder's decisions
+BLOCK_SIZES = "reference"   # --block-sizes: "synthetic" quadtree maps, or the "reference" encoder's decisions
 
 
-def make_host_frames(geom, nframes, distinct=4):
-    """`distinct` different synthetic frames, cycled to `nframes`; padded planes + bsize maps."""
+def make_host_frames(geom, nframes, distinct=4, rotate=0):
+    """`distinct` different synthetic frames, cycled to `nframes` starting at frame `rotate`; padded
+    planes + bsize maps."""
     import numpy as np
     from daala_b200 import synth
     frames = []
@@ -88,7 +84,7 @@ def make_host_frames(geom, nframes, distinct=4):
         else:
             bsize = synth.block_size_map(geom, "mixed", seed=100 + f)
         frames.append((synth.pad_planes(planes, geom), bsize))
-    return [frames[i % len(frames)] for i in range(nframes)]
+    return [frames[(i + rotate) % len(frames)] for i in range(nframes)]
 
 
 # --------------------------------------------------------------------------
@@ -149,38 +145,32 @@ class ClockSampler:
 # CPU reference pipeline (the reference's own functions via oracle/_ref)
 # --------------------------------------------------------------------------
 def cpu_pipeline_lib():
+    """The reference build with its x86 SIMD paths (what a user of the reference runs), else the
+    pure-C build, else the plain-C port."""
+    import ctypes
     from tests import oracle_lib
-    ref = None
-    path = os.path.join(ROOT, "oracle", "_ref", "libdaala_ref.so")
-    if os.path.exists(path):
-        import ctypes
-        ref = ctypes.CDLL(path)
-    if ref is not None:
-        return ref, "ref", "reference"
+    for name, build in (("libdaala_ref_simd.so", "unmodified reference sources, x86 SSE2/SSE4.1/AVX2 paths on"),
+                        ("libdaala_ref.so", "unmodified reference sources, pure C")):
+        path = os.path.join(ROOT, "oracle", "_ref", name)
+        if os.path.exists(path):
+            CPU_BUILD["build"] = build
+            return ctypes.CDLL(path), "ref", "reference"
+    CPU_BUILD["build"] = "plain-C port of the reference functions (oracle/port_*.c)"
     return oracle_lib.load_port(), "port", "port"
 
 
+CPU_BUILD = {"build": None}
 Q0 = 72            # state->quantizer for OD_SET_QUANT = 20 (coded quantizer 20 -> 0x48, src/quantizer.c:47)
 PVQ_QM_Q4 = 16     # flat state->pvq_qm_q4 entries
 
 
-def cpu_frame(lib, prefix, geom, planes, bsize):
-    """The same chain as the GPU step with the reference's own functions:
-    forward transform -> per-block PVQ (od_hv_intra_pred / CfL prediction, pvq_theta with the
-    closed-form rate) -> inverse."""
+def cpu_frame(lib, prefix, geom, planes, bsize, record=False):
+    """The same chain as the GPU step with the reference's own functions: forward transform ->
+    per-block PVQ (od_hv_intra_pred / CfL prediction, pvq_theta with the closed-form rate) -> inverse."""
     import numpy as np
-    from daala_b200 import pvq
     from tests import frame_oracle
-    qm, qm_inv = pvq.default_qm(True)
     q4 = np.full((3, 30), PVQ_QM_Q4, np.uint8)
-    luma_q = None
-    for pli in range(3):
-        d = frame_oracle.forward_plane(lib, prefix, planes[pli], geom, pli, bsize, 1)
-        dq, _ = frame_oracle.pvq_plane_pred(lib, prefix, d, geom, pli, bsize, Q0, 1, pvq.PVQ_LAMBDA, qm, qm_inv, q4,
-                                            luma_d=luma_q)
-        if pli == 0:
-            luma_q = dq
-        frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 1)
+    return frame_oracle.keyframe_chain(lib, prefix, planes, geom, bsize, Q0, q4, use_masking=1, record=record)
 
 
 _CPU_JOB = {}
@@ -205,29 +195,6 @@ def cpu_pool(geom, host_frames, workers):
     return multiprocessing.get_context("fork").Pool(workers)
 
 
-def cpu_throughput(geom, host_frames, nframes, threads, pool=None):
-    """Mpx/s of the CPU pipeline over `nframes` frames on `threads` worker processes (1: in-process)."""
-    lib, prefix, kind = cpu_pipeline_lib()
-    t0 = time.perf_counter()
-    if threads == 1 or pool is None:
-        for i in range(nframes):
-            planes, bsize = host_frames[i % len(host_frames)]
-            cpu_frame(lib, prefix, geom, planes, bsize)
-    else:
-        pool.map(_cpu_worker, range(nframes), chunksize=1)
-    dt = time.perf_counter() - t0
-    return geom.luma_pixels * nframes / dt / 1e6, dt, kind
-
-
-CPU_SAMPLE_FRAMES = 48  # ~12 s of single-core CPU work
-CPU_SAMPLE_ROWS = 512   # bounded CPU sample: a 3840x512 band (8 superblock rows) of the 4K frame
-
-
-def cpu_sample_geometry():
-    from daala_b200.frame import Geometry
-    return Geometry(PIC_W, CPU_SAMPLE_ROWS)
-
-
 def cgroup_cpu_quota():
     """CPU quota of this container in cores (cgroup v2 cpu.max / v1 cfs), or None when unlimited/unknown:
     sched_getaffinity can list far more CPUs than the container may actually use."""
@@ -244,50 +211,72 @@ def cgroup_cpu_quota():
         return None
 
 
+def usable_cores():
+    """Cores this process can really use: the affinity mask capped by the cgroup CPU quota."""
+    aff = len(os.sched_getaffinity(0))
+    quota = cgroup_cpu_quota()
+    return max(1, min(aff, int(quota + 0.5))) if quota else aff, aff, quota
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    geom = cpu_sample_geometry()
-    cores = len(os.sched_getaffinity(0))
-    host_frames = make_host_frames(geom, 2, distinct=2)
-    per_step = 2 * max(1, cores)
+    from daala_b200.frame import Geometry
+    geom = Geometry(PIC_W, PIC_H)
+    cores, aff, quota = usable_cores()
+    host_frames = make_host_frames(geom, 4, distinct=4)
+    per_step = cores                       # one whole 4K frame per worker per step (~1 s of CPU each)
     pool = cpu_pool(geom, host_frames, cores) if cores > 1 else None
-    for _ in range(max(args.warmup, 1)):
-        cpu_throughput(geom, host_frames, per_step, cores, pool)
-    times = []
-    kind = "port"
-    for _ in range(args.steps):
-        _, dt, kind = cpu_throughput(geom, host_frames, per_step, cores, pool)
-        times.append(dt)
+    lib, prefix, kind = cpu_pipeline_lib()
+
+    def one_step():
+        t0 = time.perf_counter()
+        if pool is None:
+            for i in range(per_step):
+                cpu_frame(lib, prefix, geom, *host_frames[i % len(host_frames)])
+        else:
+            pool.map(_cpu_worker, range(per_step), chunksize=1)
+        return time.perf_counter() - t0
+
+    for _ in range(max(min(args.warmup, 2), 1)):
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
     if pool is not None:
         pool.close()
     total = sum(times)
     value = geom.luma_pixels * per_step * args.steps / total / 1e6
-    sample = ("%d x 3840x%d 4:2:0 bands (8 superblock rows of the 4K frame) per step on %d worker processes (one per host core); "
-              "reference functions: prefilter + fDCT + pvq_theta(speed=1) + iDCT + postfilter" % (per_step, CPU_SAMPLE_ROWS, cores))
-    quota = cgroup_cpu_quota()
-    sample += "; container CPU quota: %s" % ("none" if quota is None else "%.2f cores" % quota)
+    sample = ("%d whole 3840x2160 4:2:0 frames per step, one per worker process on %d processes (= usable cores: "
+              "affinity %d, cgroup CPU quota %s); reference functions: prefilter + fDCT + pvq_theta(speed=1) + "
+              "iDCT + postfilter; block sizes: %s" % (per_step, cores, aff, "none" if quota is None else "%.2f" % quota,
+                                                        BLOCK_SIZES))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD + " (CPU reference functions, bounded sample)",
-                   "frames_per_step": per_step},
-        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD + " (CPU reference functions)", "frames_per_step": per_step,
+                   "block_sizes": block_sizes_text(), "quantizer": Q0},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind,
+                         "build": CPU_BUILD["build"], "sample": sample},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def block_sizes_text():
+    return ("synthetic quadtree map, sizes 4..64" if BLOCK_SIZES == "synthetic" else
+            "decided by the whole reference encoder for these frames (quant 20, complexity 7): mostly 32x32")
 
 
 # --------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------
 def run_b200(args):
+    import zlib
     import numpy as np
     import torch
     import torch.distributed as dist
+    from daala_b200 import engine
     from daala_b200.frame import Geometry
-    from daala_b200.pipeline import HotPath
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -300,315 +289,183 @@ def run_b200(args):
 
     geom = Geometry(PIC_W, PIC_H)
     F = args.frames
-    sbrow = args.shard == "sbrow"
-    if sbrow:
-        r0, nrows = geom.shard_rows(rank, world)
-    else:
-        r0, nrows = 0, geom.nvsb
-    host_frames = make_host_frames(geom, F)
     q4 = np.full((3, 30), PVQ_QM_Q4, np.uint8)
-    use_graph = not args.no_graph and not (sbrow and world > 1)   # the NCCL exchange stays host-launched
-    overlap = use_graph and not args.no_overlap
+    use_graph = not args.no_graph
+    nslots = 1 if args.no_overlap else 2
 
-    def rows(pli, halo):
-        sb = 64 >> geom.xdec[pli]
-        ph = geom.plane_shape(pli)[0]
-        return max(0, r0 * sb - halo), min(ph, (r0 + nrows) * sb + halo)
-
-    # pinned host input: this rank's rows (+2-sample halo) of every plane, block-size maps
-    pin_in = []
-    for pli in range(3):
-        a, b = rows(pli, 2)
-        t = torch.empty((F, b - a, geom.plane_shape(pli)[1]), dtype=torch.uint8).pin_memory()
-        for f in range(F):
-            t[f].copy_(torch.from_numpy(host_frames[f][0][pli][a:b]))
-        pin_in.append(t)
-    pin_bsize = torch.empty((F,) + geom.bsize_shape, dtype=torch.uint8).pin_memory()
-    for f in range(F):
-        pin_bsize[f].copy_(torch.from_numpy(host_frames[f][1]))
-
-    class Slot:
-        """One set of device buffers (+ its CUDA graph) and the pinned host buffers its results land in."""
-
-        def __init__(self):
-            hp = HotPath(geom, nframes=F, device=dev, q0=Q0, is_keyframe=1, use_masking=1, pvq_qm_q4=q4,
-                         sb_row0=r0, sb_rows=nrows, keyframe_prediction=not sbrow, pvq_groups=args.pvq_groups)
-            hp.set_block_sizes([hf[1] for hf in host_frames])
-            for b in hp.pvq_batches():
-                b.mode = args.pvq_mode
-                if getattr(b, "chain_lists", None) is not None:
-                    b.intra_mode = args.intra_mode
-            self.hp, self.fb = hp, hp.fb
-            self.pin_out = []
-            for pli in range(3):
-                a, b = rows(pli, 0)
-                self.pin_out.append(torch.empty((F, b - a, geom.plane_shape(pli)[1]), dtype=torch.uint8).pin_memory())
-            # e2e also moves what the host side of the reference consumes/produces around the hot path:
-            # block descriptors + band lists in (they follow from the block-size decision), and the PVQ
-            # symbols out (per-band indices, flags, 16-bit pulses) for the host entropy coder.
-            batches = hp.pvq_batches()
-            self.desc_dev = []
-            for b in batches:
-                self.desc_dev.append(b.blocks)
-                if getattr(b, "chain_lists", None) is None:
-                    self.desc_dev.extend(b.lists.values())
-                else:
-                    self.desc_dev.extend(b.chain_lists.values())
-                    self.desc_dev.extend(b.bulk_lists.values())
-                    self.desc_dev.extend(b.chain_waves.values())
-                    self.desc_dev.extend([b.dep_top, b.dep_left])
-            self.desc_pin = [t.cpu().pin_memory() for t in self.desc_dev]
-            self.sym_dev = [t for b in batches for t in b.symbol_tensors()]
-            self.sym_pin = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self.sym_dev]
-            self.ev_in, self.ev_comp, self.ev_out = (torch.cuda.Event() for _ in range(3))
-
-        def h2d(self):
-            for pli in range(3):
-                a, b = rows(pli, 2)
-                self.fb.pixels[pli][:, a:b].copy_(pin_in[pli], non_blocking=True)
-            self.fb.bsize.copy_(pin_bsize, non_blocking=True)
-            for dst, src in zip(self.desc_dev, self.desc_pin):
-                dst.copy_(src, non_blocking=True)
-
-        def d2h(self):
-            for pli in range(3):
-                a, b = rows(pli, 0)
-                self.pin_out[pli].copy_(self.fb.pixels_out[pli][:, a:b], non_blocking=True)
-            for dst, src in zip(self.sym_pin, self.sym_dev):
-                dst.copy_(src, non_blocking=True)
-
-    slots = [Slot() for _ in range(2 if overlap else 1)]
-    hp, fb = slots[0].hp, slots[0].fb
-    h2d_bytes = (sum(t.numel() for t in pin_in) + pin_bsize.numel()
-                 + sum(t.numel() * t.element_size() for t in slots[0].desc_pin))
-    d2h_bytes = (sum(t.numel() for t in slots[0].pin_out)
-                 + sum(t.numel() * t.element_size() for t in slots[0].sym_pin))
-
-    # multi-GPU: one all-gather per step of the 2-row lapped borders (daala_b200/sharding.py)
-    from daala_b200.sharding import BorderExchange
-    exchange = BorderExchange(geom, fb.lapped, rank, world) if sbrow else None
-
-    launches = {"n": 0}
-
-    def step(sl=slots[0]):
-        if use_graph:
-            launches["n"] += sl.hp.replay()
-        else:
-            launches["n"] += sl.hp.run(exchange if (sbrow and world > 1) else None)
+    # two engines = two sets of device + pinned host buffers; slot s holds batch s of the synthetic
+    # sequence (frames and block-size maps rotated by s), so consecutive e2e steps see different maps
+    slots, batches = [], []
+    for s in range(nslots):
+        hf = make_host_frames(geom, F, rotate=s + 2 * rank)
+        planes = [np.stack([f[0][p] for f in hf]) for p in range(3)]
+        bsize = np.stack([f[1] for f in hf])
+        eng = engine.KeyframeEngine(geom, nframes=F, q0=Q0, use_masking=1, pvq_qm_q4=q4,
+                                    persist_ctas_per_sm=args.ctas_per_sm,
+                                    max_blocks_div=1 if BLOCK_SIZES == "synthetic" else 2)
+        eng.stage_inputs(planes, bsize)
+        eng.prepare_io(symbols=True, recon=True)
+        slots.append(eng)
+        batches.append(hf)
+    eng0 = slots[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        for e in slots:
+            e.wait()
 
-    def timed(fn, steps, before=None, after=None):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        if before:
-            before()
-        for _ in range(steps):
-            fn()
-        if after:
-            after()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    def max_over_ranks(ms):
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
 
-    # upload once, warm up (and record the graphs)
-    for sl in slots:
-        sl.h2d()
-        if use_graph:
-            sl.hp.capture()
-    for _ in range(max(args.warmup, 3)):
-        step()
-    # sanity guard: the quantised reconstruction stays close to the source on my rows
-    torch.cuda.synchronize()
-    for pli in range(3):
-        a, b = rows(pli, 0)
-        err = (fb.pixels_out[pli][:, a:b].float() - fb.pixels[pli][:, a:b].float()).abs().mean().item()
-        assert err < 12.0, "reconstruction error too large (%.2f)" % err
-    total_k = sum(int(b.res_k.sum().item()) for b in hp.pvq_batches())
+    # first end-to-end pass (also uploads the inputs the device-resident timing uses) + parity check
+    for e in slots:
+        e.submit()
+    out0 = slots[0].wait()
+    for e in slots[1:]:
+        e.wait()
+    assert int(out0["counts"][engine.CNT["error"]]) == 0, "engine block capacity exceeded"
+    total_k = int(out0["luma_res"][..., 3].clip(min=0).sum()) + int(out0["chroma_res"][..., 3].clip(min=0).sum())
     assert total_k > 0, "PVQ produced no pulses"
+    dev_crc = {"recon%d" % p: zlib.crc32(np.ascontiguousarray(out0["recon%d" % p][0]).tobytes()) for p in range(3)}
+    dev_rec = [engine.band_records(out0["luma_blocks"] if p == 0 else out0["chroma_blocks"],
+                                   out0["luma_res"] if p == 0 else out0["chroma_res"], geom, p, 0) for p in range(3)]
 
+    # device-resident step time (CUDA events on the engine's stream)
     sampler = ClockSampler(local)
+    eng0.time_device(engine.PH_ALL, use_graph, max(args.warmup, 3))
+    barrier()
     if rank == 0:
         sampler.start()
-    launches["n"] = 0
-    ms = timed(step, args.steps)
-    n_launch = launches["n"]
+    ms = max_over_ranks(eng0.time_device(engine.PH_ALL, use_graph, args.steps))
 
-    # end to end: every step copies its inputs in from pinned host memory and its results out.
-    if overlap:
-        # double-buffered: copy-in of step i+1 and copy-out of step i-1 run on their own streams
-        # (both copy engines) under the compute of step i; events carry the buffer hazards.
-        cur = torch.cuda.current_stream(dev)
-        s_in, s_comp, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
-        counter = {"i": 0}
+    # end to end through the host-buffer C ABI: H2D + step + D2H per batch, engines alternate
+    def e2e_loop(steps):
+        for i in range(steps):
+            e = slots[i % nslots]
+            if i >= nslots:
+                e.wait()
+            e.submit()
+        for e in slots:
+            e.wait()
 
-        def fork():
-            for st in (s_in, s_comp, s_out):
-                st.wait_stream(cur)
-
-        def join():
-            for st in (s_in, s_comp, s_out):
-                cur.wait_stream(st)
-
-        def e2e_step():
-            sl = slots[counter["i"] % 2]
-            counter["i"] += 1
-            s_in.wait_event(sl.ev_comp)            # inputs of this slot were consumed (step i-2)
-            with torch.cuda.stream(s_in):
-                sl.h2d()
-                sl.ev_in.record(s_in)
-            s_comp.wait_event(sl.ev_in)
-            s_comp.wait_event(sl.ev_out)           # results of step i-2 have left the device
-            with torch.cuda.stream(s_comp):
-                step(sl)
-                sl.ev_comp.record(s_comp)
-            s_out.wait_event(sl.ev_comp)
-            with torch.cuda.stream(s_out):
-                sl.d2h()
-                sl.ev_out.record(s_out)
-
-        for sl in slots:
-            for ev in (sl.ev_in, sl.ev_comp, sl.ev_out):
-                ev.record(cur)
-        timed(e2e_step, 4, fork, join)
-        ms_e2e = timed(e2e_step, args.steps, fork, join)
-    else:
-        def e2e_step():
-            slots[0].h2d()
-            step()
-            slots[0].d2h()
-
-        for _ in range(2):
-            e2e_step()
-        ms_e2e = timed(e2e_step, args.steps)
+    e2e_loop(2 * nslots)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    # dominant kernel alone (forward), CUDA events on the launching stream
+    # per-phase device times
     reps = max(5, args.steps)
-    ms_fwd = timed(fb.forward, reps) / reps
-    ms_inv = timed(lambda: fb.inverse(lapped_only=True), reps) / reps
-    ms_post = timed(fb.sb_postfilter_store, reps) / reps
-    # PVQ stages on fresh transform output every repetition (re-quantising the already quantised
-    # planes of the previous pass would be a different, lighter workload)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    acc_luma = acc_all = 0.0
-    barrier()
-    for _ in range(reps):
-        fb.forward()
-        evs[0].record()
-        if hp.keyframe_prediction:
-            for bl, _, _ in hp.groups:      # the luma wavefronts alone, one group after the other
-                bl.run_luma_intra()
-        evs[1].record()
-        fb.forward()
-        evs[2].record()
-        hp.run_pvq()                        # the stage as the step runs it (groups on their streams)
-        evs[3].record()
-        torch.cuda.synchronize()
-        acc_luma += evs[0].elapsed_time(evs[1])
-        acc_all += evs[2].elapsed_time(evs[3])
-    ms_pvq_luma = acc_luma / reps if hp.keyframe_prediction else None
-    ms_pvq = acc_all / reps
+    phase_ms = {}
+    for name, ph in (("work_lists(7 kernels)", engine.PH_LISTS), ("k_forward_sb_tma", engine.PH_FORWARD),
+                     ("pvq_luma(gather+k_pvq_persist<intra>+finish)", engine.PH_PVQ_LUMA),
+                     ("pvq_chroma(cfl+gather+k_pvq_persist+finish)", engine.PH_PVQ_CHROMA),
+                     ("k_inverse_sb+k_sb_postfilter_store", engine.PH_INVERSE),
+                     ("k_pvq_persist<intra> alone", engine.PH_PVQ_LUMA | engine.PH_SEARCH_ONLY),
+                     ("k_pvq_persist<chroma> alone", engine.PH_PVQ_CHROMA | engine.PH_SEARCH_ONLY)):
+        eng0.time_device(ph, False, 1)
+        phase_ms[name] = eng0.time_device(ph, False, reps) / reps
+    # leave the planes consistent again
+    eng0.time_device(engine.PH_ALL, use_graph, 1)
+    ms_fwd = phase_ms["k_forward_sb_tma"]
+    ms_dom = phase_ms["k_pvq_persist<intra> alone"]
 
-    # dominant kernel by time share (profiles/r1q_launches.csv: 42 % of the step): the PVQ band search for
-    # the 128-coefficient bands, k_pvq_bands_coop<32,4>; timed alone on the first chroma / all-plane batch
-    import ctypes as _ct
-    from daala_b200 import pvq as _pvq, _native as _nat
-    _L = _pvq._bind()
-    _b = hp.batch
-    _lst = _b.lists[128]
-    fb.forward()
-    if hp.keyframe_prediction:
-        hp.batch_luma.run_luma_intra()
-        hp.batch_chroma.cfl_pred(hp.cfl_plane)
-    _b.gather()
-
-    def _dominant():
-        _nat.check(_L.daala_b200_pvq_encode_bands_mode(_ct.byref(_b.params), _lst.data_ptr(), _lst.numel(), 128,
-                                                       _b.mode, _ct.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
-                   "pvq_bands")
-
-    ms_dom = (timed(_dominant, reps) / reps) if _lst.numel() else 0.0
-    dom_bytes = 20.0 * 128 * _lst.numel()   # K_pvq = 20 B per coded coefficient (SURVEY.md 8(d))
-    px_job = geom.luma_pixels * F * (1 if sbrow else world)
+    px_job = geom.luma_pixels * F * world
     value = px_job / (ms / args.steps * 1e-3) / 1e6
     e2e = px_job / (ms_e2e / args.steps * 1e-3) / 1e6
-    padded_luma_shard = geom.frame_w * (nrows * 64) * F
-    algo_bytes = FWD_BYTES_PER_PX * padded_luma_shard
+    algo_bytes = FWD_BYTES_PER_PX * geom.frame_w * geom.frame_h * F
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak = float(json.load(open(peaks_path))["hbm_gbs"])
-        peak_src = "measured"
+        peak_src = "measured (MEASURED_PEAKS.json)"
     else:
-        peak, peak_src = 6650.0, "fallback"
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = algo_bytes / (ms_fwd * 1e-3) / 1e9
+    dom_bytes = 20.0 * float(eng0.totals.luma_coefs)    # K_pvq = 20 B per coded coefficient
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    profiles = load_profile_notes()
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "strong" if sbrow else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_SBROW if sbrow else WORKLOAD,
-                   "frames_per_step": F * (1 if sbrow else world),
-                   "parallelism": ("sbrow%d (NCCL all-gather of lapped border rows)" if sbrow else "frames%d (independent frames per rank)") % world,
-                   "l2": "inputs larger than L2 (%.0f MB of planes per step)" % ((geom.padded_samples * F * 9) / 1e6),
-                   "block_sizes": ("synthetic quadtree map, sizes 4..64" if BLOCK_SIZES == "synthetic" else
-                                   "decided by the reference encoder (quant 20, complexity 7)"), "quantizer": Q0,
-                   "work_lists": "block / band / wave lists derived from the block-size maps once at setup (maps are "
-                                 "fixed across steps); e2e re-uploads them every step but does not rebuild them",
-                   "pvq_pulses_per_step": total_k},
-        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 4),
-                "pipeline": ("double-buffered: copy-in / CUDA-graph compute / copy-out of consecutive steps overlap on three streams"
-                             if overlap else "serial copy-in, compute, copy-out")},
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": F * world,
+                   "parallelism": "frames%d (independent keyframes per rank, no data-path collective)" % world,
+                   "l2": "inputs larger than L2 (%.0f MB of planes per step per rank)" % ((geom.padded_samples * F * 9) / 1e6),
+                   "block_sizes": block_sizes_text(), "quantizer": Q0,
+                   "work_lists": "rebuilt on the device from the block-size maps inside every step (timed region); "
+                                 "e2e uploads different maps on consecutive steps",
+                   "pvq_pulses_first_batch": total_k},
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(eng0.h2d_bytes),
+                "d2h_bytes_per_step": int(eng0.d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 4),
+                "api": "daala_b200_kf_submit / daala_b200_kf_wait (C ABI, pinned host buffers)",
+                "pipeline": ("two engines alternate: copy-in / graph / copy-out of consecutive batches overlap"
+                             if nslots == 2 else "one engine, serial copy-in, compute, copy-out")},
         "cuda_graph": bool(use_graph),
-        "gpu_launches": n_launch,
+        "gpu_launches": engine.LAUNCHES_PER_STEP * args.steps,
         "clocks": clocks,
-        # dominant kernel (40 % of the step): not HBM-bound -- a greedy double-precision search,
-        # issue/latency-bound; its HBM fraction is reported as the contract asks
-        "roofline": {"kernel": "k_pvq_bands_coop<32,4> (PVQ search, 128-coefficient bands)", "bound": "hbm",
-                     "achieved": round(dom_bytes / (ms_dom * 1e-3) / 1e9, 1) if ms_dom else None, "peak": peak,
-                     "peak_source": peak_src, "unit": "GB/s",
-                     "frac": round(dom_bytes / (ms_dom * 1e-3) / 1e9 / peak, 4) if ms_dom else None,
-                     # ncu dram__bytes_read+write of this kernel, 146.2 MB for 38208 bands (profiles/r1q_pvq_chroma_ncu.txt);
-                     # writes are 2.6x the algorithmic 8 B/coefficient: local-memory scratch evictions
-                     "traffic": int(146.2e6 / 38208 * _lst.numel()),
-                     "traffic_source": "ncu dram bytes per band of profiles/r1q_pvq_chroma_ncu.txt (4-frame capture) x bands of this launch",
-                     "algorithmic_bytes_per_launch": int(dom_bytes),
-                     "ms_per_launch": round(ms_dom, 4),
-                     "note": "compute/latency-bound greedy search; see roofline_transform for the HBM-bound kernel"},
+        # dominant kernel by time: the persistent luma PVQ kernel -- a greedy double-precision search bound by
+        # dependency latency and FP64/integer issue, not HBM; its HBM fraction is reported as the contract asks
+        "roofline": {"kernel": "k_pvq_persist<intra> (luma PVQ search + H/V intra prediction wavefront)", "bound": "hbm",
+                     "achieved": round(dom_bytes / (ms_dom * 1e-3) / 1e9, 1), "peak": peak, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": round(dom_bytes / (ms_dom * 1e-3) / 1e9 / peak, 4),
+                     "traffic": profiles.get("pvq_traffic"), "traffic_source": profiles.get("pvq_traffic_source"),
+                     "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": round(ms_dom, 4),
+                     "note": "latency/issue-bound search; see roofline_transform for the HBM-bound kernel"},
         # the fused lapped-filter + DCT kernel the north star sets its HBM target on
         "roofline_transform": {"kernel": "k_forward_sb_tma", "bound": "hbm", "achieved": round(achieved, 1),
-                               "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                               "frac": round(achieved / peak, 4),
-                               "traffic": int(974.7e6 * (nrows / geom.nvsb) * (F / 16.0)),
-                               "traffic_source": "ncu dram__bytes_read+write, profiles/r1m_k_forward_sb_tma_ncu_full.txt (16 frames)",
+                               "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                               "traffic": profiles.get("fwd_traffic"), "traffic_source": profiles.get("fwd_traffic_source"),
                                "algorithmic_bytes_per_launch": int(algo_bytes), "ms_per_launch": round(ms_fwd, 4)},
-        "kernels_ms": {"k_forward_sb": round(ms_fwd, 4), "k_inverse_sb": round(ms_inv, 4),
-                       "k_sb_postfilter_store": round(ms_post, 4), "pvq_stage(gather+bands+scatter)": round(ms_pvq, 4),
-                       "k_pvq_luma_intra(wavefront)": None if ms_pvq_luma is None else round(ms_pvq_luma, 4)},
+        "kernels_ms": {k: round(v, 4) for k, v in phase_ms.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
-        cgeom = cpu_sample_geometry()
-        cpu_frames = make_host_frames(cgeom, 2, distinct=2)
-        v, dt, kind = cpu_throughput(cgeom, cpu_frames, CPU_SAMPLE_FRAMES, 1)
-        out["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": 1, "kind": kind,
-                               "sample": "%d x 3840x%d bands (8 superblock rows of the 4K frame), same chain "
-                                         "(reference functions, pvq_theta speed=1), 1 thread, %.1f s" % (CPU_SAMPLE_FRAMES, CPU_SAMPLE_ROWS, dt)}
+        lib, prefix, kind = cpu_pipeline_lib()
+        # parity: frame 0 of batch 0 through the reference chain, every plane and every band decision
+        t0 = time.perf_counter()
+        want = cpu_frame(lib, prefix, geom, *batches[0][0], record=True)
+        mism = 0
+        for p in range(3):
+            mism += int(zlib.crc32(want[p]["recon"].tobytes()) != dev_crc["recon%d" % p])
+            mism += int(np.count_nonzero(dev_rec[p] != want[p]["rec"]))
+        out["parity_checked"] = {"frames": 1, "against": kind, "what": "reconstruction CRC-32 of 3 planes + every per-band "
+                                 "(gain, theta, max_theta, K) of frame 0", "mismatches": mism}
+        assert mism == 0, "device results differ from the oracle (%d mismatches)" % mism
+        n = 0
+        while time.perf_counter() - t0 < 12.0:
+            cpu_frame(lib, prefix, geom, *batches[0][(n + 1) % F])
+            n += 1
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": round(geom.luma_pixels * (n + 1) / dt / 1e6, 3), "unit": UNIT, "cores": 1, "kind": kind,
+                               "build": CPU_BUILD["build"],
+                               "sample": "%d whole 3840x2160 frames, same chain (reference functions, pvq_theta speed=1), "
+                                         "1 thread, %.1f s" % (n + 1, dt)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def load_profile_notes():
+    """DRAM traffic per launch from the committed ncu captures (profiles/r2_traffic.json), if present."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except ValueError:
+            pass
+    return {}
 
 
 def main():

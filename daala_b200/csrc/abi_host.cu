@@ -228,9 +228,24 @@ void od_post_filter16(od_coeff _x[16], const od_coeff _y[16]) { lapfilter_n(16, 
 void od_pre_filter32(od_coeff _y[32], const od_coeff _x[32]) { lapfilter_n(32, false, _y, _x); }
 void od_post_filter32(od_coeff _x[32], const od_coeff _y[32]) { lapfilter_n(32, true, _x, _y); }
 
+// The reference's own table names (src/dct.c:54-84), so that linking this library INSTEAD of the
+// reference's dct.o / filter.o resolves OD_COPY(state->opt_vtbl.fdct_2d, OD_FDCT_2D_C, ...) of
+// od_state_opt_vtbl_init_c (src/state.c:341-342) and the dcttest / tools users of the 1-D tables.
+const od_dct_func_2d OD_FDCT_2D_C[6] = {od_bin_fdct4x4,   od_bin_fdct8x8,   od_bin_fdct16x16,
+                                        od_bin_fdct32x32, od_bin_fdct64x64, nullptr};
+const od_dct_func_2d OD_IDCT_2D_C[6] = {od_bin_idct4x4,   od_bin_idct8x8,   od_bin_idct16x16,
+                                        od_bin_idct32x32, od_bin_idct64x64, nullptr};
+const od_fdct_func_1d OD_FDCT_1D[6] = {od_bin_fdct4, od_bin_fdct8, od_bin_fdct16, od_bin_fdct32, od_bin_fdct64, nullptr};
+const od_idct_func_1d OD_IDCT_1D[6] = {od_bin_idct4, od_bin_idct8, od_bin_idct16, od_bin_idct32, od_bin_idct64, nullptr};
+
 // reference: OD_PRE_FILTER / OD_POST_FILTER, src/filter.c:115-127
 const od_filter_func OD_PRE_FILTER_CUDA[4] = {od_pre_filter4, od_pre_filter8, od_pre_filter16, od_pre_filter32};
 const od_filter_func OD_POST_FILTER_CUDA[4] = {od_post_filter4, od_post_filter8, od_post_filter16, od_post_filter32};
+
+// the reference's names (OD_NBSIZES = 5 entries, the last one NULL) and the 4-point filter's parameters
+const od_filter_func OD_PRE_FILTER[5] = {od_pre_filter4, od_pre_filter8, od_pre_filter16, od_pre_filter32, nullptr};
+const od_filter_func OD_POST_FILTER[5] = {od_post_filter4, od_post_filter8, od_post_filter16, od_post_filter32, nullptr};
+const int OD_FILTER_PARAMS4[4] = {85, 75, -15, 33};   // src/filter.c:137-146
 
 int daala_b200_lapfilter(int32_t* v, long count, int n, int post, void* stream) {
   return daala_b200_launch_lapfilter(v, count, n, post, (cudaStream_t)stream);

@@ -790,16 +790,22 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
     int rc = daala_b200_launch_forward(&kf->frame, 3, s);
     if (rc) return rc;
   }
-  if (phases & DAALA_B200_KF_PVQ) {
-    const int persist = kf->sms * (kf->cfg.persist_ctas_per_sm > 0 ? kf->cfg.persist_ctas_per_sm : 5);
+  const int persist = kf->sms * (kf->cfg.persist_ctas_per_sm > 0 ? kf->cfg.persist_ctas_per_sm : 5);
+  // _SEARCH_ONLY (measurement): just the persistent search kernels, on the coding-order buffers a
+  // previous full pass left behind (same inputs, same results)
+  const bool core = (phases & DAALA_B200_KF_SEARCH_ONLY) != 0;
+  if (phases & DAALA_B200_KF_PVQ_LUMA) {
     k_begin_pvq<<<1, 32, 0, s>>>(kf->lists.cnt);
-    k_gather<false><<<wide, 256, 0, s>>>(kf->luma);
+    if (!core) k_gather<false><<<wide, 256, 0, s>>>(kf->luma);
     k_pvq_persist<true><<<persist, 128, 0, s>>>(kf->luma);
-    k_finish_scatter<<<wide, 256, 0, s>>>(kf->luma);
-    k_cfl_plane<<<wide, 256, 0, s>>>(kf->chroma, kf->cfl_plane);
-    k_gather<true><<<wide, 256, 0, s>>>(kf->chroma);
+    if (!core) k_finish_scatter<<<wide, 256, 0, s>>>(kf->luma);
+  }
+  if (phases & DAALA_B200_KF_PVQ_CHROMA) {
+    if (!(phases & DAALA_B200_KF_PVQ_LUMA)) k_begin_pvq<<<1, 32, 0, s>>>(kf->lists.cnt);
+    if (!core) k_cfl_plane<<<wide, 256, 0, s>>>(kf->chroma, kf->cfl_plane);
+    if (!core) k_gather<true><<<wide, 256, 0, s>>>(kf->chroma);
     k_pvq_persist<false><<<persist, 128, 0, s>>>(kf->chroma);
-    k_finish_scatter<<<wide, 256, 0, s>>>(kf->chroma);
+    if (!core) k_finish_scatter<<<wide, 256, 0, s>>>(kf->chroma);
   }
   if (phases & DAALA_B200_KF_INVERSE) {
     int rc = daala_b200_launch_inverse(&kf->frame, 3, s);
@@ -956,6 +962,31 @@ int daala_b200_kf_run_device(daala_b200_kf* kf, int phases, int use_graph) {
     kf->captured = true;
   }
   KF_CHECK(cudaGraphLaunch(kf->exec, kf->stream));
+  return 0;
+}
+
+// `reps` repetitions of the selected phases timed with CUDA events on the engine's stream (inputs
+// resident in HBM); returns the total in milliseconds.
+int daala_b200_kf_time_device(daala_b200_kf* kf, int phases, int use_graph, int reps, float* ms) {
+  if (!kf || !ms || reps <= 0) return (int)cudaErrorInvalidValue;
+  cudaEvent_t e0, e1;
+  KF_CHECK(cudaEventCreate(&e0));
+  KF_CHECK(cudaEventCreate(&e1));
+  if (use_graph && phases == DAALA_B200_KF_ALL && !kf->captured) {
+    int rc = daala_b200_kf_run_device(kf, phases, 1);
+    if (rc) return rc;
+  }
+  KF_CHECK(cudaStreamSynchronize(kf->stream));
+  KF_CHECK(cudaEventRecord(e0, kf->stream));
+  for (int i = 0; i < reps; i++) {
+    int rc = daala_b200_kf_run_device(kf, phases, use_graph);
+    if (rc) return rc;
+  }
+  KF_CHECK(cudaEventRecord(e1, kf->stream));
+  KF_CHECK(cudaEventSynchronize(e1));
+  KF_CHECK(cudaEventElapsedTime(ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return 0;
 }
 

@@ -13,7 +13,9 @@ from .frame import Geometry
 
 c_int, c_ll, c_void_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p
 
-PH_LISTS, PH_FORWARD, PH_PVQ, PH_INVERSE, PH_ALL = 1, 2, 4, 8, 15
+PH_LISTS, PH_FORWARD, PH_PVQ_LUMA, PH_INVERSE, PH_PVQ_CHROMA = 1, 2, 4, 8, 16
+PH_PVQ, PH_ALL, PH_SEARCH_ONLY = 20, 31, 64
+LAUNCHES_PER_STEP = 18   # lists 7, forward 1, luma 4, chroma 4, inverse 2
 CNT = dict(n_luma=0, n_chroma=1, luma_coefs=2, chroma_coefs=3, items_l=4, items_c=7, epoch=16, error=17)
 
 
@@ -59,6 +61,7 @@ def _bind():
     L.daala_b200_kf_error.restype = ctypes.c_char_p
     L.daala_b200_kf_device_buffers.argtypes = [c_void_p, ctypes.POINTER(Buffers)]
     L.daala_b200_kf_run_device.argtypes = [c_void_p, c_int, c_int]
+    L.daala_b200_kf_time_device.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_float)]
     L.daala_b200_kf_count_blocks.argtypes = [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int,
                                              ctypes.POINTER(Totals)]
     for name in ("daala_b200_kf_submit", "daala_b200_kf_encode"):
@@ -242,6 +245,13 @@ class KeyframeEngine:
     # --- device-resident use -------------------------------------------------------------------
     def run_device(self, phases=PH_ALL, graph=True):
         self._check(self.L.daala_b200_kf_run_device(self.kf, phases, 1 if graph else 0), "kf_run_device")
+
+    def time_device(self, phases=PH_ALL, graph=True, reps=1):
+        """Milliseconds (CUDA events on the engine's stream) for `reps` repetitions of the phases."""
+        ms = ctypes.c_float()
+        self._check(self.L.daala_b200_kf_time_device(self.kf, phases, 1 if graph else 0, reps, ctypes.byref(ms)),
+                    "kf_time_device")
+        return float(ms.value)
 
     def upload(self, planes, bsize):
         g = self.geom

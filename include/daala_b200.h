@@ -72,6 +72,15 @@ typedef void (*od_dct_func_2d)(od_coeff *out, int out_stride, const od_coeff *in
 extern const od_dct_func_2d OD_FDCT_2D_CUDA[6];
 extern const od_dct_func_2d OD_IDCT_2D_CUDA[6];
 
+/* The same tables under the reference's own names (src/dct.c:54-84; src/dct.h:62-75), for builds that
+   link this library in place of the reference's dct.o. */
+typedef void (*od_fdct_func_1d)(od_coeff *out, const od_coeff *in, int in_stride);
+typedef void (*od_idct_func_1d)(od_coeff *out, int out_stride, const od_coeff *in);
+extern const od_dct_func_2d OD_FDCT_2D_C[6];
+extern const od_dct_func_2d OD_IDCT_2D_C[6];
+extern const od_fdct_func_1d OD_FDCT_1D[6];
+extern const od_idct_func_1d OD_IDCT_1D[6];
+
 /* 4-point lapped pre/post filter and its appliers.
    reference: src/filter.h:44-87, definitions src/filter.c:147,195,1459,1485,
    1529,1561. */
@@ -88,6 +97,9 @@ void od_post_filter32(od_coeff _x[32], const od_coeff _y[32]);
 typedef void (*od_filter_func)(od_coeff _out[], const od_coeff _in[]);
 extern const od_filter_func OD_PRE_FILTER_CUDA[4];   /* OD_PRE_FILTER, src/filter.c:115 */
 extern const od_filter_func OD_POST_FILTER_CUDA[4];  /* OD_POST_FILTER, src/filter.c:122 */
+extern const od_filter_func OD_PRE_FILTER[5];        /* the reference's names, src/filter.h:45-46 */
+extern const od_filter_func OD_POST_FILTER[5];
+extern const int OD_FILTER_PARAMS4[4];               /* src/filter.c:142 */
 void od_prefilter_split(od_coeff *c0, int stride, int bs, int f, int hfilter, int vfilter);
 void od_postfilter_split(od_coeff *c0, int stride, int bs, int f, int q, unsigned char *skip,
                          int skip_stride, int hfilter, int vfilter);
@@ -463,9 +475,12 @@ typedef struct daala_b200_kf_buffers {  /* device pointers of an engine (tests, 
 
 #define DAALA_B200_KF_LISTS 1
 #define DAALA_B200_KF_FORWARD 2
-#define DAALA_B200_KF_PVQ 4
+#define DAALA_B200_KF_PVQ_LUMA 4
 #define DAALA_B200_KF_INVERSE 8
-#define DAALA_B200_KF_ALL 15
+#define DAALA_B200_KF_PVQ_CHROMA 16
+#define DAALA_B200_KF_PVQ (DAALA_B200_KF_PVQ_LUMA | DAALA_B200_KF_PVQ_CHROMA)
+#define DAALA_B200_KF_ALL 31
+#define DAALA_B200_KF_SEARCH_ONLY 64   /* with _PVQ_*: only the persistent search kernels (measurement) */
 
 daala_b200_kf *daala_b200_kf_create(const daala_b200_kf_config *cfg);   /* NULL on failure */
 void daala_b200_kf_destroy(daala_b200_kf *kf);
@@ -474,6 +489,8 @@ int daala_b200_kf_device_buffers(daala_b200_kf *kf, daala_b200_kf_buffers *out);
 /* Runs the selected phases on the engine's stream with inputs already in HBM (asynchronous);
    use_graph: replay the captured CUDA graph (DAALA_B200_KF_ALL only). */
 int daala_b200_kf_run_device(daala_b200_kf *kf, int phases, int use_graph);
+/* `reps` repetitions of the phases timed with CUDA events on the engine's stream; *ms = total. */
+int daala_b200_kf_time_device(daala_b200_kf *kf, int phases, int use_graph, int reps, float *ms);
 /* Host-side totals implied by block-size maps (sizes of the result arrays). */
 int daala_b200_kf_count_blocks(const uint8_t *bsize, int nframes, long long frame_pitch, int bstride, int nhsb,
                                int nvsb, int sb_row0, int sb_rows, daala_b200_kf_totals *out);

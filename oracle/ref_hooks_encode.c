@@ -83,3 +83,8 @@ int oracle_ref_encode_keyframe(int w, int h, unsigned char *y, unsigned char *u,
   daala_encode_free(enc);
   return 0;
 }
+
+/* Multi-frame variant (keyframe + P frames) returning every packet's size and checksum: the
+   reference side of the drop-in link test (dropin_main.c). */
+#define ENCODE_FRAMES_NAME oracle_ref_encode_frames
+#include "encode_frames.inc"

@@ -234,7 +234,10 @@ def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "daala_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     names = set(re.findall(r"\b((?:od|daala_b200)_[a-z0-9_]+)\s*\(", hdr))
-    names |= {"OD_FDCT_2D_CUDA", "OD_IDCT_2D_CUDA"}
+    names |= {"OD_FDCT_2D_CUDA", "OD_IDCT_2D_CUDA", "OD_PRE_FILTER_CUDA", "OD_POST_FILTER_CUDA"}
+    # the reference's own table names: what its objects resolve when this library replaces dct.o / filter.o
+    names |= {"OD_FDCT_2D_C", "OD_IDCT_2D_C", "OD_FDCT_1D", "OD_IDCT_1D", "OD_PRE_FILTER", "OD_POST_FILTER",
+              "OD_FILTER_PARAMS4"}
     assert len(names) >= 60
     missing = [n for n in sorted(names) if not hasattr(L, n)]
     assert not missing, missing
@@ -257,8 +260,10 @@ def test_ctypes_mirrors_have_the_sizes_the_c_compiler_gives(tmp_path):
     import ctypes
     from daala_b200 import _native, mc, pvq
     from tests.test_gpu_dering import DeringParams
+    from daala_b200 import engine
     names = ["daala_b200_plane", "daala_b200_frame", "daala_b200_pvq_block", "daala_b200_pvq_params",
-             "daala_b200_mc_block", "daala_b200_match_job", "daala_b200_dering_params", "daala_b200_keyframe_lists"]
+             "daala_b200_mc_block", "daala_b200_match_job", "daala_b200_dering_params", "daala_b200_keyframe_lists",
+             "daala_b200_kf_config", "daala_b200_kf_totals", "daala_b200_kf_io", "daala_b200_kf_buffers"]
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "daala_b200.h"\nint main(void) {\n'
                    + "".join('  printf("%%zu\\n", sizeof(%s));\n' % n for n in names) + "  return 0;\n}\n")
@@ -268,7 +273,8 @@ def test_ctypes_mirrors_have_the_sizes_the_c_compiler_gives(tmp_path):
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [ctypes.sizeof(_native.Plane), ctypes.sizeof(_native.Frame), pvq.BLOCK_DTYPE.itemsize,
             ctypes.sizeof(pvq.PvqParams), mc.MC_BLOCK_DTYPE.itemsize, mc.MATCH_JOB_DTYPE.itemsize,
-            ctypes.sizeof(DeringParams), ctypes.sizeof(pvq._KeyframeLists)]
+            ctypes.sizeof(DeringParams), ctypes.sizeof(pvq._KeyframeLists), ctypes.sizeof(engine.Config),
+            ctypes.sizeof(engine.Totals), ctypes.sizeof(engine.IO), ctypes.sizeof(engine.Buffers)]
     assert got == want, list(zip(names, got, want))
 
 
@@ -313,3 +319,22 @@ def test_border_exchange_two_ranks_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+def test_dropin_link_test_binary_resolves_filter_and_dct_symbols_from_the_library():
+    """oracle/_ref/daala_dropin_test = the reference encoder's objects minus filter.o / dct.o, shim/cudastate.o and
+    libdaala_b200.so: every filter / DCT symbol of the reference must be UNDEFINED in the program (so the
+    dynamic linker takes it from the library) and the vtable initialisers must come from the shim."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "daala_dropin_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/daala_dropin_test not built (needs /root/reference)")
+    syms = subprocess.run(["nm", exe], capture_output=True, text=True, check=True).stdout.splitlines()
+    kind = {ln.split()[-1]: ln.split()[-2] for ln in syms if len(ln.split()) >= 2}
+    for name in ("od_apply_prefilter_frame_sbs", "od_apply_postfilter_frame_sbs", "od_prefilter_split",
+                 "od_postfilter_split", "od_haar", "od_haar_inv", "OD_FDCT_2D_C", "OD_IDCT_2D_C", "OD_FDCT_2D_CUDA",
+                 "od_mc_predict1fmv8_cuda", "od_mc_compute_sad8_8x8_cuda"):
+        assert kind.get(name) in ("U", "B", "D", "R") and kind.get(name) != "T", (name, kind.get(name))
+    for name in ("od_state_opt_vtbl_init_cuda", "od_enc_opt_vtbl_init_cuda", "od_state_opt_vtbl_init_x86",
+                 "od_enc_opt_vtbl_init_x86", "daala_encode_create", "od_pvq_encode"):
+        assert kind.get(name) == "T", (name, kind.get(name))
+    assert "od_bin_fdct8" not in kind or kind["od_bin_fdct8"] == "U"
