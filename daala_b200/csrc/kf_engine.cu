@@ -28,7 +28,7 @@
 #include "daala_b200.h"
 #include "gen/coding_order.inc"
 #include "pvq_math.cuh"
-#include "pvq_coop.cuh"
+#include "pvq_warp.cuh"
 #include "pvq_common.cuh"
 
 namespace daala_b200 {
@@ -39,16 +39,20 @@ using namespace daala_b200::pvq;
 // ---- device-side counters ----------------------------------------------------------------------
 enum Cnt {
   kNLuma = 0, kNChroma, kLumaCoefs, kChromaCoefs,
-  kNItemsL = 4,      // [3] luma items per class (n <= 16, 32, 128)
-  kNItemsC = 7,      // [3] chroma items per class
-  kTicketL = 10,     // [3]
-  kTicketC = 13,     // [3]
-  kEpoch = 16,
+  kNItemsL = 4,      // [3] luma dependency-free items per class (bands 3 / 6: classes 1 / 2)
+  kNItemsC = 7,      // [3] chroma items per class (n <= 16, 32, 128)
+  kTotalHi = 14,     // luma chain items in total
+  kNHeads = 15,      // of which ready from the start (no same-size neighbour on the side they depend on)
   kError = 17,
-  kCntWords = 32
+  // the words the persistent kernels hammer with atomics each sit in a 128-byte line of their own
+  kHeadLoL = 32,     // ticket of the luma dependency-free lists
+  kHeadLoC = 64,     // ticket of the chroma lists
+  kHeadHi = 96,      // luma chain queue: next slot to claim
+  kTailHi = 128,     //                   next slot to fill
+  kDoneHi = 160,     // chain items finished (flushed by warps when they go idle)
+  kCntWords = 192
 };
 
-constexpr int kKeyBins = 4096;     // dependency-position bins of one class
 constexpr int kTile = 1024;        // units per scan tile
 
 struct Lists {
@@ -62,13 +66,14 @@ struct Lists {
   int32_t* unit_lbase;             // [F*UH*UW] index of the first luma block whose origin is in the unit
   daala_b200_pvq_block* luma;
   daala_b200_pvq_block* chroma;
-  int32_t* dep_top;
+  int32_t* dep_top;                // same-size neighbour above / to the left (od_hv_intra_pred), or -1
   int32_t* dep_left;
-  uint32_t* items_l[3];
+  int32_t* succ_bottom;            // inverse: the block whose dep_top / dep_left is this one, or -1
+  int32_t* succ_right;
+  uint32_t* items_l[3];            // dependency-free luma items per class
   uint32_t* items_c[3];
-  int32_t* hist;                   // [3][kKeyBins]
+  uint32_t* heads;                 // chain items that are ready from the start
   int32_t* cnt;                    // [kCntWords]
-  int key_scale[3];                // band 0 (x+y), top chains (y), left chains (x): key = pos * scale
   int max_luma, max_chroma;        // capacities (blocks)
 };
 
@@ -125,7 +130,6 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const __grid_constant__ List
   __shared__ int4 carry;
   const int t = threadIdx.x;
   if (t == 0) carry = make_int4(0, 0, 0, 0);
-  for (int i = t; i < 3 * kKeyBins; i += 1024) L.hist[i] = 0;
   __syncthreads();
   for (int base = 0; base < L.ntiles; base += 1024) {
     const int i = base + t;
@@ -154,6 +158,8 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const __grid_constant__ List
       L.cnt[kNItemsL + c] = 0;
       L.cnt[kNItemsC + c] = 0;
     }
+    L.cnt[kTotalHi] = 0;
+    L.cnt[kNHeads] = 0;
     if (tot.x > L.max_luma || 2 * tot.z > L.max_chroma) L.cnt[kError] = 1;
   }
 }
@@ -207,32 +213,37 @@ __global__ void __launch_bounds__(kTile) k_unit_emit(const __grid_constant__ Lis
   put_block(L.chroma + 2 * pre.z + 1, 2 * pre.w + v.w, ux * 4, uy * 4, cbs, 2, xd, f);
 }
 
-// Position of (block, band) along its dependency chain, scaled into [0, kKeyBins): strictly larger
-// than the key of every item it depends on (od_hv_intra_pred reads the same-size TOP neighbour for
-// row-0 bands 1/4/7, the LEFT one for column-0 bands 2/5/8, both for band 0, none for 3/6), so the
-// sorted item list is a topological order.  Dependency-free bands are spread over the whole range
-// (they fill the machine while chain links wait).
-__device__ __forceinline__ int item_key(const Lists& L, int blk, int band, int x0, int y0) {
-  const int x4 = x0 >> 2, y4 = (y0 >> 2) - L.u_row0 * 2;
-  if (band == 0) return (x4 + y4) * L.key_scale[0];
-  if (band == 3 || band == 6) return (int)(((unsigned)blk * 2654435761u) >> 20);   // 12 bits
-  const int r = band % 3;
-  return r == 1 ? y4 * L.key_scale[1] : x4 * L.key_scale[2];
-}
-
 __device__ __forceinline__ int band_class(int band) { return band < 3 ? 0 : band < 6 ? 1 : 2; }
 
-// pass 0: neighbours + key histogram; pass 1: scatter into the sorted lists (hist holds the cursors).
-template <int kPass>
-__global__ void __launch_bounds__(256) k_luma_items(const __grid_constant__ Lists L) {
+// warp-aggregated append of `v` to list[*counter] by the lanes with `pred`
+__device__ __forceinline__ void append(uint32_t* list, int32_t* counter, bool pred, uint32_t v) {
+  const unsigned m = __ballot_sync(__activemask(), pred);
+  if (!pred) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(m, base, leader);
+  list[base + __popc(m & ((1u << lane) - 1u))] = v;
+}
+
+// Luma dependency structure.  od_hv_intra_pred (src/intra.c:37) predicts band b of a block from band b of
+// the same-size TOP neighbour (row-0 bands 1/4/7), the LEFT one (column-0 bands 2/5/8), both (band 0) or
+// nothing (bands 3/6).  Per block: the two neighbours and, inverted, the blocks that wait for this one;
+// per (block, band): a dependency-free item, a chain head (ready now) or a chain link (made ready by the
+// persistent kernel when its neighbours are done).
+__global__ void __launch_bounds__(256) k_luma_deps(const __grid_constant__ Lists L) {
   const int n = min(L.cnt[kNLuma], L.max_luma);
-  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < n; blk += gridDim.x * blockDim.x) {
-    const daala_b200_pvq_block b = L.luma[blk];
-    const int bs = b.bs, x0 = b.x0, y0 = b.y0, f = b.frame;
-    if (kPass == 0) {
+  const int nth = gridDim.x * blockDim.x;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += nth) {
+    const int blk = base + threadIdx.x;
+    const bool in = blk < n;
+    int bs = 0, top = -1, left = -1;
+    if (in) {
+      const daala_b200_pvq_block b = L.luma[blk];
+      const int x0 = b.x0, y0 = b.y0, f = b.frame;
+      bs = b.bs;
       const int nn = 4 << bs;
       const uint8_t* map = L.bsize + f * L.bsize_pitch;
-      int top = -1, left = -1;
       if (y0 - nn >= L.u_row0 * 8 && map[(long long)((y0 - 1) >> 3) * L.bstride + (x0 >> 3)] == bs) {
         const int ty = y0 - nn;
         top = L.unit_lbase[((long long)f * L.UH + (ty >> 3)) * L.UW + (x0 >> 3)] +
@@ -245,61 +256,26 @@ __global__ void __launch_bounds__(256) k_luma_items(const __grid_constant__ List
       }
       L.dep_top[blk] = top;
       L.dep_left[blk] = left;
+      if (top >= 0) L.succ_bottom[top] = blk;      // succ_* were preset to -1
+      if (left >= 0) L.succ_right[left] = blk;
     }
-    const int nb = num_bands(bs);
-    for (int band = 0; band < nb; band++) {
-      const int c = band_class(band);
-      int key = item_key(L, blk, band, x0, y0);
-      key = key < kKeyBins ? key : kKeyBins - 1;
-      if (kPass == 0) {
-        atomicAdd(&L.hist[c * kKeyBins + key], 1);
-      } else {
-        const int pos = atomicAdd(&L.hist[c * kKeyBins + key], 1);
-        L.items_l[c][pos] = ((uint32_t)blk << 4) | band;
-      }
+    const int nb = in ? num_bands(bs) : 0;
+    int chain = 0;
+    for (int band = 0; band < 9; band++) {
+      const bool has = band < nb;
+      const bool is_free = band == 3 || band == 6;
+      const int r = band % 3;
+      const bool waits = band == 0 ? (top >= 0 || left >= 0) : r == 1 ? top >= 0 : left >= 0;
+      const uint32_t item = ((uint32_t)blk << 4) | band;
+      if (band == 3 || band == 6) append(L.items_l[band_class(band)], &L.cnt[kNItemsL + band_class(band)], has, item);
+      else append(L.heads, &L.cnt[kNHeads], has && !waits, item);
+      chain += has && !is_free;
     }
-  }
-}
-
-// Items one warp of the persistent kernel takes per ticket, by class (32 / lanes per band).
-__host__ __device__ constexpr int items_per_warp(int cls) { return cls == 0 ? 8 : cls == 1 ? 4 : 1; }
-constexpr uint32_t kNoItem = 0xffffffffu;
-
-// 3 CTAs: exclusive scan of each class's histogram in place; totals into cnt.  Every key bin is
-// padded to a whole number of warp chunks (pad entries = kNoItem): the items one warp processes
-// together then all share one key, so none of them depends on another one of the same warp (a warp
-// waiting on itself would never finish).
-__global__ void __launch_bounds__(1024) k_hist_scan(const __grid_constant__ Lists L) {
-  __shared__ int part[1024];
-  constexpr int kPer = kKeyBins / 1024;
-  const int cls = blockIdx.x;
-  const int P = items_per_warp(cls);
-  int* hist = L.hist + cls * kKeyBins;
-  uint32_t* items = L.items_l[cls];
-  const int t = threadIdx.x;
-  int v[kPer], pv[kPer], sum = 0;
+    // total number of chain items
 #pragma unroll
-  for (int i = 0; i < kPer; i++) {
-    v[i] = hist[t * kPer + i];
-    pv[i] = (v[i] + P - 1) / P * P;
-    sum += pv[i];
+    for (int o = 16; o > 0; o >>= 1) chain += __shfl_xor_sync(0xffffffffu, chain, o);
+    if ((threadIdx.x & 31) == 0 && chain) atomicAdd(&L.cnt[kTotalHi], chain);
   }
-  part[t] = sum;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int add = t >= o ? part[t - o] : 0;
-    __syncthreads();
-    part[t] += add;
-    __syncthreads();
-  }
-  int run = part[t] - sum;
-#pragma unroll
-  for (int i = 0; i < kPer; i++) {
-    hist[t * kPer + i] = run;
-    for (int j = v[i]; j < pv[i]; j++) items[run + j] = kNoItem;
-    run += pv[i];
-  }
-  if (t == 1023) L.cnt[kNItemsL + cls] = part[1023];
 }
 
 // Chroma items: no dependencies between blocks; compaction per class (order is free).
@@ -325,12 +301,17 @@ __global__ void __launch_bounds__(256) k_chroma_items(const __grid_constant__ Li
 // ---- PVQ stage -----------------------------------------------------------------------------------
 struct Stage {
   daala_b200_pvq_params prm;
-  const uint32_t* items[3];
-  const int32_t* dep_top;          // luma: neighbours (NULL for chroma)
+  const uint32_t* items[3];        // dependency-free items per class (taken largest class first)
+  // luma only: the chain queue = [heads (static) | ring filled at run time]
+  const uint32_t* heads;
+  uint32_t* ring;
+  const int32_t* dep_top;
   const int32_t* dep_left;
-  int32_t* flags;                  // [nblocks*9] == epoch once that band's `out` is final
+  const int32_t* succ_bottom;
+  const int32_t* succ_right;
+  int32_t* join0;                  // [nblocks] band 0: neighbours finished so far (it may wait for two)
   int32_t* cnt;
-  int n_items_at, ticket_at, n_blocks_at;
+  int n_items_at, head_lo_at, n_blocks_at;
   int max_blocks;
   int16_t* res_pack;               // [nblocks*9][4]: gain, itheta, max_theta, k (what the coder reads)
   const int32_t* cfl_plane;        // chroma: prediction plane (chroma geometry), else NULL
@@ -427,118 +408,195 @@ __global__ void __launch_bounds__(256) k_cfl_plane(const __grid_constant__ Stage
   }
 }
 
-// One (block, band) item by a G-lane group; kIntra: build the band's prediction from the quantised
-// neighbours first (k_intra_band_ref of pvq_kernels.cu) after waiting for their flags.
-template <int G, int E, bool kIntra>
-__device__ __forceinline__ void run_items(const Stage& S, int cls, int epoch) {
+constexpr uint32_t kNoItem = 0xffffffffu;
+constexpr uint32_t kExit = 0xfffffffeu;
+
+__device__ __forceinline__ int ld_relaxed(const int32_t* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void push_chain(const Stage& S, int blk, int band) {
+  const int pos = atomicAdd(&S.cnt[kTailHi], 1) - S.cnt[kNHeads];
+  st_release((int*)&S.ring[pos], (int)(((uint32_t)blk << 4) | band));
+}
+
+// Next item for an idle warp (uniform), or kNoItem when the stage has nothing left for it.
+//  chroma (kIntra = false): a ticket into the item lists, largest bands first.
+//  luma: (1) a filled slot of the chain queue (heads first, then what other warps pushed), (2) a
+//  dependency-free item, (3) a ticket for a FUTURE chain slot, waited for on the slot itself (distinct
+//  addresses: no hot spot).  `done` = chain items this warp finished since it was last here; the warp
+//  whose flush completes the count releases every waiter with kExit.
+template <bool kIntra>
+__device__ __forceinline__ uint32_t next_item(const Stage& S, int lane, int* done) {
+  int slot = -1, lo = -1, nheads = 0, fin = -1;
+  if (lane == 0) {
+    const int n2 = S.cnt[S.n_items_at + 2], n1 = S.cnt[S.n_items_at + 1], n0 = S.cnt[S.n_items_at];
+    const int nlo = n0 + n1 + n2;
+    if (kIntra) {
+      nheads = S.cnt[kNHeads];
+      if (*done) {
+        const int d = atomicAdd(&S.cnt[kDoneHi], *done) + *done;
+        if (d == S.cnt[kTotalHi]) {
+          __threadfence();
+          fin = ld_relaxed(&S.cnt[kTailHi]) - nheads;   // final: every push happened before its item finished
+        }
+      }
+      if (ld_relaxed(&S.cnt[kHeadHi]) < ld_relaxed(&S.cnt[kTailHi])) slot = atomicAdd(&S.cnt[kHeadHi], 1);
+    }
+    if (slot < 0 && ld_relaxed(&S.cnt[S.head_lo_at]) < nlo) {
+      const int l = atomicAdd(&S.cnt[S.head_lo_at], 1);
+      if (l < nlo) lo = l;
+    }
+    if (kIntra && slot < 0 && lo < 0) slot = atomicAdd(&S.cnt[kHeadHi], 1);
+  }
+  *done = 0;
+  if (kIntra) {
+    fin = __shfl_sync(0xffffffffu, fin, 0);
+    if (fin >= 0) {
+      // every warp holds at most one ticket: slots [fin, fin + #warps] cover all of them, now and later
+      const int nw = (gridDim.x * blockDim.x) >> 5;
+      for (int i = lane; i <= nw; i += 32) st_release((int*)&S.ring[fin + i], (int)kExit);
+    }
+  }
+  slot = __shfl_sync(0xffffffffu, slot, 0);
+  lo = __shfl_sync(0xffffffffu, lo, 0);
+  if (slot >= 0) {
+    nheads = __shfl_sync(0xffffffffu, nheads, 0);
+    if (slot < nheads) return S.heads[slot];
+    // every lane acquires: what the producer wrote before its release is visible to all of them
+    uint32_t v;
+    while ((v = (uint32_t)ld_acquire((const int*)&S.ring[slot - nheads])) == kNoItem) __nanosleep(200);
+    return v == kExit ? kNoItem : v;
+  }
+  if (lo >= 0) {
+    const int n2 = S.cnt[S.n_items_at + 2], n1 = S.cnt[S.n_items_at + 1];
+    return lo < n2 ? S.items[2][lo] : lo < n2 + n1 ? S.items[1][lo - n2] : S.items[0][lo - n2 - n1];
+  }
+  return kNoItem;
+}
+
+// One (block, band) item by one warp.  kIntra: the band's prediction is built from the quantised
+// neighbours first (od_hv_intra_pred, src/intra.c:37-62).
+template <int E, bool kIntra>
+__device__ __forceinline__ void run_item(const Stage& S, uint32_t item, int lane) {
   const daala_b200_pvq_params& prm = S.prm;
-  const Group<G, E> grp;
-  constexpr int kPerWarp = 32 / G;
-  const int n = S.cnt[S.n_items_at + cls];
-  const uint32_t* items = S.items[cls];
+  const int blk = (int)(item >> 4), band = (int)(item & 15);
+  const daala_b200_pvq_block b = prm.blocks[blk];
+  const int bs = b.bs, pli = b.pli;
+  const int start = band_start(band);
+  const int bn = band_start(band + 1) - start;
+  const size_t off = (size_t)b.coef_off + start;
+  if (kIntra) {
+    const int r = band % 3;
+    int top = -1, left = -1;
+    if (band == 0 || r == 1) top = S.dep_top[blk];
+    if (band == 0 || r == 2) left = S.dep_left[blk];
+    if (band == 3 || band == 6) top = left = -1;
+    const int32_t* ot = top >= 0 ? prm.out + prm.blocks[top].coef_off : nullptr;
+    const int32_t* ol = left >= 0 ? prm.out + prm.blocks[left].coef_off : nullptr;
+    bool low_from_top = false;
+    if (band == 0) {
+      // coding-order indices of (0,1) (0,2) (0,3) and (1,0) (2,0) (3,0) in the 4x4 stage; double
+      // sums of exact integers as in od_hv_intra_pred (src/intra.c:51-52)
+      double g1 = 0, g2 = 0;
+      if (ot) { double a = ot[2], bb = ot[5], c = ot[9]; g1 += a * a; g1 += bb * bb; g1 += c * c; }
+      if (ol) { double a = ol[1], bb = ol[4], c = ol[7]; g2 += a * a; g2 += bb * bb; g2 += c * c; }
+      low_from_top = g1 > g2;
+    }
+    int32_t* vref = prm.ref + b.coef_off;
+    // element j of the band is owned by lane j % 32: the lane that writes ref[j] is the one that reads it
+    for (int i = start + lane; i < start + bn; i += 32) {
+      int r2, c2;
+      scan_rc(i, &r2, &c2);
+      int32_t p = 0;
+      if (r2 == 0 && c2 > 0 && ot && (c2 >= 4 || low_from_top)) p = ot[i];
+      if (c2 == 0 && r2 > 0 && ol && (r2 >= 4 || !low_from_top)) p = ol[i];
+      vref[i] = p;
+    }
+  }
+  int qidx = bs * (bs + 1) + (band + 1) - (band + 1) / 3;
+  int q = (prm.q0 * prm.pvq_qm_q4[pli][qidx]) >> 4;
+  if (q < 1) q = 1;
+  const int beta = (prm.use_masking && pli == 0 && bs > 0) ? kBeta15 : kBeta1;
+  const int qoff = (b.xdec & 1 ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
+  int itheta, max_theta, k;
+  double skip_term;
+  const int gain = quantise_band_warp<E>(lane, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off, &itheta,
+                                         &max_theta, &k, beta, &skip_term, prm.is_keyframe, pli, prm.qm + qoff,
+                                         prm.qm_inv + qoff, prm.pvq_norm_lambda);
+  if (lane == 0) {
+    const size_t r = (size_t)blk * 9 + band;
+    prm.res_skip_term[r] = skip_term;
+    short4 pk;
+    pk.x = (short)gain; pk.y = (short)itheta; pk.z = (short)max_theta; pk.w = (short)k;
+    reinterpret_cast<short4*>(S.res_pack)[r] = pk;
+  }
+}
+
+// Persistent PVQ kernel: one warp = one band at a time.  Luma (kIntra): the chain items of the H/V
+// intra predictor form a dependency graph (per size class: band 0 a 2-D wavefront, bands 1/4/7 columns,
+// bands 2/5/8 rows).  A warp that finishes a chain item CONTINUES with a successor it made ready -- a
+// column or row is walked by one warp without touching the queue -- and pushes a second ready
+// successor (band 0 forks) into the chain queue.
+template <bool kIntra>
+__global__ void __launch_bounds__(128, 4) k_pvq_persist(const __grid_constant__ Stage S) {
   const int lane = threadIdx.x & 31;
+  int done = 0;
   for (;;) {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(&S.cnt[S.ticket_at + cls], 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    const int base = t * kPerWarp;
-    if (base >= n) return;
-    const int idx = base + lane / G;
-    const uint32_t e = idx < n ? items[idx] : kNoItem;
-    const bool valid = e != kNoItem;
-    const int blk = valid ? (int)(e >> 4) : 0, band = valid ? (int)(e & 15) : 3;
-    const daala_b200_pvq_block b = prm.blocks[blk];
-    const int bs = b.bs, pli = b.pli;
-    const int start = band_start(band);
-    const int bn = band_start(band + 1) - start;
-    const size_t off = (size_t)b.coef_off + start;
-    if (kIntra) {
-      int top = -1, left = -1;
-      const int r = band % 3;
-      if (valid && (band == 0 || r == 1)) top = S.dep_top[blk];
-      if (valid && (band == 0 || r == 2)) left = S.dep_left[blk];
-      if (band == 3 || band == 6) top = left = -1;
-      // every lane polls its own group's flags; the warp leaves together
-      const int* ft = top >= 0 ? S.flags + (size_t)top * 9 + band : nullptr;
-      const int* fl = left >= 0 ? S.flags + (size_t)left * 9 + band : nullptr;
-      for (;;) {
-        const bool ready = (!ft || ld_acquire(ft) == epoch) && (!fl || ld_acquire(fl) == epoch);
-        if (__all_sync(0xffffffffu, ready)) break;
-        __nanosleep(200);
-      }
-      if (valid) {
-        const int32_t* ot = top >= 0 ? prm.out + prm.blocks[top].coef_off : nullptr;
-        const int32_t* ol = left >= 0 ? prm.out + prm.blocks[left].coef_off : nullptr;
-        bool low_from_top = false;
-        if (band == 0) {
-          // coding-order indices of (0,1) (0,2) (0,3) and (1,0) (2,0) (3,0) in the 4x4 stage; double
-          // sums of exact integers as in od_hv_intra_pred (src/intra.c:51-52)
-          double g1 = 0, g2 = 0;
-          if (ot) { double a = ot[2], bb = ot[5], c = ot[9]; g1 += a * a; g1 += bb * bb; g1 += c * c; }
-          if (ol) { double a = ol[1], bb = ol[4], c = ol[7]; g2 += a * a; g2 += bb * bb; g2 += c * c; }
-          low_from_top = g1 > g2;
-        }
-        int32_t* vref = prm.ref + b.coef_off;
-        // element j of the band is owned by lane j % G: the lane that writes ref[j] is the one that reads it
-        for (int i = start + grp.lane; i < start + bn; i += G) {
-          int r2, c2;
-          scan_rc(i, &r2, &c2);
-          int32_t p = 0;
-          if (r2 == 0 && c2 > 0 && ot && (c2 >= 4 || low_from_top)) p = ot[i];
-          if (c2 == 0 && r2 > 0 && ol && (r2 >= 4 || !low_from_top)) p = ol[i];
-          vref[i] = p;
-        }
-      }
-    }
-    if (valid) {
-      int qidx = bs * (bs + 1) + (band + 1) - (band + 1) / 3;
-      int q = (prm.q0 * prm.pvq_qm_q4[pli][qidx]) >> 4;
-      if (q < 1) q = 1;
-      const int beta = (prm.use_masking && pli == 0 && bs > 0) ? kBeta15 : kBeta1;
-      const int qoff = (b.xdec & 1 ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
-      int itheta, max_theta, k;
-      double skip_term;
-      const int gain = quantise_band_coop<G, E, false>(grp, prm.out + off, prm.in + off, prm.ref + off, bn, q,
-                                                       prm.y + off, &itheta, &max_theta, &k, beta, &skip_term,
-                                                       prm.is_keyframe, pli, prm.qm + qoff, prm.qm_inv + qoff,
-                                                       prm.pvq_norm_lambda);
-      if (grp.lane == 0) {
-        const size_t r = (size_t)blk * 9 + band;
-        prm.res_skip_term[r] = skip_term;
-        short4 pk;
-        pk.x = (short)gain; pk.y = (short)itheta; pk.z = (short)max_theta; pk.w = (short)k;
-        reinterpret_cast<short4*>(S.res_pack)[r] = pk;
-      }
-    }
-    if (kIntra) {
+    uint32_t item = next_item<kIntra>(S, lane, &done);
+    if (item == kNoItem) return;
+    for (;;) {
+      const int band = (int)(item & 15);
+      if (band >= 6) run_item<4, kIntra>(S, item, lane);
+      else run_item<1, kIntra>(S, item, lane);
+      if (!kIntra || band == 3 || band == 6) break;
+      done++;
+      // results of this item -> visible to whoever runs a successor (this warp included: other lanes)
       __threadfence();
       __syncwarp();
-      if (valid && grp.lane == 0) st_release(S.flags + (size_t)blk * 9 + band, epoch);
+      uint32_t next = kNoItem;
+      if (lane == 0) {
+        const int blk = (int)(item >> 4);
+        if (band == 0) {
+          const int nb[2] = {S.succ_bottom[blk], S.succ_right[blk]};
+          for (int i = 0; i < 2; i++) {
+            if (nb[i] < 0) continue;
+            const int need = (S.dep_top[nb[i]] >= 0) + (S.dep_left[nb[i]] >= 0);
+            if (need == 2 && atomicAdd(&S.join0[nb[i]], 1) != 1) continue;   // the other neighbour is not done yet
+            if (next == kNoItem) {
+              next = (uint32_t)nb[i] << 4;
+            } else {
+              __threadfence();   // (join) the other neighbour's results are ordered before the push
+              push_chain(S, nb[i], 0);
+            }
+          }
+        } else {
+          const int nb = band % 3 == 1 ? S.succ_bottom[blk] : S.succ_right[blk];
+          if (nb >= 0) next = ((uint32_t)nb << 4) | band;
+        }
+      }
+      next = __shfl_sync(0xffffffffu, next, 0);
+      if (next == kNoItem) break;
+      // (join) what the other neighbour's warp released before its atomic is visible to every lane
+      __threadfence();
+      item = next;
     }
   }
 }
 
-// Persistent PVQ kernel: every warp serves the three size classes, starting with `warp % 3` so that
-// all classes progress concurrently (each class is its own dependency system), and moves on when a
-// class is exhausted.  Tickets are handed out in sorted (= dependency) order to running warps only,
-// so the holder of the lowest unfinished ticket never waits on a later one: no deadlock.
-template <bool kIntra>
-__global__ void __launch_bounds__(128, 5) k_pvq_persist(const __grid_constant__ Stage S) {
-  const int epoch = S.cnt[kEpoch];
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  for (int r = 0; r < 3; r++) {
-    const int cls = (w + r) % 3;
-    if (cls == 0) run_items<4, 4, kIntra>(S, 0, epoch);
-    else if (cls == 1) run_items<8, 4, kIntra>(S, 1, epoch);
-    else run_items<32, 4, kIntra>(S, 2, epoch);
-  }
-}
-
-// Start of a PVQ stage: fresh tickets, new epoch for the dependency flags.
-__global__ void k_begin_pvq(int32_t* cnt) {
+// Start of a PVQ stage: the tickets; the chain queue starts with the heads.
+__global__ void k_begin_pvq(int32_t* cnt, int luma) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    for (int c = 0; c < 3; c++) cnt[kTicketL + c] = cnt[kTicketC + c] = 0;
-    cnt[kEpoch] += 1;
+    if (luma) {
+      cnt[kHeadLoL] = 0;
+      cnt[kHeadHi] = 0;
+      cnt[kTailHi] = cnt[kNHeads];
+      cnt[kDoneHi] = 0;
+    } else {
+      cnt[kHeadLoC] = 0;
+    }
   }
 }
 
@@ -607,6 +665,7 @@ struct daala_b200_kf {
   Stage luma, chroma;
   daala_b200_frame frame;
   size_t bytes_allocated;
+  size_t chain_cap;                // entries of the chain queue (heads / ring)
   int sms;
   char err[256];
 };
@@ -672,24 +731,20 @@ static int kf_alloc(daala_b200_kf* kf) {
   KF_CHECK(dalloc(kf, &L.chroma, (size_t)L.max_chroma));
   KF_CHECK(dalloc(kf, &L.dep_top, (size_t)L.max_luma));
   KF_CHECK(dalloc(kf, &L.dep_left, (size_t)L.max_luma));
-  // items per class: class 0 (bands 0-2) <= max(blocks) [all 4x4: one band each; 8x8: 3 per 4 units]
+  KF_CHECK(dalloc(kf, &L.succ_bottom, (size_t)L.max_luma));
+  KF_CHECK(dalloc(kf, &L.succ_right, (size_t)L.max_luma));
+  // item capacities follow from the pixel count alone: one band per 4x4 block is the densest case
   const size_t luma_shard_px = (size_t)F * L.u_rows * UW * 64;
-  const size_t pad = (size_t)kKeyBins * 8;   // per-bin padding to whole warp chunks
-  const size_t cap_l[3] = {(size_t)L.max_luma + pad, luma_shard_px * 3 / 64 + 64 + pad, luma_shard_px * 3 / 256 + 64 + pad};
+  kf->chain_cap = luma_shard_px / 16 + 64 + (size_t)kf->sms * 64;   // + one exit slot per persistent warp
+  const size_t cap_l[3] = {64, luma_shard_px / 64 + 64, luma_shard_px / 256 + 64};   // bands 3 / 6 only
   const size_t cap_c[3] = {(size_t)L.max_chroma * 3 / 2 + 64, luma_shard_px / 4 * 2 * 3 / 64 + 64,
                            luma_shard_px / 4 * 2 * 3 / 256 + 64};
   for (int c = 0; c < 3; c++) {
     KF_CHECK(dalloc(kf, &L.items_l[c], cap_l[c]));
     KF_CHECK(dalloc(kf, &L.items_c[c], cap_c[c]));
   }
-  KF_CHECK(dalloc(kf, &L.hist, (size_t)3 * kKeyBins));
+  KF_CHECK(dalloc(kf, &L.heads, kf->chain_cap));
   KF_CHECK(dalloc(kf, &L.cnt, (size_t)kCntWords));
-  // chain-position scales: strictly monotonic, filling [0, kKeyBins)
-  const int x4max = kf->plane_w[0] / 4, y4max = L.u_rows * 2;
-  L.key_scale[0] = (kKeyBins - 1) / (x4max + y4max);
-  L.key_scale[1] = (kKeyBins - 1) / y4max;
-  L.key_scale[2] = (kKeyBins - 1) / x4max;
-  for (int i = 0; i < 3; i++) if (L.key_scale[i] < 1) return (int)cudaErrorInvalidValue;   // frame too large for the key range
 
   auto setup_stage = [&](Stage& S, bool chroma) -> int {
     memset(&S, 0, sizeof(S));
@@ -725,13 +780,17 @@ static int kf_alloc(daala_b200_kf* kf) {
     for (int c = 0; c < 3; c++) S.items[c] = chroma ? L.items_c[c] : L.items_l[c];
     S.cnt = L.cnt;
     S.n_items_at = chroma ? kNItemsC : kNItemsL;
-    S.ticket_at = chroma ? kTicketC : kTicketL;
+    S.head_lo_at = chroma ? kHeadLoC : kHeadLoL;
     S.n_blocks_at = chroma ? kNChroma : kNLuma;
     S.max_blocks = (int)nblk;
     if (!chroma) {
       S.dep_top = L.dep_top;
       S.dep_left = L.dep_left;
-      KF_CHECK(dalloc(kf, &S.flags, nblk * 9));
+      S.succ_bottom = L.succ_bottom;
+      S.succ_right = L.succ_right;
+      S.heads = L.heads;
+      KF_CHECK(dalloc(kf, &S.ring, kf->chain_cap));
+      KF_CHECK(dalloc(kf, &S.join0, nblk));
     } else {
       S.cfl_plane = kf->cfl_plane;
       S.cfl_pitch = (long long)kf->plane_w[1] * kf->plane_h[1];
@@ -781,27 +840,31 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
     k_unit_tile_sums<<<L.ntiles, kTile, 0, s>>>(L);
     k_tile_scan<<<1, 1024, 0, s>>>(L);
     k_unit_emit<<<L.ntiles, kTile, 0, s>>>(L);
-    k_luma_items<0><<<wide, 256, 0, s>>>(L);
-    k_hist_scan<<<3, 1024, 0, s>>>(L);
-    k_luma_items<1><<<wide, 256, 0, s>>>(L);
+    const size_t nl = (size_t)L.max_luma * sizeof(int32_t);
+    if (cudaMemsetAsync(L.succ_bottom, 0xff, nl, s) != cudaSuccess || cudaMemsetAsync(L.succ_right, 0xff, nl, s) != cudaSuccess)
+      return (int)cudaGetLastError();
+    k_luma_deps<<<wide, 256, 0, s>>>(L);
     k_chroma_items<<<wide, 256, 0, s>>>(L);
   }
   if (phases & DAALA_B200_KF_FORWARD) {
     int rc = daala_b200_launch_forward(&kf->frame, 3, s);
     if (rc) return rc;
   }
-  const int persist = kf->sms * (kf->cfg.persist_ctas_per_sm > 0 ? kf->cfg.persist_ctas_per_sm : 5);
+  const int persist = kf->sms * (kf->cfg.persist_ctas_per_sm > 0 ? kf->cfg.persist_ctas_per_sm : 4);
   // _SEARCH_ONLY (measurement): just the persistent search kernels, on the coding-order buffers a
   // previous full pass left behind (same inputs, same results)
   const bool core = (phases & DAALA_B200_KF_SEARCH_ONLY) != 0;
   if (phases & DAALA_B200_KF_PVQ_LUMA) {
-    k_begin_pvq<<<1, 32, 0, s>>>(kf->lists.cnt);
+    if (cudaMemsetAsync(kf->luma.ring, 0xff, kf->chain_cap * sizeof(uint32_t), s) != cudaSuccess ||
+        cudaMemsetAsync(kf->luma.join0, 0, (size_t)kf->luma.max_blocks * sizeof(int32_t), s) != cudaSuccess)
+      return (int)cudaGetLastError();
+    k_begin_pvq<<<1, 32, 0, s>>>(kf->lists.cnt, 1);
     if (!core) k_gather<false><<<wide, 256, 0, s>>>(kf->luma);
     k_pvq_persist<true><<<persist, 128, 0, s>>>(kf->luma);
     if (!core) k_finish_scatter<<<wide, 256, 0, s>>>(kf->luma);
   }
   if (phases & DAALA_B200_KF_PVQ_CHROMA) {
-    if (!(phases & DAALA_B200_KF_PVQ_LUMA)) k_begin_pvq<<<1, 32, 0, s>>>(kf->lists.cnt);
+    k_begin_pvq<<<1, 32, 0, s>>>(kf->lists.cnt, 0);
     if (!core) k_cfl_plane<<<wide, 256, 0, s>>>(kf->chroma, kf->cfl_plane);
     if (!core) k_gather<true><<<wide, 256, 0, s>>>(kf->chroma);
     k_pvq_persist<false><<<persist, 128, 0, s>>>(kf->chroma);
@@ -890,7 +953,9 @@ void daala_b200_kf_destroy(daala_b200_kf* kf) {
     cudaFree(L.items_l[c]);
     cudaFree(L.items_c[c]);
   }
-  cudaFree(L.hist);
+  cudaFree(L.heads);
+  cudaFree(L.succ_bottom);
+  cudaFree(L.succ_right);
   cudaFree(L.cnt);
   for (Stage* S : {&kf->luma, &kf->chroma}) {
     cudaFree(S->prm.in);
@@ -902,7 +967,8 @@ void daala_b200_kf_destroy(daala_b200_kf* kf) {
     cudaFree(S->prm.res_skip_diff);
     cudaFree(S->prm.res_flip);
     cudaFree(S->res_pack);
-    cudaFree(S->flags);
+    cudaFree(S->ring);
+    cudaFree(S->join0);
   }
   if (kf->own_stream) cudaStreamDestroy(kf->stream);
   free(kf);
@@ -931,6 +997,9 @@ int daala_b200_kf_device_buffers(daala_b200_kf* kf, daala_b200_kf_buffers* out) 
     out->luma_items[c] = kf->lists.items_l[c];
     out->chroma_items[c] = kf->lists.items_c[c];
   }
+  out->luma_heads = kf->lists.heads;
+  out->succ_bottom = kf->lists.succ_bottom;
+  out->succ_right = kf->lists.succ_right;
   out->luma_res = kf->luma.res_pack;
   out->chroma_res = kf->chroma.res_pack;
   out->luma_y16 = kf->luma.prm.y16;
@@ -1050,7 +1119,7 @@ int daala_b200_kf_submit(daala_b200_kf* kf, const daala_b200_kf_io* io) {
   if (io->luma_skip_diff) KF_CHECK(cudaMemcpyAsync(io->luma_skip_diff, kf->luma.prm.res_skip_diff, 8 * (size_t)tot.n_luma, cudaMemcpyDeviceToHost, s));
   if (io->chroma_skip_diff) KF_CHECK(cudaMemcpyAsync(io->chroma_skip_diff, kf->chroma.prm.res_skip_diff, 8 * (size_t)tot.n_chroma, cudaMemcpyDeviceToHost, s));
   if (io->chroma_flip) KF_CHECK(cudaMemcpyAsync(io->chroma_flip, kf->chroma.prm.res_flip, 4 * (size_t)tot.n_chroma, cudaMemcpyDeviceToHost, s));
-  if (io->counts) KF_CHECK(cudaMemcpyAsync(io->counts, kf->lists.cnt, sizeof(int32_t) * kCntWords, cudaMemcpyDeviceToHost, s));
+  if (io->counts) KF_CHECK(cudaMemcpyAsync(io->counts, kf->lists.cnt, sizeof(int32_t) * 32, cudaMemcpyDeviceToHost, s));
   return 0;
 }
 

@@ -15,8 +15,9 @@ c_int, c_ll, c_void_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p
 
 PH_LISTS, PH_FORWARD, PH_PVQ_LUMA, PH_INVERSE, PH_PVQ_CHROMA = 1, 2, 4, 8, 16
 PH_PVQ, PH_ALL, PH_SEARCH_ONLY = 20, 31, 64
-LAUNCHES_PER_STEP = 18   # lists 7, forward 1, luma 4, chroma 4, inverse 2
-CNT = dict(n_luma=0, n_chroma=1, luma_coefs=2, chroma_coefs=3, items_l=4, items_c=7, epoch=16, error=17)
+LAUNCHES_PER_STEP = 17   # lists 5, forward 1, luma 4, chroma 5, inverse 2 (+ 4 memset nodes)
+CNT = dict(n_luma=0, n_chroma=1, luma_coefs=2, chroma_coefs=3, items_l=4, items_c=7,
+           total_hi=14, n_heads=15, error=17)
 
 
 class Config(ctypes.Structure):
@@ -42,7 +43,8 @@ class Buffers(ctypes.Structure):
     _fields_ = [("pixels", c_void_p * 3), ("coeffs", c_void_p * 3), ("lapped", c_void_p * 3),
                 ("pixels_out", c_void_p * 3), ("plane_w", c_int * 3), ("plane_h", c_int * 3), ("bsize", c_void_p),
                 ("counts", c_void_p), ("luma_blocks", c_void_p), ("chroma_blocks", c_void_p), ("dep_top", c_void_p),
-                ("dep_left", c_void_p), ("luma_items", c_void_p * 3), ("chroma_items", c_void_p * 3),
+                ("dep_left", c_void_p), ("succ_bottom", c_void_p), ("succ_right", c_void_p), ("luma_items", c_void_p * 3),
+                ("luma_heads", c_void_p), ("chroma_items", c_void_p * 3),
                 ("luma_res", c_void_p), ("chroma_res", c_void_p), ("luma_y16", c_void_p), ("chroma_y16", c_void_p),
                 ("luma_skip_diff", c_void_p), ("chroma_skip_diff", c_void_p), ("chroma_flip", c_void_p),
                 ("max_luma_blocks", c_int), ("max_chroma_blocks", c_int), ("stream", c_void_p),

@@ -425,7 +425,7 @@ typedef struct daala_b200_kf_config {
   const int16_t *qm, *qm_inv;  /* HOST: state->qm / qm_inv, 2*qm_stride entries each (copied) */
   int sb_row0, sb_rows;        /* superblock rows of this rank's shard (sb_rows <= 0: whole frames) */
   int max_blocks_div;          /* 0/1: capacity for all-4x4 maps; d > 1: 1/d of that (saves HBM) */
-  int persist_ctas_per_sm;     /* 0 = default (5) */
+  int persist_ctas_per_sm;     /* 0 = default */
   void *stream;                /* cudaStream_t to run on, or NULL: the engine creates its own */
 } daala_b200_kf_config;
 
@@ -463,8 +463,11 @@ typedef struct daala_b200_kf_buffers {  /* device pointers of an engine (tests, 
   uint8_t *bsize;
   int32_t *counts;
   daala_b200_pvq_block *luma_blocks, *chroma_blocks;
-  int32_t *dep_top, *dep_left;
-  uint32_t *luma_items[3], *chroma_items[3];
+  int32_t *dep_top, *dep_left;          /* same-size neighbour above / left of each luma block, or -1 */
+  int32_t *succ_bottom, *succ_right;    /* the inverse: the block that waits for this one, or -1 */
+  uint32_t *luma_items[3];              /* dependency-free luma items (bands 3 / 6) per class */
+  uint32_t *luma_heads;                 /* chain items ready from the start; counts[15] of them */
+  uint32_t *chroma_items[3];
   int16_t *luma_res, *chroma_res, *luma_y16, *chroma_y16;
   double *luma_skip_diff, *chroma_skip_diff;
   int32_t *chroma_flip;

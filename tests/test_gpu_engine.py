@@ -84,7 +84,8 @@ def _frames(geom, n, q_seed=0, mode="mixed", pic=None):
 
 def test_engine_lists_are_consistent():
     """Descriptors partition the coding-order buffers; neighbours are the same-size top / left blocks;
-    the item lists hold every (block, band) once, in an order in which dependencies come first."""
+    the item lists hold every dependency-free (block, band) once, the chain heads are the chain items without a
+    neighbour to wait for."""
     from daala_b200 import engine
     from daala_b200.frame import Geometry
     geom = Geometry(328, 200)
@@ -129,29 +130,31 @@ def test_engine_lists_are_consistent():
     assert np.array_equal(np.sort(key(chroma)), np.sort(key(wc)))
     o1, o2 = np.argsort(key(chroma)), np.argsort(key(wc))
     assert np.array_equal(chroma["bs"][o1], wc["bs"][o2]) and np.array_equal(chroma["xdec"][o1], wc["xdec"][o2])
-    # items
+    # inverse neighbours
+    sb = eng.download(eng.buf.succ_bottom, (nl,), np.int32)
+    sr = eng.download(eng.buf.succ_right, (nl,), np.int32)
+    want_sb, want_sr = np.full(nl, -1, np.int32), np.full(nl, -1, np.int32)
+    want_sb[top[top >= 0]] = np.nonzero(top >= 0)[0]
+    want_sr[left[left >= 0]] = np.nonzero(left >= 0)[0]
+    assert np.array_equal(sb, want_sb) and np.array_equal(sr, want_sr)
+    # items: dependency-free bands 3 / 6 per class, chain heads, chain total
     nbands = np.array([1, 4, 7, 9, 9])
-    for c in range(3):
+    nb = nbands[luma["bs"]]
+    assert cnt[4] == 0
+    for c, band in ((1, 3), (2, 6)):
         n = int(cnt[4 + c])
-        padded = eng.download(eng.buf.luma_items[c], (n,), np.uint32)
-        per_warp = (8, 4, 1)[c]                      # items one warp takes per ticket
-        assert n % per_warp == 0
-        real = padded != 0xffffffff                 # key bins are padded to whole warp chunks
-        items = padded[real]
-        blk, band = (items >> 4).astype(np.int64), (items & 15).astype(np.int64)
-        assert (band // 3 == c).all() and (band < nbands[luma["bs"][blk]]).all()
-        assert len(np.unique(items)) == len(items) == int((np.clip(nbands[luma["bs"]] - 3 * c, 0, 3)).sum())
-        chunk = np.nonzero(real)[0] // per_warp
-        pos = {int(e): int(ch) for e, ch in zip(items, chunk)}
-        for ch, b, bd in zip(chunk, blk, band):
-            r = bd % 3
-            if bd in (3, 6):
-                continue
-            # dependencies sit in an EARLIER warp chunk (a warp never waits on itself)
-            if (bd == 0 or r == 1) and top[b] >= 0:
-                assert pos[(int(top[b]) << 4) | int(bd)] < ch
-            if (bd == 0 or r == 2) and left[b] >= 0:
-                assert pos[(int(left[b]) << 4) | int(bd)] < ch
+        items = eng.download(eng.buf.luma_items[c], (n,), np.uint32)
+        assert ((items & 15) == band).all() and len(np.unique(items)) == n == int((nb > band).sum())
+    heads = eng.download(eng.buf.luma_heads, (int(cnt[engine.CNT["n_heads"]]),), np.uint32)
+    want_heads = set()
+    for band in (0, 1, 2, 4, 5, 7, 8):
+        r = band % 3
+        waits = ((top >= 0) | (left >= 0)) if band == 0 else (top >= 0) if r == 1 else (left >= 0)
+        for i in np.nonzero((nb > band) & ~waits)[0]:
+            want_heads.add((int(i) << 4) | band)
+    assert len(heads) == len(want_heads) and set(int(h) for h in heads) == want_heads
+    assert cnt[engine.CNT["total_hi"]] == int((nb - (nb > 3) - (nb > 6)).sum())
+    for c in range(3):
         n = int(cnt[7 + c])
         items = eng.download(eng.buf.chroma_items[c], (n,), np.uint32)
         assert len(np.unique(items)) == n == int((np.clip(nbands[chroma["bs"]] - 3 * c, 0, 3)).sum())
