@@ -42,15 +42,17 @@ enum Cnt {
   kNItemsL = 4,      // [3] luma dependency-free items per class (bands 3 / 6: classes 1 / 2)
   kNItemsC = 7,      // [3] chroma items per class (n <= 16, 32, 128)
   kTotalHi = 14,     // luma chain items in total
-  kNHeads = 15,      // of which ready from the start (no same-size neighbour on the side they depend on)
+  kNHeads = 15,      // row / column chain items ready from the start (no same-size neighbour to wait for)
+  kNHeads0 = 16,     // band-0 items ready from the start
   kError = 17,
   // the words the persistent kernels hammer with atomics each sit in a 128-byte line of their own
   kHeadLoL = 32,     // ticket of the luma dependency-free lists
   kHeadLoC = 64,     // ticket of the chroma lists
   kHeadHi = 96,      // luma chain queue: next slot to claim
   kTailHi = 128,     //                   next slot to fill
-  kDoneHi = 160,     // chain items finished (flushed by warps when they go idle)
-  kCntWords = 192
+  kDoneHi = 160,     // band-0 items finished (flushed by warps when they go idle)
+  kHeadCh = 192,     // ticket of the row / column chain heads
+  kCntWords = 224
 };
 
 constexpr int kTile = 1024;        // units per scan tile
@@ -72,7 +74,8 @@ struct Lists {
   int32_t* succ_right;
   uint32_t* items_l[3];            // dependency-free luma items per class
   uint32_t* items_c[3];
-  uint32_t* heads;                 // chain items that are ready from the start
+  uint32_t* heads;                 // row / column chain items that are ready from the start
+  uint32_t* heads0;                // band-0 items that are ready from the start
   int32_t* cnt;                    // [kCntWords]
   int max_luma, max_chroma;        // capacities (blocks)
 };
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const __grid_constant__ List
     }
     L.cnt[kTotalHi] = 0;
     L.cnt[kNHeads] = 0;
+    L.cnt[kNHeads0] = 0;
     if (tot.x > L.max_luma || 2 * tot.z > L.max_chroma) L.cnt[kError] = 1;
   }
 }
@@ -268,6 +272,7 @@ __global__ void __launch_bounds__(256) k_luma_deps(const __grid_constant__ Lists
       const bool waits = band == 0 ? (top >= 0 || left >= 0) : r == 1 ? top >= 0 : left >= 0;
       const uint32_t item = ((uint32_t)blk << 4) | band;
       if (band == 3 || band == 6) append(L.items_l[band_class(band)], &L.cnt[kNItemsL + band_class(band)], has, item);
+      else if (band == 0) append(L.heads0, &L.cnt[kNHeads0], has && !waits, item);
       else append(L.heads, &L.cnt[kNHeads], has && !waits, item);
       chain += has && !is_free;
     }
@@ -302,8 +307,10 @@ __global__ void __launch_bounds__(256) k_chroma_items(const __grid_constant__ Li
 struct Stage {
   daala_b200_pvq_params prm;
   const uint32_t* items[3];        // dependency-free items per class (taken largest class first)
-  // luma only: the chain queue = [heads (static) | ring filled at run time]
+  // luma only: row / column chain heads (static list; a chain is then walked by one warp), and the
+  // band-0 queue = [heads0 (static) | ring filled at run time]
   const uint32_t* heads;
+  const uint32_t* heads0;
   uint32_t* ring;
   const int32_t* dep_top;
   const int32_t* dep_left;
@@ -408,6 +415,10 @@ __global__ void __launch_bounds__(256) k_cfl_plane(const __grid_constant__ Stage
   }
 }
 
+// resident CTAs per SM the persistent PVQ kernel is compiled for (register cap = 65536 / 128 / this)
+#ifndef DAALA_PERSIST_MIN_CTAS
+#define DAALA_PERSIST_MIN_CTAS 8
+#endif
 constexpr uint32_t kNoItem = 0xffffffffu;
 constexpr uint32_t kExit = 0xfffffffeu;
 
@@ -418,38 +429,43 @@ __device__ __forceinline__ int ld_relaxed(const int32_t* p) {
 }
 
 __device__ __forceinline__ void push_chain(const Stage& S, int blk, int band) {
-  const int pos = atomicAdd(&S.cnt[kTailHi], 1) - S.cnt[kNHeads];
+  const int pos = atomicAdd(&S.cnt[kTailHi], 1) - S.cnt[kNHeads0];
   st_release((int*)&S.ring[pos], (int)(((uint32_t)blk << 4) | band));
 }
 
 // Next item for an idle warp (uniform), or kNoItem when the stage has nothing left for it.
 //  chroma (kIntra = false): a ticket into the item lists, largest bands first.
-//  luma: (1) a filled slot of the chain queue (heads first, then what other warps pushed), (2) a
-//  dependency-free item, (3) a ticket for a FUTURE chain slot, waited for on the slot itself (distinct
-//  addresses: no hot spot).  `done` = chain items this warp finished since it was last here; the warp
-//  whose flush completes the count releases every waiter with kExit.
+//  luma, in this order: (1) a filled slot of the band-0 queue -- band 0 is a 2-D wavefront over each
+//  same-size region, the deepest dependency structure of a frame, so it goes first; (2) the head of a row
+//  or column chain; (3) a dependency-free item; (4) a ticket for a FUTURE band-0 slot, waited for on the
+//  slot itself (distinct addresses: no hot spot).  `done` = band-0 items this warp finished since it was
+//  last here; the warp whose flush completes the count releases every waiter with kExit.
 template <bool kIntra>
 __device__ __forceinline__ uint32_t next_item(const Stage& S, int lane, int* done) {
-  int slot = -1, lo = -1, nheads = 0, fin = -1;
+  int slot = -1, head = -1, lo = -1, nheads0 = 0, fin = -1;
   if (lane == 0) {
     const int n2 = S.cnt[S.n_items_at + 2], n1 = S.cnt[S.n_items_at + 1], n0 = S.cnt[S.n_items_at];
     const int nlo = n0 + n1 + n2;
     if (kIntra) {
-      nheads = S.cnt[kNHeads];
+      nheads0 = S.cnt[kNHeads0];
       if (*done) {
         const int d = atomicAdd(&S.cnt[kDoneHi], *done) + *done;
-        if (d == S.cnt[kTotalHi]) {
+        if (d == S.cnt[kNLuma]) {   // every luma block has a band 0
           __threadfence();
-          fin = ld_relaxed(&S.cnt[kTailHi]) - nheads;   // final: every push happened before its item finished
+          fin = ld_relaxed(&S.cnt[kTailHi]) - nheads0;   // final: every push happened before its item finished
         }
       }
       if (ld_relaxed(&S.cnt[kHeadHi]) < ld_relaxed(&S.cnt[kTailHi])) slot = atomicAdd(&S.cnt[kHeadHi], 1);
+      if (slot < 0 && ld_relaxed(&S.cnt[kHeadCh]) < S.cnt[kNHeads]) {
+        const int h = atomicAdd(&S.cnt[kHeadCh], 1);
+        if (h < S.cnt[kNHeads]) head = h;
+      }
     }
-    if (slot < 0 && ld_relaxed(&S.cnt[S.head_lo_at]) < nlo) {
+    if (slot < 0 && head < 0 && ld_relaxed(&S.cnt[S.head_lo_at]) < nlo) {
       const int l = atomicAdd(&S.cnt[S.head_lo_at], 1);
       if (l < nlo) lo = l;
     }
-    if (kIntra && slot < 0 && lo < 0) slot = atomicAdd(&S.cnt[kHeadHi], 1);
+    if (kIntra && slot < 0 && head < 0 && lo < 0) slot = atomicAdd(&S.cnt[kHeadHi], 1);
   }
   *done = 0;
   if (kIntra) {
@@ -459,15 +475,17 @@ __device__ __forceinline__ uint32_t next_item(const Stage& S, int lane, int* don
       const int nw = (gridDim.x * blockDim.x) >> 5;
       for (int i = lane; i <= nw; i += 32) st_release((int*)&S.ring[fin + i], (int)kExit);
     }
+    head = __shfl_sync(0xffffffffu, head, 0);
+    if (head >= 0) return S.heads[head];
   }
   slot = __shfl_sync(0xffffffffu, slot, 0);
   lo = __shfl_sync(0xffffffffu, lo, 0);
   if (slot >= 0) {
-    nheads = __shfl_sync(0xffffffffu, nheads, 0);
-    if (slot < nheads) return S.heads[slot];
+    nheads0 = __shfl_sync(0xffffffffu, nheads0, 0);
+    if (slot < nheads0) return S.heads0[slot];
     // every lane acquires: what the producer wrote before its release is visible to all of them
     uint32_t v;
-    while ((v = (uint32_t)ld_acquire((const int*)&S.ring[slot - nheads])) == kNoItem) __nanosleep(200);
+    while ((v = (uint32_t)ld_acquire((const int*)&S.ring[slot - nheads0])) == kNoItem) __nanosleep(500);
     return v == kExit ? kNoItem : v;
   }
   if (lo >= 0) {
@@ -479,8 +497,8 @@ __device__ __forceinline__ uint32_t next_item(const Stage& S, int lane, int* don
 
 // One (block, band) item by one warp.  kIntra: the band's prediction is built from the quantised
 // neighbours first (od_hv_intra_pred, src/intra.c:37-62).
-template <int E, bool kIntra>
-__device__ __forceinline__ void run_item(const Stage& S, uint32_t item, int lane) {
+template <bool kIntra>
+__device__ __forceinline__ void run_item(const Stage& S, uint32_t item, int lane, int16_t* snap) {
   const daala_b200_pvq_params& prm = S.prm;
   const int blk = (int)(item >> 4), band = (int)(item & 15);
   const daala_b200_pvq_block b = prm.blocks[blk];
@@ -523,7 +541,7 @@ __device__ __forceinline__ void run_item(const Stage& S, uint32_t item, int lane
   const int qoff = (b.xdec & 1 ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
   int itheta, max_theta, k;
   double skip_term;
-  const int gain = quantise_band_warp<E>(lane, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off, &itheta,
+  const int gain = quantise_band_warp(lane, snap, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off, &itheta,
                                          &max_theta, &k, beta, &skip_term, prm.is_keyframe, pli, prm.qm + qoff,
                                          prm.qm_inv + qoff, prm.pvq_norm_lambda);
   if (lane == 0) {
@@ -541,18 +559,19 @@ __device__ __forceinline__ void run_item(const Stage& S, uint32_t item, int lane
 // column or row is walked by one warp without touching the queue -- and pushes a second ready
 // successor (band 0 forks) into the chain queue.
 template <bool kIntra>
-__global__ void __launch_bounds__(128, 4) k_pvq_persist(const __grid_constant__ Stage S) {
+__global__ void __launch_bounds__(128, DAALA_PERSIST_MIN_CTAS) k_pvq_persist(const __grid_constant__ Stage S) {
+  __shared__ int16_t snap_all[4][kSnapEntries];   // per warp: the pulses of every search event of a band
   const int lane = threadIdx.x & 31;
+  int16_t* snap = snap_all[threadIdx.x >> 5];
   int done = 0;
   for (;;) {
     uint32_t item = next_item<kIntra>(S, lane, &done);
     if (item == kNoItem) return;
     for (;;) {
       const int band = (int)(item & 15);
-      if (band >= 6) run_item<4, kIntra>(S, item, lane);
-      else run_item<1, kIntra>(S, item, lane);
+      run_item<kIntra>(S, item, lane, snap);
       if (!kIntra || band == 3 || band == 6) break;
-      done++;
+      done += band == 0;
       // results of this item -> visible to whoever runs a successor (this warp included: other lanes)
       __threadfence();
       __syncwarp();
@@ -592,8 +611,9 @@ __global__ void k_begin_pvq(int32_t* cnt, int luma) {
     if (luma) {
       cnt[kHeadLoL] = 0;
       cnt[kHeadHi] = 0;
-      cnt[kTailHi] = cnt[kNHeads];
+      cnt[kTailHi] = cnt[kNHeads0];
       cnt[kDoneHi] = 0;
+      cnt[kHeadCh] = 0;
     } else {
       cnt[kHeadLoC] = 0;
     }
@@ -744,6 +764,7 @@ static int kf_alloc(daala_b200_kf* kf) {
     KF_CHECK(dalloc(kf, &L.items_c[c], cap_c[c]));
   }
   KF_CHECK(dalloc(kf, &L.heads, kf->chain_cap));
+  KF_CHECK(dalloc(kf, &L.heads0, (size_t)L.max_luma));
   KF_CHECK(dalloc(kf, &L.cnt, (size_t)kCntWords));
 
   auto setup_stage = [&](Stage& S, bool chroma) -> int {
@@ -789,6 +810,7 @@ static int kf_alloc(daala_b200_kf* kf) {
       S.succ_bottom = L.succ_bottom;
       S.succ_right = L.succ_right;
       S.heads = L.heads;
+      S.heads0 = L.heads0;
       KF_CHECK(dalloc(kf, &S.ring, kf->chain_cap));
       KF_CHECK(dalloc(kf, &S.join0, nblk));
     } else {
@@ -850,7 +872,7 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
     int rc = daala_b200_launch_forward(&kf->frame, 3, s);
     if (rc) return rc;
   }
-  const int persist = kf->sms * (kf->cfg.persist_ctas_per_sm > 0 ? kf->cfg.persist_ctas_per_sm : 4);
+  const int persist = kf->sms * (kf->cfg.persist_ctas_per_sm > 0 ? kf->cfg.persist_ctas_per_sm : DAALA_PERSIST_MIN_CTAS);
   // _SEARCH_ONLY (measurement): just the persistent search kernels, on the coding-order buffers a
   // previous full pass left behind (same inputs, same results)
   const bool core = (phases & DAALA_B200_KF_SEARCH_ONLY) != 0;
@@ -954,6 +976,7 @@ void daala_b200_kf_destroy(daala_b200_kf* kf) {
     cudaFree(L.items_c[c]);
   }
   cudaFree(L.heads);
+  cudaFree(L.heads0);
   cudaFree(L.succ_bottom);
   cudaFree(L.succ_right);
   cudaFree(L.cnt);
@@ -998,6 +1021,7 @@ int daala_b200_kf_device_buffers(daala_b200_kf* kf, daala_b200_kf_buffers* out) 
     out->chroma_items[c] = kf->lists.items_c[c];
   }
   out->luma_heads = kf->lists.heads;
+  out->luma_heads0 = kf->lists.heads0;
   out->succ_bottom = kf->lists.succ_bottom;
   out->succ_right = kf->lists.succ_right;
   out->luma_res = kf->luma.res_pack;

@@ -1,23 +1,29 @@
 // Warp-per-band PVQ band quantiser (reference pvq_theta, src/pvq_encoder.c:333, with the closed-form
 // rate of od_pvq_rate, :247, and pvq_search_rdo_double, :93).
 //
-// ONE warp owns ONE band.  Design goals, in this order: (1) the latency of a single band is what the
-// keyframe luma intra wavefront is bound by (od_hv_intra_pred couples a band to the same band of the
-// top / left neighbour, src/intra.c:37), so everything that the reference does serially per band but is
-// independent per CANDIDATE runs one candidate per lane; (2) the greedy pulse search costs one
-// redux.sync per pulse instead of a five-level shuffle tree.
+// ONE warp owns ONE band.  Design goals: (1) the latency of a single band is what the keyframe luma
+// intra wavefront is bound by (od_hv_intra_pred couples a band to the same band of the top / left
+// neighbour, src/intra.c:37), so everything the reference does serially per band but is independent per
+// CANDIDATE runs one candidate per lane; (2) the greedy pulse search costs one redux.sync per pulse
+// instead of a five-level shuffle tree; (3) a small instruction footprint: the kernel is bound by
+// instruction fetch as soon as its straight-line code outgrows the 32 KB L1.5 instruction cache
+// (profiles/r2c_*), so the long double-precision sequences (log, acos, sqrt, divide) and the
+// fixed-point helpers exist once, out of line, and only the search loop is specialised by band size.
 //
-//  * Element j of the band lives in lane j % 32, slot j / 32 (E = 1 for n <= 32, E = 4 for n = 128),
-//    in registers.
+//  * Element j of the band lives in lane j % 32, slot j / 32, in registers (1 slot for n <= 32, 4 for
+//    n = 128).
 //  * Every sum the reference accumulates in double is a sum of exactly representable integers far below
 //    2^53, hence order independent: reduced as integers with redux.sync (__reduce_add_sync).
 //  * Candidates (gain i, theta j) of pvq_theta: lane c < 12 holds with-reference candidate
 //    (gain index c / 4, theta index c % 4) in the reference's insertion order, lanes 12 / 13 the
-//    no-reference gains.  Their quantised angle, K, distortion pre-test, rate constants are computed
-//    once, in parallel.  The reference's stable sort by K and its `prev_k` reuse of search results are
+//    no-reference gains.  Quantised angle, K, distortion pre-test, lambda, rate constants: computed once,
+//    in parallel.  The reference's stable sort by K and its `prev_k` reuse of search results are
 //    reproduced by processing "events" = runs of surviving candidates with equal K in ascending K order:
-//    one (incremental) search per event, then the costs of the event's candidates in parallel, then the
-//    reference's sequential `<` / `<=` fold over them.
+//    one (incremental) search per event.  The pulses of every event are parked in shared memory
+//    (16 bit), its scalars (xy, yy, sum j|y_j|) in lane `event`; after the last search the square roots,
+//    divisions and logarithms of ALL events run in parallel (one event per lane), then the costs (one
+//    candidate per lane), then the reference's sequential `<` / `<=` fold, and the winner's pulses are
+//    read back.
 //  * Per-pulse arg-max.  Plain pulses maximise (xy + x_j)^2 / (yy + 2 y_j + 1): every lane builds an
 //    f32 approximation of the ratio (relative error < 2^-20), redux.max picks the approximate maximum
 //    and the elements within 64 ulps of it are the contenders.  The exact maximum is always a
@@ -25,7 +31,10 @@
 //    products that could exceed 2^53, where the reference's own comparisons round) the contenders are
 //    compared with the reference's literal double-precision test in index order.  RDO pulses maximise
 //    a double; its f32 rounding is monotone, so the contenders are the elements whose rounded value
-//    equals the maximum.
+//    equals the maximum.  Their 1/sqrt(yy + 2 y_j + 1) factors come from lane y_j, which evaluates the
+//    reference's expression for that argument (one square root + division per pulse, not per element).
+//
+// Pulses must fit 16 bits (K <= 32767), like the symbol stream the engine hands to the host coder.
 //
 // The function compiles for the host under DAALA_B200_EMU (tests/emu/simt_emu.h supplies the warp
 // primitives on 32 fibres) so that CPU tests can pin it against the reference build.
@@ -39,13 +48,15 @@ namespace daala_b200 {
 namespace pvq {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxEvents = 14;                      // <= 12 with-reference K values + 2 no-reference gains
+constexpr int kSnapEntries = kMaxEvents * kMaxN;    // int16 entries of per-warp scratch
 
-// coverage counters of the host emulation build (tests/emu); nothing on the device
 // below this bound every product of the plain-pulse ratio test is exact in double (tests lower it to
 // force the literal-scan path)
 #ifndef DAALA_B200_PVQ_EXACT_BOUND
 #define DAALA_B200_PVQ_EXACT_BOUND 4503599627370496.
 #endif
+// coverage counters of the host emulation build (tests/emu); nothing on the device
 #ifdef DAALA_B200_EMU_STATS
 #define PVQ_WARP_STAT(i) (daala_b200_pvq_warp_stats[i]++)
 #else
@@ -62,7 +73,8 @@ __device__ __forceinline__ long long wsum64(long long s) {
   const int hi = (int)(s >> 24);
   return ((long long)wsum(hi) << 24) + wsum(lo);
 }
-__device__ __forceinline__ double wbcast(double v, int src) {
+// v of lane `src` (per-lane source allowed)
+__device__ __forceinline__ double wfetch(double v, int src) {
   int lo = __double2loint(v), hi = __double2hiint(v);
   lo = __shfl_sync(kFull, lo, src);
   hi = __shfl_sync(kFull, hi, src);
@@ -73,22 +85,45 @@ __device__ __forceinline__ int ordered_key(float f) {
   const int b = __float_as_int(f);
   return b ^ ((b >> 31) & 0x7fffffff);
 }
-
 // a[slot] of a register array without dynamic indexing
-template <int E>
-__device__ __forceinline__ int pick(const int (&a)[E], int slot) {
+__device__ __forceinline__ int pick4(const int (&a)[4], int slot) {
   int v = a[0];
 #pragma unroll
-  for (int e = 1; e < E; e++) if (slot == e) v = a[e];
+  for (int e = 1; e < 4; e++) if (slot == e) v = a[e];
   return v;
 }
 
+// ---- out-of-line helpers: one copy of each long instruction sequence ------------------------------------
+static __device__ __noinline__ double nl_log(double x) { return log(x); }
+static __device__ __noinline__ double nl_acos(double x) { return acos(x); }
+static __device__ __noinline__ double nl_sqrt(double x) { return sqrt(x); }
+static __device__ __noinline__ double nl_div(double a, double b) { return a / b; }
+static __device__ __noinline__ int nl_cos(int32_t x) { return pvq_cos(x); }
+// 1/sqrt(i) as pvq_search_rdo_double's od_rsqrt_table / 1./sqrt(i) (src/pvq_encoder.c:53,190)
+static __device__ __noinline__ double nl_rsqrt_small(int i) {
+  if (i <= 16) return kRsqrtSmall[i - 1];
+  return 1. / sqrt((double)i);
+}
+// (companded gain, gain) of a 16-bit vector with energy `acc`: od_pvq_compute_gain, src/pvq.c:824
+static __device__ __noinline__ long long nl_gain(int32_t acc, int q0, int beta, int bshift) {
+  int32_t g;
+  const int32_t cg = compute_gain_from_energy(acc, q0, &g, beta, bshift);
+  return ((long long)cg << 32) | (uint32_t)g;
+}
+// quantised angle and K of one candidate (od_pvq_compute_theta :874, od_pvq_compute_k :902)
+static __device__ __noinline__ long long nl_theta_k(int32_t qcg, int j, int ts, int noref, int n, int beta) {
+  const int32_t qtheta = noref ? 0 : compute_theta(j, ts);
+  const int k = compute_k(qcg, j, noref, n, beta);
+  return ((long long)qtheta << 32) | (uint32_t)k;
+}
+
 // od_apply_householder (src/pvq.c:560) on distributed int16 vectors; in place allowed.
-template <int E>
-__device__ __forceinline__ void householder_apply_warp(int lane, int (&out)[E], const int (&x)[E], const int (&r)[E], int n) {
+__device__ __forceinline__ void householder_apply_warp(int lane, bool big, int (&out)[4], const int (&x)[4],
+                                                       const int (&r)[4], int n) {
   int32_t l2r = 0, proj = 0;
 #pragma unroll
-  for (int e = 0; e < E; e++) {
+  for (int e = 0; e < 4; e++) {
+    if (e && !big) break;
     if (e * 32 + lane < n) {
       l2r += mul16(r[e], r[e]);
       proj += mul16(r[e], x[e]);
@@ -105,37 +140,235 @@ __device__ __forceinline__ void householder_apply_warp(int lane, int (&out)[E], 
   int outshift = 14 - proj_shift - 1 + l2r_shift;
   if (outshift > 30) outshift = 30;
 #pragma unroll
-  for (int e = 0; e < E; e++) {
+  for (int e = 0; e < 4; e++) {
+    if (e && !big) break;
     int32_t t = mul16(r[e], proj_1);
     t = outshift >= 0 ? shr_round(t, outshift) : shl(t, -outshift);
     out[e] = (int16_t)(x[e] - t);
   }
 }
 
-// One band by one warp.  x0 / r0 / out / yout / qm / qm_inv point at the band's first entry.  Scalar
-// results are identical in every lane.  int16 quantities of the reference are kept sign-extended in ints.
+// What one search phase (with-reference: the reflected vector without element m; no-reference: the
+// vector itself) keeps for all its events.
+struct SearchVec {
+  int xa[4];      // |x|, 0 past the end
+  double xd[4];   // == fabs((double)(float)xcoeff[j]): |int16| is exact in float
+  float xf[4];
+  double xx, norm_1, l1_norm;
+  int xmax, nn;
+};
+
 template <int E>
-__device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const int32_t* x0, const int32_t* r0, int n,
-                                                  int q0, int32_t* yout, int* itheta, int* max_theta, int* vk, int beta,
-                                                  double* skip_term, int is_keyframe, int pli, const int16_t* qm,
-                                                  const int16_t* qm_inv, double pvq_norm_lambda) {
+__device__ __forceinline__ void search_init(int lane, SearchVec& v, const int (&src)[4], int nn) {
+  long long sxx = 0;
+  int xmax = 0, sl1 = 0;
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    const int a = e * 32 + lane < nn ? abs(src[e]) : 0;
+    v.xa[e] = a;
+    v.xd[e] = (double)a;
+    v.xf[e] = (float)a;
+    sxx += (long long)a * a;
+    sl1 += a;
+    xmax = a > xmax ? a : xmax;
+  }
+  v.xx = (double)wsum64(sxx);
+  v.xmax = wmax(xmax);
+  v.l1_norm = (double)wsum(sl1);
+  v.norm_1 = nl_div(1., nl_sqrt(1e-30 + v.xx));
+  v.nn = nn;
+}
+
+// pvq_search_rdo_double (src/pvq_encoder.c:93) on magnitudes: ya = pulses so far (prev_k of them) in,
+// k pulses out; *xy_out, *yy_out = the reference's running sums at the end.
+template <int E>
+__device__ __forceinline__ void search_event(int lane, const SearchVec& v, int (&ya)[4], int k, int prev_k,
+                                             double lambda, double* xy_out, double* yy_out) {
+  const int nn = v.nn;
+  double xy = 0, yy = 0;
+  int i = 0;
+  if (prev_k > 0 && prev_k <= k) {
+    long long sxy = 0, syy = 0;
+    int si = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      if (e * 32 + lane >= nn) ya[e] = 0;
+      sxy += (long long)v.xa[e] * ya[e];
+      syy += (long long)ya[e] * ya[e];
+      si += ya[e];
+    }
+    xy = (double)wsum64(sxy);
+    yy = (double)wsum64(syy);
+    i = wsum(si);
+  } else if (k > 2) {
+    const double l1_inv = nl_div(1., v.l1_norm > 1e-100 ? v.l1_norm : 1e-100);
+    long long sxy = 0, syy = 0;
+    int si = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const double tmp = k * v.xd[e] * l1_inv;
+      const int f = (int)floor(tmp);
+      ya[e] = (e * 32 + lane < nn && f > 0) ? f : 0;
+      sxy += (long long)v.xa[e] * ya[e];
+      syy += (long long)ya[e] * ya[e];
+      si += ya[e];
+    }
+    xy = (double)wsum64(sxy);
+    yy = (double)wsum64(syy);
+    i = wsum(si);
+  } else {
+#pragma unroll
+    for (int e = 0; e < E; e++) ya[e] = 0;
+  }
+  const int rdo_pulses = 1 + k / 4;
+  double delta_rate = nl_div(3., (double)nn);
+  double accel_rate = 0.;
+  if (k == 1) {
+    if (nn == 15) {
+      accel_rate = -8. / 15;
+      delta_rate = 4.5 / 15 - accel_rate;
+    } else if (nn == 8) {
+      accel_rate = 5.7 / 8;
+      delta_rate = 9.3 / 8 - accel_rate;
+    }
+  }
+  for (; i < k; i++) {
+    const bool plain = i < k - rdo_pulses;
+    bool cont[E];    // contenders per slot
+    double tval[E];  // RDO: the element's objective
+    int total;
+    if (plain) {
+      const double bound = (xy + v.xmax) * (xy + v.xmax) * (yy + 2. * i + 1.);
+      if (bound < DAALA_B200_PVQ_EXACT_BOUND) {
+        const float xyf = (float)xy, yyf1 = (float)(yy + 1.);
+        unsigned key[E], kmax = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          float a = xyf + v.xf[e];
+          a *= a;
+          const float b = yyf1 + (float)(2 * ya[e]);
+          key[e] = e * 32 + lane < nn ? __float_as_uint(__fdividef(a, b)) : 0u;
+          kmax = key[e] > kmax ? key[e] : kmax;
+        }
+        const unsigned mx = wmaxu(kmax);
+        const unsigned thr = mx > 64u ? mx - 64u : 0u;
+        int cnt = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          cont[e] = e * 32 + lane < nn && key[e] >= thr;
+          cnt += cont[e];
+        }
+        total = wsum(cnt);
+      } else {
+        // products may round: the reference's literal scan over every element
+#pragma unroll
+        for (int e = 0; e < E; e++) cont[e] = e * 32 + lane < nn;
+        total = 2;
+        PVQ_WARP_STAT(3);
+      }
+#pragma unroll
+      for (int e = 0; e < E; e++) tval[e] = 0;
+    } else {
+      // lane l evaluates the reference's 1/sqrt(yy + 2 l + 1); an element with y_j pulses fetches lane y_j's
+      const double rs_lane = nl_rsqrt_small((int)(yy + 2 * lane + 1));
+      int key[E], kmax = (int)0x80000000;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const int j = e * 32 + lane;
+        const int yj = ya[e];
+        double ryy = wfetch(rs_lane, yj & 31);
+        if (yj >= 32) ryy = nl_rsqrt_small((int)(yy + 2 * yj + 1));
+        double t = xy + v.xd[e];
+        t = 2 * t * v.norm_1 * ryy - lambda * j * (delta_rate + j * accel_rate);
+        tval[e] = t;
+        key[e] = j < nn ? ordered_key((float)t) : (int)0x80000000;
+        kmax = key[e] > kmax ? key[e] : kmax;
+      }
+      const int mx = wmax(kmax);
+      int cnt = 0;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        cont[e] = e * 32 + lane < nn && key[e] == mx;
+        cnt += cont[e];
+      }
+      total = wsum(cnt);
+    }
+    PVQ_WARP_STAT(total == 1 ? 0 : plain ? 1 : 2);
+    int pos;  // index of the chosen element
+    if (total == 1) {
+      int mine = -1;
+#pragma unroll
+      for (int e = 0; e < E; e++) if (cont[e]) mine = e * 32 + lane;
+      const unsigned who = __ballot_sync(kFull, mine >= 0);
+      pos = __shfl_sync(kFull, mine, __ffs(who) - 1);
+    } else {
+      // the reference's sequential scan restricted to the contenders, in index order
+      pos = -1;
+      double ba = 0, bb = 1;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        unsigned mk = __ballot_sync(kFull, cont[e]);
+        while (mk) {
+          const int l = __ffs(mk) - 1;
+          mk &= mk - 1;
+          if (plain) {
+            const int xj = __shfl_sync(kFull, v.xa[e], l);
+            const int yj = __shfl_sync(kFull, ya[e], l);
+            double a = xy + (double)xj;
+            const double b = yy + 2 * yj + 1;
+            a *= a;
+            if (pos < 0 || a * bb > ba * b) { ba = a; bb = b; pos = e * 32 + l; }
+          } else {
+            const double t = wfetch(tval[e], l);
+            if (pos < 0 || t > ba) { ba = t; pos = e * 32 + l; }
+          }
+        }
+      }
+    }
+    const int src = pos & 31, slot = pos >> 5;
+    int sx = v.xa[0], sy = ya[0];
+#pragma unroll
+    for (int e = 1; e < E; e++) if (slot == e) { sx = v.xa[e]; sy = ya[e]; }
+    const int px = __shfl_sync(kFull, sx, src);
+    const int py = __shfl_sync(kFull, sy, src);
+    xy = xy + (double)px;
+    yy = yy + 2 * py + 1;
+#pragma unroll
+    for (int e = 0; e < E; e++) if (e * 32 + lane == pos) ya[e]++;
+  }
+  *xy_out = xy;
+  *yy_out = yy;
+}
+
+// One band by one warp.  x0 / r0 / out / yout / qm / qm_inv point at the band's first entry; `snap`:
+// kSnapEntries int16 of scratch private to the warp (shared memory).  Scalar results are identical in
+// every lane.  int16 quantities of the reference are kept sign-extended in ints.
+__device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, int32_t* out, const int32_t* x0,
+                                                  const int32_t* r0, int n, int q0, int32_t* yout, int* itheta,
+                                                  int* max_theta, int* vk, int beta, double* skip_term, int is_keyframe,
+                                                  int pli, const int16_t* qm, const int16_t* qm_inv,
+                                                  double pvq_norm_lambda) {
   const double gain_weight = 1.4;
   const double cgain_1 = 1. / kCgainOne;
   const double cgain_2 = cgain_1 * cgain_1;
   const double theta_scale = (1 << kThetaShift) * 2. / M_PI;
   const double theta_scale_1 = 1. / theta_scale;
   const double trig_1 = 1. / 32768;
-  int x16[E], r16[E], xr[E];
-  int32_t sx = 0, sr = 0;
-  int r_nonnull = 0;
+  const bool big = n > 32;
+  int x16[4], r16[4], xr[4];
+  int xshift, rshift, r_nonnull = 0;
   {
-    int32_t xv[E], rv[E];
+    int32_t xv[4], rv[4];
+    int32_t sx = 0, sr = 0;
 #pragma unroll
-    for (int e = 0; e < E; e++) {
+    for (int e = 0; e < 4; e++) {
+      xv[e] = rv[e] = 0;
+      if (e && !big) continue;
       const int j = e * 32 + lane;
-      const bool valid = j < n;
-      xv[e] = valid ? x0[j] : 0;
-      rv[e] = valid ? r0[j] : 0;
+      if (j < n) {
+        xv[e] = x0[j];
+        rv[e] = r0[j];
+      }
       const int16_t tx = (int16_t)(xv[e] >> 8), tr = (int16_t)(rv[e] >> 8);
       sx += tx * (int32_t)tx;
       sr += tr * (int32_t)tr;
@@ -144,26 +377,25 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const 
     sx = wsum(sx);
     sr = wsum(sr);
     r_nonnull = __any_sync(kFull, r_nonnull);
-    int xshift = 9 + ilog((uint32_t)(n + sx)) / 2 - 15;
-    int rshift = 9 + ilog((uint32_t)(n + sr)) / 2 - 14;
+    xshift = 9 + ilog((uint32_t)(n + sx)) / 2 - 15;
+    rshift = 9 + ilog((uint32_t)(n + sr)) / 2 - 14;
     if (xshift < 0) xshift = 0;
     if (rshift < 0) rshift = 0;
-    // from here on xshift / rshift live in sx / sr's place
-    sx = xshift;
-    sr = rshift;
 #pragma unroll
-    for (int e = 0; e < E; e++) {
+    for (int e = 0; e < 4; e++) {
+      x16[e] = r16[e] = xr[e] = 0;
+      if (e && !big) continue;
       const int j = e * 32 + lane;
       const int qmv = j < n ? qm[j] : 0;
       x16[e] = (int16_t)shr_round(xv[e] * qmv, kQmShift + xshift);
       r16[e] = (int16_t)shr_round(rv[e] * qmv, kQmShift + rshift);
     }
   }
-  const int xshift = sx, rshift = sr;
   long long scorr = 0;
   int32_t accx = 0, accr = 0;
 #pragma unroll
-  for (int e = 0; e < E; e++) {
+  for (int e = 0; e < 4; e++) {
+    if (e && !big) break;
     scorr += mul16(x16[e], r16[e]);
     accx += x16[e] * x16[e];
     accr += r16[e] * r16[e];
@@ -171,16 +403,23 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const 
   double corr = (double)wsum64(scorr);
   accx = wsum(accx);
   accr = wsum(accr);
-  int32_t g, gr;
+  // the two gains in parallel: even lanes the input's, odd lanes the reference's
+  int32_t g, gr, cg, cgr;
+  {
+    const long long pk = nl_gain(lane & 1 ? accr : accx, q0, beta, lane & 1 ? rshift : xshift);
+    const int gl = (int)(uint32_t)pk, cgl = (int)(pk >> 32);
+    g = __shfl_sync(kFull, gl, 0);
+    cg = __shfl_sync(kFull, cgl, 0);
+    gr = __shfl_sync(kFull, gl, 1);
+    cgr = __shfl_sync(kFull, cgl, 1);
+  }
   const int cfl_enabled = is_keyframe && pli != 0;
-  const int32_t cg = compute_gain_from_energy(accx, q0, &g, beta, xshift);
-  int32_t cgr = compute_gain_from_energy(accr, q0, &gr, beta, rshift);
   if (cfl_enabled) cgr = kCgainOne;
   const int icgr = shr_round(cgr, kCgainShift);
   int32_t gain_offset = cgr - shl(icgr, kCgainShift);
   double best_dist = gain_weight * cg * cg * cgain_2;
   double best_cost = best_dist + pvq_norm_lambda * 0.;  // od_pvq_rate(0, 0, -1, 0, ...) == 0
-  corr = corr / (1e-100 + g * (double)gr / shl(1, xshift + rshift));
+  corr = nl_div(corr, 1e-100 + nl_div(g * (double)gr, (double)shl(1, xshift + rshift)));
   corr = corr < 1. ? corr : 1.;
   corr = corr > -1. ? corr : -1.;
   double skip_dist;
@@ -189,8 +428,6 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const 
   } else {
     skip_dist = gain_weight * (cg - cgr) * (cg - cgr) + cgr * (double)cg * (2 - 2 * corr);
     skip_dist *= cgain_2;
-  }
-  if (!is_keyframe) {
     const int32_t scgr = gain_offset > 0 ? gain_offset : 0;
     if (icgr == 0) {
       best_dist = gain_weight * (cg - scgr) * (cg - scgr) + scgr * (double)cg * (2 - 2 * corr);
@@ -205,97 +442,104 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const 
   int32_t theta = 0;
   int m = 0, s = 1;
   if (have_ref) {
-    theta = round32(theta_scale * acos(corr));
+    theta = round32(theta_scale * nl_acos(corr));
     // od_compute_householder, src/pvq.c:498: first largest |r| (strict ">" from maxr = 0)
     int key = -1;
 #pragma unroll
-    for (int e = 0; e < E; e++) {
+    for (int e = 0; e < 4; e++) {
+      if (e && !big) break;
       const int j = e * 32 + lane;
-      const int a = j < n ? abs(r16[e]) : 0;
-      const int kk = j < n ? (a << 7) | (127 - j) : -1;
+      const int kk = j < n ? (abs(r16[e]) << 7) | (127 - j) : -1;
       key = kk > key ? kk : key;
     }
     key = wmax(key);
     m = (key >> 7) > 0 ? 127 - (key & 127) : 0;
-    const int rm = __shfl_sync(kFull, pick<E>(r16, m >> 5), m & 31);
+    const int rm = __shfl_sync(kFull, pick4(r16, m >> 5), m & 31);
     s = rm > 0 ? 1 : -1;
 #pragma unroll
-    for (int e = 0; e < E; e++)
+    for (int e = 0; e < 4; e++)
       if (e * 32 + lane == m) r16[e] = (int16_t)(r16[e] + shr_round(gr * s, rshift));
-    householder_apply_warp<E>(lane, xr, x16, r16, n);
+    householder_apply_warp(lane, big, xr, x16, r16, n);
     // drop element m: xr[j] <- xr[j + 1] for j >= m
 #pragma unroll
-    for (int e = 0; e < E; e++) {
+    for (int e = 0; e < 4; e++) {
+      if (e && !big) break;
       const int t1 = __shfl_sync(kFull, xr[e], (lane + 1) & 31);
-      const int t2 = e + 1 < E ? __shfl_sync(kFull, xr[e + 1 < E ? e + 1 : e], 0) : 0;
+      const int t2 = e + 1 < 4 ? __shfl_sync(kFull, xr[e + 1 < 4 ? e + 1 : e], 0) : 0;
       const int nxt = lane == 31 ? t2 : t1;
       if (e * 32 + lane >= m) xr[e] = nxt;
     }
-  } else {
-#pragma unroll
-    for (int e = 0; e < E; e++) xr[e] = 0;
   }
 
-  // ---- candidates: one per lane -------------------------------------------------------------------------
-  int c_gain = 0, c_theta = -1, c_ts = 0, c_k = 0;
+  // ---- candidates: one per lane (the same calls for both kinds, with per-lane arguments) ----------------
+  int c_gain = 0, c_theta = -1, c_ts = 0, c_k = 0, c_cosd = 0;
   int32_t c_qcg = 0, c_qtheta = 0;
-  bool c_alive = false;
-  double c_sinprod = 0, c_g2 = 0, c_rate_ts = 0, c_dist = 0;
-  if (lane < 12) {
-    if (have_ref) {
+  bool c_alive = false, c_valid = false;
+  double c_sinprod = 0, c_lambda = 0, c_rate_ts = 0;
+  {
+    const bool wref = lane < 12;
+    const bool nref = lane == 12 || lane == 13;
+    int i = 0, j = -1;
+    if (wref && have_ref) {
       const int gain_bound = (cg - gain_offset) >> kCgainShift;
-      const int i = (gain_bound - 1 > 1 ? gain_bound - 1 : 1) + (lane >> 2);
-      if (i <= gain_bound + 1) {
-        const int32_t qcg = shl(i, kCgainShift) + gain_offset;
-        const int ts = compute_max_theta(qcg, beta);
-        int lo = (int)floor(.5 + theta * theta_scale_1 * 2 / M_PI * ts) - 2;
-        int hi = (int)ceil(theta * theta_scale_1 * 2 / M_PI * ts);
-        if (lo < 0) lo = 0;
-        if (hi > ts - 1) hi = ts - 1;
-        const int j = lo + (lane & 3);
-        if (j <= hi) {
-          c_gain = i;
-          c_theta = j;
-          c_qcg = qcg;
-          c_ts = ts;
-          c_qtheta = compute_theta(j, ts);
-          c_k = compute_k(qcg, j, 0, n, beta);
-          const double dist_theta = 2 - 2. * pvq_cos(theta - c_qtheta) * trig_1;
-          double dist = gain_weight * (qcg - cg) * (qcg - cg) + qcg * (double)cg * dist_theta;
-          dist *= cgain_2;
-          c_alive = !(dist > dist0 + 1.0 * pvq_norm_lambda && c_k != 0);
-          const double sin_theta = pvq_sin(theta) * trig_1;
-          c_sinprod = sin_theta * pvq_sin(c_qtheta) * trig_1;
-          c_g2 = qcg * (double)cg * c_sinprod * cgain_2;
-          c_rate_ts = .9 * (M_LOG2E * log((double)ts));
-        }
-      }
-    }
-  } else if (lane < 14) {
-    if ((is_keyframe && pli == 0) || corr < .5 || cg < (int32_t)shl(2, kCgainShift)) {
+      i = (gain_bound - 1 > 1 ? gain_bound - 1 : 1) + (lane >> 2);
+      c_valid = i <= gain_bound + 1;
+      c_qcg = shl(i, kCgainShift) + gain_offset;
+    } else if (nref && ((is_keyframe && pli == 0) || corr < .5 || cg < (int32_t)shl(2, kCgainShift))) {
       const int gain_bound = cg >> kCgainShift;
-      const int i = (gain_bound > 1 ? gain_bound : 1) + (lane - 12);
-      if (i <= gain_bound + 1) {
-        c_gain = i;
-        c_qcg = shl(i, kCgainShift);
-        c_k = compute_k(c_qcg, -1, 1, n, beta);
-        double dist = gain_weight * (c_qcg - cg) * (c_qcg - cg);
-        dist *= cgain_2;
-        c_alive = !(dist > dist0 && c_k != 0);
-        c_g2 = c_qcg * (double)cg * cgain_2;
-      }
+      i = (gain_bound > 1 ? gain_bound : 1) + (lane - 12);
+      c_valid = i <= gain_bound + 1;
+      c_qcg = shl(i, kCgainShift);
     }
+    if (!c_valid) c_qcg = kCgainOne;   // harmless arguments for the idle lanes
+    if (wref) {
+      c_ts = compute_max_theta(c_qcg, beta);
+      int lo = (int)floor(.5 + nl_div(theta * theta_scale_1 * 2, M_PI) * c_ts) - 2;
+      int hi = (int)ceil(nl_div(theta * theta_scale_1 * 2, M_PI) * c_ts);
+      if (lo < 0) lo = 0;
+      if (hi > c_ts - 1) hi = c_ts - 1;
+      j = lo + (lane & 3);
+      c_valid = c_valid && j <= hi;
+    } else {
+      c_ts = 0;
+    }
+    const long long tk = nl_theta_k(c_qcg, j, c_ts, !wref, n, beta);
+    c_qtheta = (int32_t)(tk >> 32);
+    c_k = (int)(uint32_t)tk;
+    c_gain = i;
+    c_theta = wref ? j : -1;
+    // distortion pre-tests (src/pvq_encoder.c:529,582), lambda of the search, rate constants
+    c_cosd = nl_cos(theta - c_qtheta);
+    const int sin_q = nl_cos(32768 - c_qtheta), sin_t = nl_cos(32768 - theta);
+    double dist = gain_weight * (c_qcg - cg) * (c_qcg - cg);
+    double g2 = c_qcg * (double)cg;
+    if (wref) {
+      const double dist_theta = 2 - 2. * c_cosd * trig_1;
+      dist = dist + c_qcg * (double)cg * dist_theta;
+      const double sin_theta = sin_t * trig_1;
+      c_sinprod = sin_theta * sin_q * trig_1;
+      g2 = g2 * c_sinprod;
+    }
+    dist *= cgain_2;
+    g2 = g2 * cgain_2;
+    c_alive = c_valid && !(wref ? dist > dist0 + 1.0 * pvq_norm_lambda && c_k != 0 : dist > dist0 && c_k != 0);
+    c_lambda = nl_div(pvq_norm_lambda, 1e-30 + g2);
+    c_rate_ts = .9 * (M_LOG2E * nl_log((double)(c_ts > 0 ? c_ts : 1)));
   }
   unsigned alive_w = __ballot_sync(kFull, c_alive && lane < 12);
   unsigned alive_n = __ballot_sync(kFull, c_alive && lane >= 12);
 
-  // ---- events ------------------------------------------------------------------------------------------
-  int ya[E];     // pulses of the running search, magnitudes (the reference's y_tmp without signs)
-  int ybest[E];  // signed pulses of the best candidate so far
+  // ---- events: the searches ---------------------------------------------------------------------------
+  int ya[4];  // pulses of the running search, magnitudes (the reference's y_tmp without signs)
 #pragma unroll
-  for (int e = 0; e < E; e++) ya[e] = ybest[e] = 0;
-  int prev_k = 0, best_lane = -1;
-  bool noref_started = false;
+  for (int e = 0; e < 4; e++) ya[e] = 0;
+  SearchVec sv;
+  sv.nn = n;
+  sv.xx = 0;
+  int prev_k = 0, nev = 0, c_ev = -1;
+  int phase = 0;  // 1: with-reference vector loaded, 2: no-reference vector
+  double e_xy = 0, e_yy = 0, e_xx = 0;   // lane `event`: scalars of that event
+  int e_sum = 0, e_k = 0, e_zero = 0;
   while (alive_w | alive_n) {
     unsigned grp;
     int kcur, leader;
@@ -312,238 +556,92 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const 
       grp = 1u << leader;
       alive_n &= ~grp;
       kcur = __shfl_sync(kFull, c_k, leader);
-      if (!noref_started) prev_k = 0;
-      noref_started = true;
     }
-    const int nn = noref_ev ? n : n - 1;
-    double cos_dist = 0;
-    if (!noref_ev && kcur == 0) {
+    const int want = noref_ev ? 2 : 1;
+    if (phase != want) {
+      // (the first no-reference candidate of the list restarts the pulse reuse: prev_k = 0)
+      phase = want;
+      prev_k = 0;
+      if (big) search_init<4>(lane, sv, noref_ev ? x16 : xr, noref_ev ? n : n - 1);
+      else search_init<1>(lane, sv, noref_ev ? x16 : xr, noref_ev ? n : n - 1);
+    }
+    double xy = 0, yy = 0;
+    const bool zero_ev = !noref_ev && kcur == 0;
+    if (zero_ev) {
 #pragma unroll
-      for (int e = 0; e < E; e++) ya[e] = 0;
+      for (int e = 0; e < 4; e++) ya[e] = 0;
     } else {
-      // ---- pvq_search_rdo_double (src/pvq_encoder.c:93) on |x| ------------------------------------------
-      const double g2 = wbcast(c_g2, leader);
-      const int k = kcur;
-      int xa[E];
-      double xd[E];
-      float xf[E];
-      long long sxx = 0;
-      int xmax = 0, sl1 = 0;
-#pragma unroll
-      for (int e = 0; e < E; e++) {
-        const int v = noref_ev ? x16[e] : xr[e];
-        const int a = e * 32 + lane < nn ? abs(v) : 0;
-        xa[e] = a;
-        xd[e] = (double)a;  // == fabs((double)(float)xcoeff[j]): |int16| is exact in float
-        xf[e] = (float)a;
-        sxx += (long long)a * a;
-        sl1 += a;
-        xmax = a > xmax ? a : xmax;
-      }
-      const double xx = (double)wsum64(sxx);
-      xmax = wmax(xmax);
-      const double norm_1 = 1. / sqrt(1e-30 + xx);
-      const double lambda = pvq_norm_lambda / (1e-30 + g2);
-      double xy = 0, yy = 0;
-      int i = 0;
-      if (prev_k > 0 && prev_k <= k) {
-        long long sxy = 0, syy = 0;
-        int si = 0;
-#pragma unroll
-        for (int e = 0; e < E; e++) {
-          if (e * 32 + lane >= nn) ya[e] = 0;
-          sxy += (long long)xa[e] * ya[e];
-          syy += (long long)ya[e] * ya[e];
-          si += ya[e];
-        }
-        xy = (double)wsum64(sxy);
-        yy = (double)wsum64(syy);
-        i = wsum(si);
-      } else if (k > 2) {
-        const double l1_norm = (double)wsum(sl1);
-        const double l1_inv = 1. / (l1_norm > 1e-100 ? l1_norm : 1e-100);
-        long long sxy = 0, syy = 0;
-        int si = 0;
-#pragma unroll
-        for (int e = 0; e < E; e++) {
-          const double tmp = k * xd[e] * l1_inv;
-          const int f = (int)floor(tmp);
-          ya[e] = (e * 32 + lane < nn && f > 0) ? f : 0;
-          sxy += (long long)xa[e] * ya[e];
-          syy += (long long)ya[e] * ya[e];
-          si += ya[e];
-        }
-        xy = (double)wsum64(sxy);
-        yy = (double)wsum64(syy);
-        i = wsum(si);
-      } else {
-#pragma unroll
-        for (int e = 0; e < E; e++) ya[e] = 0;
-      }
-      const int rdo_pulses = 1 + k / 4;
-      double delta_rate = 3. / nn;
-      double accel_rate = 0.;
-      if (k == 1) {
-        if (nn == 15) {
-          accel_rate = -8. / nn;
-          delta_rate = 4.5 / nn - accel_rate;
-        } else if (nn == 8) {
-          accel_rate = 5.7 / nn;
-          delta_rate = 9.3 / nn - accel_rate;
-        }
-      }
-      for (; i < k; i++) {
-        const bool plain = i < k - rdo_pulses;
-        // contenders per slot
-        bool cont[E];
-        double tval[E];  // RDO: the element's objective
-        int total;
-        if (plain) {
-          const double bound = (xy + xmax) * (xy + xmax) * (yy + 2. * i + 1.);
-          if (bound < DAALA_B200_PVQ_EXACT_BOUND) {
-            const float xyf = (float)xy, yyf1 = (float)(yy + 1.);
-            unsigned key[E], kmax = 0;
-#pragma unroll
-            for (int e = 0; e < E; e++) {
-              float a = xyf + xf[e];
-              a *= a;
-              const float b = yyf1 + (float)(2 * ya[e]);
-              key[e] = e * 32 + lane < nn ? __float_as_uint(__fdividef(a, b)) : 0u;
-              kmax = key[e] > kmax ? key[e] : kmax;
-            }
-            const unsigned mx = wmaxu(kmax);
-            const unsigned thr = mx > 64u ? mx - 64u : 0u;
-            int cnt = 0;
-#pragma unroll
-            for (int e = 0; e < E; e++) {
-              cont[e] = e * 32 + lane < nn && key[e] >= thr;
-              cnt += cont[e];
-            }
-            total = wsum(cnt);
-          } else {
-            // products may round: the reference's literal scan over every element
-#pragma unroll
-            for (int e = 0; e < E; e++) cont[e] = e * 32 + lane < nn;
-            total = 2;
-            PVQ_WARP_STAT(3);
-          }
-#pragma unroll
-          for (int e = 0; e < E; e++) tval[e] = 0;
-        } else {
-          double tbl[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) tbl[j] = rsqrt_small_tbl((int)(yy + 2 * j + 1));
-          int key[E], kmax = (int)0x80000000;
-#pragma unroll
-          for (int e = 0; e < E; e++) {
-            const int j = e * 32 + lane;
-            double t = xy + xd[e];
-            const int yj = ya[e];
-            const double ryy = yj < 4 ? (yj == 0 ? tbl[0] : yj == 1 ? tbl[1] : yj == 2 ? tbl[2] : tbl[3])
-                                      : rsqrt_small_tbl((int)(yy + 2 * yj + 1));
-            t = 2 * t * norm_1 * ryy - lambda * j * (delta_rate + j * accel_rate);
-            tval[e] = t;
-            key[e] = j < nn ? ordered_key((float)t) : (int)0x80000000;
-            kmax = key[e] > kmax ? key[e] : kmax;
-          }
-          const int mx = wmax(kmax);
-          int cnt = 0;
-#pragma unroll
-          for (int e = 0; e < E; e++) {
-            cont[e] = e * 32 + lane < nn && key[e] == mx;
-            cnt += cont[e];
-          }
-          total = wsum(cnt);
-        }
-        int pos;  // index of the chosen element
-        PVQ_WARP_STAT(total == 1 ? 0 : plain ? 1 : 2);
-        if (total == 1) {
-          int mine = -1;
-#pragma unroll
-          for (int e = 0; e < E; e++) if (cont[e]) mine = e * 32 + lane;
-          const unsigned who = __ballot_sync(kFull, mine >= 0);
-          pos = __shfl_sync(kFull, mine, __ffs(who) - 1);
-        } else {
-          // the reference's sequential scan restricted to the contenders, in index order
-          pos = -1;
-          double ba = 0, bb = 1;
-#pragma unroll
-          for (int e = 0; e < E; e++) {
-            unsigned mk = __ballot_sync(kFull, cont[e]);
-            while (mk) {
-              const int l = __ffs(mk) - 1;
-              mk &= mk - 1;
-              if (plain) {
-                const int xj = __shfl_sync(kFull, xa[e], l);
-                const int yj = __shfl_sync(kFull, ya[e], l);
-                double a = xy + (double)xj;
-                const double b = yy + 2 * yj + 1;
-                a *= a;
-                if (pos < 0 || a * bb > ba * b) { ba = a; bb = b; pos = e * 32 + l; }
-              } else {
-                const double t = wbcast(tval[e], l);
-                if (pos < 0 || t > ba) { ba = t; pos = e * 32 + l; }
-              }
-            }
-          }
-        }
-        const int src = pos & 31, slot = pos >> 5;
-        const int px = __shfl_sync(kFull, pick<E>(xa, slot), src);
-        const int py = __shfl_sync(kFull, pick<E>(ya, slot), src);
-        xy = xy + (double)px;
-        yy = yy + 2 * py + 1;
-#pragma unroll
-        for (int e = 0; e < E; e++) if (e * 32 + lane == pos) ya[e]++;
-      }
-      cos_dist = xy / (1e-100 + sqrt(xx * yy));
+      const double lambda = wfetch(c_lambda, leader);
+      if (big) search_event<4>(lane, sv, ya, kcur, prev_k, lambda, &xy, &yy);
+      else search_event<1>(lane, sv, ya, kcur, prev_k, lambda, &xy, &yy);
     }
     prev_k = kcur;
-    // ---- od_pvq_rate, closed form (src/pvq_encoder.c:247), shared part of the event -------------------------
-    double rate_base = 0;
-    if (kcur != 0) {
-      int sj = 0;
+    int sj = 0;
 #pragma unroll
-      for (int e = 0; e < E; e++) if (e * 32 + lane < nn) sj += (e * 32 + lane) * ya[e];
-      const int sum = wsum(sj);
-      const double f = sum / (double)(kcur * n);
-      const double t = log(n * 2 * (1 * f + .025)) * kcur / n;
-      rate_base = (1 + .4 * f) * n * (M_LOG2E * log(1 + (0 > t ? 0 : t))) + 3;
+    for (int e = 0; e < 4; e++) {
+      if (e && !big) break;
+      const int j = e * 32 + lane;
+      if (j < sv.nn) sj += j * ya[e];
+      if (j < n) snap[nev * kMaxN + j] = (int16_t)(j < sv.nn ? ya[e] : 0);
     }
-    // ---- cost of every candidate of the event, then the reference's in-order fold ------------------------
-    double cost = 0;
-    if ((grp >> lane) & 1) {
-      double rate = rate_base;
-      double dist;
-      if (noref_ev) {
-        dist = gain_weight * (c_qcg - cg) * (c_qcg - cg) + c_qcg * (double)cg * (2 - 2 * cos_dist);
-      } else {
-        if (c_gain > 0 && c_theta >= 0) {
-          rate += c_rate_ts;
-          if (is_keyframe && pli == 0) rate += 6;
-          if (c_gain == icgr) rate -= .5;
-        }
-        const double dist_theta = 2 - 2. * pvq_cos(theta - c_qtheta) * trig_1 + c_sinprod * (2 - 2 * cos_dist);
-        dist = gain_weight * (c_qcg - cg) * (c_qcg - cg) + c_qcg * (double)cg * dist_theta;
+    sj = wsum(sj);
+    if (lane == nev) {
+      e_xy = xy;
+      e_yy = yy;
+      e_xx = sv.xx;
+      e_sum = sj;
+      e_k = kcur;
+      e_zero = zero_ev;
+    }
+    if ((grp >> lane) & 1) c_ev = nev;
+    nev++;
+  }
+
+  // ---- all events in parallel: cos distance and the shared part of od_pvq_rate (src/pvq_encoder.c:247) ---
+  double e_cos = 0, e_rate = 0;
+  {
+    const int kk = e_k > 0 ? e_k : 1;
+    const double cd = nl_div(e_xy, 1e-100 + nl_sqrt(e_xx * e_yy));
+    const double f = nl_div((double)e_sum, (double)(kk * n));
+    const double t = nl_div(nl_log(n * 2 * (1 * f + .025)) * kk, (double)n);
+    const double rate = (1 + .4 * f) * n * (M_LOG2E * nl_log(1 + (0 > t ? 0 : t))) + 3;
+    e_cos = e_zero ? 0. : cd;
+    e_rate = e_k == 0 ? 0. : rate;
+  }
+  // ---- all candidates in parallel: cost ----------------------------------------------------------------
+  double c_dist = 0, cost = 0;
+  {
+    const int src = c_ev >= 0 ? c_ev : 0;
+    const double cos_dist = wfetch(e_cos, src);
+    double rate = wfetch(e_rate, src);
+    double dist;
+    if (lane >= 12) {
+      dist = gain_weight * (c_qcg - cg) * (c_qcg - cg) + c_qcg * (double)cg * (2 - 2 * cos_dist);
+    } else {
+      if (c_gain > 0 && c_theta >= 0) {
+        rate += c_rate_ts;
+        if (is_keyframe && pli == 0) rate += 6;
+        if (c_gain == icgr) rate -= .5;
       }
-      dist *= cgain_2;
-      c_dist = dist;
-      cost = dist + pvq_norm_lambda * rate;
+      const double dist_theta = 2 - 2. * c_cosd * trig_1 + c_sinprod * (2 - 2 * cos_dist);
+      dist = gain_weight * (c_qcg - cg) * (c_qcg - cg) + c_qcg * (double)cg * dist_theta;
     }
-    bool improved = false;
-    for (unsigned gm = grp; gm; gm &= gm - 1) {
-      const int l = __ffs(gm) - 1;
-      const double cl = wbcast(cost, l);
-      if (noref_ev ? cl <= best_cost : cl < best_cost) {
+    dist *= cgain_2;
+    c_dist = dist;
+    cost = dist + pvq_norm_lambda * rate;
+  }
+  // ---- the reference's fold, in its order: events ascending, candidates of an event in insertion order ----
+  int best_lane = -1;
+  {
+    unsigned rem = __ballot_sync(kFull, c_ev >= 0);
+    while (rem) {
+      const int key = (rem >> lane) & 1 ? (c_ev << 5) | lane : 0x7fffffff;
+      const int l = wmin(key) & 31;
+      rem &= ~(1u << l);
+      const double cl = wfetch(cost, l);
+      if (l >= 12 ? cl <= best_cost : cl < best_cost) {
         best_cost = cl;
         best_lane = l;
-        improved = true;
-      }
-    }
-    if (improved) {
-#pragma unroll
-      for (int e = 0; e < E; e++) {
-        const int v = noref_ev ? x16[e] : xr[e];
-        ybest[e] = e * 32 + lane < nn ? (v < 0 ? -ya[e] : ya[e]) : 0;
       }
     }
   }
@@ -554,14 +652,26 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const 
   *itheta = is_keyframe ? -1 : 0;
   *max_theta = 0;
   theta = 0;  // best_qtheta
+  int ybest[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) ybest[e] = 0;
   if (best_lane >= 0) {
     qg = __shfl_sync(kFull, c_gain, best_lane);
     best_k = __shfl_sync(kFull, c_k, best_lane);
     *itheta = __shfl_sync(kFull, c_theta, best_lane);
     *max_theta = __shfl_sync(kFull, c_ts, best_lane);
     theta = __shfl_sync(kFull, c_qtheta, best_lane);
-    best_dist = wbcast(c_dist, best_lane);
+    best_dist = wfetch(c_dist, best_lane);
     noref = best_lane >= 12;
+    const int ev = __shfl_sync(kFull, c_ev, best_lane);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      if (e && !big) break;
+      const int j = e * 32 + lane;
+      const int v = noref ? x16[e] : xr[e];
+      const int a = j < n ? snap[ev * kMaxN + j] : 0;
+      ybest[e] = j < (noref ? n : n - 1) ? (v < 0 ? -a : a) : 0;
+    }
   }
   int skip = 0;
   if (noref) {
@@ -570,10 +680,10 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const 
     if (!is_keyframe && qg == 0) skip = icgr ? 1 : 2;
     if (qg == icgr && *itheta == 0 && !cfl_enabled) skip = 2;
   }
-  int32_t res[E];
+  int32_t res[4];
   if (skip) {
 #pragma unroll
-    for (int e = 0; e < E; e++) res[e] = (skip == 2 && e * 32 + lane < n) ? r0[e * 32 + lane] : 0;
+    for (int e = 0; e < 4; e++) res[e] = (skip == 2 && e * 32 + lane < n) ? r0[e * 32 + lane] : 0;
   } else {
     if (noref) gain_offset = 0;
     g = gain_expand(shl(qg, kCgainShift) + gain_offset, q0, beta);
@@ -581,7 +691,7 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const 
     const int nn = n - !noref;
     int syy = 0;
 #pragma unroll
-    for (int e = 0; e < E; e++) if (e * 32 + lane < nn) syy += ybest[e] * ybest[e];
+    for (int e = 0; e < 4; e++) if (e * 32 + lane < nn) syy += ybest[e] * ybest[e];
     const int yy = wsum(syy);
     int gshift = ilog((uint32_t)g) - 14;
     if (gshift < 0) gshift = 0;
@@ -594,21 +704,20 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const 
       scale = vshr_round64(rs * (int64_t)g, rsh + gshift - 16);
     }
     const int qshift = kQmInvShift - gshift;
+    int xs[4];
     if (noref) {
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const int j = e * 32 + lane;
-        const int32_t v = mul16_32_q16(ybest[e], scale);
-        res[e] = j < n ? shr_round(v * qm_inv[j], qshift) : 0;
-      }
+      for (int e = 0; e < 4; e++) xs[e] = mul16_32_q16(ybest[e], scale);
     } else {
-      scale = round32(scale * (1. / 32768) * pvq_sin(theta));
-      int xs[E], f[E];
+      scale = round32(scale * (1. / 32768) * nl_cos(32768 - theta));
+      int f[4];
 #pragma unroll
-      for (int e = 0; e < E; e++) f[e] = e * 32 + lane < nn ? (int16_t)mul16_32_q16(ybest[e], scale) : 0;
-      const int xm = (int16_t)floor(.5 + -s * (shr_round(g, gshift)) * (1. / 32768) * pvq_cos(theta));
+      for (int e = 0; e < 4; e++) f[e] = e * 32 + lane < nn ? (int16_t)mul16_32_q16(ybest[e], scale) : 0;
+      const int xm = (int16_t)floor(.5 + -s * (shr_round(g, gshift)) * (1. / 32768) * nl_cos(theta));
 #pragma unroll
-      for (int e = 0; e < E; e++) {
+      for (int e = 0; e < 4; e++) {
+        xs[e] = 0;
+        if (e && !big) continue;
         // value of element idx - 1
         const int t1 = __shfl_sync(kFull, f[e], (lane + 31) & 31);
         const int t2 = e > 0 ? __shfl_sync(kFull, f[e > 0 ? e - 1 : 0], 31) : 0;
@@ -617,16 +726,16 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int32_t* out, const 
         xs[e] = j < m ? f[e] : (j == m ? xm : fprev);
         if (j >= n) xs[e] = 0;
       }
-      householder_apply_warp<E>(lane, xs, xs, r16, n);
+      householder_apply_warp(lane, big, xs, xs, r16, n);
+    }
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const int j = e * 32 + lane;
-        res[e] = j < n ? shr_round(xs[e] * qm_inv[j], qshift) : 0;
-      }
+    for (int e = 0; e < 4; e++) {
+      const int j = e * 32 + lane;
+      res[e] = j < n ? shr_round(xs[e] * qm_inv[j], qshift) : 0;
     }
   }
 #pragma unroll
-  for (int e = 0; e < E; e++) {
+  for (int e = 0; e < 4; e++) {
     const int j = e * 32 + lane;
     if (j < n) {
       out[j] = res[e];

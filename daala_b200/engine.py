@@ -17,7 +17,7 @@ PH_LISTS, PH_FORWARD, PH_PVQ_LUMA, PH_INVERSE, PH_PVQ_CHROMA = 1, 2, 4, 8, 16
 PH_PVQ, PH_ALL, PH_SEARCH_ONLY = 20, 31, 64
 LAUNCHES_PER_STEP = 17   # lists 5, forward 1, luma 4, chroma 5, inverse 2 (+ 4 memset nodes)
 CNT = dict(n_luma=0, n_chroma=1, luma_coefs=2, chroma_coefs=3, items_l=4, items_c=7,
-           total_hi=14, n_heads=15, error=17)
+           total_hi=14, n_heads=15, n_heads0=16, error=17)
 
 
 class Config(ctypes.Structure):
@@ -44,7 +44,7 @@ class Buffers(ctypes.Structure):
                 ("pixels_out", c_void_p * 3), ("plane_w", c_int * 3), ("plane_h", c_int * 3), ("bsize", c_void_p),
                 ("counts", c_void_p), ("luma_blocks", c_void_p), ("chroma_blocks", c_void_p), ("dep_top", c_void_p),
                 ("dep_left", c_void_p), ("succ_bottom", c_void_p), ("succ_right", c_void_p), ("luma_items", c_void_p * 3),
-                ("luma_heads", c_void_p), ("chroma_items", c_void_p * 3),
+                ("luma_heads", c_void_p), ("luma_heads0", c_void_p), ("chroma_items", c_void_p * 3),
                 ("luma_res", c_void_p), ("chroma_res", c_void_p), ("luma_y16", c_void_p), ("chroma_y16", c_void_p),
                 ("luma_skip_diff", c_void_p), ("chroma_skip_diff", c_void_p), ("chroma_flip", c_void_p),
                 ("max_luma_blocks", c_int), ("max_chroma_blocks", c_int), ("stream", c_void_p),

@@ -466,7 +466,8 @@ typedef struct daala_b200_kf_buffers {  /* device pointers of an engine (tests, 
   int32_t *dep_top, *dep_left;          /* same-size neighbour above / left of each luma block, or -1 */
   int32_t *succ_bottom, *succ_right;    /* the inverse: the block that waits for this one, or -1 */
   uint32_t *luma_items[3];              /* dependency-free luma items (bands 3 / 6) per class */
-  uint32_t *luma_heads;                 /* chain items ready from the start; counts[15] of them */
+  uint32_t *luma_heads;                 /* row / column chain items ready from the start; counts[15] of them */
+  uint32_t *luma_heads0;                /* band-0 items ready from the start; counts[16] of them */
   uint32_t *chroma_items[3];
   int16_t *luma_res, *chroma_res, *luma_y16, *chroma_y16;
   double *luma_skip_diff, *chroma_skip_diff;

@@ -16,13 +16,10 @@ extern "C" int emu_quantise_band(int32_t* out, const int32_t* x0, const int32_t*
                                  const int16_t* qm, const int16_t* qm_inv, double lambda) {
   int gain[32], it[32], mt[32], k[32];
   double sd[32];
+  static int16_t snap[kSnapEntries];
   simt_emu::run_warp([&](int lane) {
-    if (n > 32)
-      gain[lane] = quantise_band_warp<4>(lane, out, x0, r0, n, q0, y, &it[lane], &mt[lane], &k[lane], beta, &sd[lane],
-                                         is_keyframe, pli, qm, qm_inv, lambda);
-    else
-      gain[lane] = quantise_band_warp<1>(lane, out, x0, r0, n, q0, y, &it[lane], &mt[lane], &k[lane], beta, &sd[lane],
-                                         is_keyframe, pli, qm, qm_inv, lambda);
+    gain[lane] = quantise_band_warp(lane, snap, out, x0, r0, n, q0, y, &it[lane], &mt[lane], &k[lane], beta, &sd[lane],
+                                    is_keyframe, pli, qm, qm_inv, lambda);
   });
   for (int l = 1; l < 32; l++) {
     if (gain[l] != gain[0] || it[l] != it[0] || mt[l] != mt[0] || k[l] != k[0] || sd[l] != sd[0]) {

@@ -145,7 +145,9 @@ def test_engine_lists_are_consistent():
         n = int(cnt[4 + c])
         items = eng.download(eng.buf.luma_items[c], (n,), np.uint32)
         assert ((items & 15) == band).all() and len(np.unique(items)) == n == int((nb > band).sum())
-    heads = eng.download(eng.buf.luma_heads, (int(cnt[engine.CNT["n_heads"]]),), np.uint32)
+    heads = np.concatenate([eng.download(eng.buf.luma_heads, (int(cnt[engine.CNT["n_heads"]]),), np.uint32),
+                            eng.download(eng.buf.luma_heads0, (int(cnt[engine.CNT["n_heads0"]]),), np.uint32)])
+    assert ((heads[:int(cnt[engine.CNT["n_heads"]])] & 15) != 0).all() and ((heads[int(cnt[engine.CNT["n_heads"]]):] & 15) == 0).all()
     want_heads = set()
     for band in (0, 1, 2, 4, 5, 7, 8):
         r = band % 3
