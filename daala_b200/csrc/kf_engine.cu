@@ -320,6 +320,7 @@ struct Stage {
   int32_t* cnt;
   int n_items_at, head_lo_at, n_blocks_at;
   int max_blocks;
+  const double* rsqrt_tbl;         // [kTableDoubles] the reference's 1/sqrt(i) and theta-rate terms (pvq_fill_rsqrt_table)
   int16_t* res_pack;               // [nblocks*9][4]: gain, itheta, max_theta, k (what the coder reads)
   const int32_t* cfl_plane;        // chroma: prediction plane (chroma geometry), else NULL
   long long cfl_pitch;
@@ -541,7 +542,7 @@ __device__ __forceinline__ void run_item(const Stage& S, uint32_t item, int lane
   const int qoff = (b.xdec & 1 ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
   int itheta, max_theta, k;
   double skip_term;
-  const int gain = quantise_band_warp(lane, snap, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off, &itheta,
+  const int gain = quantise_band_warp(lane, snap, S.rsqrt_tbl, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off, &itheta,
                                          &max_theta, &k, beta, &skip_term, prm.is_keyframe, pli, prm.qm + qoff,
                                          prm.qm_inv + qoff, prm.pvq_norm_lambda);
   if (lane == 0) {
@@ -603,6 +604,11 @@ __global__ void __launch_bounds__(128, DAALA_PERSIST_MIN_CTAS) k_pvq_persist(con
       item = next;
     }
   }
+}
+
+__global__ void k_fill_rsqrt(double* tbl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kTableDoubles) pvq_fill_rsqrt_table(tbl, i);
 }
 
 // Start of a PVQ stage: the tickets; the chain queue starts with the heads.
@@ -681,6 +687,7 @@ struct daala_b200_kf {
   uint8_t* bsize;
   int32_t* cfl_plane;
   int16_t *qm, *qm_inv;
+  double* rsqrt_tbl;
   Lists lists;
   Stage luma, chroma;
   daala_b200_frame frame;
@@ -725,6 +732,9 @@ static int kf_alloc(daala_b200_kf* kf) {
   KF_CHECK(dalloc(kf, &kf->cfl_plane, (size_t)kf->plane_w[1] * kf->plane_h[1] * F));
   KF_CHECK(dalloc(kf, &kf->qm, (size_t)2 * kf->cfg.qm_stride));
   KF_CHECK(dalloc(kf, &kf->qm_inv, (size_t)2 * kf->cfg.qm_stride));
+  KF_CHECK(dalloc(kf, &kf->rsqrt_tbl, (size_t)kTableDoubles));
+  k_fill_rsqrt<<<(kTableDoubles + 255) / 256, 256, 0, kf->stream>>>(kf->rsqrt_tbl);
+  KF_CHECK(cudaStreamSynchronize(kf->stream));
   KF_CHECK(cudaMemcpy(kf->qm, kf->cfg.qm, sizeof(int16_t) * 2 * kf->cfg.qm_stride, cudaMemcpyHostToDevice));
   KF_CHECK(cudaMemcpy(kf->qm_inv, kf->cfg.qm_inv, sizeof(int16_t) * 2 * kf->cfg.qm_stride, cudaMemcpyHostToDevice));
 
@@ -800,6 +810,7 @@ static int kf_alloc(daala_b200_kf* kf) {
     memcpy(p.pvq_qm_q4, kf->cfg.pvq_qm_q4, sizeof(p.pvq_qm_q4));
     for (int c = 0; c < 3; c++) S.items[c] = chroma ? L.items_c[c] : L.items_l[c];
     S.cnt = L.cnt;
+    S.rsqrt_tbl = kf->rsqrt_tbl;
     S.n_items_at = chroma ? kNItemsC : kNItemsL;
     S.head_lo_at = chroma ? kHeadLoC : kHeadLoL;
     S.n_blocks_at = chroma ? kNChroma : kNLuma;
@@ -964,6 +975,7 @@ void daala_b200_kf_destroy(daala_b200_kf* kf) {
   cudaFree(kf->cfl_plane);
   cudaFree(kf->qm);
   cudaFree(kf->qm_inv);
+  cudaFree(kf->rsqrt_tbl);
   Lists& L = kf->lists;
   cudaFree(L.tile_sum);
   cudaFree(L.unit_lbase);

@@ -31,8 +31,9 @@
 //    products that could exceed 2^53, where the reference's own comparisons round) the contenders are
 //    compared with the reference's literal double-precision test in index order.  RDO pulses maximise
 //    a double; its f32 rounding is monotone, so the contenders are the elements whose rounded value
-//    equals the maximum.  Their 1/sqrt(yy + 2 y_j + 1) factors come from lane y_j, which evaluates the
-//    reference's expression for that argument (one square root + division per pulse, not per element).
+//    equals the maximum.  Their 1/sqrt(yy + 2 y_j + 1) factors come from a table of the reference's
+//    expression (built once on the device with the same code; a square root + division per element and
+//    pulse was a tenth of all instructions).
 //
 // Pulses must fit 16 bits (K <= 32767), like the symbol stream the engine hands to the host coder.
 //
@@ -50,6 +51,9 @@ namespace pvq {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxEvents = 14;                      // <= 12 with-reference K values + 2 no-reference gains
 constexpr int kSnapEntries = kMaxEvents * kMaxN;    // int16 entries of per-warp scratch
+constexpr int kRsqrtEntries = 1 << 16;              // table of the reference's 1/sqrt(i), i < 65536
+constexpr int kLogEntries = 1 << 12;                // table of .9 * (M_LOG2E * log(ts)) behind it
+constexpr int kTableDoubles = kRsqrtEntries + kLogEntries;
 
 // below this bound every product of the plain-pulse ratio test is exact in double (tests lower it to
 // force the literal-scan path)
@@ -104,6 +108,11 @@ static __device__ __noinline__ double nl_rsqrt_small(int i) {
   if (i <= 16) return kRsqrtSmall[i - 1];
   return 1. / sqrt((double)i);
 }
+// entry i of the tables (kTableDoubles of them): what pvq_search_rdo_double / od_pvq_rate compute for that argument
+__device__ __forceinline__ void pvq_fill_rsqrt_table(double* rsq, int i) {
+  if (i < kRsqrtEntries) rsq[i] = i > 0 ? nl_rsqrt_small(i) : 0.;
+  else rsq[i] = .9 * (M_LOG2E * nl_log((double)(i > kRsqrtEntries ? i - kRsqrtEntries : 1)));   // od_pvq_rate's theta term
+}
 // (companded gain, gain) of a 16-bit vector with energy `acc`: od_pvq_compute_gain, src/pvq.c:824
 static __device__ __noinline__ long long nl_gain(int32_t acc, int q0, int beta, int bshift) {
   int32_t g;
@@ -155,6 +164,7 @@ struct SearchVec {
   double xd[4];   // == fabs((double)(float)xcoeff[j]): |int16| is exact in float
   float xf[4];
   double xx, norm_1, l1_norm;
+  double delta_rate;   // 3. / nn
   int xmax, nn;
 };
 
@@ -176,6 +186,7 @@ __device__ __forceinline__ void search_init(int lane, SearchVec& v, const int (&
   v.xmax = wmax(xmax);
   v.l1_norm = (double)wsum(sl1);
   v.norm_1 = nl_div(1., nl_sqrt(1e-30 + v.xx));
+  v.delta_rate = nl_div(3., (double)nn);
   v.nn = nn;
 }
 
@@ -183,7 +194,7 @@ __device__ __forceinline__ void search_init(int lane, SearchVec& v, const int (&
 // k pulses out; *xy_out, *yy_out = the reference's running sums at the end.
 template <int E>
 __device__ __forceinline__ void search_event(int lane, const SearchVec& v, int (&ya)[4], int k, int prev_k,
-                                             double lambda, double* xy_out, double* yy_out) {
+                                             double lambda, const double* rsq, double* xy_out, double* yy_out) {
   const int nn = v.nn;
   double xy = 0, yy = 0;
   int i = 0;
@@ -221,7 +232,7 @@ __device__ __forceinline__ void search_event(int lane, const SearchVec& v, int (
     for (int e = 0; e < E; e++) ya[e] = 0;
   }
   const int rdo_pulses = 1 + k / 4;
-  double delta_rate = nl_div(3., (double)nn);
+  double delta_rate = v.delta_rate;
   double accel_rate = 0.;
   if (k == 1) {
     if (nn == 15) {
@@ -269,15 +280,14 @@ __device__ __forceinline__ void search_event(int lane, const SearchVec& v, int (
 #pragma unroll
       for (int e = 0; e < E; e++) tval[e] = 0;
     } else {
-      // lane l evaluates the reference's 1/sqrt(yy + 2 l + 1); an element with y_j pulses fetches lane y_j's
-      const double rs_lane = nl_rsqrt_small((int)(yy + 2 * lane + 1));
+      // 1/sqrt(yy + 2 y_j + 1): the reference's expression, tabulated for arguments below kRsqrtEntries
+      const int iyy = yy < 1e9 ? (int)yy : 1000000000;
       int key[E], kmax = (int)0x80000000;
 #pragma unroll
       for (int e = 0; e < E; e++) {
         const int j = e * 32 + lane;
-        const int yj = ya[e];
-        double ryy = wfetch(rs_lane, yj & 31);
-        if (yj >= 32) ryy = nl_rsqrt_small((int)(yy + 2 * yj + 1));
+        const int arg = iyy + 2 * ya[e] + 1;
+        const double ryy = arg < kRsqrtEntries ? rsq[arg] : nl_rsqrt_small((int)(yy + 2 * ya[e] + 1));
         double t = xy + v.xd[e];
         t = 2 * t * v.norm_1 * ryy - lambda * j * (delta_rate + j * accel_rate);
         tval[e] = t;
@@ -341,9 +351,10 @@ __device__ __forceinline__ void search_event(int lane, const SearchVec& v, int (
 }
 
 // One band by one warp.  x0 / r0 / out / yout / qm / qm_inv point at the band's first entry; `snap`:
-// kSnapEntries int16 of scratch private to the warp (shared memory).  Scalar results are identical in
+// kSnapEntries int16 of scratch private to the warp (shared memory); `rsq`: kTableDoubles doubles
+// filled by pvq_fill_rsqrt_table.  Scalar results are identical in
 // every lane.  int16 quantities of the reference are kept sign-extended in ints.
-__device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, int32_t* out, const int32_t* x0,
+__device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const double* rsq, int32_t* out, const int32_t* x0,
                                                   const int32_t* r0, int n, int q0, int32_t* yout, int* itheta,
                                                   int* max_theta, int* vk, int beta, double* skip_term, int is_keyframe,
                                                   int pli, const int16_t* qm, const int16_t* qm_inv,
@@ -524,7 +535,8 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, int32
     g2 = g2 * cgain_2;
     c_alive = c_valid && !(wref ? dist > dist0 + 1.0 * pvq_norm_lambda && c_k != 0 : dist > dist0 && c_k != 0);
     c_lambda = nl_div(pvq_norm_lambda, 1e-30 + g2);
-    c_rate_ts = .9 * (M_LOG2E * nl_log((double)(c_ts > 0 ? c_ts : 1)));
+    c_rate_ts = c_ts < kLogEntries ? rsq[kRsqrtEntries + (c_ts > 0 ? c_ts : 1)]
+                                   : .9 * (M_LOG2E * nl_log((double)c_ts));
   }
   unsigned alive_w = __ballot_sync(kFull, c_alive && lane < 12);
   unsigned alive_n = __ballot_sync(kFull, c_alive && lane >= 12);
@@ -572,8 +584,8 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, int32
       for (int e = 0; e < 4; e++) ya[e] = 0;
     } else {
       const double lambda = wfetch(c_lambda, leader);
-      if (big) search_event<4>(lane, sv, ya, kcur, prev_k, lambda, &xy, &yy);
-      else search_event<1>(lane, sv, ya, kcur, prev_k, lambda, &xy, &yy);
+      if (big) search_event<4>(lane, sv, ya, kcur, prev_k, lambda, rsq, &xy, &yy);
+      else search_event<1>(lane, sv, ya, kcur, prev_k, lambda, rsq, &xy, &yy);
     }
     prev_k = kcur;
     int sj = 0;

@@ -64,6 +64,18 @@ void od_bin_idct32x32(od_coeff *x, int xstride, const od_coeff *y, int ystride);
 void od_bin_fdct64x64(od_coeff *y, int ystride, const od_coeff *x, int xstride);
 void od_bin_idct64x64(od_coeff *x, int xstride, const od_coeff *y, int ystride);
 /* src/dct.c:4822 / :4861 (prototypes src/dct.h): the multi-level Haar wavelet of the lossless path, n = 1 << ln */
+/* TF resolution switching, reference src/tf.h:47-67 / src/tf.c:38-277 (csrc/tf_kernels.cu).  Blocks up to
+   64x64; dst may alias src where the reference allows it. */
+void od_tf_up_h_lp(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int dx, int n);
+void od_tf_up_v_lp(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int dy, int n);
+void od_tf_up_hv_lp(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int dx, int dy, int n);
+void od_tf_up_hv(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int n);
+void od_tf_down_hv(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int n);
+void od_convert_block_down(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int curr_size,
+                           int dest_size, int filter);
+void od_tf_filter_2d(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int n);
+void od_tf_filter_inv_2d(od_coeff *dst, int dstride, const od_coeff *src, int sstride, int n);
+
 void od_haar(od_coeff *y, int ystride, const od_coeff *x, int xstride, int ln);
 void od_haar_inv(od_coeff *x, int xstride, const od_coeff *y, int ystride, int ln);
 

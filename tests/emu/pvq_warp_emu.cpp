@@ -17,8 +17,13 @@ extern "C" int emu_quantise_band(int32_t* out, const int32_t* x0, const int32_t*
   int gain[32], it[32], mt[32], k[32];
   double sd[32];
   static int16_t snap[kSnapEntries];
+  static double* rsq = nullptr;
+  if (!rsq) {
+    rsq = new double[kTableDoubles];
+    for (int i = 0; i < kTableDoubles; i++) pvq_fill_rsqrt_table(rsq, i);
+  }
   simt_emu::run_warp([&](int lane) {
-    gain[lane] = quantise_band_warp(lane, snap, out, x0, r0, n, q0, y, &it[lane], &mt[lane], &k[lane], beta, &sd[lane],
+    gain[lane] = quantise_band_warp(lane, snap, rsq, out, x0, r0, n, q0, y, &it[lane], &mt[lane], &k[lane], beta, &sd[lane],
                                     is_keyframe, pli, qm, qm_inv, lambda);
   });
   for (int l = 1; l < 32; l++) {
