@@ -54,6 +54,8 @@ def parse():
                          "OD_SET_QUANT 20, complexity 7 (daala_b200/data/bench_bsize_4k.npz); synthetic: seeded "
                          "quadtree maps with every size 4..64")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="persistent PVQ kernel CTAs per SM (0 = default)")
+    ap.add_argument("--split-free", type=int, default=1, help="dependency-free PVQ bands as phase kernels: 0 no, 1 chroma, 2 chroma + luma")
+    ap.add_argument("--level-chains", type=int, default=0, help="luma intra chains level-synchronously (1) instead of the dependency queue (0)")
     ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"])
     return ap.parse_args()
 
@@ -301,7 +303,7 @@ def run_b200(args):
         planes = [np.stack([f[0][p] for f in hf]) for p in range(3)]
         bsize = np.stack([f[1] for f in hf])
         eng = engine.KeyframeEngine(geom, nframes=F, q0=Q0, use_masking=1, pvq_qm_q4=q4,
-                                    persist_ctas_per_sm=args.ctas_per_sm,
+                                    persist_ctas_per_sm=args.ctas_per_sm, split_free=args.split_free, level_chains=args.level_chains,
                                     max_blocks_div=1 if BLOCK_SIZES == "synthetic" else 2)
         eng.stage_inputs(planes, bsize)
         eng.prepare_io(symbols=True, recon=True)

@@ -25,6 +25,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "daala_b200.h"
 #include "gen/coding_order.inc"
 #include "pvq_math.cuh"
@@ -52,10 +54,13 @@ enum Cnt {
   kTailHi = 128,     //                   next slot to fill
   kDoneHi = 160,     // band-0 items finished (flushed by warps when they go idle)
   kHeadCh = 192,     // ticket of the row / column chain heads
-  kCntWords = 224
+  kWaiters = 224,    // warps parked on a future band-0 slot
+  kCntWords = 256
 };
 
 constexpr int kTile = 1024;        // units per scan tile
+constexpr int kMaxLevels = 4096;   // (plane width + height) / 4 of an 8K frame is 3008
+constexpr int kLevelBins = kMaxLevels * 3;
 
 struct Lists {
   const uint8_t* bsize;            // [F][UH][bstride]
@@ -77,6 +82,12 @@ struct Lists {
   uint32_t* heads;                 // row / column chain items that are ready from the start
   uint32_t* heads0;                // band-0 items that are ready from the start
   int32_t* cnt;                    // [kCntWords]
+  // level path: chain items counting-sorted by dependency level (position along the chain in units of the
+  // block size; larger bands first inside a level)
+  int32_t* lvl_hist;               // [kLevelBins] counts, then exclusive offsets
+  int32_t* lvl_cursor;             // [kLevelBins]
+  uint32_t* lvl_items;             // sorted chain items
+  int nlevels;
   int max_luma, max_chroma;        // capacities (blocks)
 };
 
@@ -219,6 +230,16 @@ __global__ void __launch_bounds__(kTile) k_unit_emit(const __grid_constant__ Lis
 
 __device__ __forceinline__ int band_class(int band) { return band < 3 ? 0 : band < 6 ? 1 : 2; }
 
+// Dependency level of a chain item: its position along the chain in units of its own block size (band 0:
+// the anti-diagonal).  Items only depend on same-size neighbours, whose level is smaller by one; bin =
+// level * 3 + (2 - class) so that the 128-coefficient bands of a level come first.
+__device__ __forceinline__ int level_bin(int band, int bs, int x0, int y0, int y_first) {
+  const int sh = bs + 2, bx = x0 >> sh, by = (y0 - y_first) >> sh;
+  const int r = band % 3;
+  const int lvl = band == 0 ? bx + by : r == 1 ? by : bx;
+  return lvl * 3 + (2 - band_class(band));
+}
+
 // warp-aggregated append of `v` to list[*counter] by the lanes with `pred`
 __device__ __forceinline__ void append(uint32_t* list, int32_t* counter, bool pred, uint32_t v) {
   const unsigned m = __ballot_sync(__activemask(), pred);
@@ -275,11 +296,56 @@ __global__ void __launch_bounds__(256) k_luma_deps(const __grid_constant__ Lists
       else if (band == 0) append(L.heads0, &L.cnt[kNHeads0], has && !waits, item);
       else append(L.heads, &L.cnt[kNHeads], has && !waits, item);
       chain += has && !is_free;
+      if (has && !is_free && L.lvl_hist) {
+        const daala_b200_pvq_block b = L.luma[blk];
+        atomicAdd(&L.lvl_hist[level_bin(band, bs, b.x0, b.y0, L.u_row0 * 8)], 1);
+      }
     }
     // total number of chain items
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) chain += __shfl_xor_sync(0xffffffffu, chain, o);
     if ((threadIdx.x & 31) == 0 && chain) atomicAdd(&L.cnt[kTotalHi], chain);
+  }
+}
+
+// One CTA: exclusive scan of the level bins in place (+ a copy as scatter cursors).
+__global__ void __launch_bounds__(1024) k_level_scan(const __grid_constant__ Lists L) {
+  __shared__ int part[1024];
+  constexpr int kPer = kLevelBins / 1024;
+  const int t = threadIdx.x;
+  int v[kPer], sum = 0;
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    v[i] = L.lvl_hist[t * kPer + i];
+    sum += v[i];
+  }
+  part[t] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int add = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += add;
+    __syncthreads();
+  }
+  int run = part[t] - sum;
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    L.lvl_hist[t * kPer + i] = run;
+    L.lvl_cursor[t * kPer + i] = run;
+    run += v[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_level_scatter(const __grid_constant__ Lists L) {
+  const int n = min(L.cnt[kNLuma], L.max_luma);
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < n; blk += gridDim.x * blockDim.x) {
+    const daala_b200_pvq_block b = L.luma[blk];
+    const int nb = num_bands(b.bs);
+    for (int band = 0; band < nb; band++) {
+      if (band == 3 || band == 6) continue;
+      const int pos = atomicAdd(&L.lvl_cursor[level_bin(band, b.bs, b.x0, b.y0, L.u_row0 * 8)], 1);
+      L.lvl_items[pos] = ((uint32_t)blk << 4) | band;
+    }
   }
 }
 
@@ -320,6 +386,22 @@ struct Stage {
   int32_t* cnt;
   int n_items_at, head_lo_at, n_blocks_at;
   int max_blocks;
+  // split path (phases as separate kernels over the dependency-free item lists): context records of one
+  // chunk of items per class
+  int16_t* sp_vec[3];              // [slots][3][vstride]
+  int32_t* sp_lanes[3];            // [slots][kCtxLaneWords][16]
+  int32_t* sp_uni[3];              // [slots][kCtxUniWords]
+  int16_t* sp_snap[3];             // [slots][kMaxEvents][vstride]
+  int sp_slots[3];                 // slots per chunk
+  int sp_chunks[3];                // chunks that cover the list capacity of the class
+  // level path: chain items sorted by level; one record of context per position inside a level
+  const int32_t* lvl_off;          // [kLevelBins] exclusive offsets of the bins
+  const uint32_t* lvl_items;
+  int nlevels, lvl_slots;
+  int16_t* lv_vec; int32_t* lv_lanes; int32_t* lv_uni; int16_t* lv_snap;
+  int32_t* lv_bar;                 // grid barrier counter
+  int max_waiters;                 // warps that may park on future band-0 slots; the others exit when idle
+  int skip_lo;                     // the persistent kernel leaves the dependency-free lists to the split path
   const double* rsqrt_tbl;         // [kTableDoubles] the reference's 1/sqrt(i) and theta-rate terms (pvq_fill_rsqrt_table)
   int16_t* res_pack;               // [nblocks*9][4]: gain, itheta, max_theta, k (what the coder reads)
   const int32_t* cfl_plane;        // chroma: prediction plane (chroma geometry), else NULL
@@ -442,11 +524,11 @@ __device__ __forceinline__ void push_chain(const Stage& S, int blk, int band) {
 //  slot itself (distinct addresses: no hot spot).  `done` = band-0 items this warp finished since it was
 //  last here; the warp whose flush completes the count releases every waiter with kExit.
 template <bool kIntra>
-__device__ __forceinline__ uint32_t next_item(const Stage& S, int lane, int* done) {
+__device__ __forceinline__ uint32_t next_item(const Stage& S, int lane, int* done, bool* waiter) {
   int slot = -1, head = -1, lo = -1, nheads0 = 0, fin = -1;
   if (lane == 0) {
     const int n2 = S.cnt[S.n_items_at + 2], n1 = S.cnt[S.n_items_at + 1], n0 = S.cnt[S.n_items_at];
-    const int nlo = n0 + n1 + n2;
+    const int nlo = S.skip_lo ? 0 : n0 + n1 + n2;
     if (kIntra) {
       nheads0 = S.cnt[kNHeads0];
       if (*done) {
@@ -466,7 +548,12 @@ __device__ __forceinline__ uint32_t next_item(const Stage& S, int lane, int* don
       const int l = atomicAdd(&S.cnt[S.head_lo_at], 1);
       if (l < nlo) lo = l;
     }
-    if (kIntra && slot < 0 && head < 0 && lo < 0) slot = atomicAdd(&S.cnt[kHeadHi], 1);
+    if (kIntra && slot < 0 && head < 0 && lo < 0) {
+      // nothing to do right now: park on the next band-0 slot -- unless enough warps already do; the rest
+      // leave and free their SM resources for whatever kernel comes next (another engine's batch)
+      if (!*waiter && atomicAdd(&S.cnt[kWaiters], 1) < S.max_waiters) *waiter = true;
+      if (*waiter) slot = atomicAdd(&S.cnt[kHeadHi], 1);
+    }
   }
   *done = 0;
   if (kIntra) {
@@ -496,6 +583,40 @@ __device__ __forceinline__ uint32_t next_item(const Stage& S, int lane, int* don
   return kNoItem;
 }
 
+// The band's H/V intra prediction (od_hv_intra_pred, src/intra.c:37-62) from the quantised neighbours into
+// prm.ref.  Element j of the band is owned by lane j % 32: the lane that writes ref[j] is the one that
+// reads it.
+__device__ __forceinline__ void intra_band_ref(const Stage& S, int blk, int band, int coef_off, int lane) {
+  const daala_b200_pvq_params& prm = S.prm;
+  const int start = band_start(band);
+  const int bn = band_start(band + 1) - start;
+  const int r = band % 3;
+  int top = -1, left = -1;
+  if (band == 0 || r == 1) top = S.dep_top[blk];
+  if (band == 0 || r == 2) left = S.dep_left[blk];
+  if (band == 3 || band == 6) top = left = -1;
+  const int32_t* ot = top >= 0 ? prm.out + prm.blocks[top].coef_off : nullptr;
+  const int32_t* ol = left >= 0 ? prm.out + prm.blocks[left].coef_off : nullptr;
+  bool low_from_top = false;
+  if (band == 0) {
+    // coding-order indices of (0,1) (0,2) (0,3) and (1,0) (2,0) (3,0) in the 4x4 stage; double
+    // sums of exact integers as in od_hv_intra_pred (src/intra.c:51-52)
+    double g1 = 0, g2 = 0;
+    if (ot) { double a = ot[2], bb = ot[5], c = ot[9]; g1 += a * a; g1 += bb * bb; g1 += c * c; }
+    if (ol) { double a = ol[1], bb = ol[4], c = ol[7]; g2 += a * a; g2 += bb * bb; g2 += c * c; }
+    low_from_top = g1 > g2;
+  }
+  int32_t* vref = prm.ref + coef_off;
+  for (int i = start + lane; i < start + bn; i += 32) {
+    int r2, c2;
+    scan_rc(i, &r2, &c2);
+    int32_t p = 0;
+    if (r2 == 0 && c2 > 0 && ot && (c2 >= 4 || low_from_top)) p = ot[i];
+    if (c2 == 0 && r2 > 0 && ol && (r2 >= 4 || !low_from_top)) p = ol[i];
+    vref[i] = p;
+  }
+}
+
 // One (block, band) item by one warp.  kIntra: the band's prediction is built from the quantised
 // neighbours first (od_hv_intra_pred, src/intra.c:37-62).
 template <bool kIntra>
@@ -507,34 +628,7 @@ __device__ __forceinline__ void run_item(const Stage& S, uint32_t item, int lane
   const int start = band_start(band);
   const int bn = band_start(band + 1) - start;
   const size_t off = (size_t)b.coef_off + start;
-  if (kIntra) {
-    const int r = band % 3;
-    int top = -1, left = -1;
-    if (band == 0 || r == 1) top = S.dep_top[blk];
-    if (band == 0 || r == 2) left = S.dep_left[blk];
-    if (band == 3 || band == 6) top = left = -1;
-    const int32_t* ot = top >= 0 ? prm.out + prm.blocks[top].coef_off : nullptr;
-    const int32_t* ol = left >= 0 ? prm.out + prm.blocks[left].coef_off : nullptr;
-    bool low_from_top = false;
-    if (band == 0) {
-      // coding-order indices of (0,1) (0,2) (0,3) and (1,0) (2,0) (3,0) in the 4x4 stage; double
-      // sums of exact integers as in od_hv_intra_pred (src/intra.c:51-52)
-      double g1 = 0, g2 = 0;
-      if (ot) { double a = ot[2], bb = ot[5], c = ot[9]; g1 += a * a; g1 += bb * bb; g1 += c * c; }
-      if (ol) { double a = ol[1], bb = ol[4], c = ol[7]; g2 += a * a; g2 += bb * bb; g2 += c * c; }
-      low_from_top = g1 > g2;
-    }
-    int32_t* vref = prm.ref + b.coef_off;
-    // element j of the band is owned by lane j % 32: the lane that writes ref[j] is the one that reads it
-    for (int i = start + lane; i < start + bn; i += 32) {
-      int r2, c2;
-      scan_rc(i, &r2, &c2);
-      int32_t p = 0;
-      if (r2 == 0 && c2 > 0 && ot && (c2 >= 4 || low_from_top)) p = ot[i];
-      if (c2 == 0 && r2 > 0 && ol && (r2 >= 4 || !low_from_top)) p = ol[i];
-      vref[i] = p;
-    }
-  }
+  if (kIntra) intra_band_ref(S, blk, band, b.coef_off, lane);
   int qidx = bs * (bs + 1) + (band + 1) - (band + 1) / 3;
   int q = (prm.q0 * prm.pvq_qm_q4[pli][qidx]) >> 4;
   if (q < 1) q = 1;
@@ -554,6 +648,151 @@ __device__ __forceinline__ void run_item(const Stage& S, uint32_t item, int lane
   }
 }
 
+// ---- split path ------------------------------------------------------------------------------------------
+// The three phases of a band (pvq_warp.cuh: band_setup / band_search / band_finish) as three kernels over a
+// chunk of a dependency-free item list, the context of every band parked in an HBM record in between.
+// Why: the fused per-band code is ~50 KB of straight-line SASS plus the search loops, far beyond the
+// instruction cache; the persistent kernel spends most of its issue slots waiting for instruction fetch
+// (profiles/r2d_pvq_persist_ncu.txt: no_instruction 4.7 cycles per issued instruction).  One phase at a
+// time on the whole GPU keeps the resident code small.  Only items without dependencies can go this way
+// (chroma; luma bands 3 / 6); the intra chains stay in the persistent kernel.
+struct ItemGeom {
+  int blk, band, bn, q, beta, pli, qoff;
+  size_t off;
+};
+__device__ __forceinline__ ItemGeom item_geom(const daala_b200_pvq_params& prm, uint32_t item) {
+  ItemGeom g;
+  g.blk = (int)(item >> 4);
+  g.band = (int)(item & 15);
+  const daala_b200_pvq_block b = prm.blocks[g.blk];
+  const int bs = b.bs;
+  g.pli = b.pli;
+  const int start = band_start(g.band);
+  g.bn = band_start(g.band + 1) - start;
+  g.off = (size_t)b.coef_off + start;
+  const int qidx = bs * (bs + 1) + (g.band + 1) - (g.band + 1) / 3;
+  int q = (prm.q0 * prm.pvq_qm_q4[g.pli][qidx]) >> 4;
+  g.q = q < 1 ? 1 : q;
+  g.beta = (prm.use_masking && g.pli == 0 && bs > 0) ? kBeta15 : kBeta1;
+  g.qoff = (b.xdec & 1 ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
+  return g;
+}
+
+// kPhase 0 / 1 / 2 = setup / search / finish of the items [chunk * slots, ...) of class `cls`.
+// kZeroRef: the prediction is all zero (luma bands 3 / 6).
+template <int kPhase, bool kZeroRef, int kMode>
+__global__ void __launch_bounds__(128) k_pvq_split(const __grid_constant__ Stage S, int cls, int chunk) {
+  const daala_b200_pvq_params& prm = S.prm;
+  const int lane = threadIdx.x & 31;
+  const int slots = S.sp_slots[cls];
+  const int first = chunk * slots;
+  const int count = min(S.cnt[S.n_items_at + cls] - first, slots);
+  const int vs = cls == 2 ? 128 : 32;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < count; i += nwarps) {
+    const ItemGeom g = item_geom(prm, S.items[cls][first + i]);
+    int16_t* vec = S.sp_vec[cls] + (size_t)i * 3 * vs;
+    int32_t* lanes = S.sp_lanes[cls] + (size_t)i * kCtxLaneWords * 16;
+    int32_t* uni = S.sp_uni[cls] + (size_t)i * kCtxUniWords;
+    int16_t* snap = S.sp_snap[cls] + (size_t)i * kMaxEvents * vs;
+    const int32_t* r0 = kZeroRef ? nullptr : prm.ref + g.off;
+    BandCtx B;
+    if (kPhase == 0) {
+      band_setup<kMode>(lane, B, prm.in + g.off, r0, g.bn, g.q, g.beta, prm.is_keyframe, g.pli, prm.qm + g.qoff,
+                 prm.pvq_norm_lambda, S.rsqrt_tbl);
+      band_ctx_store_setup(lane, B, g.bn, vec, vs, lanes, uni);
+    } else if (kPhase == 1) {
+      band_ctx_load_search(lane, B, g.bn, vec, vs, lanes);
+      band_search<kMode>(lane, B, g.bn, snap, vs, S.rsqrt_tbl);
+      band_ctx_store_search(lane, B, lanes);
+    } else {
+      band_ctx_load_finish(lane, B, g.bn, vec, vs, lanes, uni);
+      int itheta, max_theta, k;
+      double skip_term;
+      const int gain = band_finish<kMode>(lane, B, snap, vs, prm.out + g.off, r0, g.bn, g.q, prm.y + g.off, &itheta, &max_theta, &k,
+                                   g.beta, &skip_term, prm.is_keyframe, g.pli, prm.qm_inv + g.qoff, prm.pvq_norm_lambda);
+      if (lane == 0) {
+        const size_t r = (size_t)g.blk * 9 + g.band;
+        prm.res_skip_term[r] = skip_term;
+        short4 pk;
+        pk.x = (short)gain; pk.y = (short)itheta; pk.z = (short)max_theta; pk.w = (short)k;
+        reinterpret_cast<short4*>(S.res_pack)[r] = pk;
+      }
+    }
+  }
+}
+
+// ---- level path -----------------------------------------------------------------------------------------
+// The luma intra chains, level-synchronously: all chain items of one dependency level are independent, so
+// the whole GPU runs phase A (prediction from the neighbours + band_setup) for the level, then phase B
+// (searches), then phase C (costs, fold, synthesis), with a grid-wide barrier in between -- at any time
+// only one phase's code is being executed anywhere (see "split path" above for why that matters), and
+// nobody ever waits on a flag.  One persistent launch, all CTAs resident (the host sizes the grid).
+__device__ __forceinline__ void grid_barrier(int32_t* bar, int* target, int nctas) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *target += nctas;
+    __threadfence();
+    atomicAdd(bar, 1);
+    while (ld_acquire(bar) < *target) {}
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128, 4) k_pvq_levels(const __grid_constant__ Stage S) {
+  const daala_b200_pvq_params& prm = S.prm;
+  __shared__ int bar_target;
+  if (threadIdx.x == 0) bar_target = 0;
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int total = S.cnt[kTotalHi];
+  constexpr int vs = 128;
+  for (int lvl = 0; lvl < S.nlevels; lvl++) {
+    const int base = S.lvl_off[lvl * 3];
+    const int end = lvl + 1 < kMaxLevels ? S.lvl_off[(lvl + 1) * 3] : total;
+    if (end - base > S.lvl_slots && threadIdx.x == 0 && blockIdx.x == 0) S.cnt[kError] = 2;
+    const int n = min(end - base, S.lvl_slots);
+    if (n <= 0) continue;   // uniform: every CTA reads the same offsets
+    for (int phase = 0; phase < 3; phase++) {
+      for (int i = w; i < n; i += nwarps) {
+        const uint32_t item = S.lvl_items[base + i];
+        const ItemGeom g = item_geom(prm, item);
+        int16_t* vec = S.lv_vec + (size_t)i * 3 * vs;
+        int32_t* lanes = S.lv_lanes + (size_t)i * kCtxLaneWords * 16;
+        int32_t* uni = S.lv_uni + (size_t)i * kCtxUniWords;
+        int16_t* snap = S.lv_snap + (size_t)i * kMaxEvents * vs;
+        BandCtx B;
+        if (phase == 0) {
+          intra_band_ref(S, g.blk, g.band, (int)(g.off - band_start(g.band)), lane);
+          band_setup<0>(lane, B, prm.in + g.off, prm.ref + g.off, g.bn, g.q, g.beta, prm.is_keyframe, g.pli,
+                        prm.qm + g.qoff, prm.pvq_norm_lambda, S.rsqrt_tbl);
+          band_ctx_store_setup(lane, B, g.bn, vec, vs, lanes, uni);
+        } else if (phase == 1) {
+          band_ctx_load_search(lane, B, g.bn, vec, vs, lanes);
+          band_search<0>(lane, B, g.bn, snap, vs, S.rsqrt_tbl);
+          band_ctx_store_search(lane, B, lanes);
+        } else {
+          band_ctx_load_finish(lane, B, g.bn, vec, vs, lanes, uni);
+          int itheta, max_theta, k;
+          double skip_term;
+          const int gain = band_finish<0>(lane, B, snap, vs, prm.out + g.off, prm.ref + g.off, g.bn, g.q, prm.y + g.off,
+                                          &itheta, &max_theta, &k, g.beta, &skip_term, prm.is_keyframe, g.pli,
+                                          prm.qm_inv + g.qoff, prm.pvq_norm_lambda);
+          if (lane == 0) {
+            const size_t r = (size_t)g.blk * 9 + g.band;
+            prm.res_skip_term[r] = skip_term;
+            short4 pk;
+            pk.x = (short)gain; pk.y = (short)itheta; pk.z = (short)max_theta; pk.w = (short)k;
+            reinterpret_cast<short4*>(S.res_pack)[r] = pk;
+          }
+        }
+      }
+      grid_barrier(S.lv_bar, &bar_target, gridDim.x);
+    }
+  }
+}
+
 // Persistent PVQ kernel: one warp = one band at a time.  Luma (kIntra): the chain items of the H/V
 // intra predictor form a dependency graph (per size class: band 0 a 2-D wavefront, bands 1/4/7 columns,
 // bands 2/5/8 rows).  A warp that finishes a chain item CONTINUES with a successor it made ready -- a
@@ -565,8 +804,9 @@ __global__ void __launch_bounds__(128, DAALA_PERSIST_MIN_CTAS) k_pvq_persist(con
   const int lane = threadIdx.x & 31;
   int16_t* snap = snap_all[threadIdx.x >> 5];
   int done = 0;
+  bool waiter = false;
   for (;;) {
-    uint32_t item = next_item<kIntra>(S, lane, &done);
+    uint32_t item = next_item<kIntra>(S, lane, &done, &waiter);
     if (item == kNoItem) return;
     for (;;) {
       const int band = (int)(item & 15);
@@ -620,6 +860,7 @@ __global__ void k_begin_pvq(int32_t* cnt, int luma) {
       cnt[kTailHi] = cnt[kNHeads0];
       cnt[kDoneHi] = 0;
       cnt[kHeadCh] = 0;
+      cnt[kWaiters] = 0;
     } else {
       cnt[kHeadLoC] = 0;
     }
@@ -688,6 +929,17 @@ struct daala_b200_kf {
   int32_t* cfl_plane;
   int16_t *qm, *qm_inv;
   double* rsqrt_tbl;
+  int16_t* sp_vec[3];
+  int32_t* sp_lanes[3];
+  int32_t* sp_uni[3];
+  int16_t* sp_snap[3];
+  int sp_slots[3];
+  int16_t* lv_vec;
+  int32_t* lv_lanes;
+  int32_t* lv_uni;
+  int16_t* lv_snap;
+  int32_t* lv_bar;
+  int lvl_slots, lvl_grid;
   Lists lists;
   Stage luma, chroma;
   daala_b200_frame frame;
@@ -773,6 +1025,35 @@ static int kf_alloc(daala_b200_kf* kf) {
     KF_CHECK(dalloc(kf, &L.items_l[c], cap_l[c]));
     KF_CHECK(dalloc(kf, &L.items_c[c], cap_c[c]));
   }
+  if (kf->cfg.split_free > 0) {
+    // context records of one chunk of items per class (pvq_warp.cuh: band_ctx_*)
+    const int slots[3] = {1 << 19, 1 << 19, 3 << 15};
+    for (int c = 0; c < 3; c++) {
+      const int vs = c == 2 ? 128 : 32;
+      kf->sp_slots[c] = slots[c];
+      KF_CHECK(dalloc(kf, &kf->sp_vec[c], (size_t)slots[c] * 3 * vs));
+      KF_CHECK(dalloc(kf, &kf->sp_lanes[c], (size_t)slots[c] * kCtxLaneWords * 16));
+      KF_CHECK(dalloc(kf, &kf->sp_uni[c], (size_t)slots[c] * kCtxUniWords));
+      KF_CHECK(dalloc(kf, &kf->sp_snap[c], (size_t)slots[c] * kMaxEvents * vs));
+    }
+  }
+  if (kf->cfg.level_chains) {
+    KF_CHECK(dalloc(kf, &L.lvl_hist, (size_t)kLevelBins));
+    KF_CHECK(dalloc(kf, &L.lvl_cursor, (size_t)kLevelBins));
+    KF_CHECK(dalloc(kf, &L.lvl_items, kf->chain_cap));
+    L.nlevels = (kf->plane_w[0] + L.u_rows * 8) / 4 + 2;
+    if (L.nlevels >= kMaxLevels) return (int)cudaErrorInvalidValue;
+    kf->lvl_slots = 2048 * F;
+    KF_CHECK(dalloc(kf, &kf->lv_vec, (size_t)kf->lvl_slots * 3 * 128));
+    KF_CHECK(dalloc(kf, &kf->lv_lanes, (size_t)kf->lvl_slots * kCtxLaneWords * 16));
+    KF_CHECK(dalloc(kf, &kf->lv_uni, (size_t)kf->lvl_slots * kCtxUniWords));
+    KF_CHECK(dalloc(kf, &kf->lv_snap, (size_t)kf->lvl_slots * kMaxEvents * 128));
+    KF_CHECK(dalloc(kf, &kf->lv_bar, (size_t)32));
+    int per_sm = 0;
+    KF_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pvq_levels, 128, 0));
+    if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+    kf->lvl_grid = per_sm * kf->sms;   // all CTAs resident: the kernel synchronises the whole grid
+  }
   KF_CHECK(dalloc(kf, &L.heads, kf->chain_cap));
   KF_CHECK(dalloc(kf, &L.heads0, (size_t)L.max_luma));
   KF_CHECK(dalloc(kf, &L.cnt, (size_t)kCntWords));
@@ -811,6 +1092,28 @@ static int kf_alloc(daala_b200_kf* kf) {
     for (int c = 0; c < 3; c++) S.items[c] = chroma ? L.items_c[c] : L.items_l[c];
     S.cnt = L.cnt;
     S.rsqrt_tbl = kf->rsqrt_tbl;
+    for (int c = 0; c < 3; c++) {
+      S.sp_vec[c] = kf->sp_vec[c];
+      S.sp_lanes[c] = kf->sp_lanes[c];
+      S.sp_uni[c] = kf->sp_uni[c];
+      S.sp_snap[c] = kf->sp_snap[c];
+      S.sp_slots[c] = kf->sp_slots[c];
+      const size_t cap = chroma ? cap_c[c] : cap_l[c];
+      S.sp_chunks[c] = kf->sp_slots[c] > 0 ? (int)((cap + kf->sp_slots[c] - 1) / kf->sp_slots[c]) : 0;
+    }
+    S.skip_lo = chroma ? 0 : kf->cfg.split_free > 1;
+    S.max_waiters = kf->sms * 8;
+    if (!chroma) {
+      S.lvl_off = L.lvl_hist;
+      S.lvl_items = L.lvl_items;
+      S.nlevels = L.nlevels;
+      S.lvl_slots = kf->lvl_slots;
+      S.lv_vec = kf->lv_vec;
+      S.lv_lanes = kf->lv_lanes;
+      S.lv_uni = kf->lv_uni;
+      S.lv_snap = kf->lv_snap;
+      S.lv_bar = kf->lv_bar;
+    }
     S.n_items_at = chroma ? kNItemsC : kNItemsL;
     S.head_lo_at = chroma ? kHeadLoC : kHeadLoL;
     S.n_blocks_at = chroma ? kNChroma : kNLuma;
@@ -865,6 +1168,25 @@ static int kf_alloc(daala_b200_kf* kf) {
 }
 
 // Everything between "inputs are in HBM" and "results are in HBM", on kf->stream.
+// the three phase kernels over every chunk of every class of a stage's dependency-free lists
+template <bool kZeroRef>
+static void enqueue_split(daala_b200_kf* kf, const Stage& S, cudaStream_t s) {
+  const int grid = kf->sms * 16;
+  for (int cls = 2; cls >= 0; cls--) {
+    for (int chunk = 0; chunk < S.sp_chunks[cls]; chunk++) {
+      if (cls == 2) {
+        k_pvq_split<0, kZeroRef, 2><<<grid, 128, 0, s>>>(S, cls, chunk);
+        k_pvq_split<1, kZeroRef, 2><<<grid, 128, 0, s>>>(S, cls, chunk);
+        k_pvq_split<2, kZeroRef, 2><<<grid, 128, 0, s>>>(S, cls, chunk);
+      } else {
+        k_pvq_split<0, kZeroRef, 1><<<grid, 128, 0, s>>>(S, cls, chunk);
+        k_pvq_split<1, kZeroRef, 1><<<grid, 128, 0, s>>>(S, cls, chunk);
+        k_pvq_split<2, kZeroRef, 1><<<grid, 128, 0, s>>>(S, cls, chunk);
+      }
+    }
+  }
+}
+
 static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
   cudaStream_t s = kf->stream;
   const Lists& L = kf->lists;
@@ -876,7 +1198,12 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
     const size_t nl = (size_t)L.max_luma * sizeof(int32_t);
     if (cudaMemsetAsync(L.succ_bottom, 0xff, nl, s) != cudaSuccess || cudaMemsetAsync(L.succ_right, 0xff, nl, s) != cudaSuccess)
       return (int)cudaGetLastError();
+    if (L.lvl_hist && cudaMemsetAsync(L.lvl_hist, 0, sizeof(int32_t) * kLevelBins, s) != cudaSuccess) return (int)cudaGetLastError();
     k_luma_deps<<<wide, 256, 0, s>>>(L);
+    if (L.lvl_hist) {
+      k_level_scan<<<1, 1024, 0, s>>>(L);
+      k_level_scatter<<<wide, 256, 0, s>>>(L);
+    }
     k_chroma_items<<<wide, 256, 0, s>>>(L);
   }
   if (phases & DAALA_B200_KF_FORWARD) {
@@ -893,14 +1220,21 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
       return (int)cudaGetLastError();
     k_begin_pvq<<<1, 32, 0, s>>>(kf->lists.cnt, 1);
     if (!core) k_gather<false><<<wide, 256, 0, s>>>(kf->luma);
-    k_pvq_persist<true><<<persist, 128, 0, s>>>(kf->luma);
+    if (kf->cfg.split_free > 1) enqueue_split<true>(kf, kf->luma, s);
+    if (kf->cfg.level_chains) {
+      if (cudaMemsetAsync(kf->lv_bar, 0, sizeof(int32_t) * 32, s) != cudaSuccess) return (int)cudaGetLastError();
+      k_pvq_levels<<<kf->lvl_grid, 128, 0, s>>>(kf->luma);
+    } else {
+      k_pvq_persist<true><<<persist, 128, 0, s>>>(kf->luma);
+    }
     if (!core) k_finish_scatter<<<wide, 256, 0, s>>>(kf->luma);
   }
   if (phases & DAALA_B200_KF_PVQ_CHROMA) {
     k_begin_pvq<<<1, 32, 0, s>>>(kf->lists.cnt, 0);
     if (!core) k_cfl_plane<<<wide, 256, 0, s>>>(kf->chroma, kf->cfl_plane);
     if (!core) k_gather<true><<<wide, 256, 0, s>>>(kf->chroma);
-    k_pvq_persist<false><<<persist, 128, 0, s>>>(kf->chroma);
+    if (kf->cfg.split_free > 0) enqueue_split<false>(kf, kf->chroma, s);
+    else k_pvq_persist<false><<<persist, 128, 0, s>>>(kf->chroma);
     if (!core) k_finish_scatter<<<wide, 256, 0, s>>>(kf->chroma);
   }
   if (phases & DAALA_B200_KF_INVERSE) {
@@ -919,6 +1253,7 @@ daala_b200_kf* daala_b200_kf_create(const daala_b200_kf_config* cfg) {
   daala_b200_kf* kf = (daala_b200_kf*)calloc(1, sizeof(daala_b200_kf));
   if (!kf) return nullptr;
   kf->cfg = *cfg;
+  if (kf->cfg.level_chains && kf->cfg.split_free < 2) kf->cfg.split_free = 2;   // the level kernel only walks the chains
   kf->nhsb = (cfg->pic_w + 63) / 64;
   kf->nvsb = (cfg->pic_h + 63) / 64;
   kf->F = cfg->nframes;
@@ -976,6 +1311,12 @@ void daala_b200_kf_destroy(daala_b200_kf* kf) {
   cudaFree(kf->qm);
   cudaFree(kf->qm_inv);
   cudaFree(kf->rsqrt_tbl);
+  for (int c = 0; c < 3; c++) {
+    cudaFree(kf->sp_vec[c]);
+    cudaFree(kf->sp_lanes[c]);
+    cudaFree(kf->sp_uni[c]);
+    cudaFree(kf->sp_snap[c]);
+  }
   Lists& L = kf->lists;
   cudaFree(L.tile_sum);
   cudaFree(L.unit_lbase);
@@ -989,6 +1330,14 @@ void daala_b200_kf_destroy(daala_b200_kf* kf) {
   }
   cudaFree(L.heads);
   cudaFree(L.heads0);
+  cudaFree(L.lvl_hist);
+  cudaFree(L.lvl_cursor);
+  cudaFree(L.lvl_items);
+  cudaFree(kf->lv_vec);
+  cudaFree(kf->lv_lanes);
+  cudaFree(kf->lv_uni);
+  cudaFree(kf->lv_snap);
+  cudaFree(kf->lv_bar);
   cudaFree(L.succ_bottom);
   cudaFree(L.succ_right);
   cudaFree(L.cnt);
@@ -1124,6 +1473,13 @@ int daala_b200_kf_count_blocks(const uint8_t* bsize, int nframes, long long fram
   return 0;
 }
 
+// With level_chains the compute phases of different engines never overlap on the device: the level kernel
+// synchronises its whole grid and needs every CTA resident, which two such kernels in flight could deny
+// each other.  Copies of one
+// engine still overlap the compute of another (that is what double buffering is for).
+static std::mutex g_compute_mu;
+static cudaEvent_t g_last_compute = nullptr;
+
 int daala_b200_kf_submit(daala_b200_kf* kf, const daala_b200_kf_io* io) {
   if (!kf || !io) return (int)cudaErrorInvalidValue;
   cudaStream_t s = kf->stream;
@@ -1135,8 +1491,15 @@ int daala_b200_kf_submit(daala_b200_kf* kf, const daala_b200_kf_io* io) {
   }
   const size_t map_bytes = (size_t)kf->nhsb * 8 * kf->nvsb * 8 * F;
   KF_CHECK(cudaMemcpyAsync(kf->bsize, io->bsize, map_bytes, cudaMemcpyHostToDevice, s));
-  int rc = daala_b200_kf_run_device(kf, DAALA_B200_KF_ALL, 1);
-  if (rc) return rc;
+  int rc;
+  {
+    std::lock_guard<std::mutex> lock(g_compute_mu);
+    if (!g_last_compute) KF_CHECK(cudaEventCreateWithFlags(&g_last_compute, cudaEventDisableTiming));
+    else if (kf->cfg.level_chains) KF_CHECK(cudaStreamWaitEvent(s, g_last_compute, 0));
+    rc = daala_b200_kf_run_device(kf, DAALA_B200_KF_ALL, 1);
+    if (rc) return rc;
+    KF_CHECK(cudaEventRecord(g_last_compute, s));
+  }
   daala_b200_kf_totals tot;
   if (io->totals) tot = *io->totals;
   else daala_b200_kf_count_blocks(io->bsize, F, (long long)kf->nhsb * 8 * kf->nvsb * 8, kf->nhsb * 8, kf->nhsb, kf->nvsb,

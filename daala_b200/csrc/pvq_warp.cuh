@@ -350,23 +350,152 @@ __device__ __forceinline__ void search_event(int lane, const SearchVec& v, int (
   *yy_out = yy;
 }
 
-// One band by one warp.  x0 / r0 / out / yout / qm / qm_inv point at the band's first entry; `snap`:
-// kSnapEntries int16 of scratch private to the warp (shared memory); `rsq`: kTableDoubles doubles
-// filled by pvq_fill_rsqrt_table.  Scalar results are identical in
-// every lane.  int16 quantities of the reference are kept sign-extended in ints.
-__device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const double* rsq, int32_t* out, const int32_t* x0,
-                                                  const int32_t* r0, int n, int q0, int32_t* yout, int* itheta,
-                                                  int* max_theta, int* vk, int beta, double* skip_term, int is_keyframe,
-                                                  int pli, const int16_t* qm, const int16_t* qm_inv,
-                                                  double pvq_norm_lambda) {
+// What the three phases of one band share: registers in the fused path (quantise_band_warp), records in
+// HBM when the phases run as separate kernels (band_state_store / _load).
+struct BandCtx {
+  int x16[4], r16[4], xr[4];             // the vectors (int16 values), r16 after od_compute_householder
+  int32_t cg, g, gain_offset;            // uniform
+  int icgr, m, s;
+  double best_dist, best_cost, skip_dist;
+  int c_gain, c_theta, c_ts, c_k, c_cosd, c_alive, c_ev;   // lane c: candidate c
+  int32_t c_qcg, c_qtheta;
+  double c_sinprod, c_lambda, c_rate_ts;
+  double e_xy, e_yy, e_xx;               // lane e: event e
+  int e_sum, e_k, e_zero;
+};
+
+// ---- the context as a record in HBM (phases as separate kernels) ---------------------------------------
+// vec: int16 [3][vstride] (x16, r16, xr); lanes: int32 [kCtxLaneWords][16] (only lanes 0..15 carry
+// candidates / events); uni: int32 [kCtxUniWords].
+constexpr int kCtxLaneWords = 24;
+constexpr int kCtxUniWords = 16;
+
+__device__ __forceinline__ void ctx_put_d(int32_t* lanes, int w, int lane, double v) {
+  lanes[w * 16 + lane] = __double2loint(v);
+  lanes[(w + 1) * 16 + lane] = __double2hiint(v);
+}
+__device__ __forceinline__ double ctx_get_d(const int32_t* lanes, int w, int lane) {
+  return __hiloint2double(lanes[(w + 1) * 16 + lane], lanes[w * 16 + lane]);
+}
+
+// after band_setup
+__device__ __forceinline__ void band_ctx_store_setup(int lane, const BandCtx& B, int n, int16_t* vec, int vstride,
+                                                     int32_t* lanes, int32_t* uni) {
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int j = e * 32 + lane;
+    if (j < n) {
+      vec[j] = (int16_t)B.x16[e];
+      vec[vstride + j] = (int16_t)B.r16[e];
+      vec[2 * vstride + j] = (int16_t)B.xr[e];
+    }
+  }
+  if (lane < 16) {
+    lanes[0 * 16 + lane] = B.c_gain;
+    lanes[1 * 16 + lane] = B.c_theta;
+    lanes[2 * 16 + lane] = B.c_ts;
+    lanes[3 * 16 + lane] = B.c_k;
+    lanes[4 * 16 + lane] = B.c_cosd;
+    lanes[5 * 16 + lane] = B.c_alive;
+    lanes[6 * 16 + lane] = B.c_qcg;
+    lanes[7 * 16 + lane] = B.c_qtheta;
+    ctx_put_d(lanes, 8, lane, B.c_sinprod);
+    ctx_put_d(lanes, 10, lane, B.c_lambda);
+    ctx_put_d(lanes, 12, lane, B.c_rate_ts);
+  }
+  if (lane == 0) {
+    uni[0] = B.cg; uni[1] = B.g; uni[2] = B.gain_offset; uni[3] = B.icgr; uni[4] = B.m; uni[5] = B.s;
+    uni[6] = __double2loint(B.best_dist); uni[7] = __double2hiint(B.best_dist);
+    uni[8] = __double2loint(B.best_cost); uni[9] = __double2hiint(B.best_cost);
+    uni[10] = __double2loint(B.skip_dist); uni[11] = __double2hiint(B.skip_dist);
+  }
+}
+// what band_search needs
+__device__ __forceinline__ void band_ctx_load_search(int lane, BandCtx& B, int n, const int16_t* vec, int vstride,
+                                                     const int32_t* lanes) {
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int j = e * 32 + lane;
+    B.x16[e] = j < n ? vec[j] : 0;
+    B.xr[e] = j < n ? vec[2 * vstride + j] : 0;
+  }
+  const int l = lane & 15;
+  B.c_k = lanes[3 * 16 + l];
+  B.c_alive = lane < 16 ? lanes[5 * 16 + l] : 0;
+  B.c_lambda = ctx_get_d(lanes, 10, l);
+}
+// after band_search
+__device__ __forceinline__ void band_ctx_store_search(int lane, const BandCtx& B, int32_t* lanes) {
+  if (lane < 16) {
+    lanes[14 * 16 + lane] = B.c_ev;
+    ctx_put_d(lanes, 15, lane, B.e_xy);
+    ctx_put_d(lanes, 17, lane, B.e_yy);
+    ctx_put_d(lanes, 19, lane, B.e_xx);
+    lanes[21 * 16 + lane] = B.e_sum;
+    lanes[22 * 16 + lane] = B.e_k;
+    lanes[23 * 16 + lane] = B.e_zero;
+  }
+}
+// everything, for band_finish
+__device__ __forceinline__ void band_ctx_load_finish(int lane, BandCtx& B, int n, const int16_t* vec, int vstride,
+                                                     const int32_t* lanes, const int32_t* uni) {
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int j = e * 32 + lane;
+    B.x16[e] = j < n ? vec[j] : 0;
+    B.r16[e] = j < n ? vec[vstride + j] : 0;
+    B.xr[e] = j < n ? vec[2 * vstride + j] : 0;
+  }
+  const int l = lane & 15;
+  const bool on = lane < 16;
+  B.c_gain = lanes[0 * 16 + l];
+  B.c_theta = lanes[1 * 16 + l];
+  B.c_ts = lanes[2 * 16 + l];
+  B.c_k = lanes[3 * 16 + l];
+  B.c_cosd = lanes[4 * 16 + l];
+  B.c_alive = on ? lanes[5 * 16 + l] : 0;
+  B.c_qcg = lanes[6 * 16 + l];
+  B.c_qtheta = lanes[7 * 16 + l];
+  B.c_sinprod = ctx_get_d(lanes, 8, l);
+  B.c_lambda = ctx_get_d(lanes, 10, l);
+  B.c_rate_ts = ctx_get_d(lanes, 12, l);
+  B.c_ev = on ? lanes[14 * 16 + l] : -1;
+  B.e_xy = on ? ctx_get_d(lanes, 15, l) : 0.;
+  B.e_yy = on ? ctx_get_d(lanes, 17, l) : 0.;
+  B.e_xx = on ? ctx_get_d(lanes, 19, l) : 0.;
+  B.e_sum = on ? lanes[21 * 16 + l] : 0;
+  B.e_k = on ? lanes[22 * 16 + l] : 0;
+  B.e_zero = on ? lanes[23 * 16 + l] : 0;
+  B.cg = uni[0]; B.g = uni[1]; B.gain_offset = uni[2]; B.icgr = uni[3]; B.m = uni[4]; B.s = uni[5];
+  B.best_dist = __hiloint2double(uni[7], uni[6]);
+  B.best_cost = __hiloint2double(uni[9], uni[8]);
+  B.skip_dist = __hiloint2double(uni[11], uni[10]);
+}
+
+// Phase A of a band: everything of pvq_theta (src/pvq_encoder.c:333) before the first search.
+// x0 / r0 / qm point at the band's first entry (r0 == NULL: no prediction, all zero).  int16 quantities of the reference are kept sign-extended
+// in ints; scalar results are identical in every lane.
+// kMode (all phases): 0 = the band size decides at run time, 1 = n <= 32 only, 2 = n = 128 only (kernels that
+// serve one size class drop the other one's code and registers).
+template <int kMode>
+__device__ __forceinline__ void band_setup(int lane, BandCtx& B, const int32_t* x0, const int32_t* r0, int n, int q0,
+                                           int beta, int is_keyframe, int pli, const int16_t* qm,
+                                           double pvq_norm_lambda, const double* rsq) {
+  int (&x16)[4] = B.x16; int (&r16)[4] = B.r16; int (&xr)[4] = B.xr;
+  int32_t &cg = B.cg, &g = B.g, &gain_offset = B.gain_offset;
+  int &icgr = B.icgr, &m = B.m, &s = B.s;
+  double &best_dist = B.best_dist, &best_cost = B.best_cost, &skip_dist = B.skip_dist;
+  int &c_gain = B.c_gain, &c_theta = B.c_theta, &c_ts = B.c_ts, &c_k = B.c_k, &c_cosd = B.c_cosd, &c_alive = B.c_alive;
+  int32_t &c_qcg = B.c_qcg, &c_qtheta = B.c_qtheta;
+  double &c_sinprod = B.c_sinprod, &c_lambda = B.c_lambda, &c_rate_ts = B.c_rate_ts;
+
   const double gain_weight = 1.4;
   const double cgain_1 = 1. / kCgainOne;
   const double cgain_2 = cgain_1 * cgain_1;
   const double theta_scale = (1 << kThetaShift) * 2. / M_PI;
   const double theta_scale_1 = 1. / theta_scale;
   const double trig_1 = 1. / 32768;
-  const bool big = n > 32;
-  int x16[4], r16[4], xr[4];
+  const bool big = kMode == 0 ? n > 32 : kMode == 2;
   int xshift, rshift, r_nonnull = 0;
   {
     int32_t xv[4], rv[4];
@@ -378,7 +507,7 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
       const int j = e * 32 + lane;
       if (j < n) {
         xv[e] = x0[j];
-        rv[e] = r0[j];
+        rv[e] = r0 ? r0[j] : 0;
       }
       const int16_t tx = (int16_t)(xv[e] >> 8), tr = (int16_t)(rv[e] >> 8);
       sx += tx * (int32_t)tx;
@@ -415,7 +544,7 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
   accx = wsum(accx);
   accr = wsum(accr);
   // the two gains in parallel: even lanes the input's, odd lanes the reference's
-  int32_t g, gr, cg, cgr;
+  int32_t gr, cgr;
   {
     const long long pk = nl_gain(lane & 1 ? accr : accx, q0, beta, lane & 1 ? rshift : xshift);
     const int gl = (int)(uint32_t)pk, cgl = (int)(pk >> 32);
@@ -426,14 +555,13 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
   }
   const int cfl_enabled = is_keyframe && pli != 0;
   if (cfl_enabled) cgr = kCgainOne;
-  const int icgr = shr_round(cgr, kCgainShift);
-  int32_t gain_offset = cgr - shl(icgr, kCgainShift);
-  double best_dist = gain_weight * cg * cg * cgain_2;
-  double best_cost = best_dist + pvq_norm_lambda * 0.;  // od_pvq_rate(0, 0, -1, 0, ...) == 0
+  icgr = shr_round(cgr, kCgainShift);
+  gain_offset = cgr - shl(icgr, kCgainShift);
+  best_dist = gain_weight * cg * cg * cgain_2;
+  best_cost = best_dist + pvq_norm_lambda * 0.;  // od_pvq_rate(0, 0, -1, 0, ...) == 0
   corr = nl_div(corr, 1e-100 + nl_div(g * (double)gr, (double)shl(1, xshift + rshift)));
   corr = corr < 1. ? corr : 1.;
   corr = corr > -1. ? corr : -1.;
-  double skip_dist;
   if (is_keyframe) {
     skip_dist = gain_weight * cg * cg * cgain_2;
   } else {
@@ -451,7 +579,8 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
   // ---- with-reference setup: angle, Householder reflection (uniform) ------------------------------------
   const bool have_ref = r_nonnull && corr > 0;
   int32_t theta = 0;
-  int m = 0, s = 1;
+  m = 0;
+  s = 1;
   if (have_ref) {
     theta = round32(theta_scale * nl_acos(corr));
     // od_compute_householder, src/pvq.c:498: first largest |r| (strict ">" from maxr = 0)
@@ -483,10 +612,9 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
   }
 
   // ---- candidates: one per lane (the same calls for both kinds, with per-lane arguments) ----------------
-  int c_gain = 0, c_theta = -1, c_ts = 0, c_k = 0, c_cosd = 0;
-  int32_t c_qcg = 0, c_qtheta = 0;
-  bool c_alive = false, c_valid = false;
-  double c_sinprod = 0, c_lambda = 0, c_rate_ts = 0;
+  c_gain = 0; c_theta = -1; c_ts = 0; c_k = 0; c_cosd = 0; c_qcg = 0; c_qtheta = 0;
+  c_sinprod = 0; c_lambda = 0; c_rate_ts = 0;
+  bool c_valid = false;
   {
     const bool wref = lane < 12;
     const bool nref = lane == 12 || lane == 13;
@@ -538,6 +666,19 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
     c_rate_ts = c_ts < kLogEntries ? rsq[kRsqrtEntries + (c_ts > 0 ? c_ts : 1)]
                                    : .9 * (M_LOG2E * nl_log((double)c_ts));
   }
+}
+
+// Phase B: the searches of all events.  `snap`: kSnapEntries int16 private to the band.
+template <int kMode>
+__device__ __forceinline__ void band_search(int lane, BandCtx& B, int n, int16_t* snap, int snap_stride,
+                                            const double* rsq) {
+  const bool big = kMode == 0 ? n > 32 : kMode == 2;
+  const int (&x16)[4] = B.x16; const int (&xr)[4] = B.xr;
+  const int &c_k = B.c_k, &c_alive = B.c_alive;
+  const double &c_lambda = B.c_lambda;
+  int &c_ev = B.c_ev;
+  double &e_xy = B.e_xy, &e_yy = B.e_yy, &e_xx = B.e_xx;
+  int &e_sum = B.e_sum, &e_k = B.e_k, &e_zero = B.e_zero;
   unsigned alive_w = __ballot_sync(kFull, c_alive && lane < 12);
   unsigned alive_n = __ballot_sync(kFull, c_alive && lane >= 12);
 
@@ -548,10 +689,10 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
   SearchVec sv;
   sv.nn = n;
   sv.xx = 0;
-  int prev_k = 0, nev = 0, c_ev = -1;
+  int prev_k = 0, nev = 0;
+  c_ev = -1;
   int phase = 0;  // 1: with-reference vector loaded, 2: no-reference vector
-  double e_xy = 0, e_yy = 0, e_xx = 0;   // lane `event`: scalars of that event
-  int e_sum = 0, e_k = 0, e_zero = 0;
+  e_xy = 0; e_yy = 0; e_xx = 0; e_sum = 0; e_k = 0; e_zero = 0;   // lane `event`: scalars of that event
   while (alive_w | alive_n) {
     unsigned grp;
     int kcur, leader;
@@ -594,7 +735,7 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
       if (e && !big) break;
       const int j = e * 32 + lane;
       if (j < sv.nn) sj += j * ya[e];
-      if (j < n) snap[nev * kMaxN + j] = (int16_t)(j < sv.nn ? ya[e] : 0);
+      if (j < n) snap[nev * snap_stride + j] = (int16_t)(j < sv.nn ? ya[e] : 0);
     }
     sj = wsum(sj);
     if (lane == nev) {
@@ -609,6 +750,33 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
     nev++;
   }
 
+}
+
+// Phase C: costs, the reference's fold, synthesis of the winner (od_pvq_synthesis_partial, src/pvq.c:1037).
+// Returns the coded gain index.
+template <int kMode>
+__device__ __forceinline__ int band_finish(int lane, const BandCtx& B, const int16_t* snap, int snap_stride, int32_t* out,
+                                           const int32_t* r0, int n, int q0, int32_t* yout, int* itheta,
+                                           int* max_theta, int* vk, int beta, double* skip_term, int is_keyframe,
+                                           int pli, const int16_t* qm_inv, double pvq_norm_lambda) {
+  const double gain_weight = 1.4;
+  const double cgain_1 = 1. / kCgainOne;
+  const double cgain_2 = cgain_1 * cgain_1;
+  const double trig_1 = 1. / 32768;
+  const bool big = kMode == 0 ? n > 32 : kMode == 2;
+  const int cfl_enabled = is_keyframe && pli != 0;
+  const int (&x16)[4] = B.x16; const int (&r16)[4] = B.r16; const int (&xr)[4] = B.xr;
+  const int32_t cg = B.cg;
+  int32_t g = B.g, gain_offset = B.gain_offset;
+  const int icgr = B.icgr, m = B.m, s = B.s;
+  double best_dist = B.best_dist, best_cost = B.best_cost;
+  const double skip_dist = B.skip_dist;
+  const int c_gain = B.c_gain, c_theta = B.c_theta, c_ts = B.c_ts, c_k = B.c_k, c_cosd = B.c_cosd, c_ev = B.c_ev;
+  const int32_t c_qcg = B.c_qcg, c_qtheta = B.c_qtheta;
+  const double c_sinprod = B.c_sinprod, c_rate_ts = B.c_rate_ts;
+  const double e_xy = B.e_xy, e_yy = B.e_yy, e_xx = B.e_xx;
+  const int e_sum = B.e_sum, e_k = B.e_k, e_zero = B.e_zero;
+  int32_t theta = 0;
   // ---- all events in parallel: cos distance and the shared part of od_pvq_rate (src/pvq_encoder.c:247) ---
   double e_cos = 0, e_rate = 0;
   {
@@ -663,7 +831,7 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
   int noref = is_keyframe ? 1 : 0;
   *itheta = is_keyframe ? -1 : 0;
   *max_theta = 0;
-  theta = 0;  // best_qtheta
+  // theta: best_qtheta
   int ybest[4];
 #pragma unroll
   for (int e = 0; e < 4; e++) ybest[e] = 0;
@@ -681,7 +849,7 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
       if (e && !big) break;
       const int j = e * 32 + lane;
       const int v = noref ? x16[e] : xr[e];
-      const int a = j < n ? snap[ev * kMaxN + j] : 0;
+      const int a = j < n ? snap[ev * snap_stride + j] : 0;
       ybest[e] = j < (noref ? n : n - 1) ? (v < 0 ? -a : a) : 0;
     }
   }
@@ -695,7 +863,7 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
   int32_t res[4];
   if (skip) {
 #pragma unroll
-    for (int e = 0; e < 4; e++) res[e] = (skip == 2 && e * 32 + lane < n) ? r0[e * 32 + lane] : 0;
+    for (int e = 0; e < 4; e++) res[e] = (skip == 2 && r0 && e * 32 + lane < n) ? r0[e * 32 + lane] : 0;
   } else {
     if (noref) gain_offset = 0;
     g = gain_expand(shl(qg, kCgainShift) + gain_offset, q0, beta);
@@ -761,6 +929,20 @@ __device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const
     const int a = qg + 1, b = icgr + 1;
     return noref ? qg - 1 : (a < b ? -2 * (a - b) - 1 : (a < 2 * b ? 2 * (a - b) : a - 1));
   }
+}
+
+// One band by one warp, the three phases back to back.  `snap`: kSnapEntries int16 of scratch private to
+// the warp (shared memory); `rsq`: kTableDoubles doubles filled by pvq_fill_rsqrt_table.
+__device__ __forceinline__ int quantise_band_warp(int lane, int16_t* snap, const double* rsq, int32_t* out, const int32_t* x0,
+                                                  const int32_t* r0, int n, int q0, int32_t* yout, int* itheta,
+                                                  int* max_theta, int* vk, int beta, double* skip_term, int is_keyframe,
+                                                  int pli, const int16_t* qm, const int16_t* qm_inv,
+                                                  double pvq_norm_lambda) {
+  BandCtx B;
+  band_setup<0>(lane, B, x0, r0, n, q0, beta, is_keyframe, pli, qm, pvq_norm_lambda, rsq);
+  band_search<0>(lane, B, n, snap, kMaxN, rsq);
+  return band_finish<0>(lane, B, snap, kMaxN, out, r0, n, q0, yout, itheta, max_theta, vk, beta, skip_term, is_keyframe, pli,
+                     qm_inv, pvq_norm_lambda);
 }
 
 }  // namespace pvq

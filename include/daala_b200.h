@@ -438,6 +438,12 @@ typedef struct daala_b200_kf_config {
   int sb_row0, sb_rows;        /* superblock rows of this rank's shard (sb_rows <= 0: whole frames) */
   int max_blocks_div;          /* 0/1: capacity for all-4x4 maps; d > 1: 1/d of that (saves HBM) */
   int persist_ctas_per_sm;     /* 0 = default */
+  int split_free;              /* dependency-free bands as three phase kernels (setup / search / finish) with
+                                  the band context in HBM records instead of the persistent kernel:
+                                  0 = no, 1 = chroma, 2 = chroma and luma bands 3 / 6 */
+  int level_chains;            /* luma intra chains: 0 = persistent kernel with a dependency queue, 1 = one
+                                  level-synchronous kernel (phases separated by grid barriers); implies
+                                  split_free = 2 */
   void *stream;                /* cudaStream_t to run on, or NULL: the engine creates its own */
 } daala_b200_kf_config;
 

@@ -26,6 +26,34 @@ extern "C" int emu_quantise_band(int32_t* out, const int32_t* x0, const int32_t*
     gain[lane] = quantise_band_warp(lane, snap, rsq, out, x0, r0, n, q0, y, &it[lane], &mt[lane], &k[lane], beta, &sd[lane],
                                     is_keyframe, pli, qm, qm_inv, lambda);
   });
+  if (getenv("DAALA_B200_EMU_SPLIT")) {
+    // the same band through the three phases with the context parked in a record in between
+    static int16_t vec[3 * kMaxN];
+    static int32_t lanes[kCtxLaneWords * 16], uni[kCtxUniWords];
+    static int16_t gsnap[kSnapEntries];
+    const int vs = n > 32 ? 128 : 32;
+    simt_emu::run_warp([&](int lane) {
+      BandCtx B;
+      if (n > 32) band_setup<2>(lane, B, x0, r0, n, q0, beta, is_keyframe, pli, qm, lambda, rsq);
+      else band_setup<1>(lane, B, x0, r0, n, q0, beta, is_keyframe, pli, qm, lambda, rsq);
+      band_ctx_store_setup(lane, B, n, vec, vs, lanes, uni);
+    });
+    simt_emu::run_warp([&](int lane) {
+      BandCtx B;
+      band_ctx_load_search(lane, B, n, vec, vs, lanes);
+      if (n > 32) band_search<2>(lane, B, n, gsnap, vs, rsq);
+      else band_search<1>(lane, B, n, gsnap, vs, rsq);
+      band_ctx_store_search(lane, B, lanes);
+    });
+    simt_emu::run_warp([&](int lane) {
+      BandCtx B;
+      band_ctx_load_finish(lane, B, n, vec, vs, lanes, uni);
+      gain[lane] = n > 32 ? band_finish<2>(lane, B, gsnap, vs, out, r0, n, q0, y, &it[lane], &mt[lane], &k[lane], beta,
+                                           &sd[lane], is_keyframe, pli, qm_inv, lambda)
+                          : band_finish<1>(lane, B, gsnap, vs, out, r0, n, q0, y, &it[lane], &mt[lane], &k[lane], beta,
+                                           &sd[lane], is_keyframe, pli, qm_inv, lambda);
+    });
+  }
   for (int l = 1; l < 32; l++) {
     if (gain[l] != gain[0] || it[l] != it[0] || mt[l] != mt[0] || k[l] != k[0] || sd[l] != sd[0]) {
       fprintf(stderr, "emu_quantise_band: lanes disagree on scalar results\n");

@@ -178,6 +178,22 @@ def test_engine_keyframe_chain_matches_oracle(size, q0, nf):
     eng.close()
 
 
+@pytest.mark.parametrize("split", [1, 2, 3])
+def test_engine_split_phase_kernels_match_oracle(split):
+    """The dependency-free bands (chroma; with split = 2 also luma bands 3 / 6) through the three phase
+    kernels with the band context parked in HBM records (daala_b200_kf_config.split_free) instead of the
+    persistent kernel: same results, bit for bit."""
+    from daala_b200 import engine
+    from daala_b200.frame import Geometry
+    geom = Geometry(328, 200)
+    q4 = np.full((3, 30), 16, np.uint8)
+    # split 3: additionally the luma intra chains level-synchronously (daala_b200_kf_config.level_chains)
+    eng = engine.KeyframeEngine(geom, nframes=2, q0=72, pvq_qm_q4=q4, split_free=min(split, 2), level_chains=int(split == 3))
+    _check_batch(eng, geom, _frames(geom, 2), 72, q4)
+    _check_batch(eng, geom, _frames(geom, 2, q_seed=3, mode="64"), 72, q4)
+    eng.close()
+
+
 @pytest.mark.parametrize("mode", ["4", "8", "16", "32", "64"])
 def test_engine_uniform_block_sizes(mode):
     from daala_b200 import engine
