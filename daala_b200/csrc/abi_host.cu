@@ -283,8 +283,14 @@ void od_mc_predict1fmv8_cuda(void* state, unsigned char* dst, const unsigned cha
   const size_t win = (size_t)W * H, job_off = (win + 15) & ~(size_t)15, out_off = job_off + 16;
   c.ensure(out_off + (size_t)nx * ny);
   unsigned char* p = (unsigned char*)c.pinned;
+  // stage only what od_mc_predict1fmv8_c reads (src/mc.c:94): the 2 + 3 sample apron exists in a direction only
+  // when the vector has a fractional part there -- an integer vector touches the block alone, and the caller's
+  // buffer may end right after it
   const unsigned char* s0 = src + ((mvx >> 3) - 2) + (ptrdiff_t)((mvy >> 3) - 2) * systride;
-  for (int r = 0; r < H; r++) memcpy(p + (size_t)r * W, s0 + (ptrdiff_t)r * systride, W);
+  const int c_lo = (mvx & 7) ? 0 : 2, c_hi = (mvx & 7) ? W : 2 + nx;
+  const int r_lo = (mvy & 7) ? 0 : 2, r_hi = (mvy & 7) ? H : 2 + ny;
+  memset(p, 0, win);
+  for (int r = r_lo; r < r_hi; r++) memcpy(p + (size_t)r * W + c_lo, s0 + (ptrdiff_t)r * systride + c_lo, c_hi - c_lo);
   daala_b200_match_job job;
   memset(&job, 0, sizeof(job));
   job.mvx = mvx & 7; job.mvy = mvy & 7; job.x0 = 2; job.y0 = 2; job.log_blk = (uint8_t)log_xblk_sz;

@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(256) k_dering_sb(const __grid_constant__ daala
 
 extern "C" int daala_b200_dering_plane(const daala_b200_dering_params* prm, void* stream) {
   if (!prm || prm->nhsb < 1 || prm->nvsb < 1 || prm->xdec < 0 || prm->xdec > 1) return (int)cudaErrorInvalidValue;
+  // not in place: a superblock's apron would read its neighbours' filtered output
+  if (!prm->x || !prm->y || (const void*)prm->x == (const void*)prm->y) return (int)cudaErrorInvalidValue;
   dim3 grid(prm->nhsb, prm->nvsb);
   daala_b200::dering::k_dering_sb<<<grid, 256, 0, (cudaStream_t)stream>>>(*prm);
   return (int)cudaGetLastError();

@@ -585,7 +585,9 @@ __device__ __forceinline__ uint32_t next_item(const Stage& S, int lane, int* don
 
 // The band's H/V intra prediction (od_hv_intra_pred, src/intra.c:37-62) from the quantised neighbours into
 // prm.ref.  Element j of the band is owned by lane j % 32: the lane that writes ref[j] is the one that
-// reads it.
+// reads it.  The neighbours' `out` is read past L1 (ld.global.cg): bands 0, 1, 2 of a block share a 128-byte
+// line, so this SM may hold a copy of the line from before the band that is read now was written, and the
+// plain fences that order the producers' stores do not invalidate L1.
 __device__ __forceinline__ void intra_band_ref(const Stage& S, int blk, int band, int coef_off, int lane) {
   const daala_b200_pvq_params& prm = S.prm;
   const int start = band_start(band);
@@ -602,8 +604,8 @@ __device__ __forceinline__ void intra_band_ref(const Stage& S, int blk, int band
     // coding-order indices of (0,1) (0,2) (0,3) and (1,0) (2,0) (3,0) in the 4x4 stage; double
     // sums of exact integers as in od_hv_intra_pred (src/intra.c:51-52)
     double g1 = 0, g2 = 0;
-    if (ot) { double a = ot[2], bb = ot[5], c = ot[9]; g1 += a * a; g1 += bb * bb; g1 += c * c; }
-    if (ol) { double a = ol[1], bb = ol[4], c = ol[7]; g2 += a * a; g2 += bb * bb; g2 += c * c; }
+    if (ot) { double a = __ldcg(ot + 2), bb = __ldcg(ot + 5), c = __ldcg(ot + 9); g1 += a * a; g1 += bb * bb; g1 += c * c; }
+    if (ol) { double a = __ldcg(ol + 1), bb = __ldcg(ol + 4), c = __ldcg(ol + 7); g2 += a * a; g2 += bb * bb; g2 += c * c; }
     low_from_top = g1 > g2;
   }
   int32_t* vref = prm.ref + coef_off;
@@ -611,8 +613,8 @@ __device__ __forceinline__ void intra_band_ref(const Stage& S, int blk, int band
     int r2, c2;
     scan_rc(i, &r2, &c2);
     int32_t p = 0;
-    if (r2 == 0 && c2 > 0 && ot && (c2 >= 4 || low_from_top)) p = ot[i];
-    if (c2 == 0 && r2 > 0 && ol && (r2 >= 4 || !low_from_top)) p = ol[i];
+    if (r2 == 0 && c2 > 0 && ot && (c2 >= 4 || low_from_top)) p = __ldcg(ot + i);
+    if (c2 == 0 && r2 > 0 && ol && (r2 >= 4 || !low_from_top)) p = __ldcg(ol + i);
     vref[i] = p;
   }
 }
@@ -985,8 +987,6 @@ static int kf_alloc(daala_b200_kf* kf) {
   KF_CHECK(dalloc(kf, &kf->qm, (size_t)2 * kf->cfg.qm_stride));
   KF_CHECK(dalloc(kf, &kf->qm_inv, (size_t)2 * kf->cfg.qm_stride));
   KF_CHECK(dalloc(kf, &kf->rsqrt_tbl, (size_t)kTableDoubles));
-  k_fill_rsqrt<<<(kTableDoubles + 255) / 256, 256, 0, kf->stream>>>(kf->rsqrt_tbl);
-  KF_CHECK(cudaStreamSynchronize(kf->stream));
   KF_CHECK(cudaMemcpy(kf->qm, kf->cfg.qm, sizeof(int16_t) * 2 * kf->cfg.qm_stride, cudaMemcpyHostToDevice));
   KF_CHECK(cudaMemcpy(kf->qm_inv, kf->cfg.qm_inv, sizeof(int16_t) * 2 * kf->cfg.qm_stride, cudaMemcpyHostToDevice));
 
@@ -1102,7 +1102,7 @@ static int kf_alloc(daala_b200_kf* kf) {
       S.sp_chunks[c] = kf->sp_slots[c] > 0 ? (int)((cap + kf->sp_slots[c] - 1) / kf->sp_slots[c]) : 0;
     }
     S.skip_lo = chroma ? 0 : kf->cfg.split_free > 1;
-    S.max_waiters = kf->sms * 8;
+    S.max_waiters = getenv("DAALA_B200_MAX_WAITERS") ? atoi(getenv("DAALA_B200_MAX_WAITERS")) : kf->sms * 8;
     if (!chroma) {
       S.lvl_off = L.lvl_hist;
       S.lvl_items = L.lvl_items;
@@ -1164,6 +1164,13 @@ static int kf_alloc(daala_b200_kf* kf) {
   f.nframes = F;
   f.sb_row0 = kf->cfg.sb_row0;
   f.sb_rows = kf->cfg.sb_rows;
+  // dalloc's cudaMemset runs on the legacy default stream, asynchronously, and the engine's stream does not
+  // synchronise with it (cudaStreamNonBlocking): wait for every clear before anything is launched -- the table
+  // fill below used to race with the clear of its own buffer (intermittently all-zero 1/sqrt table)
+  KF_CHECK(cudaDeviceSynchronize());
+  k_fill_rsqrt<<<(kTableDoubles + 255) / 256, 256, 0, kf->stream>>>(kf->rsqrt_tbl);
+  KF_CHECK(cudaGetLastError());
+  KF_CHECK(cudaStreamSynchronize(kf->stream));
   return 0;
 }
 

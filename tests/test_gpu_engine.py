@@ -58,14 +58,15 @@ def _check_batch(eng, geom, frames, q0, q4, use_masking=1, planes_checked=(0, 1,
     for f in range(F):
         want = frame_oracle.keyframe_chain(lib, prefix, frames[f][0], geom, frames[f][1], q0, q4, use_masking)
         for pli in planes_checked:
-            assert np.array_equal(out["recon%d" % pli][f], want[pli]["recon"]), ("recon", f, pli)
             blocks = out["luma_blocks"] if pli == 0 else out["chroma_blocks"]
             res = out["luma_res"] if pli == 0 else out["chroma_res"]
             y16 = out["luma_y16"] if pli == 0 else out["chroma_y16"]
             got = engine.band_records(blocks, res, geom, pli, f)
             bad = np.argwhere(got != want[pli]["rec"])
-            assert len(bad) == 0, ("band decisions", f, pli, len(bad), bad[:5], got[tuple(bad[0][:3])], want[pli]["rec"][tuple(bad[0][:3])])
+            assert len(bad) == 0, ("band decisions", f, pli, len(bad), bad[:8].tolist(), got[tuple(bad[0][:3])].tolist(),
+                                   want[pli]["rec"][tuple(bad[0][:3])].tolist())
             assert np.array_equal(_y_plane(blocks, y16, geom, pli, f, tabs), want[pli]["yplane"]), ("pulses", f, pli)
+            assert np.array_equal(out["recon%d" % pli][f], want[pli]["recon"]), ("recon", f, pli)
         dq = [eng.coeff_plane(p)[f] for p in range(3)]
         for pli in planes_checked:
             assert np.array_equal(dq[pli], want[pli]["dq"]), ("quantised plane", f, pli)
