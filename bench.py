@@ -367,12 +367,13 @@ def run_b200(args):
     # per-phase device times
     reps = max(5, args.steps)
     phase_ms = {}
-    for name, ph in (("work_lists(7 kernels)", engine.PH_LISTS), ("k_forward_sb_tma", engine.PH_FORWARD),
+    chroma_kernels = "k_pvq_split<setup|search|finish>" if args.split_free > 0 else "k_pvq_persist"
+    for name, ph in (("work_lists(5 kernels)", engine.PH_LISTS), ("k_forward_sb_tma", engine.PH_FORWARD),
                      ("pvq_luma(gather+k_pvq_persist<intra>+finish)", engine.PH_PVQ_LUMA),
-                     ("pvq_chroma(cfl+gather+k_pvq_persist+finish)", engine.PH_PVQ_CHROMA),
+                     ("pvq_chroma(cfl+gather+%s+finish)" % chroma_kernels, engine.PH_PVQ_CHROMA),
                      ("k_inverse_sb+k_sb_postfilter_store", engine.PH_INVERSE),
                      ("k_pvq_persist<intra> alone", engine.PH_PVQ_LUMA | engine.PH_SEARCH_ONLY),
-                     ("k_pvq_persist<chroma> alone", engine.PH_PVQ_CHROMA | engine.PH_SEARCH_ONLY)):
+                     ("chroma band kernels alone", engine.PH_PVQ_CHROMA | engine.PH_SEARCH_ONLY)):
         eng0.time_device(ph, False, 1)
         phase_ms[name] = eng0.time_device(ph, False, reps) / reps
     # leave the planes consistent again
@@ -409,6 +410,11 @@ def run_b200(args):
                    "block_sizes": block_sizes_text(), "quantizer": Q0,
                    "work_lists": "rebuilt on the device from the block-size maps inside every step (timed region); "
                                  "e2e uploads different maps on consecutive steps",
+                   "pvq": "one warp per band; luma intra chains in a persistent kernel with a dependency queue%s; "
+                          "chroma%s as three phase kernels (setup / search / finish, band context in HBM)" % (
+                              " (level-synchronous variant)" if args.level_chains else "",
+                              " and luma bands 3/6" if args.split_free > 1 else "") if args.split_free > 0 else
+                          "one warp per band, persistent kernels for luma (dependency queue) and chroma",
                    "pvq_pulses_first_batch": total_k},
         "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(eng0.h2d_bytes),
                 "d2h_bytes_per_step": int(eng0.d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 4),
@@ -416,7 +422,7 @@ def run_b200(args):
                 "pipeline": ("two engines alternate: copy-in / graph / copy-out of consecutive batches overlap"
                              if nslots == 2 else "one engine, serial copy-in, compute, copy-out")},
         "cuda_graph": bool(use_graph),
-        "gpu_launches": engine.LAUNCHES_PER_STEP * args.steps,
+        "gpu_launches": eng0.launches_per_step() * args.steps,
         "clocks": clocks,
         # dominant kernel by time: the persistent luma PVQ kernel -- a greedy double-precision search bound by
         # dependency latency and FP64/integer issue, not HBM; its HBM fraction is reported as the contract asks

@@ -1367,6 +1367,18 @@ void daala_b200_kf_destroy(daala_b200_kf* kf) {
 
 const char* daala_b200_kf_error(const daala_b200_kf* kf) { return kf ? kf->err : "null engine"; }
 
+// Kernel launches of one whole step (kf_enqueue_step with DAALA_B200_KF_ALL), memset nodes not counted.
+int daala_b200_kf_launches_per_step(const daala_b200_kf* kf) {
+  if (!kf) return 0;
+  auto split = [](const Stage& S) { return 3 * (S.sp_chunks[0] + S.sp_chunks[1] + S.sp_chunks[2]); };
+  int n = 5 + (kf->cfg.level_chains ? 2 : 0);                                    // work lists
+  n += 1;                                                                         // forward
+  n += 3 + 1 + (kf->cfg.split_free > 1 ? split(kf->luma) : 0);                    // luma: begin, gather, chains, finish
+  n += 4 + (kf->cfg.split_free > 0 ? split(kf->chroma) : 1);                      // chroma: begin, cfl, gather, bands, finish
+  n += 2;                                                                         // inverse, SB postfilter + store
+  return n;
+}
+
 int daala_b200_kf_device_buffers(daala_b200_kf* kf, daala_b200_kf_buffers* out) {
   if (!kf || !out) return (int)cudaErrorInvalidValue;
   memset(out, 0, sizeof(*out));

@@ -15,7 +15,6 @@ c_int, c_ll, c_void_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p
 
 PH_LISTS, PH_FORWARD, PH_PVQ_LUMA, PH_INVERSE, PH_PVQ_CHROMA = 1, 2, 4, 8, 16
 PH_PVQ, PH_ALL, PH_SEARCH_ONLY = 20, 31, 64
-LAUNCHES_PER_STEP = 17   # lists 5, forward 1, luma 4, chroma 5, inverse 2 (+ 4 memset nodes)
 CNT = dict(n_luma=0, n_chroma=1, luma_coefs=2, chroma_coefs=3, items_l=4, items_c=7,
            total_hi=14, n_heads=15, n_heads0=16, error=17)
 
@@ -62,6 +61,7 @@ def _bind():
     L.daala_b200_kf_error.argtypes = [c_void_p]
     L.daala_b200_kf_error.restype = ctypes.c_char_p
     L.daala_b200_kf_device_buffers.argtypes = [c_void_p, ctypes.POINTER(Buffers)]
+    L.daala_b200_kf_launches_per_step.argtypes = [c_void_p]
     L.daala_b200_kf_run_device.argtypes = [c_void_p, c_int, c_int]
     L.daala_b200_kf_time_device.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_float)]
     L.daala_b200_kf_count_blocks.argtypes = [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int,
@@ -133,6 +133,9 @@ class KeyframeEngine:
         self._io = None
         self._out = None
         self.totals = None
+
+    def launches_per_step(self):
+        return int(self.L.daala_b200_kf_launches_per_step(self.kf))
 
     def close(self):
         if getattr(self, "kf", None):

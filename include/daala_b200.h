@@ -508,6 +508,7 @@ daala_b200_kf *daala_b200_kf_create(const daala_b200_kf_config *cfg);   /* NULL 
 void daala_b200_kf_destroy(daala_b200_kf *kf);
 const char *daala_b200_kf_error(const daala_b200_kf *kf);
 int daala_b200_kf_device_buffers(daala_b200_kf *kf, daala_b200_kf_buffers *out);
+int daala_b200_kf_launches_per_step(const daala_b200_kf *kf);   /* kernel launches of one whole step */
 /* Runs the selected phases on the engine's stream with inputs already in HBM (asynchronous);
    use_graph: replay the captured CUDA graph (DAALA_B200_KF_ALL only). */
 int daala_b200_kf_run_device(daala_b200_kf *kf, int phases, int use_graph);

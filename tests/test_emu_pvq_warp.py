@@ -55,11 +55,18 @@ def _same(a, b):
 
 # the second build lowers the "products are exact" bound so that the literal-scan path of the plain
 # pulses (taken on the device only when a product could exceed 2^53) runs on ordinary inputs
-@pytest.mark.parametrize("name,extra,seeds", [("libpvq_warp_emu.so", [], (1, 2, 3)),
-                                              ("libpvq_warp_emu_scan.so", ["-DDAALA_B200_PVQ_EXACT_BOUND=1e12"], (1,))])
-def test_warp_quantiser_matches_reference(name, extra, seeds):
+# third run: the same bands through the three phases with the band context parked in a record in between
+# (the split kernels of the engine), size-class specialised instantiations
+@pytest.mark.parametrize("name,extra,seeds,split", [("libpvq_warp_emu.so", [], (1, 2, 3), False),
+                                                    ("libpvq_warp_emu_scan.so", ["-DDAALA_B200_PVQ_EXACT_BOUND=1e12"], (1,), False),
+                                                    ("libpvq_warp_emu.so", [], (4,), True)])
+def test_warp_quantiser_matches_reference(name, extra, seeds, split, monkeypatch):
     ref = oracle_lib.load_ref()
     emu = _build(name, extra)
+    if split:
+        monkeypatch.setenv("DAALA_B200_EMU_SPLIT", "1")
+    else:
+        monkeypatch.delenv("DAALA_B200_EMU_SPLIT", raising=False)
     qm, qm_inv = pvq_cases.reference_qm(ref)
     stats = (ctypes.c_longlong * 4).in_dll(emu, "daala_b200_pvq_warp_stats")
     n = 0
