@@ -55,6 +55,7 @@ def parse():
                          "quadtree maps with every size 4..64")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="persistent PVQ kernel CTAs per SM (0 = default)")
     ap.add_argument("--split-free", type=int, default=1, help="dependency-free PVQ bands as phase kernels: 0 no, 1 chroma, 2 chroma + luma")
+    ap.add_argument("--prepass", type=int, default=0, help="luma no-reference searches ahead of the chains (1) or inside them (0)")
     ap.add_argument("--level-chains", type=int, default=0, help="luma intra chains level-synchronously (1) instead of the dependency queue (0)")
     ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"])
     return ap.parse_args()
@@ -303,7 +304,7 @@ def run_b200(args):
         planes = [np.stack([f[0][p] for f in hf]) for p in range(3)]
         bsize = np.stack([f[1] for f in hf])
         eng = engine.KeyframeEngine(geom, nframes=F, q0=Q0, use_masking=1, pvq_qm_q4=q4,
-                                    persist_ctas_per_sm=args.ctas_per_sm, split_free=args.split_free, level_chains=args.level_chains,
+                                    persist_ctas_per_sm=args.ctas_per_sm, split_free=args.split_free, level_chains=args.level_chains, noref_prepass=args.prepass,
                                     max_blocks_div=1 if BLOCK_SIZES == "synthetic" else 2)
         eng.stage_inputs(planes, bsize)
         eng.prepare_io(symbols=True, recon=True)
@@ -345,6 +346,20 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     ms = max_over_ranks(eng0.time_device(engine.PH_ALL, use_graph, args.steps))
+    # the same with both engines' graphs in flight (inputs resident, no copies): the tail of one batch's luma
+    # dependency chains overlaps the next batch's work
+    ms_pipelined = None
+    if nslots == 2 and use_graph:
+        for e in slots:
+            e.run_device(engine.PH_ALL, True)
+        for e in slots:
+            e.wait()
+        t0 = time.perf_counter()
+        for i in range(2 * args.steps):
+            slots[i % 2].run_device(engine.PH_ALL, True)
+        for e in slots:
+            e.wait()
+        ms_pipelined = max_over_ranks((time.perf_counter() - t0) * 1e3) / 2
 
     # end to end through the host-buffer C ABI: H2D + step + D2H per batch, engines alternate
     def e2e_loop(steps):
@@ -422,6 +437,9 @@ def run_b200(args):
                 "pipeline": ("two engines alternate: copy-in / graph / copy-out of consecutive batches overlap"
                              if nslots == 2 else "one engine, serial copy-in, compute, copy-out")},
         "cuda_graph": bool(use_graph),
+        "value_two_batches_in_flight": None if ms_pipelined is None else {
+            "value": round(px_job / (ms_pipelined / args.steps * 1e-3) / 1e6, 2), "ms_per_step": round(ms_pipelined / args.steps, 4),
+            "note": "both engines' graphs enqueued back to back on their own streams, inputs resident, wall clock"},
         "gpu_launches": eng0.launches_per_step() * args.steps,
         "clocks": clocks,
         # dominant kernel by time: the persistent luma PVQ kernel -- a greedy double-precision search bound by

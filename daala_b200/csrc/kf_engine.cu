@@ -400,6 +400,9 @@ struct Stage {
   int nlevels, lvl_slots;
   int16_t* lv_vec; int32_t* lv_lanes; int32_t* lv_uni; int16_t* lv_snap;
   int32_t* lv_bar;                 // grid barrier counter
+  // luma: the no-reference events of every chain band, searched ahead of the chains (k_pvq_prepass)
+  int32_t* pre_ev;                 // [coefs / 8][kPreEvWords], record of a band at (coef_off + band start) >> 3
+  int16_t* pre_snap;               // [2 * coefs]: the events' pulses at 2 * (coef_off + band start)
   int max_waiters;                 // warps that may park on future band-0 slots; the others exit when idle
   int skip_lo;                     // the persistent kernel leaves the dependency-free lists to the split path
   const double* rsqrt_tbl;         // [kTableDoubles] the reference's 1/sqrt(i) and theta-rate terms (pvq_fill_rsqrt_table)
@@ -499,9 +502,20 @@ __global__ void __launch_bounds__(256) k_cfl_plane(const __grid_constant__ Stage
 }
 
 // resident CTAs per SM the persistent PVQ kernel is compiled for (register cap = 65536 / 128 / this)
+#ifndef DAALA_PERSIST_SPECIALISE
+#define DAALA_PERSIST_SPECIALISE 0
+#endif
 #ifndef DAALA_PERSIST_MIN_CTAS
 #define DAALA_PERSIST_MIN_CTAS 8
 #endif
+// warps per CTA of the persistent kernel.  1: a warp that runs out of work frees its registers and shared
+// memory at once (a CTA only retires when all of its warps have), so the next kernel -- another engine's
+// batch -- fills the SM while the last dependency chains of this one are still being walked.
+#ifndef DAALA_PERSIST_WARPS
+#define DAALA_PERSIST_WARPS 1
+#endif
+constexpr int kPersistThreads = 32 * DAALA_PERSIST_WARPS;
+constexpr int kPersistCtas = DAALA_PERSIST_MIN_CTAS * 4 / DAALA_PERSIST_WARPS;   // per SM, same number of warps
 constexpr uint32_t kNoItem = 0xffffffffu;
 constexpr uint32_t kExit = 0xfffffffeu;
 
@@ -638,9 +652,26 @@ __device__ __forceinline__ void run_item(const Stage& S, uint32_t item, int lane
   const int qoff = (b.xdec & 1 ? prm.qm_stride : 0) + ((((1 << (2 * bs)) - 1) << 4) / 3) + start;
   int itheta, max_theta, k;
   double skip_term;
-  const int gain = quantise_band_warp(lane, snap, S.rsqrt_tbl, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off, &itheta,
-                                         &max_theta, &k, beta, &skip_term, prm.is_keyframe, pli, prm.qm + qoff,
-                                         prm.qm_inv + qoff, prm.pvq_norm_lambda);
+  const bool pre = kIntra && S.pre_ev && band != 3 && band != 6;
+  // size-class specialised instantiations (DAALA_PERSIST_SPECIALISE): a band then executes less straight-line
+  // code, at the price of a larger kernel
+  const int32_t* pev = pre ? S.pre_ev + (off >> 3) * kPreEvWords : nullptr;
+  const int16_t* psn = pre ? S.pre_snap + 2 * off : nullptr;
+  int gain;
+#if DAALA_PERSIST_SPECIALISE
+  if (bn > 32)
+    gain = quantise_band_warp<2>(lane, snap, S.rsqrt_tbl, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off,
+                                 &itheta, &max_theta, &k, beta, &skip_term, prm.is_keyframe, pli, prm.qm + qoff,
+                                 prm.qm_inv + qoff, prm.pvq_norm_lambda, pev, psn);
+  else
+    gain = quantise_band_warp<1>(lane, snap, S.rsqrt_tbl, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off,
+                                 &itheta, &max_theta, &k, beta, &skip_term, prm.is_keyframe, pli, prm.qm + qoff,
+                                 prm.qm_inv + qoff, prm.pvq_norm_lambda, pev, psn);
+#else
+  gain = quantise_band_warp<0>(lane, snap, S.rsqrt_tbl, prm.out + off, prm.in + off, prm.ref + off, bn, q, prm.y + off,
+                               &itheta, &max_theta, &k, beta, &skip_term, prm.is_keyframe, pli, prm.qm + qoff,
+                               prm.qm_inv + qoff, prm.pvq_norm_lambda, pev, psn);
+#endif
   if (lane == 0) {
     const size_t r = (size_t)blk * 9 + band;
     prm.res_skip_term[r] = skip_term;
@@ -724,6 +755,34 @@ __global__ void __launch_bounds__(128) k_pvq_split(const __grid_constant__ Stage
   }
 }
 
+// ---- prepass ---------------------------------------------------------------------------------------------
+// Keyframe luma always evaluates the no-reference candidates of pvq_theta (src/pvq_encoder.c:573-606), and
+// they depend on the input vector alone: their searches (two from scratch per band, the larger half of a
+// chain band's work) run here for every chain band at once, fully parallel, and the chain walk imports the
+// results (band_noref_export / band_search's pre_ev) -- that work leaves the dependency-bound kernel.
+template <int kMode>
+__global__ void __launch_bounds__(128) k_pvq_prepass(const __grid_constant__ Stage S) {
+  const daala_b200_pvq_params& prm = S.prm;
+  __shared__ int16_t snap_all[4][2 * kMaxN];
+  const int lane = threadIdx.x & 31;
+  int16_t* snap = snap_all[threadIdx.x >> 5];
+  const int nblk = min(S.cnt[S.n_blocks_at], S.max_blocks);
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  // kMode 1: bands 0, 1, 2, 4, 5 (n <= 32); kMode 2: bands 7, 8 (n = 128)
+  const int per = kMode == 2 ? 2 : 5;
+  for (long long i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < (long long)nblk * per; i += nwarps) {
+    const int blk = (int)(i / per), sel = (int)(i % per);
+    const int band = kMode == 2 ? 7 + sel : (sel < 3 ? sel : sel + 1);
+    if (band >= num_bands(prm.blocks[blk].bs)) continue;
+    const ItemGeom g = item_geom(prm, ((uint32_t)blk << 4) | band);
+    BandCtx B;
+    band_setup<kMode>(lane, B, prm.in + g.off, nullptr, g.bn, g.q, g.beta, prm.is_keyframe, g.pli, prm.qm + g.qoff,
+                      prm.pvq_norm_lambda, S.rsqrt_tbl);
+    band_search<kMode>(lane, B, g.bn, snap, kMaxN, S.rsqrt_tbl);
+    band_noref_export(lane, B, g.bn, snap, kMaxN, S.pre_ev + (g.off >> 3) * kPreEvWords, S.pre_snap + 2 * g.off);
+  }
+}
+
 // ---- level path -----------------------------------------------------------------------------------------
 // The luma intra chains, level-synchronously: all chain items of one dependency level are independent, so
 // the whole GPU runs phase A (prediction from the neighbours + band_setup) for the level, then phase B
@@ -801,8 +860,8 @@ __global__ void __launch_bounds__(128, 4) k_pvq_levels(const __grid_constant__ S
 // column or row is walked by one warp without touching the queue -- and pushes a second ready
 // successor (band 0 forks) into the chain queue.
 template <bool kIntra>
-__global__ void __launch_bounds__(128, DAALA_PERSIST_MIN_CTAS) k_pvq_persist(const __grid_constant__ Stage S) {
-  __shared__ int16_t snap_all[4][kSnapEntries];   // per warp: the pulses of every search event of a band
+__global__ void __launch_bounds__(kPersistThreads, kPersistCtas) k_pvq_persist(const __grid_constant__ Stage S) {
+  __shared__ int16_t snap_all[DAALA_PERSIST_WARPS][kSnapEntries];   // per warp: the pulses of every search event of a band
   const int lane = threadIdx.x & 31;
   int16_t* snap = snap_all[threadIdx.x >> 5];
   int done = 0;
@@ -1103,6 +1162,10 @@ static int kf_alloc(daala_b200_kf* kf) {
     }
     S.skip_lo = chroma ? 0 : kf->cfg.split_free > 1;
     S.max_waiters = getenv("DAALA_B200_MAX_WAITERS") ? atoi(getenv("DAALA_B200_MAX_WAITERS")) : kf->sms * 8;
+    if (!chroma && kf->cfg.noref_prepass) {
+      KF_CHECK(dalloc(kf, &S.pre_ev, (ncoef / 8 + 2) * kPreEvWords));
+      KF_CHECK(dalloc(kf, &S.pre_snap, 2 * ncoef));
+    }
     if (!chroma) {
       S.lvl_off = L.lvl_hist;
       S.lvl_items = L.lvl_items;
@@ -1217,7 +1280,7 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
     int rc = daala_b200_launch_forward(&kf->frame, 3, s);
     if (rc) return rc;
   }
-  const int persist = kf->sms * (kf->cfg.persist_ctas_per_sm > 0 ? kf->cfg.persist_ctas_per_sm : DAALA_PERSIST_MIN_CTAS);
+  const int persist = kf->sms * (kf->cfg.persist_ctas_per_sm > 0 ? kf->cfg.persist_ctas_per_sm : kPersistCtas);
   // _SEARCH_ONLY (measurement): just the persistent search kernels, on the coding-order buffers a
   // previous full pass left behind (same inputs, same results)
   const bool core = (phases & DAALA_B200_KF_SEARCH_ONLY) != 0;
@@ -1228,11 +1291,15 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
     k_begin_pvq<<<1, 32, 0, s>>>(kf->lists.cnt, 1);
     if (!core) k_gather<false><<<wide, 256, 0, s>>>(kf->luma);
     if (kf->cfg.split_free > 1) enqueue_split<true>(kf, kf->luma, s);
+    if (kf->luma.pre_ev) {
+      k_pvq_prepass<2><<<kf->sms * 16, 128, 0, s>>>(kf->luma);
+      k_pvq_prepass<1><<<kf->sms * 16, 128, 0, s>>>(kf->luma);
+    }
     if (kf->cfg.level_chains) {
       if (cudaMemsetAsync(kf->lv_bar, 0, sizeof(int32_t) * 32, s) != cudaSuccess) return (int)cudaGetLastError();
       k_pvq_levels<<<kf->lvl_grid, 128, 0, s>>>(kf->luma);
     } else {
-      k_pvq_persist<true><<<persist, 128, 0, s>>>(kf->luma);
+      k_pvq_persist<true><<<persist, kPersistThreads, 0, s>>>(kf->luma);
     }
     if (!core) k_finish_scatter<<<wide, 256, 0, s>>>(kf->luma);
   }
@@ -1241,7 +1308,7 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
     if (!core) k_cfl_plane<<<wide, 256, 0, s>>>(kf->chroma, kf->cfl_plane);
     if (!core) k_gather<true><<<wide, 256, 0, s>>>(kf->chroma);
     if (kf->cfg.split_free > 0) enqueue_split<false>(kf, kf->chroma, s);
-    else k_pvq_persist<false><<<persist, 128, 0, s>>>(kf->chroma);
+    else k_pvq_persist<false><<<persist, kPersistThreads, 0, s>>>(kf->chroma);
     if (!core) k_finish_scatter<<<wide, 256, 0, s>>>(kf->chroma);
   }
   if (phases & DAALA_B200_KF_INVERSE) {
@@ -1360,6 +1427,8 @@ void daala_b200_kf_destroy(daala_b200_kf* kf) {
     cudaFree(S->res_pack);
     cudaFree(S->ring);
     cudaFree(S->join0);
+    cudaFree(S->pre_ev);
+    cudaFree(S->pre_snap);
   }
   if (kf->own_stream) cudaStreamDestroy(kf->stream);
   free(kf);
@@ -1373,7 +1442,7 @@ int daala_b200_kf_launches_per_step(const daala_b200_kf* kf) {
   auto split = [](const Stage& S) { return 3 * (S.sp_chunks[0] + S.sp_chunks[1] + S.sp_chunks[2]); };
   int n = 5 + (kf->cfg.level_chains ? 2 : 0);                                    // work lists
   n += 1;                                                                         // forward
-  n += 3 + 1 + (kf->cfg.split_free > 1 ? split(kf->luma) : 0);                    // luma: begin, gather, chains, finish
+  n += 3 + 1 + (kf->cfg.split_free > 1 ? split(kf->luma) : 0) + (kf->luma.pre_ev ? 2 : 0);   // luma: begin, gather, [prepass], chains, finish
   n += 4 + (kf->cfg.split_free > 0 ? split(kf->chroma) : 1);                      // chroma: begin, cfl, gather, bands, finish
   n += 2;                                                                         // inverse, SB postfilter + store
   return n;

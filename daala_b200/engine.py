@@ -23,7 +23,7 @@ class Config(ctypes.Structure):
     _fields_ = [("pic_w", c_int), ("pic_h", c_int), ("nframes", c_int), ("q0", c_int), ("use_masking", c_int),
                 ("qm_stride", c_int), ("pvq_norm_lambda", ctypes.c_double), ("pvq_qm_q4", (ctypes.c_ubyte * 32) * 3),
                 ("qm", c_void_p), ("qm_inv", c_void_p), ("sb_row0", c_int), ("sb_rows", c_int),
-                ("max_blocks_div", c_int), ("persist_ctas_per_sm", c_int), ("split_free", c_int), ("level_chains", c_int), ("stream", c_void_p)]
+                ("max_blocks_div", c_int), ("persist_ctas_per_sm", c_int), ("split_free", c_int), ("noref_prepass", c_int), ("level_chains", c_int), ("stream", c_void_p)]
 
 
 class Totals(ctypes.Structure):
@@ -101,7 +101,7 @@ class KeyframeEngine:
     """One engine = one set of device buffers + one CUDA graph for batches of `nframes` keyframes."""
 
     def __init__(self, geom, nframes=1, q0=38, use_masking=1, lam=pvq.PVQ_LAMBDA, pvq_qm_q4=None, qm=None,
-                 qm_inv=None, sb_row0=0, sb_rows=0, max_blocks_div=0, persist_ctas_per_sm=0, split_free=0, level_chains=0, pinned=True):
+                 qm_inv=None, sb_row0=0, sb_rows=0, max_blocks_div=0, persist_ctas_per_sm=0, split_free=0, level_chains=0, noref_prepass=0, pinned=True):
         self.L = _bind()
         self.geom, self.F = geom, nframes
         if qm is None:
@@ -121,6 +121,7 @@ class KeyframeEngine:
         cfg.max_blocks_div, cfg.persist_ctas_per_sm = int(max_blocks_div), int(persist_ctas_per_sm)
         cfg.split_free = int(split_free)
         cfg.level_chains = int(level_chains)
+        cfg.noref_prepass = int(noref_prepass)
         self.kf = self.L.daala_b200_kf_create(ctypes.byref(cfg))
         if not self.kf:
             raise RuntimeError("daala_b200_kf_create failed (no CUDA device, or out of memory)")

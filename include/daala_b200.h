@@ -441,6 +441,8 @@ typedef struct daala_b200_kf_config {
   int split_free;              /* dependency-free bands as three phase kernels (setup / search / finish) with
                                   the band context in HBM records instead of the persistent kernel:
                                   0 = no, 1 = chroma, 2 = chroma and luma bands 3 / 6 */
+  int noref_prepass;           /* 1: the no-reference searches of every luma chain band run ahead of the chains in a
+                                  fully parallel kernel (they do not depend on the prediction) */
   int level_chains;            /* luma intra chains: 0 = persistent kernel with a dependency queue, 1 = one
                                   level-synchronous kernel (phases separated by grid barriers); implies
                                   split_free = 2 */

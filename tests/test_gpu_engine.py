@@ -179,6 +179,20 @@ def test_engine_keyframe_chain_matches_oracle(size, q0, nf):
     eng.close()
 
 
+def test_engine_noref_prepass_matches_oracle():
+    """The no-reference searches of the luma chain bands ahead of the chains (daala_b200_kf_config.noref_prepass),
+    imported by the persistent kernel: same results, on mixed and on uniform maps, two batches per engine."""
+    from daala_b200 import engine
+    from daala_b200.frame import Geometry
+    geom = Geometry(328, 200)
+    q4 = np.full((3, 30), 16, np.uint8)
+    eng = engine.KeyframeEngine(geom, nframes=2, q0=72, pvq_qm_q4=q4, split_free=1, noref_prepass=1)
+    _check_batch(eng, geom, _frames(geom, 2), 72, q4)
+    _check_batch(eng, geom, _frames(geom, 2, q_seed=5, mode="32"), 72, q4)
+    _check_batch(eng, geom, _frames(geom, 2, q_seed=6, mode="4"), 72, q4)
+    eng.close()
+
+
 @pytest.mark.parametrize("split", [1, 2, 3])
 def test_engine_split_phase_kernels_match_oracle(split):
     """The dependency-free bands (chroma; with split = 2 also luma bands 3 / 6) through the three phase
