@@ -304,12 +304,85 @@ k_blend_packed(const unsigned char* __restrict__ preds, int pitch, unsigned char
   }
 }
 
+
+// od_mv_est_bma_sad (src/mcenc.c:2224) for one candidate per CTA: per plane the single-MV prediction of the
+// displaced block (half-pel BMA vector scaled to the plane, mc_predict1fmv) and its SAD against the current
+// picture through od_enc_sad's clipping to the active picture region (src/mcenc.c:1615-1680: blocks hang over
+// the picture edge, and over its top / left for the centred BMA blocks); chroma SADs enter >> OD_MC_CHROMA_SCALE.
+struct BmaPlanes {
+  const unsigned char* cur[3];
+  const unsigned char* ref[3];
+  int cur_stride[3], ref_stride[3];
+  int pic_w, pic_h, nplanes;
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_bma_sad(const __grid_constant__ BmaPlanes P, const daala_b200_bma_job* __restrict__ jobs, int32_t* __restrict__ result) {
+  __shared__ __align__(16) unsigned char pred[kMaxN * kMaxN];
+  __shared__ short buf[(kMaxN + kApron) * kMaxN];
+  __shared__ int partial[kThreads / 32];
+  const daala_b200_bma_job job = jobs[blockIdx.x];
+  int total = 0;
+  for (int pli = 0; pli < P.nplanes; pli++) {
+    const int dec = pli > 0;
+    const int ln = job.log_mvb_sz + 3 - dec, n = 1 << ln;   // OD_LOG_MVBSIZE_MIN = 3
+    int x = job.bx >> dec, y = job.by >> dec;
+    predict_block(pred, buf, P.ref[pli] + (ptrdiff_t)y * P.ref_stride[pli] + x, P.ref_stride[pli],
+                  job.mvx * (1 << (2 - dec)), job.mvy * (1 << (2 - dec)), ln, ln);
+    int w = n, h = n, px = 0, py = 0;
+    if (x < 0) { w += x; px = -x; x = 0; }
+    if (y < 0) { h += y; py = -y; y = 0; }
+    const int plane_w = (P.pic_w + dec) >> dec, plane_h = (P.pic_h + dec) >> dec;   // OD_PLANE_SZ
+    w = min(w, plane_w - x);
+    h = min(h, plane_h - y);
+    int acc = 0;
+    if (w > 0 && h > 0) {
+      const unsigned char* c0 = P.cur[pli] + (size_t)y * P.cur_stride[pli] + x;
+      for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+        const int r = i / w, c = i - r * w;
+        acc += abs((int)c0[(size_t)r * P.cur_stride[pli] + c] - (int)pred[(r + py) * n + c + px]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) partial[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int sad = 0;
+      for (int k = 0; k < kThreads / 32; k++) sad += partial[k];
+      total += sad >> (dec ? 2 : 0);
+    }
+    __syncthreads();   // pred / buf / partial are reused by the next plane
+  }
+  if (threadIdx.x == 0) result[blockIdx.x] = total;
+}
+
 }  // namespace mc
 }  // namespace daala_b200
 
 using namespace daala_b200::mc;
 
 extern "C" {
+
+int daala_b200_mv_bma_sad(const uint8_t* const cur[3], const int cur_stride[3], const uint8_t* const ref[3],
+                                     const int ref_stride[3], int pic_w, int pic_h, int nplanes,
+                                     const daala_b200_bma_job* jobs, int count, int32_t* result, void* stream) {
+  if (!cur || !ref || !jobs || !result || nplanes < 1 || nplanes > 3 || count < 0) return (int)cudaErrorInvalidValue;
+  if (count == 0) return 0;
+  daala_b200::mc::BmaPlanes P;
+  for (int i = 0; i < 3; i++) {
+    P.cur[i] = i < nplanes ? cur[i] : nullptr;
+    P.ref[i] = i < nplanes ? ref[i] : nullptr;
+    P.cur_stride[i] = i < nplanes ? cur_stride[i] : 0;
+    P.ref_stride[i] = i < nplanes ? ref_stride[i] : 0;
+  }
+  P.pic_w = pic_w;
+  P.pic_h = pic_h;
+  P.nplanes = nplanes;
+  daala_b200::mc::k_bma_sad<<<count, daala_b200::mc::kThreads, 0, (cudaStream_t)stream>>>(P, jobs, result);
+  return (int)cudaGetLastError();
+}
+
 
 int daala_b200_mc_predict_blocks(const uint8_t* ref, int ref_stride, uint8_t* dst, int dst_stride,
                                  const daala_b200_mc_block* blocks, int count, void* stream) {

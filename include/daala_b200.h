@@ -563,6 +563,19 @@ int daala_b200_mc_predict_blocks(const uint8_t *ref, int ref_stride, uint8_t *ds
 int daala_b200_mc_match_candidates(const uint8_t *cur, int cur_stride, const uint8_t *ref, int ref_stride,
                                    const daala_b200_match_job *jobs, int count, int use_satd, int32_t *result,
                                    void *stream);
+/* od_mv_est_bma_sad (static, src/mcenc.c:2224): the complete cost of a half-pel BMA candidate -- per plane
+   the displaced block's single-MV prediction and its SAD against the current picture through od_enc_sad's
+   clipping to the picture (src/mcenc.c:1615), chroma >> OD_MC_CHROMA_SCALE, summed.  (bx, by): luma position
+   of the block (may be negative: BMA blocks are centred on grid points); (mvx, mvy): half-pel units;
+   block edge = 8 << log_mvb_sz luma pixels (log_mvb_sz 0..3).  cur[p]: pixel (0,0) of the current picture's planes; ref[p]:
+   pixel (0,0) of reference planes padded like state->ref_imgs (od_img_edge_ext).  nplanes = 3 with
+   OD_MC_USE_CHROMA, else 1. */
+typedef struct daala_b200_bma_job {
+  int32_t bx, by, mvx, mvy, log_mvb_sz;
+} daala_b200_bma_job;
+int daala_b200_mv_bma_sad(const uint8_t *const cur[3], const int cur_stride[3], const uint8_t *const ref[3],
+                          const int ref_stride[3], int pic_w, int pic_h, int nplanes,
+                          const daala_b200_bma_job *jobs, int count, int32_t *result, void *stream);
 /* Batched mc_predict1fmv: job q's block goes to dst + q*dst_pitch (row stride
    = block width).  log_yblk < 0: square blocks. */
 int daala_b200_mc_predict1fmv_batch(const uint8_t *ref, int ref_stride, uint8_t *dst, int dst_pitch,

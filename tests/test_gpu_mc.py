@@ -283,3 +283,65 @@ def test_inter_frame_chain_mv_grid_to_pvq_matches_reference():
         rec = frame_oracle.inverse_plane(lib, prefix, dq, geom, pli, bsize, 0)
         assert np.array_equal(hp.fb.pixels_out[pli][0].cpu().numpy(), rec), "recon plane %d" % pli
     assert coded > 0
+
+
+def test_bma_candidate_cost_matches_reference():
+    """daala_b200_mv_bma_sad against the reference's own od_mv_est_bma_sad (static, src/mcenc.c:2224) run on
+    a real od_state: all three planes, chroma >> 2, blocks hanging over every picture edge (od_enc_sad's
+    clipping, including the negative origins of centred BMA blocks), every block size, fractional and
+    integer half-pel vectors."""
+    import ctypes
+    import torch
+    from daala_b200 import _native, synth
+    from daala_b200.frame import Geometry
+    L = _native.lib()
+    ref = oracle_lib.load_ref()
+    if ref is None:
+        pytest.skip("needs oracle/_ref")
+    pic_w, pic_h = 200, 130
+    geom = Geometry(pic_w, pic_h)
+    cur, _ = synth.frame(pic_w, pic_h, f=3)
+    prev, _ = synth.frame(pic_w, pic_h, f=2)
+    cur = synth.pad_planes(cur, geom)
+    prev = synth.pad_planes(prev, geom)
+    rng = np.random.default_rng(11)
+    jobs = []
+    for log_sz in range(0, 4):                       # 8x8 .. 64x64 luma (OD_LOG_MVBSIZE_MIN = 3)
+        n = 8 << log_sz
+        for _ in range(40):
+            bx = int(rng.integers(-n // 2, pic_w)) & ~1
+            by = int(rng.integers(-n // 2, pic_h)) & ~1
+            jobs.append((bx, by, int(rng.integers(-40, 41)), int(rng.integers(-40, 41)), log_sz))
+        jobs.append((0, 0, 0, 0, log_sz))
+        jobs.append((pic_w - n // 2 & ~1, pic_h - n // 2 & ~1, 6, -4, log_sz))
+    jobs = np.array(jobs, np.int32)
+    a = oracle_lib.addr
+    for use_chroma in (1, 0):
+        want = np.zeros(len(jobs), np.int32)
+        rc = ref.oracle_ref_bma_sad(pic_w, pic_h, a(cur[0]), a(cur[1]), a(cur[2]), a(prev[0]), a(prev[1]), a(prev[2]),
+                                    use_chroma, a(jobs), len(jobs), a(want))
+        assert rc == 0
+        pad = 96
+        dev_cur, dev_ref, cs, rs, cptr, rptr = [], [], [], [], [], []
+        for p in range(3):
+            pd = pad >> (1 if p else 0)
+            dev_cur.append(torch.from_numpy(cur[p]).cuda())
+            padded = torch.from_numpy(np.pad(prev[p], pd, mode="edge")).cuda()   # od_img_edge_ext
+            dev_ref.append(padded)
+            cs.append(cur[p].shape[1])
+            rs.append(padded.shape[1])
+            cptr.append(dev_cur[p].data_ptr())
+            rptr.append(padded.data_ptr() + pd * padded.shape[1] + pd)
+        d_jobs = torch.from_numpy(jobs).cuda()
+        d_out = torch.zeros(len(jobs), dtype=torch.int32, device="cuda")
+        P3 = ctypes.c_void_p * 3
+        I3 = ctypes.c_int * 3
+        L.daala_b200_mv_bma_sad.argtypes = [P3, I3, P3, I3, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        rc = L.daala_b200_mv_bma_sad(P3(*cptr), I3(*cs), P3(*rptr), I3(*rs), pic_w, pic_h, 3 if use_chroma else 1,
+                                     d_jobs.data_ptr(), len(jobs), d_out.data_ptr(), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (use_chroma, len(bad), jobs[bad[:5]].tolist(), got[bad[:5]].tolist(), want[bad[:5]].tolist())
