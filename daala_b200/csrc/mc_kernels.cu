@@ -112,16 +112,13 @@ __device__ __forceinline__ SplitWeights split_weights(int oc, int s, int lx, int
   return w;
 }
 
-__global__ void __launch_bounds__(kThreads)
-k_obmc_blocks(const unsigned char* __restrict__ ref, int ref_stride, unsigned char* __restrict__ dst,
-              int dst_stride, const daala_b200_mc_block* __restrict__ blocks) {
-  __shared__ unsigned char pred[4][kMaxN * kMaxN];
-  __shared__ short buf[(kMaxN + kApron) * kMaxN];
-  const daala_b200_mc_block b = blocks[blockIdx.x];
+// OBMC prediction of one block (od_mc_predict_singleref, src/mc.c:1965) by the CTA into out[j * out_stride + i]:
+// up to four single-MV predictions (re-used when two corners share a MV) + od_mc_blend_full(_split)8_c.
+__device__ void obmc_block(unsigned char* out, int out_stride, unsigned char (&pred)[4][kMaxN * kMaxN], short* buf,
+                           const unsigned char* ref, int ref_stride, const daala_b200_mc_block& b) {
   const int lx = b.log_xblk, ly = b.log_yblk;
   const int nx = 1 << lx, ny = 1 << ly;
   const unsigned char* src = ref + (size_t)b.y0 * ref_stride + b.x0;
-  // od_mc_predict_singleref re-uses a prediction when two corners share a MV
   int which[4];
   for (int k = 0; k < 4; k++) {
     which[k] = k;
@@ -130,7 +127,6 @@ k_obmc_blocks(const unsigned char* __restrict__ ref, int ref_stride, unsigned ch
     }
     if (which[k] == k) predict_block(pred[k], buf, src, ref_stride, b.mvx[k], b.mvy[k], lx, ly);
   }
-  unsigned char* out = dst + (size_t)b.y0 * dst_stride + b.x0;
   const unsigned char* p0 = pred[which[0]];
   const unsigned char* p1 = pred[which[1]];
   const unsigned char* p2 = pred[which[2]];
@@ -142,7 +138,7 @@ k_obmc_blocks(const unsigned char* __restrict__ ref, int ref_stride, unsigned ch
       int a = p0[idx], c = p3[idx];
       a = (a << lx) + (p1[idx] - a) * i;
       c = (c << lx) + (p2[idx] - c) * i;
-      out[(size_t)j * dst_stride + i] = (unsigned char)(((a << ly) + (c - a) * j + (1 << (l2 - 1))) >> l2);
+      out[(size_t)j * out_stride + i] = (unsigned char)(((a << ly) + (c - a) * j + (1 << (l2 - 1))) >> l2);
     }
   } else {
     const SplitWeights w = split_weights(b.oc, b.s, lx, ly);
@@ -153,9 +149,18 @@ k_obmc_blocks(const unsigned char* __restrict__ ref, int ref_stride, unsigned ch
       int acc = (a << l2p1) + (p1[idx] - a) * (w.s0[1] + j * w.dsdj[1] + i * (w.dsdi[1] + j * w.dd[1]))
                 + (p2[idx] - a) * (w.s0[2] + j * w.dsdj[2] + i * (w.dsdi[2] + j * w.dd[2]))
                 + (p3[idx] - a) * (w.s0[3] + j * w.dsdj[3] + i * (w.dsdi[3] + j * w.dd[3]));
-      out[(size_t)j * dst_stride + i] = (unsigned char)((acc + (1 << (l2p1 - 1))) >> l2p1);
+      out[(size_t)j * out_stride + i] = (unsigned char)((acc + (1 << (l2p1 - 1))) >> l2p1);
     }
   }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_obmc_blocks(const unsigned char* __restrict__ ref, int ref_stride, unsigned char* __restrict__ dst,
+              int dst_stride, const daala_b200_mc_block* __restrict__ blocks) {
+  __shared__ unsigned char pred[4][kMaxN * kMaxN];
+  __shared__ short buf[(kMaxN + kApron) * kMaxN];
+  const daala_b200_mc_block b = blocks[blockIdx.x];
+  obmc_block(dst + (size_t)b.y0 * dst_stride + b.x0, dst_stride, pred, buf, ref, ref_stride, b);
 }
 
 // 8-point Walsh-Hadamard on registers (ordering is irrelevant for a sum of magnitudes).
@@ -357,12 +362,71 @@ k_bma_sad(const __grid_constant__ BmaPlanes P, const daala_b200_bma_job* __restr
   if (threadIdx.x == 0) result[blockIdx.x] = total;
 }
 
+// od_mv_est_sad (src/mcenc.c:2267): the OBMC prediction of a MV-grid block in every plane and its SAD against the
+// current picture (od_enc_sad: clipped to the picture), chroma >> OD_MC_CHROMA_SCALE.  One CTA per candidate,
+// blocks[3 * job + plane] = the plane's block record (od_state_pred_block_from_setup's MVs).
+__global__ void __launch_bounds__(kThreads)
+k_est_sad(const __grid_constant__ BmaPlanes P, const daala_b200_mc_block* __restrict__ blocks, int32_t* __restrict__ result) {
+  __shared__ unsigned char pred[4][kMaxN * kMaxN];
+  __shared__ short buf[(kMaxN + kApron) * kMaxN];
+  __shared__ unsigned char blend[kMaxN * kMaxN];
+  __shared__ int partial[kThreads / 32];
+  int total = 0;
+  for (int pli = 0; pli < P.nplanes; pli++) {
+    const daala_b200_mc_block b = blocks[3 * blockIdx.x + pli];
+    const int dec = pli > 0;
+    const int nx = 1 << b.log_xblk, ny = 1 << b.log_yblk;
+    obmc_block(blend, nx, pred, buf, P.ref[pli], P.ref_stride[pli], b);
+    __syncthreads();
+    const int plane_w = (P.pic_w + dec) >> dec, plane_h = (P.pic_h + dec) >> dec;   // OD_PLANE_SZ
+    const int w = min(nx, plane_w - (int)b.x0), h = min(ny, plane_h - (int)b.y0);
+    int acc = 0;
+    if (w > 0 && h > 0) {
+      const unsigned char* c0 = P.cur[pli] + (size_t)b.y0 * P.cur_stride[pli] + b.x0;
+      for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+        const int r = i / w, c = i - r * w;
+        acc += abs((int)c0[(size_t)r * P.cur_stride[pli] + c] - (int)blend[r * nx + c]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) partial[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int sad = 0;
+      for (int k = 0; k < kThreads / 32; k++) sad += partial[k];
+      total += sad >> (dec ? 2 : 0);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) result[blockIdx.x] = total;
+}
+
 }  // namespace mc
 }  // namespace daala_b200
 
 using namespace daala_b200::mc;
 
 extern "C" {
+
+int daala_b200_mv_est_sad(const uint8_t* const cur[3], const int cur_stride[3], const uint8_t* const ref[3],
+                          const int ref_stride[3], int pic_w, int pic_h, int nplanes,
+                          const daala_b200_mc_block* blocks, int count, int32_t* result, void* stream) {
+  if (!cur || !ref || !blocks || !result || nplanes < 1 || nplanes > 3 || count < 0) return (int)cudaErrorInvalidValue;
+  if (count == 0) return 0;
+  daala_b200::mc::BmaPlanes P;
+  for (int i = 0; i < 3; i++) {
+    P.cur[i] = i < nplanes ? cur[i] : nullptr;
+    P.ref[i] = i < nplanes ? ref[i] : nullptr;
+    P.cur_stride[i] = i < nplanes ? cur_stride[i] : 0;
+    P.ref_stride[i] = i < nplanes ? ref_stride[i] : 0;
+  }
+  P.pic_w = pic_w;
+  P.pic_h = pic_h;
+  P.nplanes = nplanes;
+  daala_b200::mc::k_est_sad<<<count, daala_b200::mc::kThreads, 0, (cudaStream_t)stream>>>(P, blocks, result);
+  return (int)cudaGetLastError();
+}
 
 int daala_b200_mv_bma_sad(const uint8_t* const cur[3], const int cur_stride[3], const uint8_t* const ref[3],
                                      const int ref_stride[3], int pic_w, int pic_h, int nplanes,

@@ -63,7 +63,13 @@ def leaves(valid):
 def block_list(valid, mv, xdec=0):
     """daala_b200_mc_block records (mc.MC_BLOCK_DTYPE) of one plane: `valid` bool
     [(nvmvbs+1), (nhmvbs+1)], `mv` int32 [.., .., 2] in 1/8 luma pixel."""
-    vx, vy, l, oc, s = leaves(valid)
+    return blocks_for(*leaves(valid), mv, xdec)
+
+
+def blocks_for(vx, vy, l, oc, s, mv, xdec=0):
+    """Block records of given MV blocks (vertex position, log size, outside corner, split state): what
+    od_state_pred_block_from_setup (src/state.c:627) derives for one plane."""
+    vx, vy, l, oc, s = (np.asarray(a, np.int64) for a in (vx, vy, l, oc, s))
     d = np.array(_D)
     sdx = np.array(_SETUP_DX)[oc, s]   # offsets
     sdy = np.array(_SETUP_DY)[oc, s]

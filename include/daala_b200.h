@@ -576,6 +576,13 @@ typedef struct daala_b200_bma_job {
 int daala_b200_mv_bma_sad(const uint8_t *const cur[3], const int cur_stride[3], const uint8_t *const ref[3],
                           const int ref_stride[3], int pic_w, int pic_h, int nplanes,
                           const daala_b200_bma_job *jobs, int count, int32_t *result, void *stream);
+/* od_mv_est_sad (static, src/mcenc.c:2267): the OBMC-based cost of `count` MV-grid blocks.  blocks[3 * q + p] is
+   candidate q's block record in plane p (od_state_pred_block_from_setup, src/state.c:627: four corner MVs scaled
+   for the plane, oc, s); prediction of every plane (od_mc_predict) + od_enc_sad against the current picture,
+   chroma >> OD_MC_CHROMA_SCALE.  Planes as for daala_b200_mv_bma_sad. */
+int daala_b200_mv_est_sad(const uint8_t *const cur[3], const int cur_stride[3], const uint8_t *const ref[3],
+                          const int ref_stride[3], int pic_w, int pic_h, int nplanes,
+                          const daala_b200_mc_block *blocks, int count, int32_t *result, void *stream);
 /* Batched mc_predict1fmv: job q's block goes to dst + q*dst_pitch (row stride
    = block width).  log_yblk < 0: square blocks. */
 int daala_b200_mc_predict1fmv_batch(const uint8_t *ref, int ref_stride, uint8_t *dst, int dst_pitch,

@@ -345,3 +345,64 @@ def test_bma_candidate_cost_matches_reference():
         got = d_out.cpu().numpy()
         bad = np.nonzero(got != want)[0]
         assert len(bad) == 0, (use_chroma, len(bad), jobs[bad[:5]].tolist(), got[bad[:5]].tolist(), want[bad[:5]].tolist())
+
+
+def test_obmc_candidate_cost_matches_reference():
+    """daala_b200_mv_est_sad against the reference's own od_mv_est_sad (static, src/mcenc.c:2267) on a real
+    od_state with a random MV grid: OBMC prediction of all three planes from the grid (every outside corner /
+    split state the grid produces, all block sizes) + od_enc_sad with clipping at the picture edge, chroma >> 2."""
+    import ctypes
+    import torch
+    from daala_b200 import _native, mc, mvgrid, synth
+    from daala_b200.frame import Geometry
+    L = _native.lib()
+    ref = oracle_lib.load_ref()
+    if ref is None:
+        pytest.skip("needs oracle/_ref")
+    pic_w, pic_h = 200, 130
+    geom = Geometry(pic_w, pic_h)
+    W, H = geom.frame_w, geom.frame_h
+    cur, _ = synth.frame(pic_w, pic_h, f=3)
+    prev, _ = synth.frame(pic_w, pic_h, f=2)
+    cur = synth.pad_planes(cur, geom)
+    prev = synth.pad_planes(prev, geom)
+    rng = np.random.default_rng(21)
+    valid, mv = _random_mv_grid(rng, H // 8, W // 8)
+    vx, vy, l, oc, s = mvgrid.leaves(valid)
+    jobs = np.ascontiguousarray(np.stack([vx, vy, oc, s, l], axis=1).astype(np.int32))
+    a = oracle_lib.addr
+    vmap = np.ascontiguousarray(valid.astype(np.uint8))
+    mvc = np.ascontiguousarray(mv)
+    for use_chroma in (1, 0):
+        want = np.zeros(len(jobs), np.int32)
+        rc = ref.oracle_ref_mv_est_sad(pic_w, pic_h, a(cur[0]), a(cur[1]), a(cur[2]), a(prev[0]), a(prev[1]), a(prev[2]),
+                                       a(vmap), a(mvc), use_chroma, a(jobs), len(jobs), a(want))
+        assert rc == 0
+        blocks = np.zeros((len(jobs), 3), mc.MC_BLOCK_DTYPE)
+        for p in range(3):
+            blocks[:, p] = mvgrid.blocks_for(vx, vy, l, oc, s, mv, xdec=1 if p else 0)
+        pad = 96
+        keep, cs, rs, cptr, rptr = [], [], [], [], []
+        for p in range(3):
+            pd = pad >> (1 if p else 0)
+            dc = torch.from_numpy(cur[p]).cuda()
+            dr = torch.from_numpy(np.pad(prev[p], pd, mode="edge")).cuda()   # od_img_edge_ext
+            keep += [dc, dr]
+            cs.append(cur[p].shape[1])
+            rs.append(dr.shape[1])
+            cptr.append(dc.data_ptr())
+            rptr.append(dr.data_ptr() + pd * dr.shape[1] + pd)
+        d_blocks = torch.from_numpy(np.ascontiguousarray(blocks).view(np.uint8).reshape(-1)).cuda()
+        d_out = torch.zeros(len(jobs), dtype=torch.int32, device="cuda")
+        P3 = ctypes.c_void_p * 3
+        I3 = ctypes.c_int * 3
+        L.daala_b200_mv_est_sad.argtypes = [P3, I3, P3, I3, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        rc = L.daala_b200_mv_est_sad(P3(*cptr), I3(*cs), P3(*rptr), I3(*rs), pic_w, pic_h, 3 if use_chroma else 1,
+                                     d_blocks.data_ptr(), len(jobs), d_out.data_ptr(), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (use_chroma, len(bad), len(jobs), jobs[bad[:5]].tolist(), got[bad[:5]].tolist(), want[bad[:5]].tolist())
+    assert len(jobs) > 50 and len(np.unique(l)) >= 3
