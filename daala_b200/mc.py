@@ -16,7 +16,9 @@ MATCH_JOB_DTYPE = np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("x0", "<u2"), ("y0"
                             ("pad_", "u1", 3)])
 OD_BUFFER_PADDING = 96
 
-assert MC_BLOCK_DTYPE.itemsize == 40 and MATCH_JOB_DTYPE.itemsize == 16
+BMA_JOB_DTYPE = np.dtype([("bx", "<i4"), ("by", "<i4"), ("mvx", "<i4"), ("mvy", "<i4"), ("log_mvb_sz", "<i4")])
+
+assert MC_BLOCK_DTYPE.itemsize == 40 and MATCH_JOB_DTYPE.itemsize == 16 and BMA_JOB_DTYPE.itemsize == 20
 
 
 def _bind():
@@ -27,6 +29,9 @@ def _bind():
     L.daala_b200_mc_predict_blocks.argtypes = [vp, ci, vp, ci, vp, ci, vp]
     L.daala_b200_mc_match_candidates.argtypes = [vp, ci, vp, ci, vp, ci, ci, vp, vp]
     L.daala_b200_mc_predict1fmv_batch.argtypes = [vp, ci, vp, ci, vp, ci, ci, vp]
+    p3, i3 = ctypes.c_void_p * 3, ctypes.c_int * 3
+    L.daala_b200_mv_bma_sad.argtypes = [p3, i3, p3, i3, ci, ci, ci, vp, ci, vp, vp]
+    L.daala_b200_mv_est_sad.argtypes = [p3, i3, p3, i3, ci, ci, ci, vp, ci, vp, vp]
     L._mc_bound = True
     return L
 
@@ -72,4 +77,31 @@ def match_candidates(cur, ref, jobs_dev, count, use_satd=False, out=None, stream
     _native.check(L.daala_b200_mc_match_candidates(cur.data_ptr(), cur.stride(0), ref.origin_ptr, ref.stride,
                                                    jobs_dev.data_ptr(), count, int(use_satd), out.data_ptr(),
                                                    _stream(stream, cur.device)), "mc_match_candidates")
+    return out
+
+
+def _planes(cur, ref):
+    p3, i3 = ctypes.c_void_p * 3, ctypes.c_int * 3
+    return (p3(*[c.data_ptr() for c in cur]), i3(*[c.stride(0) for c in cur]), p3(*[r.origin_ptr for r in ref]),
+            i3(*[r.stride for r in ref]))
+
+
+def bma_sad(cur, ref, pic_w, pic_h, jobs_dev, count, out=None, use_chroma=True, stream=None):
+    """od_mv_est_bma_sad of `count` half-pel BMA candidates (BMA_JOB_DTYPE); cur: three 2-D uint8 tensors,
+    ref: three PaddedPlane (chroma padded by OD_BUFFER_PADDING >> 1 at least)."""
+    L = _bind()
+    if out is None:
+        out = torch.empty(count, dtype=torch.int32, device=cur[0].device)
+    _native.check(L.daala_b200_mv_bma_sad(*_planes(cur, ref), pic_w, pic_h, 3 if use_chroma else 1, jobs_dev.data_ptr(),
+                                          count, out.data_ptr(), _stream(stream, cur[0].device)), "mv_bma_sad")
+    return out
+
+
+def est_sad(cur, ref, pic_w, pic_h, blocks_dev, count, out=None, use_chroma=True, stream=None):
+    """od_mv_est_sad of `count` MV-grid blocks; blocks_dev: [count][3] MC_BLOCK_DTYPE records (one per plane)."""
+    L = _bind()
+    if out is None:
+        out = torch.empty(count, dtype=torch.int32, device=cur[0].device)
+    _native.check(L.daala_b200_mv_est_sad(*_planes(cur, ref), pic_w, pic_h, 3 if use_chroma else 1, blocks_dev.data_ptr(),
+                                          count, out.data_ptr(), _stream(stream, cur[0].device)), "mv_est_sad")
     return out
