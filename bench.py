@@ -36,6 +36,11 @@ UNIT = "Mpixels/s"
 PIC_W, PIC_H = 3840, 2160
 WORKLOAD = ("3840x2160 4:2:0 all-intra hot path: lapped prefilter + fDCT(4..64, quadtree map) + PVQ band "
             "quantisation (keyframe: luma H/V intra prediction, chroma CfL) + iDCT + lapped postfilter")
+
+
+def workload_text():
+    return WORKLOAD + (" + deringing filter (od_dering of every superblock at the level the reference encoder chose "
+                       "for it)" if DERING else "")
 FWD_BYTES_PER_PX = 7.5   # SURVEY.md 8(d) K_fwd: 1.5 B in + 6 B out per padded luma pixel (4:2:0)
 
 
@@ -55,6 +60,7 @@ def parse():
                          "quadtree maps with every size 4..64")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="persistent PVQ kernel CTAs per SM (0 = default)")
     ap.add_argument("--split-free", type=int, default=1, help="dependency-free PVQ bands as phase kernels: 0 no, 1 chroma, 2 chroma + luma")
+    ap.add_argument("--dering", type=int, default=1, help="reconstruction through od_dering with the reference encoder's per-superblock levels (config 4: PVQ + deringing)")
     ap.add_argument("--prepass", type=int, default=0, help="luma no-reference searches ahead of the chains (1) or inside them (0)")
     ap.add_argument("--level-chains", type=int, default=0, help="luma intra chains level-synchronously (1) instead of the dependency queue (0)")
     ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"])
@@ -65,6 +71,7 @@ def parse():
 # synthetic workload (host side)
 # --------------------------------------------------------------------------
 BLOCK_SIZES = "reference"   # --block-sizes: "synthetic" quadtree maps, or the "reference" encoder's decisions
+DERING = 1                  # --dering
 
 
 def make_host_frames(geom, nframes, distinct=4, rotate=0):
@@ -84,9 +91,11 @@ def make_host_frames(geom, nframes, distinct=4, rotate=0):
         planes, seed = synth.frame(geom.pic_w, geom.pic_h, f=f, seed=seed)
         if real is not None:
             bsize = np.ascontiguousarray(real["bsize_%d" % (f % 4)][:geom.bsize_shape[0]])
+            levels = np.ascontiguousarray(real["dering_%d" % (f % 4)][:geom.nvsb]).astype(np.uint8)
         else:
             bsize = synth.block_size_map(geom, "mixed", seed=100 + f)
-        frames.append((synth.pad_planes(planes, geom), bsize))
+            levels = np.random.default_rng(200 + f).integers(0, 6, size=(geom.nvsb, geom.nhsb)).astype(np.uint8)
+        frames.append((synth.pad_planes(planes, geom), bsize, levels))
     return [frames[(i + rotate) % len(frames)] for i in range(nframes)]
 
 
@@ -167,13 +176,14 @@ Q0 = 72            # state->quantizer for OD_SET_QUANT = 20 (coded quantizer 20 
 PVQ_QM_Q4 = 16     # flat state->pvq_qm_q4 entries
 
 
-def cpu_frame(lib, prefix, geom, planes, bsize, record=False):
+def cpu_frame(lib, prefix, geom, planes, bsize, levels=None, record=False):
     """The same chain as the GPU step with the reference's own functions: forward transform ->
     per-block PVQ (od_hv_intra_pred / CfL prediction, pvq_theta with the closed-form rate) -> inverse."""
     import numpy as np
     from tests import frame_oracle
     q4 = np.full((3, 30), PVQ_QM_Q4, np.uint8)
-    return frame_oracle.keyframe_chain(lib, prefix, planes, geom, bsize, Q0, q4, use_masking=1, record=record)
+    return frame_oracle.keyframe_chain(lib, prefix, planes, geom, bsize, Q0, q4, use_masking=1, record=record,
+                                       dering_levels=levels if DERING else None)
 
 
 _CPU_JOB = {}
@@ -185,8 +195,8 @@ def _cpu_worker(i):
         _CPU_JOB["lib"] = cpu_pipeline_lib()
     lib, prefix, _ = _CPU_JOB["lib"]
     frames = _CPU_JOB["frames"]
-    planes, bsize = frames[i % len(frames)]
-    cpu_frame(lib, prefix, _CPU_JOB["geom"], planes, bsize)
+    planes, bsize, levels = frames[i % len(frames)]
+    cpu_frame(lib, prefix, _CPU_JOB["geom"], planes, bsize, levels)
     return i
 
 
@@ -257,7 +267,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD + " (CPU reference functions)", "frames_per_step": per_step,
+        "config": {"workload": workload_text() + " (CPU reference functions)", "frames_per_step": per_step,
                    "block_sizes": block_sizes_text(), "quantizer": Q0},
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind,
                          "build": CPU_BUILD["build"], "sample": sample},
@@ -303,10 +313,12 @@ def run_b200(args):
         hf = make_host_frames(geom, F, rotate=s + 2 * rank)
         planes = [np.stack([f[0][p] for f in hf]) for p in range(3)]
         bsize = np.stack([f[1] for f in hf])
-        eng = engine.KeyframeEngine(geom, nframes=F, q0=Q0, use_masking=1, pvq_qm_q4=q4,
+        eng = engine.KeyframeEngine(geom, nframes=F, q0=Q0, use_masking=1, pvq_qm_q4=q4, dering=DERING,
                                     persist_ctas_per_sm=args.ctas_per_sm, split_free=args.split_free, level_chains=args.level_chains, noref_prepass=args.prepass,
                                     max_blocks_div=1 if BLOCK_SIZES == "synthetic" else 2)
         eng.stage_inputs(planes, bsize)
+        if DERING:
+            eng.stage_dering_levels(np.stack([f[2] for f in hf]))
         eng.prepare_io(symbols=True, recon=True)
         slots.append(eng)
         batches.append(hf)
@@ -419,7 +431,7 @@ def run_b200(args):
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": F * world,
+        "config": {"workload": workload_text(), "frames_per_step": F * world,
                    "parallelism": "frames%d (independent keyframes per rank, no data-path collective)" % world,
                    "l2": "inputs larger than L2 (%.0f MB of planes per step per rank)" % ((geom.padded_samples * F * 9) / 1e6),
                    "block_sizes": block_sizes_text(), "quantizer": Q0,
@@ -476,7 +488,7 @@ def run_b200(args):
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": round(geom.luma_pixels * (n + 1) / dt / 1e6, 3), "unit": UNIT, "cores": 1, "kind": kind,
                                "build": CPU_BUILD["build"],
-                               "sample": "%d whole 3840x2160 frames, same chain (reference functions, pvq_theta speed=1), "
+                               "sample": "%d whole 3840x2160 frames, same chain (reference functions, pvq_theta speed=1, od_dering), "
                                          "1 thread, %.1f s" % (n + 1, dt)}
     print(json.dumps(out))
     if world > 1:
@@ -495,9 +507,10 @@ def load_profile_notes():
 
 
 def main():
-    global BLOCK_SIZES
+    global BLOCK_SIZES, DERING
     args = parse()
     BLOCK_SIZES = args.block_sizes
+    DERING = int(args.dering)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -31,7 +31,7 @@ class Frame(ctypes.Structure):
         ("plane", Plane * 3), ("bsize", c_void_p), ("bstride", c_int), ("nhsb", c_int),
         ("nvsb", c_int), ("pic_w", c_int), ("pic_h", c_int), ("haar_dc", c_int),
         ("nframes", c_int), ("sb_row0", c_int), ("sb_rows", c_int), ("pad_", c_int),
-        ("bsize_frame_pitch", c_ll),
+        ("bsize_frame_pitch", c_ll), ("post16", ctypes.c_void_p * 3),
     ]
 
 

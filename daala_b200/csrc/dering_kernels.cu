@@ -78,7 +78,18 @@ __device__ int find_direction(const int16_t* img, int coeff_shift, int32_t* var)
   return best;
 }
 
-__global__ void __launch_bounds__(256) k_dering_sb(const __grid_constant__ daala_b200_dering_params p) {
+// frames of a batch: blockIdx.z, element pitches between consecutive frames (all zero for a single plane)
+struct BatchPitch {
+  long long y, x, dir, thr;
+};
+
+__global__ void __launch_bounds__(256) k_dering_sb(const __grid_constant__ daala_b200_dering_params p0,
+                                                   const __grid_constant__ BatchPitch bp) {
+  daala_b200_dering_params p = p0;
+  p.y += blockIdx.z * bp.y;
+  p.x += blockIdx.z * bp.x;
+  p.dir += blockIdx.z * bp.dir;
+  if (p.sb_threshold) p.sb_threshold += blockIdx.z * bp.thr;
   __shared__ int16_t win[kPitch * kPitch];    // unfiltered input + apron
   __shared__ int16_t mid[kPitch * kPitch];    // pass-1 output inside the superblock, input in the apron
   __shared__ int s_thr[64];
@@ -184,6 +195,18 @@ extern "C" int daala_b200_dering_plane(const daala_b200_dering_params* prm, void
   // not in place: a superblock's apron would read its neighbours' filtered output
   if (!prm->x || !prm->y || (const void*)prm->x == (const void*)prm->y) return (int)cudaErrorInvalidValue;
   dim3 grid(prm->nhsb, prm->nvsb);
-  daala_b200::dering::k_dering_sb<<<grid, 256, 0, (cudaStream_t)stream>>>(*prm);
+  daala_b200::dering::BatchPitch bp = {0, 0, 0, 0};
+  daala_b200::dering::k_dering_sb<<<grid, 256, 0, (cudaStream_t)stream>>>(*prm, bp);
+  return (int)cudaGetLastError();
+}
+
+// The same for `nframes` planes of one geometry in one launch (internal: the keyframe engine's deringing stage).
+extern "C" int daala_b200_dering_plane_batch(const daala_b200_dering_params* prm, int nframes, long long y_pitch,
+                                             long long x_pitch, long long dir_pitch, long long thr_pitch, void* stream) {
+  if (!prm || nframes < 1 || prm->nhsb < 1 || prm->nvsb < 1 || prm->xdec < 0 || prm->xdec > 1) return (int)cudaErrorInvalidValue;
+  if (!prm->x || !prm->y || (const void*)prm->x == (const void*)prm->y) return (int)cudaErrorInvalidValue;
+  dim3 grid(prm->nhsb, prm->nvsb, nframes);
+  daala_b200::dering::BatchPitch bp = {y_pitch, x_pitch, dir_pitch, thr_pitch};
+  daala_b200::dering::k_dering_sb<<<grid, 256, 0, (cudaStream_t)stream>>>(*prm, bp);
   return (int)cudaGetLastError();
 }

@@ -539,6 +539,17 @@ __device__ __forceinline__ void sb_postfilter_store_body(const FrameXformParams&
     if (e == 0 ? top : bottom) lap4_inplace<true>(tile_s + (e ? B : 0) * P + c, P);
   }
   __syncthreads();
+  if (prm.post16[blockIdx.y]) {
+    // the deringing stage's input (state->etmp): the filtered samples as int16, two per 32-bit store
+    int16_t* d16 = prm.post16[blockIdx.y] + fr * pl.pixel_out_frame_pitch + (size_t)y0 * pl.pixel_out_stride + x0;
+    for (int i = threadIdx.x; i < B * B / 2; i += kPostThreads) {
+      int r = i / (B / 2), c2 = (i % (B / 2)) * 2;
+      const int* p = tile_s + (r + kHalo) * P + c2 + kHalo;
+      const unsigned w = ((unsigned)p[0] & 0xffffu) | ((unsigned)p[1] << 16);
+      *reinterpret_cast<unsigned*>(d16 + (size_t)r * pl.pixel_out_stride + c2) = w;
+    }
+    return;
+  }
   uint8_t* dst = pl.pixels_out + fr * pl.pixel_out_frame_pitch + (size_t)y0 * pl.pixel_out_stride + x0;
   // Four pixels per thread, packed into one 32-bit store.
   for (int i = threadIdx.x; i < B * B / 4; i += kPostThreads) {

@@ -961,6 +961,30 @@ __global__ void __launch_bounds__(256) k_finish_scatter(const __grid_constant__ 
   }
 }
 
+// ---- deringing stage (optional) ---------------------------------------------------------------------------
+// od_encode_coefficients' final deringing application (src/encode.c:2812-2842) with the per-superblock levels
+// given by the caller (the level SEARCH is serial: CDF adaptation + neighbour context; like the block sizes its
+// result is an input of the hot path): etmp = ctmp after the SB-edge postfilter, od_dering of every superblock
+// with threshold = OD_DERING_GAIN_TABLE[level] * quantizer^0.84182 (* 0.6 on chroma), od_coeff_to_ref_plane.
+// (c + 8 >> 4) + 128 clamped: od_coeff_to_ref_plane, src/state.c:1283
+__global__ void k_i16_to_u8(const int16_t* __restrict__ src, uint8_t* __restrict__ dst, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int v = ((src[i] + 8) >> 4) + 128;
+    dst[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+  }
+}
+// thr[pl][f][sb] = table[pl][level[f][sb]]
+__global__ void k_dering_thresholds(const uint8_t* __restrict__ level, int32_t* __restrict__ thr_luma,
+                                    int32_t* __restrict__ thr_chroma, int n, int4 tl_lo, int2 tl_hi, int4 tc_lo, int2 tc_hi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int tl[6] = {tl_lo.x, tl_lo.y, tl_lo.z, tl_lo.w, tl_hi.x, tl_hi.y};
+  const int tc[6] = {tc_lo.x, tc_lo.y, tc_lo.z, tc_lo.w, tc_hi.x, tc_hi.y};
+  const int g = level[i] < 6 ? level[i] : 5;
+  thr_luma[i] = tl[g];
+  thr_chroma[i] = tc[g];
+}
+
 }  // namespace kf
 }  // namespace daala_b200
 
@@ -971,6 +995,10 @@ using namespace daala_b200::kf;
 
 extern "C" int daala_b200_launch_forward(const daala_b200_frame* prm, int nplanes, cudaStream_t stream);
 extern "C" int daala_b200_launch_inverse(const daala_b200_frame* prm, int nplanes, cudaStream_t stream);
+extern "C" int daala_b200_launch_inverse_lapped_only(const daala_b200_frame* prm, int nplanes, cudaStream_t stream);
+extern "C" int daala_b200_launch_sb_postfilter_store(const daala_b200_frame* prm, int nplanes, cudaStream_t stream);
+extern "C" int daala_b200_dering_plane_batch(const daala_b200_dering_params* prm, int nframes, long long y_pitch,
+                                             long long x_pitch, long long dir_pitch, long long thr_pitch, void* stream);
 
 struct daala_b200_kf {
   daala_b200_kf_config cfg;
@@ -1001,6 +1029,13 @@ struct daala_b200_kf {
   int16_t* lv_snap;
   int32_t* lv_bar;
   int lvl_slots, lvl_grid;
+  // deringing stage
+  uint8_t* dering_level;           // [F][nvsb][nhsb]
+  int32_t *dering_thr[2];          // luma / chroma thresholds per superblock
+  int16_t *dering_in[3], *dering_out[3];
+  int32_t* dering_dir;             // [F][nvsb*8][nhsb*8]
+  uint8_t* dering_skip;            // all zero: keyframes never mark a block skipped (src/encode.c:1690)
+  int dering_tbl[2][6];
   Lists lists;
   Stage luma, chroma;
   daala_b200_frame frame;
@@ -1227,6 +1262,26 @@ static int kf_alloc(daala_b200_kf* kf) {
   f.nframes = F;
   f.sb_row0 = kf->cfg.sb_row0;
   f.sb_rows = kf->cfg.sb_rows;
+  if (kf->cfg.dering) {
+    const size_t nsb = (size_t)F * kf->nhsb * kf->nvsb;
+    KF_CHECK(dalloc(kf, &kf->dering_level, nsb));
+    KF_CHECK(dalloc(kf, &kf->dering_thr[0], nsb));
+    KF_CHECK(dalloc(kf, &kf->dering_thr[1], nsb));
+    KF_CHECK(dalloc(kf, &kf->dering_dir, nsb * 64));
+    KF_CHECK(dalloc(kf, &kf->dering_skip, nsb * 256 + 64));
+    for (int p = 0; p < 3; p++) {
+      const size_t n = (size_t)kf->plane_w[p] * kf->plane_h[p] * F;
+      KF_CHECK(dalloc(kf, &kf->dering_in[p], n));
+      KF_CHECK(dalloc(kf, &kf->dering_out[p], n));
+    }
+    // thresholds per level: (int)(OD_DERING_GAIN_TABLE[gi] * pow(quantizer, 0.84182) * (luma ? 1 : 0.6)), src/encode.c:2697,2822
+    const double gain[6] = {0, 0.5, 0.707, 1, 1.41, 2};
+    const double base = pow((double)kf->cfg.q0, 0.84182);
+    for (int g = 0; g < 6; g++) {
+      kf->dering_tbl[0][g] = (int)(gain[g] * base * 1);
+      kf->dering_tbl[1][g] = (int)(gain[g] * base * 0.6);
+    }
+  }
   // dalloc's cudaMemset runs on the legacy default stream, asynchronously, and the engine's stream does not
   // synchronise with it (cudaStreamNonBlocking): wait for every clear before anything is launched -- the table
   // fill below used to race with the clear of its own buffer (intermittently all-zero 1/sqrt table)
@@ -1311,9 +1366,51 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
     else k_pvq_persist<false><<<persist, kPersistThreads, 0, s>>>(kf->chroma);
     if (!core) k_finish_scatter<<<wide, 256, 0, s>>>(kf->chroma);
   }
-  if (phases & DAALA_B200_KF_INVERSE) {
+  if ((phases & DAALA_B200_KF_INVERSE) && !kf->cfg.dering) {
     int rc = daala_b200_launch_inverse(&kf->frame, 3, s);
     if (rc) return rc;
+  }
+  if ((phases & DAALA_B200_KF_INVERSE) && kf->cfg.dering) {
+    // iDCT + split postfilters -> lapped planes; SB-edge postfilter -> etmp (int16, the fused kernel's optional
+    // output); od_dering of all frames per plane in one launch, luma first (it writes the direction map chroma
+    // reads); -> u8
+    int rc = daala_b200_launch_inverse_lapped_only(&kf->frame, 3, s);
+    if (rc) return rc;
+    daala_b200_frame f16 = kf->frame;
+    for (int p = 0; p < 3; p++) f16.post16[p] = kf->dering_in[p];
+    rc = daala_b200_launch_sb_postfilter_store(&f16, 3, s);
+    if (rc) return rc;
+    const int nsb = kf->nhsb * kf->nvsb;
+    k_dering_thresholds<<<(kf->F * nsb + 255) / 256, 256, 0, s>>>(
+        kf->dering_level, kf->dering_thr[0], kf->dering_thr[1], kf->F * nsb,
+        make_int4(kf->dering_tbl[0][0], kf->dering_tbl[0][1], kf->dering_tbl[0][2], kf->dering_tbl[0][3]),
+        make_int2(kf->dering_tbl[0][4], kf->dering_tbl[0][5]),
+        make_int4(kf->dering_tbl[1][0], kf->dering_tbl[1][1], kf->dering_tbl[1][2], kf->dering_tbl[1][3]),
+        make_int2(kf->dering_tbl[1][4], kf->dering_tbl[1][5]));
+    for (int p = 0; p < 3; p++) {
+      const long long per = (long long)kf->plane_w[p] * kf->plane_h[p];
+      daala_b200_dering_params dp;
+      memset(&dp, 0, sizeof(dp));
+      dp.y = kf->dering_out[p];
+      dp.x = kf->dering_in[p];
+      dp.dir = kf->dering_dir;
+      dp.bskip = kf->dering_skip;
+      dp.sb_threshold = kf->dering_thr[p ? 1 : 0];
+      dp.ystride = dp.xstride = kf->plane_w[p];
+      dp.dir_stride = kf->nhsb * 8;
+      dp.skip_stride = kf->nhsb * 16;
+      dp.nhsb = kf->nhsb;
+      dp.nvsb = kf->nvsb;
+      dp.xdec = p ? 1 : 0;
+      dp.pli = p;
+      dp.threshold = 0;
+      dp.overlap = 1;      // OD_DERING_CHECK_OVERLAP
+      dp.coeff_shift = 4;  // OD_COEFF_SHIFT
+      rc = daala_b200_dering_plane_batch(&dp, kf->F, per, per, (long long)nsb * 64, nsb, s);
+      if (rc) return rc;
+    }
+    for (int p = 0; p < 3; p++)
+      k_i16_to_u8<<<wide, 256, 0, s>>>(kf->dering_out[p], kf->pixels_out[p], (long)kf->plane_w[p] * kf->plane_h[p] * kf->F);
   }
   return (int)cudaGetLastError();
 }
@@ -1412,6 +1509,15 @@ void daala_b200_kf_destroy(daala_b200_kf* kf) {
   cudaFree(kf->lv_uni);
   cudaFree(kf->lv_snap);
   cudaFree(kf->lv_bar);
+  cudaFree(kf->dering_level);
+  cudaFree(kf->dering_thr[0]);
+  cudaFree(kf->dering_thr[1]);
+  cudaFree(kf->dering_dir);
+  cudaFree(kf->dering_skip);
+  for (int p = 0; p < 3; p++) {
+    cudaFree(kf->dering_in[p]);
+    cudaFree(kf->dering_out[p]);
+  }
   cudaFree(L.succ_bottom);
   cudaFree(L.succ_right);
   cudaFree(L.cnt);
@@ -1444,7 +1550,8 @@ int daala_b200_kf_launches_per_step(const daala_b200_kf* kf) {
   n += 1;                                                                         // forward
   n += 3 + 1 + (kf->cfg.split_free > 1 ? split(kf->luma) : 0) + (kf->luma.pre_ev ? 2 : 0);   // luma: begin, gather, [prepass], chains, finish
   n += 4 + (kf->cfg.split_free > 0 ? split(kf->chroma) : 1);                      // chroma: begin, cfl, gather, bands, finish
-  n += 2;                                                                         // inverse, SB postfilter + store
+  if (!kf->cfg.dering) n += 2;                                                    // inverse, SB postfilter + store
+  else n += 1 + 1 + 1 + 3 + 3;   // inverse, SB postfilter -> int16, thresholds, dering per plane, store
   return n;
 }
 
@@ -1579,6 +1686,10 @@ int daala_b200_kf_submit(daala_b200_kf* kf, const daala_b200_kf_io* io) {
   }
   const size_t map_bytes = (size_t)kf->nhsb * 8 * kf->nvsb * 8 * F;
   KF_CHECK(cudaMemcpyAsync(kf->bsize, io->bsize, map_bytes, cudaMemcpyHostToDevice, s));
+  if (kf->cfg.dering) {
+    if (!io->dering_level) return (int)cudaErrorInvalidValue;
+    KF_CHECK(cudaMemcpyAsync(kf->dering_level, io->dering_level, (size_t)kf->nhsb * kf->nvsb * F, cudaMemcpyHostToDevice, s));
+  }
   int rc;
   {
     std::lock_guard<std::mutex> lock(g_compute_mu);

@@ -23,7 +23,7 @@ class Config(ctypes.Structure):
     _fields_ = [("pic_w", c_int), ("pic_h", c_int), ("nframes", c_int), ("q0", c_int), ("use_masking", c_int),
                 ("qm_stride", c_int), ("pvq_norm_lambda", ctypes.c_double), ("pvq_qm_q4", (ctypes.c_ubyte * 32) * 3),
                 ("qm", c_void_p), ("qm_inv", c_void_p), ("sb_row0", c_int), ("sb_rows", c_int),
-                ("max_blocks_div", c_int), ("persist_ctas_per_sm", c_int), ("split_free", c_int), ("noref_prepass", c_int), ("level_chains", c_int), ("stream", c_void_p)]
+                ("max_blocks_div", c_int), ("persist_ctas_per_sm", c_int), ("split_free", c_int), ("dering", c_int), ("noref_prepass", c_int), ("level_chains", c_int), ("stream", c_void_p)]
 
 
 class Totals(ctypes.Structure):
@@ -31,7 +31,7 @@ class Totals(ctypes.Structure):
 
 
 class IO(ctypes.Structure):
-    _fields_ = [("pixels", c_void_p * 3), ("bsize", c_void_p), ("totals", ctypes.POINTER(Totals)),
+    _fields_ = [("pixels", c_void_p * 3), ("bsize", c_void_p), ("dering_level", c_void_p), ("totals", ctypes.POINTER(Totals)),
                 ("pixels_out", c_void_p * 3), ("luma_blocks", c_void_p), ("chroma_blocks", c_void_p),
                 ("luma_res", c_void_p), ("chroma_res", c_void_p), ("luma_y16", c_void_p), ("chroma_y16", c_void_p),
                 ("luma_skip_diff", c_void_p), ("chroma_skip_diff", c_void_p), ("chroma_flip", c_void_p),
@@ -101,7 +101,7 @@ class KeyframeEngine:
     """One engine = one set of device buffers + one CUDA graph for batches of `nframes` keyframes."""
 
     def __init__(self, geom, nframes=1, q0=38, use_masking=1, lam=pvq.PVQ_LAMBDA, pvq_qm_q4=None, qm=None,
-                 qm_inv=None, sb_row0=0, sb_rows=0, max_blocks_div=0, persist_ctas_per_sm=0, split_free=0, level_chains=0, noref_prepass=0, pinned=True):
+                 qm_inv=None, sb_row0=0, sb_rows=0, max_blocks_div=0, persist_ctas_per_sm=0, split_free=0, level_chains=0, noref_prepass=0, dering=0, pinned=True):
         self.L = _bind()
         self.geom, self.F = geom, nframes
         if qm is None:
@@ -122,6 +122,8 @@ class KeyframeEngine:
         cfg.split_free = int(split_free)
         cfg.level_chains = int(level_chains)
         cfg.noref_prepass = int(noref_prepass)
+        cfg.dering = int(dering)
+        self.dering = int(dering)
         self.kf = self.L.daala_b200_kf_create(ctypes.byref(cfg))
         if not self.kf:
             raise RuntimeError("daala_b200_kf_create failed (no CUDA device, or out of memory)")
@@ -187,6 +189,12 @@ class KeyframeEngine:
                                                       ctypes.byref(t)), "count_blocks")
         return t
 
+    def stage_dering_levels(self, levels):
+        """levels: [F, nvsb, nhsb] uint8 (0..5), staged next to the other inputs (engines created with dering=1)."""
+        g = self.geom
+        a = self._arr("dlev", (self.F, g.nvsb, g.nhsb), np.uint8)
+        a[...] = levels
+
     def stage_inputs(self, planes, bsize):
         """Copies one batch into the engine's (pinned) host input buffers.  planes: per plane an array
         [F, h, w] u8 (padded geometry); bsize: [F, nvsb*8, nhsb*8]."""
@@ -205,6 +213,8 @@ class KeyframeEngine:
         for p in range(3):
             io.pixels[p] = self._arr("in%d" % p, (self.F,) + g.plane_shape(p), np.uint8).ctypes.data
         io.bsize = self._arr("bsize", (self.F,) + tuple(g.bsize_shape), np.uint8).ctypes.data
+        if self.dering:
+            io.dering_level = self._arr("dlev", (self.F, g.nvsb, g.nhsb), np.uint8).ctypes.data
         io.totals = ctypes.pointer(t)
         out = {}
         if recon:
@@ -239,10 +249,12 @@ class KeyframeEngine:
         self._check(self.L.daala_b200_kf_wait(self.kf), "kf_wait")
         return self._out
 
-    def encode(self, planes, bsize, symbols=True, recon=True):
+    def encode(self, planes, bsize, symbols=True, recon=True, dering_levels=None):
         """One batch end to end through the C ABI with host buffers; returns the result arrays (views of
         the engine's host buffers: copy what must survive the next call)."""
         self.stage_inputs(planes, bsize)
+        if self.dering:
+            self.stage_dering_levels(dering_levels)
         self.prepare_io(symbols, recon)
         self.submit()
         out = self.wait()

@@ -194,6 +194,10 @@ typedef struct daala_b200_frame {
                               multi-GPU shard of this rank; whole frame = 0, nvsb */
   int pad_;
   long long bsize_frame_pitch;
+  /* Optional: when post16[p] is set, daala_b200_sb_postfilter_store_frame writes plane p after the superblock
+     postfilter as int16 (the reference's etmp, input of od_dering) with the geometry of pixels_out, INSTEAD of
+     the clamped 8-bit pixels. */
+  int16_t *post16[3];
 } daala_b200_frame;
 
 /* u8 planes -> coefficient planes: od_ref_plane_to_coeff (src/state.c:1259) +
@@ -441,6 +445,9 @@ typedef struct daala_b200_kf_config {
   int split_free;              /* dependency-free bands as three phase kernels (setup / search / finish) with
                                   the band context in HBM records instead of the persistent kernel:
                                   0 = no, 1 = chroma, 2 = chroma and luma bands 3 / 6 */
+  int dering;                  /* 1: the reconstruction goes through od_dering with the per-superblock levels of
+                                  daala_b200_kf_io.dering_level (the final application of src/encode.c:2812-2842; the
+                                  level search stays with the caller, like the block-size decision) */
   int noref_prepass;           /* 1: the no-reference searches of every luma chain band run ahead of the chains in a
                                   fully parallel kernel (they do not depend on the prediction) */
   int level_chains;            /* luma intra chains: 0 = persistent kernel with a dependency queue, 1 = one
@@ -464,6 +471,7 @@ typedef struct daala_b200_kf_totals {
 typedef struct daala_b200_kf_io {
   const uint8_t *pixels[3];
   const uint8_t *bsize;
+  const uint8_t *dering_level;          /* [nframes][nvsb][nhsb] levels 0..5 (state->dering_level); config.dering only */
   const daala_b200_kf_totals *totals;   /* optional: result of _count_blocks for `bsize` */
   uint8_t *pixels_out[3];
   daala_b200_pvq_block *luma_blocks, *chroma_blocks;

@@ -26,4 +26,8 @@ int oracle_ref_pvq_theta(od_coeff *out, const od_coeff *x0, const od_coeff *r0,
 #define X_HV_PRED(pred, d, w, bx, by, bsize, bstride, bs) \
   od_hv_intra_pred(pred, d, w, bx, by, (unsigned char *)(bsize), bstride, bs)
 #define X_CFL_PRED(pred, n, luma, lw, bs, obs) od_resample_luma_coeffs(pred, n, luma, lw, 1, 1, bs, obs)
+#include "dering.h"
+#define X_DERING(y, ys, x, xs, sbx, sby, nhsb, nvsb, xdec, dir, pli, bskip, ss, thr) \
+  od_dering(&OD_DERING_VTBL_C, y, ys, x, xs, 8, 8, sbx, sby, nhsb, nvsb, xdec, dir, pli, bskip, ss, thr, \
+   OD_DERING_CHECK_OVERLAP, OD_COEFF_SHIFT)
 #include "pipeline_driver.inc"

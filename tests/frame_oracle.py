@@ -65,7 +65,7 @@ def pvq_plane_pred(lib, prefix, d, geom, pli, bsize, q0, use_masking, lam, qm, q
 
 
 def keyframe_chain(lib, prefix, planes, geom, bsize, q0, qm_q4, use_masking=1, lam=0.147, qm=None, qm_inv=None,
-                   record=True):
+                   record=True, dering_levels=None):
     """One keyframe through the oracle's whole chain (forward -> PVQ with luma H/V intra prediction and
     chroma CfL -> inverse).  Returns per plane a dict: dq (quantised coefficient plane), recon (u8),
     stats, and with record=True rec ([h/4, w/4, 9, 4] int16 band decisions at each block's origin,
@@ -92,6 +92,18 @@ def keyframe_chain(lib, prefix, planes, geom, bsize, q0, qm_q4, use_masking=1, l
            addr(rec) if record else None, addr(yplane) if record else None)
         if pli == 0:
             luma_q = d
-        recon = inverse_plane(lib, prefix, d, geom, pli, bsize, 1)
+        recon = inverse_plane(lib, prefix, d, geom, pli, bsize, 1) if dering_levels is None else None
         out.append(dict(dq=d, recon=recon, stats=stats, rec=rec, yplane=yplane))
+    if dering_levels is not None:
+        # reconstruction with the deringing application (levels [nvsb, nhsb] given): oracle/pipeline_driver.inc
+        ds = [np.ascontiguousarray(o["dq"], np.int32).copy() for o in out]
+        recs = [np.zeros(geom.plane_shape(p), np.uint8) for p in range(3)]
+        bs = np.ascontiguousarray(bsize, dtype=np.uint8)
+        lv = np.ascontiguousarray(dering_levels, np.uint8)
+        assert lv.shape == (geom.nvsb, geom.nhsb)
+        getattr(lib, "oracle_%s_inverse_frame_dering" % prefix)(
+            addr(ds[0]), addr(ds[1]), addr(ds[2]), addr(recs[0]), addr(recs[1]), addr(recs[2]), geom.nhsb, geom.nvsb,
+            addr(bs), bs.shape[1], geom.pic_w, geom.pic_h, int(q0), addr(lv))
+        for p in range(3):
+            out[p]["recon"] = recs[p]
     return out

@@ -259,3 +259,65 @@ def test_engine_baseline_sizes_q72_match_oracle(size, maps):
     eng = engine.KeyframeEngine(geom, nframes=1, q0=72, pvq_qm_q4=q4)
     _check_batch(eng, geom, [(planes, bsize)], 72, q4)
     eng.close()
+
+
+def test_engine_dering_stage_matches_oracle():
+    """daala_b200_kf_config.dering: the reconstruction through od_dering with caller-supplied per-superblock
+    levels (the final application of src/encode.c:2812-2842 on keyframes: no block is marked skipped, luma
+    directions re-used by chroma, chroma thresholds * 0.6, level 0 = untouched).  Oracle: the reference chain
+    up to the lapped planes, the reference's SB-edge postfilter, the pinned deringing port per superblock."""
+    import ctypes
+    from daala_b200 import engine
+    from daala_b200.frame import Geometry
+    lib, prefix = _oracle()
+    if prefix != "ref":
+        pytest.skip("needs the reference build (od_apply_postfilter_frame_sbs)")
+    port = oracle_lib.load_port()
+    geom = Geometry(328, 200)
+    q0, q4 = 72, np.full((3, 30), 16, np.uint8)
+    F = 2
+    frames = _frames(geom, F)
+    rng = np.random.default_rng(3)
+    levels = rng.integers(0, 6, size=(F, geom.nvsb, geom.nhsb)).astype(np.uint8)
+    levels[0, 0, 0] = 0
+    eng = engine.KeyframeEngine(geom, nframes=F, q0=q0, pvq_qm_q4=q4, split_free=1, dering=1)
+    out = eng.encode([np.stack([f[0][p] for f in frames]) for p in range(3)], np.stack([f[1] for f in frames]),
+                     dering_levels=levels)
+    gain = [0, 0.5, 0.707, 1, 1.41, 2]
+    base = float(q0) ** 0.84182
+    Dir = (ctypes.c_int * 8) * 8
+    a = oracle_lib.addr
+    for f in range(F):
+        want = frame_oracle.keyframe_chain(lib, prefix, frames[f][0], geom, frames[f][1], q0, q4, 1)
+        # the same through the oracle's frame driver (the reference's own od_dering), which bench.py uses
+        want_d = frame_oracle.keyframe_chain(lib, prefix, frames[f][0], geom, frames[f][1], q0, q4, 1, dering_levels=levels[f])
+        for pli in range(3):
+            assert np.array_equal(out["recon%d" % pli][f], want_d[pli]["recon"]), ("dering recon vs od_dering", f, pli)
+        dirs = {}
+        for pli in range(3):
+            xdec = 1 if pli else 0
+            c = frame_oracle.inverse_plane(lib, prefix, want[pli]["dq"], geom, pli, frames[f][1], 1, lapped_only=True)
+            c = np.ascontiguousarray(c, np.int32)
+            h, w = c.shape
+            lib.od_apply_postfilter_frame_sbs(a(c), w, geom.nhsb, geom.nvsb, xdec, xdec)
+            x16 = c.astype(np.int16)
+            y16 = x16.copy()
+            sb = 64 >> xdec
+            units = 16 >> xdec
+            skip_stride = geom.nhsb * units
+            bskip = np.zeros((geom.nvsb * units, skip_stride), np.uint8)
+            for sby in range(geom.nvsb):
+                for sbx in range(geom.nhsb):
+                    g = int(levels[f, sby, sbx])
+                    if g == 0:
+                        continue
+                    thr = int(gain[g] * base * (0.6 if pli else 1))
+                    d = dirs.setdefault((sby, sbx), Dir())
+                    yb = np.zeros((sb, sb), np.int16)
+                    port.port_dering(a(yb), sb, a(x16, sby * sb * w + sbx * sb), w, 8, 8, sbx, sby, geom.nhsb, geom.nvsb,
+                                     xdec, d, pli, a(bskip, (sby * units) * skip_stride + sbx * units), skip_stride, thr, 1, 4)
+                    y16[sby * sb:(sby + 1) * sb, sbx * sb:(sbx + 1) * sb] = yb
+            rec = np.clip(((y16.astype(np.int32) + 8) >> 4) + 128, 0, 255).astype(np.uint8)
+            got = out["recon%d" % pli][f]
+            assert np.array_equal(got, rec), ("dering recon", f, pli, int((got != rec).sum()))
+    eng.close()

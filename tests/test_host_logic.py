@@ -249,7 +249,7 @@ def test_native_struct_layouts_match_the_header():
     import ctypes
     from daala_b200 import _native, mc, pvq
     assert ctypes.sizeof(_native.Plane) == 4 * 8 + 6 * 4 + 4 * 8
-    assert ctypes.sizeof(_native.Frame) == 3 * ctypes.sizeof(_native.Plane) + 8 + 10 * 4 + 8
+    assert ctypes.sizeof(_native.Frame) == 3 * ctypes.sizeof(_native.Plane) + 8 + 10 * 4 + 8 + 3 * 8   # + post16[3]
     assert pvq.BLOCK_DTYPE.itemsize == 12
     assert mc.MC_BLOCK_DTYPE.itemsize == 40 and mc.MATCH_JOB_DTYPE.itemsize == 16
     assert ctypes.sizeof(pvq.PvqParams) % 8 == 0
