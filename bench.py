@@ -480,7 +480,11 @@ def run_b200(args):
             mism += int(np.count_nonzero(dev_rec[p] != want[p]["rec"]))
         out["parity_checked"] = {"frames": 1, "against": kind, "what": "reconstruction CRC-32 of 3 planes + every per-band "
                                  "(gain, theta, max_theta, K) of frame 0", "mismatches": mism}
-        assert mism == 0, "device results differ from the oracle (%d mismatches)" % mism
+        if mism:
+            # still print the line (flagged) so that the failure is visible in the record, then exit non-zero
+            out["parity_failed"] = True
+            sys.stderr.write("bench.py: device results differ from the oracle (%d mismatches): the numbers of this run "
+                             "do not count\n" % mism)
         n = 0
         while time.perf_counter() - t0 < 12.0:
             cpu_frame(lib, prefix, geom, *batches[0][(n + 1) % F])
@@ -490,9 +494,11 @@ def run_b200(args):
                                "build": CPU_BUILD["build"],
                                "sample": "%d whole 3840x2160 frames, same chain (reference functions, pvq_theta speed=1, od_dering), "
                                          "1 thread, %.1f s" % (n + 1, dt)}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if out.get("parity_failed"):
+        sys.exit(1)
 
 
 def load_profile_notes():
