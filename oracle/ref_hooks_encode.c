@@ -88,3 +88,101 @@ int oracle_ref_encode_keyframe(int w, int h, unsigned char *y, unsigned char *u,
    reference side of the drop-in link test (dropin_main.c). */
 #define ENCODE_FRAMES_NAME oracle_ref_encode_frames
 #include "encode_frames.inc"
+
+/* The deringing level search of od_encode_coefficients (src/encode.c:2680-2811) as a driver over the
+   reference's own od_compute_dist, od_dering, od_encode_cdf_cost and od_encode_cdf_adapt: luma
+   reconstruction `ctmp` (od_coeff, stride nhsb*64) against the 8-bit source.  bskip may be NULL (nothing
+   skipped).  cdf is state->adapt.dering_cdf ([11][6], in/out); dist_out (nullable) receives the six
+   distortions of every superblock, [6][nvsb*nhsb]; levels the decisions. */
+int oracle_ref_dering_search(unsigned char *src, int src_stride, const od_coeff *ctmp, int nhsb, int nvsb,
+ int quantizer, int coded_quantizer, int qm, int use_activity_masking, int is_keyframe, double dering_lambda,
+ const unsigned char *bskip, int skip_stride, uint16_t *cdf, int increment, unsigned char *levels,
+ double *dist_out) {
+  daala_enc_ctx *enc;
+  od_state *state;
+  int16_t *etmp;
+  unsigned char *noskip;
+  int w;
+  int nsb;
+  int sb;
+  int k;
+  double base;
+  enc = (daala_enc_ctx *)calloc(1, sizeof(*enc));
+  state = &enc->state;
+  enc->qm = qm;
+  enc->use_activity_masking = use_activity_masking;
+  state->coded_quantizer = coded_quantizer;
+  od_ec_enc_init(&enc->ec, 1 << 16);
+  w = nhsb*OD_BSIZE_MAX;
+  nsb = nhsb*nvsb;
+  etmp = (int16_t *)malloc(sizeof(*etmp)*w*nvsb*OD_BSIZE_MAX);
+  for (k = 0; k < w*nvsb*OD_BSIZE_MAX; k++) etmp[k] = (int16_t)ctmp[k];
+  noskip = NULL;
+  if (bskip == NULL) {
+    skip_stride = nhsb*16;
+    noskip = (unsigned char *)calloc((size_t)skip_stride*nvsb*16, 1);
+    bskip = noskip;
+  }
+  base = pow(quantizer, 0.84182);
+  for (sb = 0; sb < nsb; sb++) {
+    od_coeff orig[OD_BSIZE_MAX*OD_BSIZE_MAX];
+    od_coeff cand[OD_BSIZE_MAX*OD_BSIZE_MAX];
+    int16_t filt[OD_BSIZE_MAX*OD_BSIZE_MAX];
+    int dir[OD_DERING_NBLOCKS][OD_DERING_NBLOCKS];
+    double score[OD_DERING_LEVELS];
+    const unsigned char *sk;
+    int sbx;
+    int sby;
+    int gi;
+    int any;
+    int c;
+    int best;
+    sbx = sb%nhsb;
+    sby = sb/nhsb;
+    sk = bskip + sby*16*skip_stride + sbx*16;
+    any = 0;
+    for (k = 0; k < 256; k++) any |= !sk[(k >> 4)*skip_stride + (k & 15)];
+    levels[sb] = 0;
+    if (dist_out) for (gi = 0; gi < OD_DERING_LEVELS; gi++) dist_out[gi*nsb + sb] = 0;
+    if (!any) continue;
+    od_ref_buf_to_coeff(state, orig, OD_BSIZE_MAX, 0, src + sby*OD_BSIZE_MAX*src_stride + sbx*OD_BSIZE_MAX,
+     1, src_stride, OD_BSIZE_MAX, OD_BSIZE_MAX);
+    c = 0;
+    if (is_keyframe) {
+      int up;
+      int left;
+      up = left = sby > 0 ? levels[sb - nhsb] : 0;
+      if (sbx > 0) {
+        left = levels[sb - 1];
+        if (sby == 0) up = left;
+      }
+      c = up + left;
+    }
+    for (gi = 0; gi < OD_DERING_LEVELS; gi++) {
+      double d;
+      if (gi == 0) {
+        for (k = 0; k < OD_BSIZE_MAX*OD_BSIZE_MAX; k++) {
+          cand[k] = ctmp[(sby*OD_BSIZE_MAX + (k >> 6))*w + sbx*OD_BSIZE_MAX + (k & 63)];
+        }
+      }
+      else {
+        od_dering(&OD_DERING_VTBL_C, filt, OD_BSIZE_MAX, etmp + sby*OD_BSIZE_MAX*w + sbx*OD_BSIZE_MAX, w,
+         OD_DERING_NBLOCKS, OD_DERING_NBLOCKS, sbx, sby, nhsb, nvsb, 0, dir, 0, (unsigned char *)sk, skip_stride,
+         (int)(OD_DERING_GAIN_TABLE[gi]*base), OD_DERING_CHECK_OVERLAP, OD_COEFF_SHIFT);
+        for (k = 0; k < OD_BSIZE_MAX*OD_BSIZE_MAX; k++) cand[k] = filt[k];
+      }
+      d = od_compute_dist(enc, orig, cand, OD_BSIZE_MAX);
+      if (dist_out) dist_out[gi*nsb + sb] = d;
+      score[gi] = d + dering_lambda*od_encode_cdf_cost(gi, cdf + c*OD_DERING_LEVELS, OD_DERING_LEVELS);
+    }
+    best = 0;
+    for (gi = 1; gi < OD_DERING_LEVELS; gi++) if (score[gi] < score[best]) best = gi;
+    levels[sb] = best;
+    od_encode_cdf_adapt(&enc->ec, best, cdf + c*OD_DERING_LEVELS, OD_DERING_LEVELS, increment);
+  }
+  od_ec_enc_clear(&enc->ec);
+  free(noskip);
+  free(etmp);
+  free(enc);
+  return 0;
+}
