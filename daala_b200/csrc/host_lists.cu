@@ -131,6 +131,8 @@ daala_b200_keyframe_lists* daala_b200_host_keyframe_lists(const uint8_t* bsize, 
                                                           long long bsize_frame_pitch, int bstride, int nhsb,
                                                           int nvsb, int nthreads) {
   if (!bsize || nframes < 1 || nframes > 255 || nhsb < 1 || nvsb < 1) return nullptr;
+  // coef_off is 32-bit: a batch never holds more coded coefficients than luma samples
+  if ((long long)nframes * nhsb * nvsb * 4096 >= (1ll << 31)) return nullptr;
   auto* L = (daala_b200_keyframe_lists*)calloc(1, sizeof(daala_b200_keyframe_lists));
   if (!L) return nullptr;
   const bool prof = getenv("DAALA_B200_PROFILE_LISTS") != nullptr;

@@ -243,6 +243,8 @@ def assign_offsets(blocks):
     n2 = (16 << (2 * blocks["bs"].astype(np.int64)))
     length = np.minimum(n2, 512)
     off = np.concatenate([[0], np.cumsum(length)])
+    if int(off[-1]) >= 1 << 31:
+        raise ValueError("batch holds %d coded coefficients; coef_off is 32-bit: split the batch" % int(off[-1]))
     blocks["coef_off"] = off[:-1]
     return int(off[-1])
 
