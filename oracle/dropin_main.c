@@ -10,6 +10,8 @@
  *      equality with the pure-C reference build loaded from libdaala_ref.so.
  *   2. A keyframe (and optionally a P frame) through daala_encode_* with quant 20 / complexity 7: the
  *      coded packets must be byte-identical to the pure-C reference build's.
+ *   3. The same packets through the reference DECODER (daala_decode_*) of each build: the pictures decoded on
+ *      the CUDA back end must equal the pure-C decoder's (decoder reuse).
  * Exit status 0 = all equal. */
 #include <dlfcn.h>
 #include <stdio.h>
@@ -19,12 +21,14 @@
 #include "dct.h"
 #include "filter.h"
 
-typedef int (*encode_frames_fn)(int w, int h, int nframes, int quant, int complexity, long *bytes, unsigned *sums);
+typedef int (*encode_frames_fn)(int w, int h, int nframes, int quant, int complexity, long *bytes, unsigned *sums,
+ unsigned *decsums);
 
 /* Encodes `nframes` synthetic frames (first one a keyframe, the rest P frames) and returns each
    packet's size and checksum.  Compiled into this program (GPU back end) AND into libdaala_ref.so
    (ref_hooks_encode.c includes this file's twin, oracle_ref_encode_frames). */
-int oracle_dropin_encode_frames(int w, int h, int nframes, int quant, int complexity, long *bytes, unsigned *sums);
+int oracle_dropin_encode_frames(int w, int h, int nframes, int quant, int complexity, long *bytes, unsigned *sums,
+ unsigned *decsums);
 
 static unsigned lcg(unsigned *s) { *s = *s*1103515245u + 12345u; return (*s >> 16) & 0x7fff; }
 
@@ -83,14 +87,18 @@ int main(int argc, char **argv) {
   {
     long b0[8], b1[8];
     unsigned s0[8], s1[8];
+    unsigned d0[8], d1[8];
     int i;
     if (nframes > 8) nframes = 8;
-    if (oracle_dropin_encode_frames(w, h, nframes, 20, 7, b0, s0)) { fprintf(stderr, "GPU-backed encode failed\n"); return 3; }
-    if ((*ref_encode)(w, h, nframes, 20, 7, b1, s1)) { fprintf(stderr, "reference encode failed\n"); return 3; }
+    if (oracle_dropin_encode_frames(w, h, nframes, 20, 7, b0, s0, d0)) { fprintf(stderr, "GPU-backed encode failed\n"); return 3; }
+    if ((*ref_encode)(w, h, nframes, 20, 7, b1, s1, d1)) { fprintf(stderr, "reference encode failed\n"); return 3; }
     for (i = 0; i < nframes; i++) {
       printf("frame %d: packet %ld bytes sum %08x (GPU back end) vs %ld bytes sum %08x (pure C reference)%s\n", i,
        b0[i], s0[i], b1[i], s1[i], b0[i] == b1[i] && s0[i] == s1[i] ? "" : "  <-- DIFFERENT");
       if (b0[i] != b1[i] || s0[i] != s1[i]) fails++;
+      printf("frame %d: decoded picture sum %08x (GPU back end) vs %08x (pure C reference)%s\n", i, d0[i], d1[i],
+       d0[i] == d1[i] ? "" : "  <-- DIFFERENT");
+      if (d0[i] != d1[i]) fails++;
     }
   }
   printf("%s\n", fails ? "DROP-IN LINK TEST FAILED" : "drop-in link test ok");

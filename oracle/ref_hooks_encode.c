@@ -86,6 +86,7 @@ int oracle_ref_encode_keyframe(int w, int h, unsigned char *y, unsigned char *u,
 
 /* Multi-frame variant (keyframe + P frames) returning every packet's size and checksum: the
    reference side of the drop-in link test (dropin_main.c). */
+#include "daala/daaladec.h"
 #define ENCODE_FRAMES_NAME oracle_ref_encode_frames
 #include "encode_frames.inc"
 

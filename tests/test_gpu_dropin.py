@@ -1,7 +1,9 @@
 """Drop-in link test on the GPU: the reference encoder's own objects linked
 against libdaala_b200.so instead of its filter.o / dct.o, vtables filled by shim/cudastate.c.  The
 program (oracle/dropin_main.c) checks the function tables dcttest-style and encodes frames through
-daala_encode_*; packets must be byte-identical to the pure-C reference build's."""
+daala_encode_*; packets must be byte-identical to the pure-C reference build's, and the same packets decoded by
+the reference DECODER of each build (daala_decode_*: its inverse transforms, postfilters and motion compensation
+run on the CUDA back end in the drop-in build) must give identical pictures."""
 import os
 import subprocess
 
@@ -20,6 +22,7 @@ def _run(w, h, nframes, timeout):
     print(r.stdout)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     assert "drop-in link test ok" in r.stdout and "table checks: ok" in r.stdout
+    assert r.stdout.count("decoded picture sum") == nframes and "DIFFERENT" not in r.stdout
     return r.stdout
 
 
