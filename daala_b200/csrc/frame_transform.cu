@@ -133,94 +133,82 @@ struct SbLists {
   unsigned char wcnt[8][9];  // per-(virtual-)warp counts while the lists are being built
 };
 __device__ __forceinline__ constexpr int blk_base(int c) { return c == 0 ? 0 : c == 1 ? 256 : c == 2 ? 320 : c == 3 ? 336 : 340; }
-__device__ __forceinline__ constexpr int node_base(int l) { return l == 0 ? 0 : l == 1 ? 64 : l == 2 ? 80 : 84; }
+// 0, 64, 80, 84: one byte per level (a select chain costs four instructions where l is a run-time value)
+__device__ __forceinline__ constexpr int node_base(int l) { return (int)((0x54504000u >> (8 * l)) & 0xffu); }
 constexpr unsigned short kGateH = 0x4000;  // hfilter allowed (node inside the picture horizontally)
 constexpr unsigned short kGateV = 0x8000;  // vfilter allowed
 
 // Must be called by all threads; ends with the lists visible to the CTA.
-// Deterministic compaction: per category a warp ballot gives the rank inside
-// the warp, per-warp counts in shared memory give the offsets across warps.
+// One thread per 8x8-luma unit of the superblock (64 units, warps 0 and 1): the leaf / split-node flags of a
+// unit follow from its own block-size entry and its alignment, so nine ballots give the rank inside the warp
+// and one count of warp 0 the offset of warp 1.  A luma unit coded as 4x4 blocks emits its four leaves.
 template <int XDEC>
 __device__ __forceinline__ void build_lists(SbLists& L, const unsigned char* bsize, int bstride, int sbx,
                                             int sby, int x0, int y0, int pic_w, int pic_h) {
+  static_assert(kThreads >= 64, "one thread per 8x8-luma unit");
   constexpr int B = kMaxB >> XDEC;
-  constexpr int U = B / 4;  // 4x4 units per side
-  constexpr int kVWarps = 256 / 32;               // the 256 luma units, 32 per (virtual) warp
-  constexpr int kIters = 256 / kThreads;          // unit slices each thread walks
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  int c_it[kIters];
-  // category 0..4: leaf origin of class c; 5..8: split node of edge 8 << (cat - 5)
-  unsigned short rank_it[kIters][9];
-  unsigned flags_it[kIters];
-#pragma unroll
-  for (int it = 0; it < kIters; it++) {
-    const int t = it * kThreads + threadIdx.x, vwarp = t >> 5;
-    const bool active = t < U * U;
-    const int ux = t % U, uy = t / U;
-    int c = -1;
-    if (active) {
-      // the 8x8-luma unit covering this 4x4 unit: luma (ux>>1, uy>>1), 4:2:0 chroma (ux, uy)
-      const int bx = XDEC ? ux : ux >> 1, by = XDEC ? uy : uy >> 1;
-      const int obs = bsize[(sby * 8 + by) * bstride + sbx * 8 + bx];
-      c = (obs > XDEC ? obs : XDEC) - XDEC;   // log2(n) - 2
-    }
-    c_it[it] = c;
-    unsigned fl = 0;
+  constexpr int USZ = 8 >> XDEC;                 // unit edge in plane pixels
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int bx = t & 7, by = (t >> 3) & 7;
+  unsigned flags = 0;
+  unsigned rank[9];
+  if (t < 64) {
+    const int obs = bsize[(sby * 8 + by) * bstride + sbx * 8 + bx];
+    const int c = (obs > XDEC ? obs : XDEC) - XDEC;   // log2(n) - 2 of the leaf covering this unit
+    const unsigned lt = (1u << lane) - 1u;
+    const int xy = bx | by;
+    // category 0..4: leaf origin of class c; 5..8: split node of edge 8 << (cat - 5)
 #pragma unroll
     for (int cat = 0; cat < 9; cat++) {
-      bool f = false;
-      if (active) {
-        if (cat < 5) {
-          const int n4 = 1 << cat;
-          f = c == cat && !(ux & (n4 - 1)) && !(uy & (n4 - 1));
-        } else {
-          const int l = cat - 5, S = 8 << l, s4 = 2 << l;
-          // a node exists at unit positions aligned to its size and is split iff the leaf at its
-          // corner is smaller (src/encode.c:1466: the block size is read at the corner)
-          f = S <= B && !(ux & (s4 - 1)) && !(uy & (s4 - 1)) && c + 2 < 3 + l;
-        }
+      bool f;
+      if (cat < 5) {
+        // leaf edge 4 << cat pixels = this many units (a 4x4 luma leaf is half a unit: every unit qualifies)
+        const int a = XDEC ? (1 << cat) : (cat ? (1 << (cat - 1)) : 1);
+        f = c == cat && !(xy & (a - 1));
+      } else {
+        // a node exists at positions aligned to its size and is split iff the leaf at its corner is
+        // smaller (src/encode.c:1466: the block size is read at the corner)
+        const int l = cat - 5, S = 8 << l;
+        const int a = XDEC ? (2 << l) : (1 << l);
+        f = S <= B && !(xy & (a - 1)) && c < 1 + l;
       }
       const unsigned b = __ballot_sync(0xffffffffu, f);
-      fl |= (unsigned)f << cat;
-      rank_it[it][cat] = (unsigned short)__popc(b & lt);
-      if (lane == 0) L.wcnt[vwarp][cat] = (unsigned char)__popc(b);
+      flags |= (unsigned)f << cat;
+      rank[cat] = __popc(b & lt);
+      if (lane == 0) L.wcnt[w][cat] = (unsigned char)__popc(b);
     }
-    flags_it[it] = fl;
   }
   __syncthreads();
-#pragma unroll
-  for (int it = 0; it < kIters; it++) {
-    const int t = it * kThreads + threadIdx.x, vwarp = t >> 5;
-    const int ux = t % U, uy = t / U;
-    const unsigned short pos = (unsigned short)(((uy * 4) << 8) | (ux * 4));
+  if (t < 64) {
+    const unsigned short pos = (unsigned short)(((by * USZ) << 8) | (bx * USZ));
 #pragma unroll
     for (int cat = 0; cat < 9; cat++) {
-      int off = 0, total = 0;
-#pragma unroll
-      for (int w = 0; w < kVWarps; w++) {
-        const int n = L.wcnt[w][cat];
-        if (w < vwarp) off += n;
-        total += n;
-      }
+      const int n0 = L.wcnt[0][cat], n1 = L.wcnt[1][cat];
+      const int at = (w ? n0 : 0) + (int)rank[cat];
+      constexpr bool kQuad = XDEC == 0;           // luma 4x4 leaves come four to a unit
       if (t == 0) {
-        if (cat < 5) L.nblk[cat] = total; else L.nnode[cat - 5] = total;
+        if (cat < 5) L.nblk[cat] = (cat == 0 && kQuad) ? 4 * (n0 + n1) : n0 + n1;
+        else L.nnode[cat - 5] = n0 + n1;
       }
-      if (flags_it[it] & (1u << cat)) {
-        if (cat < 5) {
-          L.blk[blk_base(cat) + off + rank_it[it][cat]] = pos;
+      if (flags & (1u << cat)) {
+        if (cat == 0 && kQuad) {
+          L.blk[4 * at + 0] = pos;
+          L.blk[4 * at + 1] = (unsigned short)(pos + 4);
+          L.blk[4 * at + 2] = (unsigned short)(pos + (4 << 8));
+          L.blk[4 * at + 3] = (unsigned short)(pos + (4 << 8) + 4);
+        } else if (cat < 5) {
+          L.blk[blk_base(cat) + at] = pos;
         } else {
           const int S = 8 << (cat - 5);
           unsigned short v = pos;
           // gates compare PLANE coordinates with the LUMA picture size (src/encode.c:1487-1488)
-          if (x0 + ux * 4 + S <= pic_w) v |= kGateH;
-          if (y0 + uy * 4 + S <= pic_h) v |= kGateV;
-          L.node[node_base(cat - 5) + off + rank_it[it][cat]] = v;
+          if (x0 + bx * USZ + S <= pic_w) v |= kGateH;
+          if (y0 + by * USZ + S <= pic_h) v |= kGateV;
+          L.node[node_base(cat - 5) + at] = v;
         }
       }
     }
   }
-  (void)c_it;
   __syncthreads();
 }
 
@@ -241,13 +229,23 @@ __device__ __forceinline__ void transform_pass(int* tile, const SbLists& L, bool
     const int px = (pos & 255) + (along_columns ? k : 0);
     const int py = (pos >> 8) + (along_columns ? 0 : k);
     int* p = tile + py * P + px;
-    const int stride = along_columns ? P : 1;
     int v[N];
+    // compile-time strides (immediate offsets) for both directions around ONE copy of the network
+    if (along_columns) {
 #pragma unroll
-    for (int q = 0; q < N; q++) v[q] = p[q * stride];
+      for (int q = 0; q < N; q++) v[q] = p[q * P];
+    } else {
+#pragma unroll
+      for (int q = 0; q < N; q++) v[q] = p[q];
+    }
     if (kFwd) Lifting<N>::fwd(v); else Lifting<N>::inv(v);
+    if (along_columns) {
 #pragma unroll
-    for (int q = 0; q < N; q++) p[q * stride] = v[q];
+      for (int q = 0; q < N; q++) p[q * P] = v[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < N; q++) p[q] = v[q];
+    }
   }
 }
 
@@ -315,6 +313,42 @@ __device__ __forceinline__ void haar_dc_level(int* tile, const SbLists& L, int l
 }
 
 // ---------------------------------------------------------------------------
+// Superblock tile <-> int32 plane, four columns per thread.  Eight lanes cover 32 columns of one row and a
+// warp four rows: the rows sit P = 5 (mod 32) words apart in shared memory, so the four scalar shared
+// accesses of a warp touch 32 different banks, and every row segment is one 128-byte global transaction.
+// Needs 16-byte aligned rows (checked by the caller, which keeps the scalar loop for odd layouts).
+// ---------------------------------------------------------------------------
+template <int B, int P, bool kToGlobal, int kNumThreads = kThreads>
+__device__ __forceinline__ void tile_copy4(int* tile, int32_t* g, size_t gstride) {
+  constexpr int kHalves = B / 32;
+  constexpr int kWarps = kNumThreads / 32;
+  static_assert(kWarps % kHalves == 0 && B % (4 * (kWarps / kHalves)) == 0, "row groups must tile the superblock");
+  constexpr int kRowsPerIter = 4 * (kWarps / kHalves);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = (warp % kHalves) * 32 + (lane & 7) * 4;
+  const int row0 = (warp / kHalves) * 4 + (lane >> 3);
+  int* sp = tile + row0 * P + col;
+  int32_t* gp = g + (size_t)row0 * gstride + col;
+#pragma unroll 8
+  for (int r = row0; r < B; r += kRowsPerIter) {
+    if (kToGlobal) {
+      *reinterpret_cast<int4*>(gp) = make_int4(sp[0], sp[1], sp[2], sp[3]);
+    } else {
+      const int4 v = *reinterpret_cast<const int4*>(gp);
+      sp[0] = v.x;
+      sp[1] = v.y;
+      sp[2] = v.z;
+      sp[3] = v.w;
+    }
+    sp += kRowsPerIter * P;
+    gp += (size_t)kRowsPerIter * gstride;
+  }
+}
+__device__ __forceinline__ bool rows_aligned16(const void* p, long long stride_elems) {
+  return ((reinterpret_cast<uintptr_t>(p) | (uintptr_t)(stride_elems * 4)) & 15u) == 0;
+}
+
+// ---------------------------------------------------------------------------
 // Forward kernel.  grid = (nhsb*sb_rows, nplanes, nframes).
 // ---------------------------------------------------------------------------
 template <int XDEC, bool kTma>
@@ -346,16 +380,21 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
     build_lists<XDEC>(lists, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, s.x0, s.y0,
                       prm.pic_w, prm.pic_h);
     mbar_wait(bar, 0);
-    for (int i = threadIdx.x; i < T * (T / 4); i += kThreads) {
-      int r = i / (T / 4), c4 = (i - r * (T / 4)) * 4;
-      // window byte c4 sits at raw byte 14 + c4: half-word aligned, so merge two words
-      const unsigned* rw = reinterpret_cast<const unsigned*>(raw + r * RW + (RawTile<XDEC>::skip & ~3) + c4);
-      unsigned w = __funnelshift_r(rw[0], rw[1], 8 * (RawTile<XDEC>::skip & 3));
-      int* t = tile_s + r * P + c4;
-      t[0] = ((int)(w & 255u) - 128) * 16;
-      t[1] = ((int)((w >> 8) & 255u) - 128) * 16;
-      t[2] = ((int)((w >> 16) & 255u) - 128) * 16;
-      t[3] = ((int)(w >> 24) - 128) * 16;
+    // one aligned raw word (four window bytes) per item: window column c sits at raw byte skip + c, so the
+    // words kW0 .. kW0 + kWords - 1 of a row hold the T columns, the first and the last one only partly
+    constexpr int kSkip = RawTile<XDEC>::skip;
+    constexpr int kW0 = kSkip / 4;
+    constexpr int kWords = (kSkip + T + 3) / 4 - kW0;
+    for (int i = threadIdx.x; i < T * kWords; i += kThreads) {
+      const int r = i / kWords, m = i - r * kWords;
+      const unsigned w = *reinterpret_cast<const unsigned*>(raw + r * RW + 4 * (kW0 + m));
+      const int c0 = 4 * (kW0 + m) - kSkip;
+      int* t = tile_s + r * P + c0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int c = c0 + j;
+        if (c >= 0 && c < T) t[j] = ((int)((w >> (8 * j)) & 255u) - 128) * 16;
+      }
     }
   } else {
     build_lists<XDEC>(lists, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, s.x0, s.y0,
@@ -414,6 +453,10 @@ __device__ __forceinline__ void forward_sb_body(const FrameXformParams& prm, con
     }
   }
   int32_t* dst = pl.coeffs + fr * pl.coeff_frame_pitch + (size_t)s.y0 * pl.coeff_stride + s.x0;
+  if (rows_aligned16(dst, pl.coeff_stride)) {
+    tile_copy4<B, P, true>(tile, dst, pl.coeff_stride);
+    return;
+  }
   for (int i = threadIdx.x; i < B * B; i += kThreads) {
     int r = i / B, c = i % B;
     dst[(size_t)r * pl.coeff_stride + c] = tile[r * P + c];
@@ -461,9 +504,13 @@ __device__ __forceinline__ void inverse_sb_body(const FrameXformParams& prm, con
   s.x0 = sbx * B;
   s.y0 = sby * B;
   const int32_t* srcp = pl.coeffs + fr * pl.coeff_frame_pitch + (size_t)s.y0 * pl.coeff_stride + s.x0;
-  for (int i = threadIdx.x; i < B * B; i += kThreads) {
-    int r = i / B, c = i % B;
-    tile[r * P + c] = srcp[(size_t)r * pl.coeff_stride + c];
+  if (rows_aligned16(srcp, pl.coeff_stride)) {
+    tile_copy4<B, P, false>(tile, const_cast<int32_t*>(srcp), pl.coeff_stride);
+  } else {
+    for (int i = threadIdx.x; i < B * B; i += kThreads) {
+      int r = i / B, c = i % B;
+      tile[r * P + c] = srcp[(size_t)r * pl.coeff_stride + c];
+    }
   }
   build_lists<XDEC>(lists, prm.bsize + fr * prm.bsize_frame_pitch, prm.bstride, sbx, sby, s.x0, s.y0,
                     prm.pic_w, prm.pic_h);  // ends with a CTA barrier: tile and lists are visible
@@ -486,6 +533,10 @@ __device__ __forceinline__ void inverse_sb_body(const FrameXformParams& prm, con
     __syncthreads();
   }
   int32_t* dst = pl.lapped + fr * pl.lapped_frame_pitch + (size_t)s.y0 * pl.lapped_stride + s.x0;
+  if (rows_aligned16(dst, pl.lapped_stride)) {
+    tile_copy4<B, P, true>(tile, dst, pl.lapped_stride);
+    return;
+  }
   for (int i = threadIdx.x; i < B * B; i += kThreads) {
     int r = i / B, c = i % B;
     dst[(size_t)r * pl.lapped_stride + c] = tile[r * P + c];
@@ -519,12 +570,34 @@ __device__ __forceinline__ void sb_postfilter_store_body(const FrameXformParams&
   const int32_t* lap = pl.lapped + fr * pl.lapped_frame_pitch;
   const int x0 = sbx * B, y0 = sby * B;
   const int pw = prm.nhsb * B, ph = prm.nvsb * B;
-  for (int i = threadIdx.x; i < T * T; i += kPostThreads) {
-    int r = i / T, c = i - r * T;
-    int gx = x0 + c - kHalo, gy = y0 + r - kHalo;
-    int v = 0;
-    if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = lap[(size_t)gy * pl.lapped_stride + gx];
-    tile_s[r * P + c] = v;
+  const int32_t* core = lap + (size_t)y0 * pl.lapped_stride + x0;
+  if (rows_aligned16(core, pl.lapped_stride)) {
+    // the superblock itself with 128-bit loads, then the 2-sample frame around it (zero outside the plane)
+    tile_copy4<B, P, false, kPostThreads>(tile_s + kHalo * P + kHalo, const_cast<int32_t*>(core), pl.lapped_stride);
+    for (int i = threadIdx.x; i < 4 * T + 4 * B; i += kPostThreads) {
+      int r, c;
+      if (i < 4 * T) {
+        const int k = i / T;                 // rows -2, -1, B, B+1 of the window, all T columns
+        r = k < 2 ? k : B + k;
+        c = i - k * T;
+      } else {
+        const int j = i - 4 * T, k = j / B;  // columns -2, -1, B, B+1, the B rows in between
+        c = k < 2 ? k : B + k;
+        r = j - k * B + kHalo;
+      }
+      const int gx = x0 + c - kHalo, gy = y0 + r - kHalo;
+      int v = 0;
+      if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = lap[(size_t)gy * pl.lapped_stride + gx];
+      tile_s[r * P + c] = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < T * T; i += kPostThreads) {
+      int r = i / T, c = i - r * T;
+      int gx = x0 + c - kHalo, gy = y0 + r - kHalo;
+      int v = 0;
+      if (gx >= 0 && gx < pw && gy >= 0 && gy < ph) v = lap[(size_t)gy * pl.lapped_stride + gx];
+      tile_s[r * P + c] = v;
+    }
   }
   __syncthreads();
   const bool left = sbx > 0, right = sbx + 1 < prm.nhsb;
