@@ -39,6 +39,10 @@ WORKLOAD = ("3840x2160 4:2:0 all-intra hot path: lapped prefilter + fDCT(4..64, 
 
 
 def workload_text():
+    if DERING == 2:
+        return WORKLOAD + (" + deringing with its level search (src/encode.c:2708-2842: od_dering at 5 thresholds + "
+                           "od_compute_dist of the 6 candidates per 64x64 superblock, adaptive-CDF rate, decision, "
+                           "application to the three planes)")
     return WORKLOAD + (" + deringing filter (od_dering of every superblock at the level the reference encoder chose "
                        "for it)" if DERING else "")
 FWD_BYTES_PER_PX = 7.5   # SURVEY.md 8(d) K_fwd: 1.5 B in + 6 B out per padded luma pixel (4:2:0)
@@ -60,7 +64,9 @@ def parse():
                          "quadtree maps with every size 4..64")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="persistent PVQ kernel CTAs per SM (0 = default)")
     ap.add_argument("--split-free", type=int, default=1, help="dependency-free PVQ bands as phase kernels: 0 no, 1 chroma, 2 chroma + luma")
-    ap.add_argument("--dering", type=int, default=1, help="reconstruction through od_dering with the reference encoder's per-superblock levels (config 4: PVQ + deringing)")
+    ap.add_argument("--dering", type=int, default=1,
+                    help="config 4's 'PVQ + deringing': 1 = reconstruction through od_dering at the per-superblock levels "
+                         "the whole reference encoder chose; 2 = the chain searches the levels itself (both arms); 0 = off")
     ap.add_argument("--prepass", type=int, default=0, help="luma no-reference searches ahead of the chains (1) or inside them (0)")
     ap.add_argument("--level-chains", type=int, default=0, help="luma intra chains level-synchronously (1) instead of the dependency queue (0)")
     ap.add_argument("--shard", default="frames", choices=["frames", "sbrow"])
@@ -173,6 +179,8 @@ def cpu_pipeline_lib():
 
 CPU_BUILD = {"build": None}
 Q0 = 72            # state->quantizer for OD_SET_QUANT = 20 (coded quantizer 20 -> 0x48, src/quantizer.c:47)
+CODED_Q = 20       # state->coded_quantizer (scale of od_compute_dist in the deringing search)
+DERING_LAMBDA = 0.67 * 0.147 * Q0 * Q0    # enc->dering_lambda, src/rate.c:1086
 PVQ_QM_Q4 = 16     # flat state->pvq_qm_q4 entries
 
 
@@ -183,7 +191,9 @@ def cpu_frame(lib, prefix, geom, planes, bsize, levels=None, record=False):
     from tests import frame_oracle
     q4 = np.full((3, 30), PVQ_QM_Q4, np.uint8)
     return frame_oracle.keyframe_chain(lib, prefix, planes, geom, bsize, Q0, q4, use_masking=1, record=record,
-                                       dering_levels=levels if DERING else None)
+                                       dering_levels=levels if DERING == 1 else None,
+                                       dering_search=dict(coded_quantizer=CODED_Q, dering_lambda=DERING_LAMBDA)
+                                       if DERING == 2 else None)
 
 
 _CPU_JOB = {}
@@ -313,11 +323,12 @@ def run_b200(args):
         hf = make_host_frames(geom, F, rotate=s + 2 * rank)
         planes = [np.stack([f[0][p] for f in hf]) for p in range(3)]
         bsize = np.stack([f[1] for f in hf])
-        eng = engine.KeyframeEngine(geom, nframes=F, q0=Q0, use_masking=1, pvq_qm_q4=q4, dering=DERING,
+        eng = engine.KeyframeEngine(geom, nframes=F, q0=Q0, use_masking=1, pvq_qm_q4=q4, dering=DERING, coded_quantizer=CODED_Q,
+                                    dering_lambda=DERING_LAMBDA,
                                     persist_ctas_per_sm=args.ctas_per_sm, split_free=args.split_free, level_chains=args.level_chains, noref_prepass=args.prepass,
                                     max_blocks_div=1 if BLOCK_SIZES == "synthetic" else 2)
         eng.stage_inputs(planes, bsize)
-        if DERING:
+        if DERING == 1:
             eng.stage_dering_levels(np.stack([f[2] for f in hf]))
         eng.prepare_io(symbols=True, recon=True)
         slots.append(eng)
@@ -348,6 +359,7 @@ def run_b200(args):
     total_k = int(out0["luma_res"][..., 3].clip(min=0).sum()) + int(out0["chroma_res"][..., 3].clip(min=0).sum())
     assert total_k > 0, "PVQ produced no pulses"
     dev_crc = {"recon%d" % p: zlib.crc32(np.ascontiguousarray(out0["recon%d" % p][0]).tobytes()) for p in range(3)}
+    dev_levels = out0["dering_levels"][0].copy() if DERING else None
     dev_rec = [engine.band_records(out0["luma_blocks"] if p == 0 else out0["chroma_blocks"],
                                    out0["luma_res"] if p == 0 else out0["chroma_res"], geom, p, 0) for p in range(3)]
 
@@ -478,8 +490,11 @@ def run_b200(args):
         for p in range(3):
             mism += int(zlib.crc32(want[p]["recon"].tobytes()) != dev_crc["recon%d" % p])
             mism += int(np.count_nonzero(dev_rec[p] != want[p]["rec"]))
+        if DERING == 2:
+            mism += int(np.count_nonzero(dev_levels != want[0]["dering_levels"]))
         out["parity_checked"] = {"frames": 1, "against": kind, "what": "reconstruction CRC-32 of 3 planes + every per-band "
-                                 "(gain, theta, max_theta, K) of frame 0", "mismatches": mism}
+                                 "(gain, theta, max_theta, K) of frame 0" + (" + the deringing level of every superblock"
+                                                                           if DERING == 2 else ""), "mismatches": mism}
         if mism:
             # still print the line (flagged) so that the failure is visible in the record, then exit non-zero
             out["parity_failed"] = True
@@ -492,8 +507,8 @@ def run_b200(args):
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": round(geom.luma_pixels * (n + 1) / dt / 1e6, 3), "unit": UNIT, "cores": 1, "kind": kind,
                                "build": CPU_BUILD["build"],
-                               "sample": "%d whole 3840x2160 frames, same chain (reference functions, pvq_theta speed=1, od_dering), "
-                                         "1 thread, %.1f s" % (n + 1, dt)}
+                               "sample": "%d whole 3840x2160 frames, same chain (reference functions, pvq_theta speed=1, od_dering%s), "
+                                         "1 thread, %.1f s" % (n + 1, " + level search" if DERING == 2 else "", dt)}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

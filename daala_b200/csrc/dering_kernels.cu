@@ -117,14 +117,22 @@ __global__ void __launch_bounds__(256) k_dering_sb(const __grid_constant__ daala
     int d, thr;
     if (p.pli == 0) {
       int32_t var;
-      d = find_direction(in + by * 8 * kPitch + bx * 8, p.coeff_shift, &var);
-      *dslot = d;
+      if (p.dir_format == 2) {
+        // direction and variance of an earlier pass over the same input (the level search filters one plane
+        // five times, and the final application a sixth)
+        const int packed = *dslot;
+        d = packed & 7;
+        var = packed >> 3;
+      } else {
+        d = find_direction(in + by * 8 * kPitch + bx * 8, p.coeff_shift, &var);
+        *dslot = p.dir_format == 1 ? (d | (var << 3)) : d;
+      }
       int v = var >> 6;
       if (v > 32767) v = 32767;
       const int lg = v ? 32 - __clz(v) : 0;
       thr = (base * kThreshQ8[lg] + 128) >> 8;
     } else {
-      d = *dslot;
+      d = p.dir_format ? (*dslot & 7) : *dslot;
       thr = base;
     }
     // skipped neighbourhood -> untouched (DAALA_ODINTRIN form, src/dering.c:298-318)

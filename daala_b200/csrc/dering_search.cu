@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "daala_b200.h"
+#include "dering_search.h"
 
 namespace daala_b200 {
 namespace dering_search {
@@ -46,6 +47,65 @@ __global__ void __launch_bounds__(256) k_pack_sb(const int16_t* __restrict__ pla
     const uint8_t* s = src + (size_t)sby * 64 * sstride + sbx * 64;
     int32_t* o = orig + (size_t)sb * 4096;
     for (int idx = threadIdx.x; idx < 4096; idx += 256) o[idx] = ((int)s[(size_t)(idx >> 6) * sstride + (idx & 63)] - 128) * 16;
+  }
+}
+
+// The same for a batch: grid (nsb, F).
+__global__ void __launch_bounds__(256) k_pack_sb_batch(const int16_t* __restrict__ plane, long long ppitch, int pstride,
+                                                       const uint8_t* __restrict__ src, long long spitch, int sstride,
+                                                       int nhsb, int32_t* __restrict__ cand, int32_t* __restrict__ orig) {
+  const int sb = blockIdx.x, sbx = sb % nhsb, sby = sb / nhsb, f = blockIdx.y;
+  const size_t slot = ((size_t)f * gridDim.x + sb) * 4096;
+  const int16_t* p = plane + f * ppitch + (size_t)sby * 64 * pstride + sbx * 64;
+  for (int idx = threadIdx.x; idx < 4096; idx += 256) cand[slot + idx] = p[(size_t)(idx >> 6) * pstride + (idx & 63)];
+  if (orig) {
+    const uint8_t* s = src + f * spitch + (size_t)sby * 64 * sstride + sbx * 64;
+    for (int idx = threadIdx.x; idx < 4096; idx += 256)
+      orig[slot + idx] = ((int)s[(size_t)(idx >> 6) * sstride + (idx & 63)] - 128) * 16;
+  }
+}
+
+// The decision of daala_b200_dering_decide on the device, one thread per (key)frame: every frame starts from the
+// initial CDFs (the adaptation state is reset per frame).  Same operations as the host function; log() is the CUDA
+// library's, so a decision could differ from the host's only where two scores agree to the last bits.
+__global__ void k_dering_decide(const double* __restrict__ dist, int nframes, int nhdr, int nvdr, double lambda,
+                                uint8_t* __restrict__ levels) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nframes) return;
+  const int nsb = nhdr * nvdr;
+  const size_t per_level = (size_t)nframes * nsb;
+  const double* d = dist + (size_t)f * nsb;
+  uint8_t* lv = levels + (size_t)f * nsb;
+  unsigned short cdf[kContexts][kLevels];
+  for (int c = 0; c < kContexts; c++)
+    for (int j = 0; j < kLevels; j++) cdf[c][j] = (unsigned short)(32 * j + 32);
+  for (int sby = 0; sby < nvdr; sby++) {
+    for (int sbx = 0; sbx < nhdr; sbx++) {
+      const int sb = sby * nhdr + sbx;
+      int left = 0, up = 0;
+      if (sby > 0) left = up = lv[sb - nhdr];
+      if (sbx > 0) {
+        left = lv[sb - 1];
+        if (sby == 0) up = left;
+      }
+      unsigned short* m = cdf[up + left];
+      const int total = m[kLevels - 1];
+      int best = 0;
+      double best_dist = 0;
+      for (int gi = 0; gi < kLevels; gi++) {
+        const int prev = gi ? m[gi - 1] : 0;
+        const double prob = (m[gi] - prev) / (double)total;
+        const double score = d[gi * per_level + sb] + lambda * -(M_LOG2E * log(prob));
+        if (gi == 0 || score < best_dist) {
+          best_dist = score;
+          best = gi;
+        }
+      }
+      lv[sb] = (uint8_t)best;
+      if (m[kLevels - 1] + 128 > 32767)
+        for (int i = 0; i < kLevels; i++) m[i] = (unsigned short)((m[i] >> 1) + i + 1);
+      for (int i = best; i < kLevels; i++) m[i] = (unsigned short)(m[i] + 128);
+    }
   }
 }
 
@@ -111,6 +171,9 @@ extern "C" int daala_b200_dering_decide(const double* dist, int nhdr, int nvdr, 
   }
   return 0;
 }
+
+extern "C" int daala_b200_dering_plane_batch(const daala_b200_dering_params* prm, int nframes, long long y_pitch,
+                                             long long x_pitch, long long dir_pitch, long long thr_pitch, void* stream);
 
 extern "C" int daala_b200_dering_search(const daala_b200_dering_search_params* p, uint16_t* cdf, int increment,
                                         uint8_t* levels, double* dist_out, void* stream_) {
@@ -188,4 +251,51 @@ extern "C" int daala_b200_dering_search(const daala_b200_dering_search_params* p
                                          p->bskip ? coded.data() : nullptr, cdf, increment, levels);
   done(cudaSuccess);
   return r;
+}
+
+extern "C" int daala_b200_dering_search_enqueue(const daala_b200_dering_search_batch* b, void* stream_) {
+  if (!b || !b->etmp || !b->src || !b->filt || !b->orig || !b->cand || !b->dir || !b->zskip || !b->dist || !b->levels ||
+      b->nframes < 1 || b->nhsb < 1 || b->nvsb < 1)
+    return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int nsb = b->nhsb * b->nvsb, F = b->nframes;
+  const int w = b->nhsb * 64, h = b->nvsb * 64;
+  const long long filt_pitch = (long long)w * h;
+  for (int gi = 0; gi < kLevels; gi++) {
+    const int16_t* plane = b->etmp;
+    long long ppitch = b->etmp_pitch;
+    int pstride = b->etmp_stride;
+    if (gi) {
+      daala_b200_dering_params dp;
+      memset(&dp, 0, sizeof(dp));
+      dp.y = b->filt;
+      dp.x = b->etmp;
+      dp.dir = b->dir;
+      dp.bskip = b->zskip;
+      dp.ystride = w;
+      dp.xstride = b->etmp_stride;
+      dp.dir_stride = b->nhsb * 8;
+      dp.skip_stride = b->nhsb * 16;
+      dp.nhsb = b->nhsb;
+      dp.nvsb = b->nvsb;
+      dp.threshold = b->threshold[gi];
+      dp.overlap = 1;
+      dp.coeff_shift = 4;
+      dp.dir_format = gi == 1 ? 1 : 2;   // the direction search runs once; later passes re-use direction and variance
+      const int r = daala_b200_dering_plane_batch(&dp, F, filt_pitch, b->etmp_pitch, (long long)nsb * 64, 0, st);
+      if (r) return r;
+      plane = b->filt;
+      ppitch = filt_pitch;
+      pstride = w;
+    }
+    k_pack_sb_batch<<<dim3(nsb, F), 256, 0, st>>>(plane, ppitch, pstride, b->src, b->src_pitch, b->src_stride, b->nhsb,
+                                                  b->cand, gi == 0 ? b->orig : nullptr);
+    cudaError_t e = cudaGetLastError();
+    if (e) return (int)e;
+    const int r = daala_b200_compute_dist(b->orig, b->cand, F * nsb, 64, b->qm_is_flat, b->use_activity_masking,
+                                          b->coded_quantizer, b->dist + (size_t)gi * F * nsb, st);
+    if (r) return r;
+  }
+  k_dering_decide<<<(F + 31) / 32, 32, 0, st>>>(b->dist, F, b->nhsb, b->nvsb, b->dering_lambda, b->levels);
+  return (int)cudaGetLastError();
 }

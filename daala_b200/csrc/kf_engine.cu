@@ -28,6 +28,7 @@
 #include <mutex>
 
 #include "daala_b200.h"
+#include "dering_search.h"
 #include "gen/coding_order.inc"
 #include "pvq_math.cuh"
 #include "pvq_warp.cuh"
@@ -1036,6 +1037,9 @@ struct daala_b200_kf {
   int32_t* dering_dir;             // [F][nvsb*8][nhsb*8]
   uint8_t* dering_skip;            // all zero: keyframes never mark a block skipped (src/encode.c:1690)
   int dering_tbl[2][6];
+  // level search (cfg.dering == 2): packed superblock pairs and the 6 x F x nsb distortions
+  int32_t *dering_orig, *dering_cand;
+  double* dering_dist;
   Lists lists;
   Stage luma, chroma;
   daala_b200_frame frame;
@@ -1274,6 +1278,11 @@ static int kf_alloc(daala_b200_kf* kf) {
       KF_CHECK(dalloc(kf, &kf->dering_in[p], n));
       KF_CHECK(dalloc(kf, &kf->dering_out[p], n));
     }
+    if (kf->cfg.dering == 2) {
+      KF_CHECK(dalloc(kf, &kf->dering_orig, nsb * 4096));
+      KF_CHECK(dalloc(kf, &kf->dering_cand, nsb * 4096));
+      KF_CHECK(dalloc(kf, &kf->dering_dist, nsb * 6));
+    }
     // thresholds per level: (int)(OD_DERING_GAIN_TABLE[gi] * pow(quantizer, 0.84182) * (luma ? 1 : 0.6)), src/encode.c:2697,2822
     const double gain[6] = {0, 0.5, 0.707, 1, 1.41, 2};
     const double base = pow((double)kf->cfg.q0, 0.84182);
@@ -1381,6 +1390,33 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
     rc = daala_b200_launch_sb_postfilter_store(&f16, 3, s);
     if (rc) return rc;
     const int nsb = kf->nhsb * kf->nvsb;
+    const bool search = kf->cfg.dering == 2;
+    if (search) {
+      // the level search of src/encode.c:2708-2811 for every frame of the batch: levels -> kf->dering_level
+      daala_b200_dering_search_batch sb;
+      memset(&sb, 0, sizeof(sb));
+      sb.etmp = kf->dering_in[0];
+      sb.src = kf->pixels[0];
+      sb.etmp_pitch = sb.src_pitch = (long long)kf->plane_w[0] * kf->plane_h[0];
+      sb.etmp_stride = sb.src_stride = kf->plane_w[0];
+      sb.nframes = kf->F;
+      sb.nhsb = kf->nhsb;
+      sb.nvsb = kf->nvsb;
+      for (int g = 0; g < 6; g++) sb.threshold[g] = kf->dering_tbl[0][g];
+      sb.coded_quantizer = kf->cfg.coded_quantizer;
+      sb.qm_is_flat = kf->cfg.qm_is_flat;
+      sb.use_activity_masking = kf->cfg.use_masking;
+      sb.dering_lambda = kf->cfg.dering_lambda;
+      sb.filt = kf->dering_out[0];     // free until the final application below overwrites it
+      sb.orig = kf->dering_orig;
+      sb.cand = kf->dering_cand;
+      sb.dir = kf->dering_dir;
+      sb.zskip = kf->dering_skip;
+      sb.dist = kf->dering_dist;
+      sb.levels = kf->dering_level;
+      rc = daala_b200_dering_search_enqueue(&sb, s);
+      if (rc) return rc;
+    }
     k_dering_thresholds<<<(kf->F * nsb + 255) / 256, 256, 0, s>>>(
         kf->dering_level, kf->dering_thr[0], kf->dering_thr[1], kf->F * nsb,
         make_int4(kf->dering_tbl[0][0], kf->dering_tbl[0][1], kf->dering_tbl[0][2], kf->dering_tbl[0][3]),
@@ -1406,6 +1442,7 @@ static int kf_enqueue_step(daala_b200_kf* kf, int phases) {
       dp.threshold = 0;
       dp.overlap = 1;      // OD_DERING_CHECK_OVERLAP
       dp.coeff_shift = 4;  // OD_COEFF_SHIFT
+      dp.dir_format = search ? 2 : 0;   // after a search the direction map is already there (packed with the variance)
       rc = daala_b200_dering_plane_batch(&dp, kf->F, per, per, (long long)nsb * 64, nsb, s);
       if (rc) return rc;
     }
@@ -1510,6 +1547,9 @@ void daala_b200_kf_destroy(daala_b200_kf* kf) {
   cudaFree(kf->lv_snap);
   cudaFree(kf->lv_bar);
   cudaFree(kf->dering_level);
+  cudaFree(kf->dering_orig);
+  cudaFree(kf->dering_cand);
+  cudaFree(kf->dering_dist);
   cudaFree(kf->dering_thr[0]);
   cudaFree(kf->dering_thr[1]);
   cudaFree(kf->dering_dir);
@@ -1552,6 +1592,7 @@ int daala_b200_kf_launches_per_step(const daala_b200_kf* kf) {
   n += 4 + (kf->cfg.split_free > 0 ? split(kf->chroma) : 1);                      // chroma: begin, cfl, gather, bands, finish
   if (!kf->cfg.dering) n += 2;                                                    // inverse, SB postfilter + store
   else n += 1 + 1 + 1 + 3 + 3;   // inverse, SB postfilter -> int16, thresholds, dering per plane, store
+  if (kf->cfg.dering == 2) n += 5 + 6 + 6 + 1;   // level search: 5 filtered candidates, 6 packs, 6 distortion passes, decision
   return n;
 }
 
@@ -1686,7 +1727,7 @@ int daala_b200_kf_submit(daala_b200_kf* kf, const daala_b200_kf_io* io) {
   }
   const size_t map_bytes = (size_t)kf->nhsb * 8 * kf->nvsb * 8 * F;
   KF_CHECK(cudaMemcpyAsync(kf->bsize, io->bsize, map_bytes, cudaMemcpyHostToDevice, s));
-  if (kf->cfg.dering) {
+  if (kf->cfg.dering == 1) {
     if (!io->dering_level) return (int)cudaErrorInvalidValue;
     KF_CHECK(cudaMemcpyAsync(kf->dering_level, io->dering_level, (size_t)kf->nhsb * kf->nvsb * F, cudaMemcpyHostToDevice, s));
   }
@@ -1718,6 +1759,8 @@ int daala_b200_kf_submit(daala_b200_kf* kf, const daala_b200_kf_io* io) {
   if (io->chroma_skip_diff) KF_CHECK(cudaMemcpyAsync(io->chroma_skip_diff, kf->chroma.prm.res_skip_diff, 8 * (size_t)tot.n_chroma, cudaMemcpyDeviceToHost, s));
   if (io->chroma_flip) KF_CHECK(cudaMemcpyAsync(io->chroma_flip, kf->chroma.prm.res_flip, 4 * (size_t)tot.n_chroma, cudaMemcpyDeviceToHost, s));
   if (io->counts) KF_CHECK(cudaMemcpyAsync(io->counts, kf->lists.cnt, sizeof(int32_t) * 32, cudaMemcpyDeviceToHost, s));
+  if (io->dering_level_out && kf->cfg.dering)
+    KF_CHECK(cudaMemcpyAsync(io->dering_level_out, kf->dering_level, (size_t)kf->nhsb * kf->nvsb * F, cudaMemcpyDeviceToHost, s));
   return 0;
 }
 

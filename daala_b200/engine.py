@@ -23,7 +23,8 @@ class Config(ctypes.Structure):
     _fields_ = [("pic_w", c_int), ("pic_h", c_int), ("nframes", c_int), ("q0", c_int), ("use_masking", c_int),
                 ("qm_stride", c_int), ("pvq_norm_lambda", ctypes.c_double), ("pvq_qm_q4", (ctypes.c_ubyte * 32) * 3),
                 ("qm", c_void_p), ("qm_inv", c_void_p), ("sb_row0", c_int), ("sb_rows", c_int),
-                ("max_blocks_div", c_int), ("persist_ctas_per_sm", c_int), ("split_free", c_int), ("dering", c_int), ("noref_prepass", c_int), ("level_chains", c_int), ("stream", c_void_p)]
+                ("max_blocks_div", c_int), ("persist_ctas_per_sm", c_int), ("split_free", c_int), ("dering", c_int), ("noref_prepass", c_int), ("level_chains", c_int), ("stream", c_void_p),
+                ("coded_quantizer", c_int), ("qm_is_flat", c_int), ("dering_lambda", ctypes.c_double)]
 
 
 class Totals(ctypes.Structure):
@@ -35,7 +36,7 @@ class IO(ctypes.Structure):
                 ("pixels_out", c_void_p * 3), ("luma_blocks", c_void_p), ("chroma_blocks", c_void_p),
                 ("luma_res", c_void_p), ("chroma_res", c_void_p), ("luma_y16", c_void_p), ("chroma_y16", c_void_p),
                 ("luma_skip_diff", c_void_p), ("chroma_skip_diff", c_void_p), ("chroma_flip", c_void_p),
-                ("counts", c_void_p)]
+                ("counts", c_void_p), ("dering_level_out", c_void_p)]
 
 
 class Buffers(ctypes.Structure):
@@ -101,7 +102,8 @@ class KeyframeEngine:
     """One engine = one set of device buffers + one CUDA graph for batches of `nframes` keyframes."""
 
     def __init__(self, geom, nframes=1, q0=38, use_masking=1, lam=pvq.PVQ_LAMBDA, pvq_qm_q4=None, qm=None,
-                 qm_inv=None, sb_row0=0, sb_rows=0, max_blocks_div=0, persist_ctas_per_sm=0, split_free=0, level_chains=0, noref_prepass=0, dering=0, pinned=True):
+                 qm_inv=None, sb_row0=0, sb_rows=0, max_blocks_div=0, persist_ctas_per_sm=0, split_free=0, level_chains=0, noref_prepass=0, dering=0, coded_quantizer=0,
+                 qm_is_flat=0, dering_lambda=None, pinned=True):
         self.L = _bind()
         self.geom, self.F = geom, nframes
         if qm is None:
@@ -123,6 +125,12 @@ class KeyframeEngine:
         cfg.level_chains = int(level_chains)
         cfg.noref_prepass = int(noref_prepass)
         cfg.dering = int(dering)
+        # dering == 2 (level search): scale of od_compute_dist and enc->dering_lambda = 0.67 * OD_PVQ_LAMBDA * q^2
+        # (src/rate.c:1086; the target quantizer is this engine's q0)
+        cfg.coded_quantizer = int(coded_quantizer)
+        cfg.qm_is_flat = int(qm_is_flat)
+        cfg.dering_lambda = float(0.67 * pvq.PVQ_LAMBDA * q0 * q0 if dering_lambda is None else dering_lambda)
+        self.dering_lambda = cfg.dering_lambda
         self.dering = int(dering)
         self.kf = self.L.daala_b200_kf_create(ctypes.byref(cfg))
         if not self.kf:
@@ -213,7 +221,7 @@ class KeyframeEngine:
         for p in range(3):
             io.pixels[p] = self._arr("in%d" % p, (self.F,) + g.plane_shape(p), np.uint8).ctypes.data
         io.bsize = self._arr("bsize", (self.F,) + tuple(g.bsize_shape), np.uint8).ctypes.data
-        if self.dering:
+        if self.dering == 1:
             io.dering_level = self._arr("dlev", (self.F, g.nvsb, g.nhsb), np.uint8).ctypes.data
         io.totals = ctypes.pointer(t)
         out = {}
@@ -237,6 +245,9 @@ class KeyframeEngine:
                 setattr(io, k, out[k].ctypes.data)
         out["counts"] = self._arr("cnt", (32,), np.int32)
         io.counts = out["counts"].ctypes.data
+        if self.dering:
+            out["dering_levels"] = self._arr("dlev_out", (self.F, g.nvsb, g.nhsb), np.uint8)
+            io.dering_level_out = out["dering_levels"].ctypes.data
         self._io, self._out = io, out
         self.h2d_bytes = sum(int(np.prod(g.plane_shape(p))) for p in range(3)) * self.F + int(np.prod(g.bsize_shape)) * self.F
         self.d2h_bytes = sum(v.nbytes for v in out.values())
@@ -253,7 +264,7 @@ class KeyframeEngine:
         """One batch end to end through the C ABI with host buffers; returns the result arrays (views of
         the engine's host buffers: copy what must survive the next call)."""
         self.stage_inputs(planes, bsize)
-        if self.dering:
+        if self.dering == 1:
             self.stage_dering_levels(dering_levels)
         self.prepare_io(symbols, recon)
         self.submit()

@@ -375,7 +375,10 @@ typedef struct daala_b200_dering_params {
   const int32_t *sb_threshold;
   int ystride, xstride, dir_stride, skip_stride;
   int nhsb, nvsb, xdec, pli;
-  int threshold, overlap, coeff_shift, pad_;
+  int threshold, overlap, coeff_shift;
+  int dir_format;   /* 0: dir holds plain directions 0..7.  1: the luma pass stores direction | variance << 3;
+                       2: the luma pass READS that instead of searching again (same input plane, another
+                       threshold); chroma passes mask the direction out when dir_format != 0 */
 } daala_b200_dering_params;
 int daala_b200_dering_plane(const daala_b200_dering_params *prm, void *stream);
 
@@ -474,14 +477,21 @@ typedef struct daala_b200_kf_config {
                                   the band context in HBM records instead of the persistent kernel:
                                   0 = no, 1 = chroma, 2 = chroma and luma bands 3 / 6 */
   int dering;                  /* 1: the reconstruction goes through od_dering with the per-superblock levels of
-                                  daala_b200_kf_io.dering_level (the final application of src/encode.c:2812-2842; the
-                                  level search stays with the caller, like the block-size decision) */
+                                  daala_b200_kf_io.dering_level (the final application of src/encode.c:2812-2842).
+                                  2: the engine also SEARCHES the levels (src/encode.c:2708-2811: five filtered
+                                  candidates + the unfiltered one scored by od_compute_dist + lambda * adaptive-CDF
+                                  rate, decision per frame on the device) and returns them in
+                                  daala_b200_kf_io.dering_level_out; needs coded_quantizer / qm_is_flat /
+                                  dering_lambda below */
   int noref_prepass;           /* 1: the no-reference searches of every luma chain band run ahead of the chains in a
                                   fully parallel kernel (they do not depend on the prediction) */
   int level_chains;            /* luma intra chains: 0 = persistent kernel with a dependency queue, 1 = one
                                   level-synchronous kernel (phases separated by grid barriers); implies
                                   split_free = 2 */
   void *stream;                /* cudaStream_t to run on, or NULL: the engine creates its own */
+  int coded_quantizer;         /* state->coded_quantizer (scale of od_compute_dist, src/encode.c:1221); dering == 2 */
+  int qm_is_flat;              /* enc->qm == OD_FLAT_QM: od_compute_dist is the plain squared error; dering == 2 */
+  double dering_lambda;        /* enc->dering_lambda (src/rate.c:1086); dering == 2 */
 } daala_b200_kf_config;
 
 typedef struct daala_b200_kf_totals {
@@ -508,6 +518,7 @@ typedef struct daala_b200_kf_io {
   double *luma_skip_diff, *chroma_skip_diff;
   int32_t *chroma_flip;
   int32_t *counts;                      /* 32 ints of device-side counters (diagnostics) */
+  uint8_t *dering_level_out;            /* [nframes][nvsb][nhsb]: the levels applied (config.dering == 2: the searched ones) */
 } daala_b200_kf_io;
 
 typedef struct daala_b200_kf_buffers {  /* device pointers of an engine (tests, device-resident callers) */

@@ -15,6 +15,9 @@
   port_pvq_theta(out, x0, r0, n, q, y, it, mt, k, beta, sd, kf, pli, qm, qmi, lam)
 #define X_HV_PRED(pred, d, w, bx, by, bsize, bstride, bs) port_hv_intra_pred(pred, d, w, bx, by, bsize, bstride, bs)
 #define X_CFL_PRED(pred, n, luma, lw, bs, obs) port_resample_luma_coeffs_420(pred, n, luma, lw, bs, (obs) == 0)
+/* the level search exists only on the reference build (od_encode_cdf_* of the reference's entropy coder) */
+#include <stdlib.h>
+#define X_DERING_SEARCH(src, ss, ctmp, nhsb, nvsb, q, cq, qm, masking, lambda, cdf, levels) abort()
 #define X_DERING(y, ys, x, xs, sbx, sby, nhsb, nvsb, xdec, dir, pli, bskip, ss, thr) \
   port_dering(y, ys, x, xs, 8, 8, sbx, sby, nhsb, nvsb, xdec, dir, pli, bskip, ss, thr, 1, 4)
 #include "pipeline_driver.inc"

@@ -1,6 +1,7 @@
 /* oracle/ref_hooks_encode.c -- TEST INFRASTRUCTURE ONLY.
  * Compiles the reference's src/encode.c in place (see ref_hooks_pvq.c). */
 #include "encode.c"
+#include "ref_dering_vtbl.h"
 
 /* od_compute_dist (static, src/encode.c:1180) on a minimal encoder context: only enc->qm,
    enc->use_activity_masking and enc->state.coded_quantizer are read. */
@@ -91,7 +92,8 @@ int oracle_ref_encode_keyframe(int w, int h, unsigned char *y, unsigned char *u,
 #include "encode_frames.inc"
 
 /* The deringing level search of od_encode_coefficients (src/encode.c:2680-2811) as a driver over the
-   reference's own od_compute_dist, od_dering, od_encode_cdf_cost and od_encode_cdf_adapt: luma
+   reference's own od_compute_dist, od_dering (with the function table of this build, ref_dering_vtbl.h),
+   od_encode_cdf_cost and od_encode_cdf_adapt: luma
    reconstruction `ctmp` (od_coeff, stride nhsb*64) against the 8-bit source.  bskip may be NULL (nothing
    skipped).  cdf is state->adapt.dering_cdf ([11][6], in/out); dist_out (nullable) receives the six
    distortions of every superblock, [6][nvsb*nhsb]; levels the decisions. */
@@ -167,7 +169,7 @@ int oracle_ref_dering_search(unsigned char *src, int src_stride, const od_coeff 
         }
       }
       else {
-        od_dering(&OD_DERING_VTBL_C, filt, OD_BSIZE_MAX, etmp + sby*OD_BSIZE_MAX*w + sbx*OD_BSIZE_MAX, w,
+        od_dering(oracle_dering_vtbl(), filt, OD_BSIZE_MAX, etmp + sby*OD_BSIZE_MAX*w + sbx*OD_BSIZE_MAX, w,
          OD_DERING_NBLOCKS, OD_DERING_NBLOCKS, sbx, sby, nhsb, nvsb, 0, dir, 0, (unsigned char *)sk, skip_stride,
          (int)(OD_DERING_GAIN_TABLE[gi]*base), OD_DERING_CHECK_OVERLAP, OD_COEFF_SHIFT);
         for (k = 0; k < OD_BSIZE_MAX*OD_BSIZE_MAX; k++) cand[k] = filt[k];

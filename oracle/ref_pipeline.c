@@ -26,8 +26,14 @@ int oracle_ref_pvq_theta(od_coeff *out, const od_coeff *x0, const od_coeff *r0,
 #define X_HV_PRED(pred, d, w, bx, by, bsize, bstride, bs) \
   od_hv_intra_pred(pred, d, w, bx, by, (unsigned char *)(bsize), bstride, bs)
 #define X_CFL_PRED(pred, n, luma, lw, bs, obs) od_resample_luma_coeffs(pred, n, luma, lw, 1, 1, bs, obs)
-#include "dering.h"
+#include "ref_dering_vtbl.h"
+int oracle_ref_dering_search(unsigned char *src, int src_stride, const od_coeff *ctmp, int nhsb, int nvsb,
+ int quantizer, int coded_quantizer, int qm, int use_activity_masking, int is_keyframe, double dering_lambda,
+ const unsigned char *bskip, int skip_stride, uint16_t *cdf, int increment, unsigned char *levels,
+ double *dist_out);
+#define X_DERING_SEARCH(src, ss, ctmp, nhsb, nvsb, q, cq, qm, masking, lambda, cdf, levels) \
+  oracle_ref_dering_search(src, ss, ctmp, nhsb, nvsb, q, cq, qm, masking, 1, lambda, NULL, 0, cdf, 128, levels, NULL)
 #define X_DERING(y, ys, x, xs, sbx, sby, nhsb, nvsb, xdec, dir, pli, bskip, ss, thr) \
-  od_dering(&OD_DERING_VTBL_C, y, ys, x, xs, 8, 8, sbx, sby, nhsb, nvsb, xdec, dir, pli, bskip, ss, thr, \
+  od_dering(oracle_dering_vtbl(), y, ys, x, xs, 8, 8, sbx, sby, nhsb, nvsb, xdec, dir, pli, bskip, ss, thr, \
    OD_DERING_CHECK_OVERLAP, OD_COEFF_SHIFT)
 #include "pipeline_driver.inc"

@@ -65,11 +65,14 @@ def pvq_plane_pred(lib, prefix, d, geom, pli, bsize, q0, use_masking, lam, qm, q
 
 
 def keyframe_chain(lib, prefix, planes, geom, bsize, q0, qm_q4, use_masking=1, lam=0.147, qm=None, qm_inv=None,
-                   record=True, dering_levels=None):
+                   record=True, dering_levels=None, dering_search=None):
     """One keyframe through the oracle's whole chain (forward -> PVQ with luma H/V intra prediction and
     chroma CfL -> inverse).  Returns per plane a dict: dq (quantised coefficient plane), recon (u8),
     stats, and with record=True rec ([h/4, w/4, 9, 4] int16 band decisions at each block's origin,
-    -32768 where no band) and yplane (pulse vectors in raster order)."""
+    -32768 where no band) and yplane (pulse vectors in raster order).
+    dering_levels: [nvsb, nhsb] levels -> reconstruction through the deringing application.
+    dering_search: dict(coded_quantizer=, dering_lambda=, qm=1) -> the levels are searched the way the encoder does
+    (src/encode.c:2708-2811, reference build only) and returned as out[0]["dering_levels"]."""
     from daala_b200 import pvq
     if qm is None:
         qm, qm_inv = pvq.default_qm(True)
@@ -92,7 +95,7 @@ def keyframe_chain(lib, prefix, planes, geom, bsize, q0, qm_q4, use_masking=1, l
            addr(rec) if record else None, addr(yplane) if record else None)
         if pli == 0:
             luma_q = d
-        recon = inverse_plane(lib, prefix, d, geom, pli, bsize, 1) if dering_levels is None else None
+        recon = inverse_plane(lib, prefix, d, geom, pli, bsize, 1) if dering_levels is None and dering_search is None else None
         out.append(dict(dq=d, recon=recon, stats=stats, rec=rec, yplane=yplane))
     if dering_levels is not None:
         # reconstruction with the deringing application (levels [nvsb, nhsb] given): oracle/pipeline_driver.inc
@@ -106,4 +109,20 @@ def keyframe_chain(lib, prefix, planes, geom, bsize, q0, qm_q4, use_masking=1, l
             addr(bs), bs.shape[1], geom.pic_w, geom.pic_h, int(q0), addr(lv))
         for p in range(3):
             out[p]["recon"] = recs[p]
+    if dering_search is not None:
+        ds = [np.ascontiguousarray(o["dq"], np.int32).copy() for o in out]
+        recs = [np.zeros(geom.plane_shape(p), np.uint8) for p in range(3)]
+        bs = np.ascontiguousarray(bsize, dtype=np.uint8)
+        lv = np.zeros((geom.nvsb, geom.nhsb), np.uint8)
+        src = np.ascontiguousarray(planes[0], np.uint8)
+        fn = getattr(lib, "oracle_%s_inverse_frame_dering_search" % prefix)
+        fn.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int] * 2 + [ctypes.c_void_p] + [ctypes.c_int] * 4 + [
+            ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_double, ctypes.c_void_p]
+        fn(addr(ds[0]), addr(ds[1]), addr(ds[2]), addr(recs[0]), addr(recs[1]), addr(recs[2]), geom.nhsb, geom.nvsb,
+           addr(bs), bs.shape[1], geom.pic_w, geom.pic_h, int(q0), addr(src), src.shape[1],
+           int(dering_search["coded_quantizer"]), int(dering_search.get("qm", 1)), int(use_masking),
+           float(dering_search["dering_lambda"]), addr(lv))
+        for p in range(3):
+            out[p]["recon"] = recs[p]
+        out[0]["dering_levels"] = lv
     return out

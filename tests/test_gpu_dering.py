@@ -19,7 +19,7 @@ class DeringParams(ctypes.Structure):
                 ("ystride", ctypes.c_int), ("xstride", ctypes.c_int), ("dir_stride", ctypes.c_int),
                 ("skip_stride", ctypes.c_int), ("nhsb", ctypes.c_int), ("nvsb", ctypes.c_int), ("xdec", ctypes.c_int),
                 ("pli", ctypes.c_int), ("threshold", ctypes.c_int), ("overlap", ctypes.c_int),
-                ("coeff_shift", ctypes.c_int), ("pad_", ctypes.c_int)]
+                ("coeff_shift", ctypes.c_int), ("dir_format", ctypes.c_int)]
 
 
 @pytest.mark.parametrize("xdec", [0, 1])
@@ -63,7 +63,7 @@ def test_dering_plane_matches_oracle(xdec, threshold, overlap):
     p = DeringParams(y=y_dev.data_ptr(), x=x_dev.data_ptr(), dir=dir_dev.data_ptr(), bskip=skip_dev.data_ptr(),
                      sb_threshold=None, ystride=w, xstride=w, dir_stride=nhsb * 8, skip_stride=skip_stride,
                      nhsb=nhsb, nvsb=nvsb, xdec=xdec, pli=1 if xdec else 0, threshold=threshold, overlap=overlap,
-                     coeff_shift=4, pad_=0)
+                     coeff_shift=4, dir_format=0)
     assert L.daala_b200_dering_plane(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
     torch.cuda.synchronize()
     assert np.array_equal(dir_dev.cpu().numpy(), want_dir)

@@ -321,3 +321,45 @@ def test_engine_dering_stage_matches_oracle():
             got = out["recon%d" % pli][f]
             assert np.array_equal(got, rec), ("dering recon", f, pli, int((got != rec).sum()))
     eng.close()
+
+
+@pytest.mark.parametrize("q0", [72, 38])
+def test_engine_dering_search_matches_reference(q0):
+    """daala_b200_kf_config.dering = 2: the engine searches the deringing levels itself (src/encode.c:2708-2811: five
+    filtered candidates and the unfiltered reconstruction scored by od_compute_dist + lambda * adaptive-CDF rate, one
+    decision thread per frame) and applies them.  Oracle: the reference chain up to the SB-edge postfilter (ctmp),
+    then the reference's own loop (oracle/ref_hooks_encode.c::oracle_ref_dering_search) on ctmp and the source
+    luma; the levels must be identical, and the reconstruction equal to the oracle's deringing application at
+    those levels."""
+    from daala_b200 import engine
+    from daala_b200.frame import Geometry
+    from tests import test_dering_search as ds
+    lib, prefix = _oracle()
+    if prefix != "ref":
+        pytest.skip("needs the reference build (od_compute_dist, od_dering, od_encode_cdf_*)")
+    geom = Geometry(328, 200)
+    q4 = np.full((3, 30), 16, np.uint8)
+    F = 3
+    frames = _frames(geom, F, q_seed=q0)
+    eng = engine.KeyframeEngine(geom, nframes=F, q0=q0, pvq_qm_q4=q4, split_free=1, dering=2, coded_quantizer=q0)
+    out = eng.encode([np.stack([f[0][p] for f in frames]) for p in range(3)], np.stack([f[1] for f in frames]))
+    got_levels = out["dering_levels"].copy()
+    a = oracle_lib.addr
+    seen = set()
+    for f in range(F):
+        want = frame_oracle.keyframe_chain(lib, prefix, frames[f][0], geom, frames[f][1], q0, q4, 1)
+        c = frame_oracle.inverse_plane(lib, prefix, want[0]["dq"], geom, 0, frames[f][1], 1, lapped_only=True)
+        c = np.ascontiguousarray(c, np.int32)
+        lib.od_apply_postfilter_frame_sbs(a(c), c.shape[1], geom.nhsb, geom.nvsb, 0, 0)
+        cdf = np.zeros((11, 6), np.uint16)
+        cdf[:] = 32 * np.arange(1, 7, dtype=np.uint16)
+        src = np.ascontiguousarray(frames[f][0][0], np.uint8)
+        lv_ref, _ = ds.ref_search(lib, src, c, geom.nhsb, geom.nvsb, q0, 1, 1, eng.dering_lambda, None, cdf)
+        lv_ref = lv_ref.reshape(geom.nvsb, geom.nhsb)
+        assert np.array_equal(got_levels[f], lv_ref), (f, got_levels[f], lv_ref)
+        seen |= set(lv_ref.ravel().tolist())
+        want_d = frame_oracle.keyframe_chain(lib, prefix, frames[f][0], geom, frames[f][1], q0, q4, 1, dering_levels=lv_ref)
+        for pli in range(3):
+            assert np.array_equal(out["recon%d" % pli][f], want_d[pli]["recon"]), ("recon at the searched levels", f, pli)
+    assert len(seen) >= 2, seen
+    eng.close()
