@@ -271,8 +271,9 @@ def run_reference(args):
     value = geom.luma_pixels * per_step * args.steps / total / 1e6
     sample = ("%d whole 3840x2160 4:2:0 frames per step, one per worker process on %d processes (= usable cores: "
               "affinity %d, cgroup CPU quota %s); reference functions: prefilter + fDCT + pvq_theta(speed=1) + "
-              "iDCT + postfilter; block sizes: %s" % (per_step, cores, aff, "none" if quota is None else "%.2f" % quota,
-                                                        BLOCK_SIZES))
+              "iDCT + postfilter%s; block sizes: %s" % (per_step, cores, aff, "none" if quota is None else "%.2f" % quota,
+                                                          " + od_dering" + (" with its level search" if DERING == 2 else "")
+                                                          if DERING else "", BLOCK_SIZES))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3),
