@@ -338,3 +338,29 @@ def test_dropin_link_test_binary_resolves_filter_and_dct_symbols_from_the_librar
                  "od_enc_opt_vtbl_init_x86", "daala_encode_create", "od_pvq_encode"):
         assert kind.get(name) == "T", (name, kind.get(name))
     assert "od_bin_fdct8" not in kind or kind["od_bin_fdct8"] == "U"
+
+
+def test_no_gpu_means_a_loud_failure_not_a_cpu_fallback():
+    """Without a CUDA device the product path refuses to run: the engine's constructor raises, a drop-in symbol
+    (void signature, nothing to return an error through) terminates the process with a message.  Only meaningful
+    where there is no GPU (the build container); skipped on a GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from daala_b200 import engine
+    from daala_b200.frame import Geometry
+    with pytest.raises(RuntimeError, match="daala_b200_kf_create failed"):
+        engine.KeyframeEngine(Geometry(128, 128), nframes=1)
+    code = ("import ctypes, numpy as np\n"
+            "from daala_b200 import _native\n"
+            "L = _native.lib()\n"
+            "x = np.zeros(16, np.int32); y = np.zeros(16, np.int32)\n"
+            "L.od_bin_fdct4x4.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]\n"
+            "L.od_bin_fdct4x4(y.ctypes.data, 4, x.ctypes.data, 4)\n"
+            "print('computed without a GPU')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode != 0 and "computed without a GPU" not in r.stdout
+    assert "no CPU fallback exists" in r.stderr
